@@ -1,0 +1,451 @@
+// flowz -- C++ EDSL surface of zignal-b200 (header-only, C++17, no Boost).
+//
+// Source-level stand-in for the reference's <flowz/flowz.hpp> (andre-bergner/zignal,
+// /root/reference/flowz/flowz.hpp): the same spellings build the same graphs --
+//
+//     _1 ... _6, make_placeholder<n>()        :75-82, 1252-1257
+//     make_terminal(x), std::ref(param)       :68-72, flowz/README.md:42-63
+//     a |= b  (and a >> b)   series           :92   (>>: experimental_steps/wires_mono_only.cpp:37)
+//     a | b                  parallel         :91
+//     (a , b)                fan-out          :90
+//     ~a                     feedback         :93
+//     _k[_n]  (and _k[-n])   unit delays      :84-85 (_[-n]: experimental_steps/delay_expression.cpp:99)
+//     + - * / unary -        leaf arithmetic  :769-772
+//     compile(expr)                           :1233-1249
+//     f(x1, ..., xN) -> std::tuple<...>, currying with fewer arguments   :1193-1229
+//     input_arity, output_arity, max_input_delays, transforms::make_canonical,
+//     make_binary_feedback                    :162-246, 443-506, 794-805, 100-102
+//
+// -- but nothing is evaluated by template expansion.  An expression is a small typed tree whose
+// only compile-time content is its wire counts (needed for the std::tuple return type and for the
+// argument-count check).  compile() sends the tree as text through the C ABI
+// (include/zignal_b200.h); the library canonicalises it, lowers it to a flat tick program and
+//   * ticks it on the host for the scalar operator() (one voice, one sample -- the reference's
+//     whole API), and
+//   * evaluates it block-wise for many channels on a B200 through block_evaluator (new).
+//
+// Known deviations from the reference (documented in DESIGN.md): outputs are float (double if a
+// double is involved) rather than the per-wire C++ result type; canonical forms are compared
+// with operator== on run-time trees, not with std::is_same on types.
+#pragma once
+
+#include <array>
+#include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../zignal_b200.h"
+
+namespace flowz {
+
+struct error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+namespace detail {
+
+inline void check(int status) {
+    if (status != ZG_OK) throw error(zg_last_error());
+}
+
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+// writer state: parameters ($k) are numbered in order of first appearance
+struct writer {
+    std::ostringstream os;
+    std::vector<const float*> refs;
+    int ref_index(const float* p) {
+        for (size_t i = 0; i < refs.size(); ++i)
+            if (refs[i] == p) return (int)i;
+        refs.push_back(p);
+        return (int)refs.size() - 1;
+    }
+};
+
+struct expr_tag {};
+template <class T> constexpr bool is_expr_v = std::is_base_of<expr_tag, std::decay_t<T>>::value;
+
+namespace tag {
+struct plus {}; struct minus {}; struct multiplies {}; struct divides {}; struct negate {};
+struct sequence {}; struct parallel {}; struct channel {}; struct feedback {}; struct binary_feedback {};
+}
+
+template <class Tag> struct symbol;
+template <> struct symbol<tag::plus> { static constexpr const char* s = " + "; };
+template <> struct symbol<tag::minus> { static constexpr const char* s = " - "; };
+template <> struct symbol<tag::multiplies> { static constexpr const char* s = "*"; };
+template <> struct symbol<tag::divides> { static constexpr const char* s = "/"; };
+template <> struct symbol<tag::sequence> { static constexpr const char* s = " |= "; };
+template <> struct symbol<tag::parallel> { static constexpr const char* s = " | "; };
+template <> struct symbol<tag::channel> { static constexpr const char* s = " , "; };
+
+// ---- terminals --------------------------------------------------------------------------------
+
+template <int N> struct placeholder_expr;
+
+template <int K>
+struct delayed_expr : expr_tag {
+    static constexpr int in = K, out = 1;
+    static constexpr bool has_double = false;
+    int n;
+    void write(writer& w) const { w.os << "_" << K << "[_" << n << "]"; }
+};
+
+template <int K>
+struct placeholder_expr : expr_tag {
+    static_assert(K >= 1, "placeholders are numbered from 1");
+    static constexpr int in = K, out = 1;
+    static constexpr bool has_double = false;
+    void write(writer& w) const { w.os << "_" << K; }
+    template <int N>
+    delayed_expr<K> operator[](placeholder_expr<N>) const { return {{}, N}; }    // _k[_n]
+    delayed_expr<K> operator[](int n) const {                                    // _k[-n]
+        if (n == 0) throw error("a delay of 0 is the wire itself");
+        return {{}, n < 0 ? -n : n};
+    }
+};
+
+template <class T>
+struct literal_expr : expr_tag {
+    static constexpr int in = 0, out = 1;
+    static constexpr bool has_double = std::is_same<T, double>::value;
+    T value;
+    void write(writer& w) const {
+        char buf[64];
+        if constexpr (std::is_integral<T>::value) std::snprintf(buf, sizeof buf, "%d", (int)value);
+        else if constexpr (std::is_same<T, float>::value) std::snprintf(buf, sizeof buf, "%af", (double)value);
+        else std::snprintf(buf, sizeof buf, "%a", (double)value);
+        if (buf[0] == '-') w.os << "(" << buf << ")"; else w.os << buf;
+    }
+};
+
+struct ref_expr : expr_tag {                       // std::ref(x): non-owning, read at every tick
+    static constexpr int in = 0, out = 1;
+    static constexpr bool has_double = false;
+    const float* p;
+    void write(writer& w) const { w.os << "$" << w.ref_index(p); }
+};
+
+// ---- operator nodes ---------------------------------------------------------------------------
+
+template <class Tag, class A>
+struct unary_expr : expr_tag {
+    A a;
+    static constexpr int in = std::is_same<Tag, tag::feedback>::value ? cmax(0, A::in - A::out) : A::in;
+    static constexpr int out = std::is_same<Tag, tag::feedback>::value ? A::out : 1;
+    static constexpr bool has_double = A::has_double;
+    void write(writer& w) const {
+        w.os << (std::is_same<Tag, tag::feedback>::value ? "(~" : "(-");
+        a.write(w);
+        w.os << ")";
+    }
+};
+
+template <class Tag, class A, class B>
+struct binary_expr : expr_tag {
+    A a;
+    B b;
+    static constexpr bool has_double = A::has_double || B::has_double;
+    static constexpr int in =
+        std::is_same<Tag, tag::sequence>::value ? A::in + cmax(0, B::in - A::out)
+        : std::is_same<Tag, tag::parallel>::value ? A::in + B::in
+        : std::is_same<Tag, tag::binary_feedback>::value ? cmax(0, A::in - B::out) + cmax(0, B::in - A::out)
+        : cmax(A::in, B::in);
+    static constexpr int out =
+        std::is_same<Tag, tag::sequence>::value ? B::out + cmax(0, A::out - B::in)
+        : (std::is_same<Tag, tag::parallel>::value || std::is_same<Tag, tag::channel>::value) ? A::out + B::out
+        : std::is_same<Tag, tag::binary_feedback>::value ? B::out
+        : 1;
+    void write(writer& w) const {
+        if constexpr (std::is_same<Tag, tag::binary_feedback>::value) {
+            w.os << "bfb("; a.write(w); w.os << " , "; b.write(w); w.os << ")";
+        } else {
+            w.os << "("; a.write(w); w.os << symbol<Tag>::s; b.write(w); w.os << ")";
+        }
+    }
+};
+
+// ---- lifting plain values into terminals ------------------------------------------------------
+
+template <class T, class = void> struct as_expr_impl;
+template <class T>
+struct as_expr_impl<T, std::enable_if_t<is_expr_v<T>>> {
+    using type = std::decay_t<T>;
+    static type make(const T& t) { return t; }
+};
+template <class T>
+struct as_expr_impl<T, std::enable_if_t<std::is_arithmetic<std::decay_t<T>>::value>> {
+    using V = std::conditional_t<std::is_integral<std::decay_t<T>>::value, int,
+              std::conditional_t<std::is_same<std::decay_t<T>, float>::value, float, double>>;
+    using type = literal_expr<V>;
+    static type make(const T& t) { return {{}, (V)t}; }
+};
+template <class T>
+struct as_expr_impl<std::reference_wrapper<T>, void> {
+    static_assert(std::is_same<std::remove_const_t<T>, float>::value, "std::ref parameters must be float");
+    using type = ref_expr;
+    static type make(std::reference_wrapper<T> r) { return {{}, &r.get()}; }
+};
+template <class T> using as_expr_t = typename as_expr_impl<std::decay_t<T>>::type;
+template <class T> as_expr_t<T> as_expr(const T& t) { return as_expr_impl<std::decay_t<T>>::make(t); }
+
+template <class T> constexpr bool is_operand_v =
+    is_expr_v<T> || std::is_arithmetic<std::decay_t<T>>::value;
+template <class T> struct is_refw : std::false_type {};
+template <class T> struct is_refw<std::reference_wrapper<T>> : std::true_type {};
+template <class A, class B> constexpr bool arith_ok_v =
+    (is_expr_v<A> && (is_operand_v<B> || is_refw<std::decay_t<B>>::value)) ||
+    (is_expr_v<B> && (is_operand_v<A> || is_refw<std::decay_t<A>>::value));
+
+template <class Tag, class A, class B>
+binary_expr<Tag, as_expr_t<A>, as_expr_t<B>> make_binary(const A& a, const B& b) {
+    return {{}, as_expr(a), as_expr(b)};
+}
+
+template <class E>
+std::string to_text(const E& e, std::vector<const float*>* refs = nullptr) {
+    writer w;
+    e.write(w);
+    if (refs) *refs = w.refs;
+    return w.os.str();
+}
+
+}  // namespace detail
+
+// ---- operators (found by ADL on detail:: types; also visible via `using namespace flowz`) --------
+
+namespace detail {
+
+#define FLOWZ_ARITH(op, T)                                                           \
+    template <class A, class B, class = std::enable_if_t<arith_ok_v<A, B>>>          \
+    auto operator op(const A& a, const B& b) { return make_binary<tag::T>(a, b); }
+FLOWZ_ARITH(+, plus)
+FLOWZ_ARITH(-, minus)
+FLOWZ_ARITH(*, multiplies)
+FLOWZ_ARITH(/, divides)
+#undef FLOWZ_ARITH
+
+#define FLOWZ_COMB(op, T)                                                                      \
+    template <class A, class B, class = std::enable_if_t<is_expr_v<A> && is_expr_v<B>>>       \
+    auto operator op(const A& a, const B& b) { return make_binary<tag::T>(a, b); }
+FLOWZ_COMB(|=, sequence)
+FLOWZ_COMB(>>, sequence)
+FLOWZ_COMB(|, parallel)
+#undef FLOWZ_COMB
+
+template <class A, class B, class = std::enable_if_t<is_expr_v<A> && is_expr_v<B>>>
+auto operator,(const A& a, const B& b) { return make_binary<tag::channel>(a, b); }
+
+template <class A, class = std::enable_if_t<is_expr_v<A>>>
+unary_expr<tag::negate, A> operator-(const A& a) { return {{}, a}; }
+template <class A, class = std::enable_if_t<is_expr_v<A>>>
+unary_expr<tag::feedback, A> operator~(const A& a) { return {{}, a}; }
+
+}  // namespace detail
+
+// ---- building blocks ------------------------------------------------------------------------------
+
+template <int n>
+detail::placeholder_expr<n> make_placeholder() { return {}; }
+
+template <class X>
+auto make_terminal(X x) { return detail::as_expr(x); }
+
+template <class L, class R>
+auto make_binary_feedback(const L& l, const R& r) { return detail::make_binary<detail::tag::binary_feedback>(l, r); }
+
+const auto _1 = make_placeholder<1>();
+const auto _2 = make_placeholder<2>();
+const auto _3 = make_placeholder<3>();
+const auto _4 = make_placeholder<4>();
+const auto _5 = make_placeholder<5>();
+const auto _6 = make_placeholder<6>();
+
+template <class E> std::string to_string(const E& e) { return detail::to_text(e); }
+
+// ---- static analysis function objects (usable like the reference's transforms) -------------------
+
+struct input_arity {
+    template <class E> int operator()(const E& e) const {
+        int n = 0; detail::check(zg_expr_arity(detail::to_text(e).c_str(), &n, nullptr)); return n;
+    }
+};
+struct output_arity {
+    template <class E> int operator()(const E& e) const {
+        int n = 0; detail::check(zg_expr_arity(detail::to_text(e).c_str(), nullptr, &n)); return n;
+    }
+};
+namespace detail {
+template <class E> std::vector<int> delays_of(const E& e, int which) {
+    int buf[64], n = 0;
+    check(zg_expr_delays(to_text(e).c_str(), which, buf, 64, &n));
+    return std::vector<int>(buf, buf + (n < 64 ? n : 64));
+}
+}
+struct max_input_delays {
+    template <class E> std::vector<int> operator()(const E& e) const { return detail::delays_of(e, 0); }
+};
+struct min_input_delays {
+    template <class E> std::vector<int> operator()(const E& e) const { return detail::delays_of(e, 1); }
+};
+
+// A run-time expression (result of a rewrite).  Compares structurally with any expression.
+struct dyn_expr : detail::expr_tag {
+    std::string text;
+    void write(detail::writer& w) const { w.os << text; }
+};
+template <class A, class B, class = std::enable_if_t<detail::is_expr_v<A> && detail::is_expr_v<B>>>
+bool same_expr(const A& a, const B& b) {
+    // normalise both sides through the library's parser/printer
+    auto norm = [](const std::string& s) {
+        std::vector<char> buf(s.size() * 4 + 256);
+        // make_canonical is the identity on trees without '~'
+        detail::check(zg_expr_canonical(s.c_str(), buf.data(), buf.size()));
+        return std::string(buf.data());
+    };
+    return norm(detail::to_text(a)) == norm(detail::to_text(b));
+}
+
+namespace transforms {
+using flowz::input_arity;
+using flowz::output_arity;
+using flowz::max_input_delays;
+using flowz::min_input_delays;
+struct make_canonical {                                  // flowz.hpp:794-805
+    template <class E> dyn_expr operator()(const E& e) const {
+        std::string s = detail::to_text(e);
+        std::vector<char> buf(s.size() * 8 + 1024);
+        detail::check(zg_expr_canonical(s.c_str(), buf.data(), buf.size()));
+        dyn_expr d; d.text = buf.data(); return d;
+    }
+};
+}  // namespace transforms
+
+// ---- block evaluator: `channels` voices of one compiled graph on one B200 ----------------------------
+
+class block_evaluator {
+    std::shared_ptr<zg_plan> plan_;
+public:
+    block_evaluator() = default;
+    explicit block_evaluator(zg_plan* p) : plan_(p, zg_plan_destroy) {}
+    zg_plan* handle() const { return plan_.get(); }
+    // device pointers, planar [channels][ld] (or interleaved, per the plan), asynchronous on `stream`
+    void process(const float* const* in, float* const* out, int64_t n_samples, int64_t ld_in,
+                 int64_t ld_out, void* stream = nullptr) {
+        detail::check(zg_process(plan_.get(), (const void* const*)in, (void* const*)out, n_samples, ld_in, ld_out, stream));
+    }
+    // host pointers: H2D, kernel, D2H, synchronise
+    void process_host(const float* const* in, float* const* out, int64_t n_samples, int64_t ld_in, int64_t ld_out) {
+        detail::check(zg_process_host(plan_.get(), (const void* const*)in, (void* const*)out, n_samples, ld_in, ld_out));
+    }
+    void reset() { detail::check(zg_state_reset(plan_.get())); }
+    void set_param(int index, const float* values, int64_t n) { detail::check(zg_param_set(plan_.get(), index, values, n)); }
+    zg_plan_info info() const { zg_plan_info i; detail::check(zg_plan_get_info(plan_.get(), &i)); return i; }
+};
+
+// ---- compile() and the callable it returns -----------------------------------------------------------
+
+namespace detail {
+template <class T, size_t... Is>
+auto make_result_tuple(const double* v, std::index_sequence<Is...>) { return std::make_tuple((T)v[Is]...); }
+
+template <class T> constexpr int dtype_of() {
+    return std::is_integral<T>::value ? ZG_I32 : std::is_same<T, float>::value ? ZG_F32 : ZG_F64;
+}
+}  // namespace detail
+
+template <size_t arity, size_t n_out, bool has_double>
+class stateful_lambda {
+    std::shared_ptr<zg_graph> graph_;
+    std::unique_ptr<zg_voice, void (*)(zg_voice*)> voice_{nullptr, zg_voice_destroy};
+    std::vector<const float*> refs_;
+
+    void refresh_params() {
+        for (size_t i = 0; i < refs_.size(); ++i) detail::check(zg_voice_set_param(voice_.get(), (int)i, *refs_[i]));
+    }
+
+public:
+    stateful_lambda(const std::string& text, std::vector<const float*> refs) : refs_(std::move(refs)) {
+        zg_graph* g = nullptr;
+        detail::check(zg_graph_compile(text.c_str(), &g));
+        graph_.reset(g, zg_graph_destroy);
+        zg_voice* v = nullptr;
+        detail::check(zg_voice_create(g, &v));
+        voice_.reset(v);
+    }
+    // copying the callable copies its state (flowz.hpp:1206-1207)
+    stateful_lambda(const stateful_lambda& o) : graph_(o.graph_), refs_(o.refs_) {
+        zg_voice* v = nullptr;
+        detail::check(zg_voice_clone(o.voice_.get(), &v));
+        voice_.reset(v);
+    }
+    stateful_lambda& operator=(const stateful_lambda& o) {
+        if (this != &o) { stateful_lambda t(o); std::swap(graph_, t.graph_); std::swap(voice_, t.voice_); std::swap(refs_, t.refs_); }
+        return *this;
+    }
+    stateful_lambda(stateful_lambda&&) = default;
+    stateful_lambda& operator=(stateful_lambda&&) = default;
+
+    // one tick; with fewer than `arity` arguments returns a closure waiting for the rest (:1203-1212)
+    template <class... Args, class = std::enable_if_t<sizeof...(Args) <= arity>>
+    auto operator()(const Args&... args) {
+        static_assert((std::is_arithmetic<Args>::value && ...), "tick arguments must be arithmetic");
+        if constexpr (sizeof...(Args) == arity) {
+            using T = std::conditional_t<has_double || (std::is_same<Args, double>::value || ...), double, float>;
+            double in[arity ? arity : 1] = {(double)args...};
+            int dt[arity ? arity : 1] = {detail::dtype_of<Args>()...};
+            double out[n_out];
+            refresh_params();
+            detail::check(zg_voice_tick(voice_.get(), in, dt, out, nullptr));
+            return detail::make_result_tuple<T>(out, std::make_index_sequence<n_out>{});
+        } else {
+            return [args..., self = *this](const auto&... rest) mutable { return self(args..., rest...); };
+        }
+    }
+
+    static constexpr size_t input_count = arity;
+    static constexpr size_t output_count = n_out;
+    const zg_graph* graph() const { return graph_.get(); }
+    std::string canonical() const { return zg_graph_canonical(graph_.get()); }
+    std::string dump() const { return zg_graph_dump(graph_.get()); }
+    std::vector<float> state() const {
+        float* s; int n;
+        detail::check(zg_voice_state(voice_.get(), &s, &n));
+        return std::vector<float>(s, s + n);
+    }
+
+    // B200 block evaluator for `channels` independent voices of this graph (state starts at zero).
+    block_evaluator on_device(int64_t channels, int mode = ZG_MODE_FAST, int device = 0) const {
+        zg_plan_opts o;
+        zg_plan_opts_default(&o);
+        o.device = device; o.channels = channels; o.mode = mode;
+        return on_device(o);
+    }
+    block_evaluator on_device(const zg_plan_opts& o) const {
+        zg_plan* p = nullptr;
+        detail::check(zg_plan_create(graph_.get(), &o, &p));
+        block_evaluator be(p);
+        for (size_t i = 0; i < refs_.size(); ++i) be.set_param((int)i, refs_[i], 1);
+        return be;
+    }
+};
+
+struct compile_fn {
+    template <class E, class = std::enable_if_t<detail::is_expr_v<E>>>
+    auto operator()(const E& e) const {
+        std::vector<const float*> refs;
+        std::string text = detail::to_text(e, &refs);
+        return stateful_lambda<(size_t)E::in, (size_t)E::out, E::has_double>(text, std::move(refs));
+    }
+};
+inline constexpr compile_fn compile{};
+
+}  // namespace flowz

@@ -1,0 +1,174 @@
+/* zignal-b200 :: C ABI of the B200-native flowz evaluator.
+ *
+ * The reference (andre-bergner/zignal, /root/reference) is a header-only C++14 EDSL; it has no
+ * FFI layer.  Its whole public surface for the evaluated path is
+ *
+ *     auto f = flowz::compile(expr);          flowz/flowz.hpp:1233-1249
+ *     std::tuple<...> y = f(x1, ..., xN);     flowz/flowz.hpp:1225-1229   (one sample, one voice)
+ *
+ * This header is the boundary a binding for that path talks to.  The C++ shim
+ * include/flowz/flowz.hpp (same spellings as the reference) and the Python test harness
+ * (zignal_b200/__init__.py, ctypes) are the two clients.  Every entry point names the reference
+ * code it stands in for.  All functions are extern "C", take plain pointers/sizes, never throw,
+ * and return 0 (ZG_OK) or a negative zg_status; the message is in zg_last_error() (thread local).
+ *
+ * Expressions travel as text in flowz syntax with C++ operator precedence:
+ *     _k              input wire k (1-based)                    flowz.hpp:75-82, 1252-1257
+ *     _k[_n]  _k[-n]  wire k delayed by n samples               flowz.hpp:84-85 / prototypes
+ *     a |= b, a >> b  series                                    flowz.hpp:92 / wires_mono_only.cpp:37
+ *     a | b           parallel (splits the inputs)              flowz.hpp:91
+ *     (a , b)         fan-out ("channel")                       flowz.hpp:90
+ *     ~a              feedback                                  flowz.hpp:93
+ *     + - * / unary - leaf arithmetic (C++ built-in semantics)  flowz.hpp:769-772
+ *     0.5f 0.5 2      float / double / int literal terminals    flowz.hpp:68-72
+ *     $k              run-time parameter k (std::ref terminal)  flowz/README.md:42-63
+ */
+#ifndef ZIGNAL_B200_H
+#define ZIGNAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum zg_status {
+    ZG_OK = 0,
+    ZG_ERR_PARSE = -1,        /* malformed expression text */
+    ZG_ERR_GRAPH = -2,        /* expression is not a valid flowz graph (a compile error in the reference) */
+    ZG_ERR_ARG = -3,          /* bad argument */
+    ZG_ERR_UNSUPPORTED = -4,  /* valid graph, but not supported by the requested path */
+    ZG_ERR_CUDA = -5,         /* CUDA / NVRTC failure, or no usable device */
+    ZG_ERR_INTERNAL = -6
+} zg_status;
+
+typedef enum zg_dtype { ZG_I32 = 0, ZG_F32 = 1, ZG_F64 = 2 } zg_dtype;
+
+typedef struct zg_graph zg_graph; /* immutable, shareable between threads        */
+typedef struct zg_voice zg_voice; /* one voice on the host: state_ of stateful_lambda */
+typedef struct zg_plan zg_plan;   /* C channels of one graph on one GPU          */
+
+const char* zg_last_error(void);
+const char* zg_version(void);
+
+/* ---- static analysis on a bare expression (no front panel) -----------------------------------
+ * input_arity / output_arity            flowz.hpp:162-246
+ * max_input_delays / min_input_delays   flowz.hpp:443-506  (which: 0 = max, 1 = min; -1 = unused)
+ * make_canonical                        flowz.hpp:794-805  (text of the rewritten expression)   */
+int zg_expr_arity(const char* expr, int* n_in, int* n_out);
+int zg_expr_delays(const char* expr, int which, int* delays, int capacity, int* count);
+int zg_expr_canonical(const char* expr, char* buf, size_t capacity);
+
+/* ---- compile()  flowz.hpp:1233-1249 -----------------------------------------------------------
+ * front panel (:273-277) + canonical form (:794-935) + state layout (:685-725) + lowering to the
+ * flat tick program that both the host tick and the CUDA kernels execute.                      */
+int zg_graph_compile(const char* expr, zg_graph** out);
+void zg_graph_destroy(zg_graph* g);
+
+typedef struct zg_graph_info {
+    int n_in;      /* input_arity of the user expression                                       */
+    int n_out;     /* output_arity                                                             */
+    int n_params;  /* number of $k parameters                                                  */
+    int n_state;   /* floats of delay-line state per channel after line sharing                */
+    int n_lines;   /* delay lines                                                              */
+    int n_nodes;   /* SSA nodes of one tick                                                    */
+    int all_f32;   /* 1 if the tick is pure fp32 when fed fp32 inputs (device path requirement) */
+} zg_graph_info;
+int zg_graph_get_info(const zg_graph* g, zg_graph_info* info);
+/* canonical expression / SSA dump; valid until the graph is destroyed (print_state stand-in) */
+const char* zg_graph_canonical(const zg_graph* g);
+const char* zg_graph_dump(const zg_graph* g);
+
+/* ---- host voice: stateful_lambda (flowz.hpp:1181-1230) ----------------------------------------
+ * zg_voice_tick is operator()(args...) for exactly n_in arguments; in_dtypes[i] says what C++
+ * type argument i had (int stays int inside the tick, as with the reference's templates).
+ * State starts at zero (:1191) and persists across ticks; zg_voice_clone copies it (:1207).    */
+int zg_voice_create(const zg_graph* g, zg_voice** out);
+int zg_voice_clone(const zg_voice* v, zg_voice** out);
+void zg_voice_destroy(zg_voice* v);
+int zg_voice_tick(zg_voice* v, const double* in, const int* in_dtypes, double* out, int* out_dtypes);
+int zg_voice_set_param(zg_voice* v, int index, float value);
+int zg_voice_state(zg_voice* v, float** state, int* n_state);
+
+/* ---- device plan: the block evaluator (new; replaces the caller's per-sample for-loop,
+ *      test/benchmark.cpp:137-147, for `channels` independent voices at once) ------------------ */
+typedef enum zg_mode {
+    ZG_MODE_EXACT = 0, /* separately rounded mul/add, lane per channel: bit-identical to the x86
+                          non-FMA build of the reference (CMakeLists.txt:17-19)                 */
+    ZG_MODE_FAST = 1   /* FMA contraction (+ verified time-split when enabled): <= 1e-5 block-relative */
+} zg_mode;
+
+typedef enum zg_layout {
+    ZG_PLANAR = 0,      /* buffer[c * ld + t] : one contiguous block per channel */
+    ZG_INTERLEAVED = 1  /* buffer[t * ld + c] : one frame per sample             */
+} zg_layout;
+
+typedef enum zg_input_kind {
+    ZG_IN_BUFFER = 0, /* samples come from the caller's buffer                                  */
+    ZG_IN_DIRAC = 1,  /* 1.0 at stream position 0, else 0; synthesised in the kernel (in[i] may be NULL) */
+    ZG_IN_ZERO = 2    /* all zeros; synthesised in the kernel                                   */
+} zg_input_kind;
+
+#define ZG_MAX_WIRES 8
+
+typedef struct zg_plan_opts {
+    int device;           /* CUDA device ordinal                                                */
+    int64_t channels;     /* C: independent voices evaluated by this plan                       */
+    int mode;             /* zg_mode                                                            */
+    int layout;           /* zg_layout                                                          */
+    int io_dtype;         /* ZG_F32 (bf16 storage: see DESIGN.md, later round)                  */
+    int time_split;       /* FAST mode only: 0 = off, 1 = auto (use P>1 lanes per channel when the
+                             graph is linear, its state decays and there are too few channels to
+                             fill the GPU), >1 = force P (must be 2,4,8,16 or 32)                 */
+    int input_kind[ZG_MAX_WIRES];
+    int force_jit;        /* 1 = never use the prebuilt biquad kernels (tests)                  */
+    int reserved[7];
+} zg_plan_opts;
+
+void zg_plan_opts_default(zg_plan_opts* o);
+/* The kernel zg_plan_create() would specialise for this graph (the generated-tick path), as CUDA
+ * source (want_cubin = 0) or as an sm_100a cubin (want_cubin = 1).  Needs libnvrtc only -- no
+ * device -- so it doubles as an offline build check.  buf may be NULL to query *size.           */
+int zg_graph_kernel_compile(const zg_graph* g, const zg_plan_opts* opts, int uniform_params, int want_cubin,
+                            char* buf, size_t capacity, size_t* size);
+int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out);
+void zg_plan_destroy(zg_plan* p);
+
+typedef struct zg_plan_info {
+    char kernel[96];      /* name of the kernel this plan launches                              */
+    int jit;              /* 1 = specialised with NVRTC at plan time, 0 = prebuilt in the library */
+    int lanes_per_channel;/* P of the time split (1 = lane per channel)                         */
+    int warmup_samples;   /* W of the time split                                                */
+    int regs_per_thread;
+    int smem_bytes;
+    int launches;         /* kernels launched by this plan so far                               */
+    int threads_per_cta;  /* geometry of the last launch                                        */
+    int stages;           /* TMA pipeline depth per warp of the last launch                     */
+    int uniform_params;   /* 1 = all parameters are scalars and travel in the constant bank     */
+} zg_plan_info;
+int zg_plan_get_info(const zg_plan* p, zg_plan_info* info);
+
+/* One block of n_samples for all channels.  in[i] / out[j] are DEVICE pointers to fp32 buffers in
+ * the plan's layout; ld is the leading dimension in elements (planar: >= n_samples, multiple of 4;
+ * interleaved: >= channels, multiple of 4).  Buffers must be 16-byte aligned.  Asynchronous on
+ * `stream` (a cudaStream_t, may be NULL).  Consecutive calls continue the stream exactly like
+ * consecutive ticks: state is read at block start and written back at block end.               */
+int zg_process(zg_plan* p, const void* const* in, void* const* out, int64_t n_samples,
+               int64_t ld_in, int64_t ld_out, void* stream);
+/* Same, with HOST pointers: copies in, runs, copies out, synchronises (what a CPU-side caller of
+ * the reference would switch to).                                                              */
+int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t n_samples,
+                    int64_t ld_in, int64_t ld_out);
+
+/* state: [n_state][channels] floats, slot order as in zg_graph_dump(); host pointers */
+int zg_state_reset(zg_plan* p);
+int zg_state_get(zg_plan* p, float* host, size_t n_floats);
+int zg_state_set(zg_plan* p, const float* host, size_t n_floats);
+/* $index for all channels: n == 1 broadcasts a scalar, n == channels sets one value per channel */
+int zg_param_set(zg_plan* p, int index, const float* host_values, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZIGNAL_B200_H */

@@ -1,0 +1,66 @@
+"""The oracle against every known-answer vector the reference's tests hold."""
+import numpy as np
+import pytest
+
+import flowz_oracle as fo
+import reference_vectors as rv
+
+
+@pytest.mark.parametrize("expr,left,right,line", rv.CANONICAL_SPLITS, ids=[f"tests.cpp:{c[3]}" for c in rv.CANONICAL_SPLITS])
+def test_canonical_split(expr, left, right, line):
+    got = fo.make_canonical(fo.parse(expr))
+    want = fo.bfb(fo.parse(left), fo.parse(right))
+    assert str(got) == str(want)
+
+
+@pytest.mark.parametrize("expr,n_in,n_out,delays,line", rv.CANONICAL_ARITY)
+def test_canonical_arity(expr, n_in, n_out, delays, line):
+    x = fo.make_canonical(fo.parse(expr))
+    assert fo.input_arity(x) == n_in
+    assert fo.output_arity(x) == n_out
+    assert fo.max_input_delays(x) == delays
+
+
+@pytest.mark.parametrize("expr,n_in,n_out,ins,outs,line", rv.WIRES_AROUND)
+def test_wires_around_boxes(expr, n_in, n_out, ins, outs, line):
+    e = fo.parse(expr)
+    assert (fo.input_arity(e), fo.output_arity(e)) == (n_in, n_out)
+    res = fo.Oracle(expr).tick(*ins, dtype=fo.I32)
+    assert tuple(int(v[0]) for _, v in res) == outs
+    assert all(dt == fo.I32 for dt, _ in res)          # ints stay ints (proto::_default on the argument types)
+
+
+@pytest.mark.parametrize("expr,steps,line", rv.TICKS, ids=[f"{c[0]}@{c[2]}" for c in rv.TICKS])
+def test_known_answer_ticks(expr, steps, line):
+    o = fo.Oracle(expr)
+    for ins, outs in steps:
+        res = o.tick(*ins, dtype=fo.I32)
+        assert tuple(int(v[0]) for _, v in res) == outs
+
+
+def test_state_starts_at_zero_and_is_float():
+    # value-initialised std::array<float,N> (flowz.hpp:1191, 1245): first output of a delay is 0,
+    # and an int pushed into a line comes back as float
+    o = fo.Oracle("_1[_1]")
+    (dt0, y0), = o.tick(7, dtype=fo.I32)
+    (dt1, y1), = o.tick(0, dtype=fo.I32)
+    assert y0[0] == 0 and y1[0] == 7 and dt1 == fo.F32
+
+
+def test_c_backend_matches_numpy_backend():
+    rng_in = fo.noise(3, 257, seed=5)
+    for expr in (fo.biquad_cascade(2), "~(_2 + 0.9f*_1[_1])", "_1 |= (_1[_1] , _1[_3]) |= _1 - _2",
+                 "~(0x1.fp0f*_1[_1] - _1[_2] + _2) |= ~(_2 + 0.5f*_1[_1])"):
+        a = fo.Oracle(expr, channels=3).process([rng_in])
+        b = fo.COracle(expr, channels=3).process([rng_in])
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), expr
+
+
+def test_streaming_equals_one_block():
+    x = fo.noise(2, 300, seed=1)
+    expr = fo.biquad_cascade(3)
+    whole = fo.COracle(expr, 2).process([x])[0]
+    o = fo.COracle(expr, 2)
+    parts = np.concatenate([o.process([x[:, :100]])[0], o.process([x[:, 100:101]])[0], o.process([x[:, 101:]])[0]], axis=1)
+    assert np.array_equal(whole, parts)

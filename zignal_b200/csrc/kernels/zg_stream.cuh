@@ -1,0 +1,379 @@
+// zignal-b200 :: streaming block evaluator skeleton for sm_100a (hand-written; the per-sample tick is
+// a functor -- prebuilt for biquad cascades (zg_biquad.cuh), generated per graph for everything else).
+//
+// What it replaces: the caller's per-sample loop around stateful_lambda::operator()
+// (reference test/benchmark.cpp:137-147 calling flowz/flowz.hpp:1225-1229), for `channels`
+// independent voices at once.
+//
+// Design (B200):
+//   * one LANE per virtual lane v = (channel c, time segment p).  P = 1: lane per channel.  P > 1
+//     ("time split", fast mode, linear graphs with decaying state only): the block is cut into P
+//     segments per channel, lane p evaluates segment p after warming its state up on the W samples
+//     before its segment (outputs discarded), which restores the state to within the tolerance
+//     verified at plan time.  Lane 0 of a channel starts from the true stored state.
+//   * all delay-line state and per-channel parameters stay in REGISTERS for the whole block; state
+//     is read from HBM once at block start and written once at block end ([n_state][channels]).
+//   * samples move HBM -> smem -> HBM with TMA (cp.async.bulk.tensor) in tiles of 32 lanes x 32
+//     samples (4 KB, rows of 128 B, hardware SWIZZLE_128B).  With that swizzle a lane reads/writes
+//     its own row 16 bytes at a time (LDS.128/STS.128) and every quarter-warp covers all 32 banks:
+//     conflict free without padding.  Outputs overwrite the consumed inputs in place and the same
+//     tile is stored back with TMA, so a stage costs 4 KB per wire.
+//   * every WARP runs its own pipeline (own stages, own mbarriers, lane 0 issues the TMA): no
+//     __syncthreads anywhere; S stages = 1 computing, 1 draining its store, S-2 loads in flight.
+//   * grid = one warp per 32 virtual lanes; CTAs are 1..4 warps, sized by the host so that the
+//     resident warps per SM divide the work evenly (148 SMs).
+#pragma once
+
+namespace zgk {
+
+struct alignas(64) TensorMap { unsigned long long opaque[16]; };   // CUtensorMap, 128 bytes
+
+constexpr int kMaxWires = 8;
+constexpr int kTileT = 32;          // samples per tile row (128 bytes of fp32)
+constexpr int kTileBytes = 4096;    // 32 rows x 128 bytes
+constexpr int kMaxState = 64;       // state floats per channel a register-resident tick may keep
+constexpr int kMaxUniform = 64;     // uniform parameters passed by value
+
+struct StreamArgs {
+    TensorMap in_map[kMaxWires];    // planar: 3-D {seg_len, P, C}; interleaved: 2-D {C, T}
+    TensorMap out_map[kMaxWires];
+    float* state;                   // [n_state][ch_stride]
+    const float* params;            // [n_params][ch_stride]
+    long long ch_stride;
+    long long stream_pos;           // absolute index of sample 0 of this block (dirac inputs)
+    int channels;
+    int seg_len;                    // samples per lane = n_samples / P
+    int seg_tiles;                  // ceil(seg_len / 32)
+    int lanes_p;                    // P (power of two <= 32)
+    int log2_p;
+    int warm_tiles;                 // W / 32
+    int stages;                     // S >= 2
+    unsigned dirac_mask;            // synthesised input k is a dirac (else zeros)
+    int state_row[kMaxState];       // row of state slot j inside `state` (prebuilt ticks use their
+                                    // own slot order; generated ticks use the identity)
+    float uparams[kMaxUniform];     // kUniform kernels: parameter values shared by all channels,
+                                    // read straight from the constant bank (no register, no HBM)
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* map, int x, int y, int z,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z),
+        "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const TensorMap* map, int x, int y,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const TensorMap* map, int x, int y, int z, const void* src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
+                 "r"(x), "r"(y), "r"(z), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const TensorMap* map, int x, int y, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
+                 "r"(x), "r"(y), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const TensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int N>
+struct Arr {                       // zero-length-safe register array
+    float v[N > 0 ? N : 1];
+    __device__ __forceinline__ float& operator[](int i) { return v[i]; }
+    __device__ __forceinline__ const float& operator[](int i) const { return v[i]; }
+};
+
+struct UniformParams {             // view of StreamArgs::uparams (kernel parameter space)
+    const float* base;
+    __device__ __forceinline__ float operator[](int i) const { return base[i]; }
+};
+
+__host__ __device__ constexpr int popcount_u32(unsigned v) { return v == 0 ? 0 : (int)(v & 1u) + popcount_u32(v >> 1); }
+
+// ---- the streaming loop ---------------------------------------------------------------------------
+//
+// Tick must provide
+//   static constexpr int N_IN, N_OUT, N_STATE, N_PARAM;
+//   static constexpr unsigned SYNTH_MASK;         // bit k set: input k is synthesised (dirac/zero)
+//   template <class P>                            // P = Arr<N_PARAM> or UniformParams
+//   static __device__ void tick(const Arr<N_IN>& x, Arr<N_OUT>& y, Arr<N_STATE>& s, const P& p);
+
+template <class Tick, bool kInterleaved, bool kUniform>
+__device__ __forceinline__ void stream_block(const StreamArgs& a) {
+    constexpr int NI = Tick::N_IN, NO = Tick::N_OUT, NS = Tick::N_STATE, NP = Tick::N_PARAM;
+    constexpr int NT = (NI > NO ? NI : NO) > 0 ? (NI > NO ? NI : NO) : 1;   // tiles per stage
+    constexpr unsigned kAllIn = NI > 0 ? ((1u << NI) - 1u) : 0u;
+    constexpr unsigned kBufMask = kAllIn & ~Tick::SYNTH_MASK;
+    constexpr int kNumBuf = popcount_u32(kBufMask);
+
+    extern __shared__ __align__(1024) unsigned char smem[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int S = a.stages;
+    const int P = kInterleaved ? 1 : a.lanes_p;
+    const int lg = kInterleaved ? 0 : a.log2_p;
+    const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
+    const long long c0ll = gw * (32 >> lg);
+    if (c0ll >= a.channels) return;                    // warp-uniform
+    const int c0 = (int)c0ll;
+    const int p = lane & (P - 1);
+    const int ch = c0 + (lane >> lg);
+    const bool ch_ok = ch < a.channels;
+
+    // SWIZZLE_128B works on 1024-byte atoms of the shared address: align the tile area explicitly
+    // (the host reserves the slack) instead of trusting the placement of dynamic shared memory
+    unsigned char* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    unsigned char* my = tiles + (size_t)warp * S * NT * kTileBytes;
+    unsigned long long* bars =
+        reinterpret_cast<unsigned long long*>(tiles + (size_t)warps_per_cta * S * NT * kTileBytes) + warp * S;
+
+    // ---- state and parameters into registers ----
+    static_assert(NS <= kMaxState, "too much state for a register-resident tick");
+    static_assert(!kUniform || NP <= kMaxUniform, "too many uniform parameters");
+    Arr<NS> s;
+#pragma unroll
+    for (int j = 0; j < NS; ++j)
+        s[j] = (ch_ok && p == 0) ? a.state[(long long)a.state_row[j] * a.ch_stride + ch] : 0.f;
+    Arr<kUniform ? 0 : NP> prm_reg;
+    if (!kUniform) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) prm_reg[j] = ch_ok ? a.params[(long long)j * a.ch_stride + ch] : 0.f;
+    }
+    const UniformParams prm_uni{a.uparams};
+    // `prm` is whichever of the two this instantiation uses
+    auto run_tick = [&](const Arr<NI>& x, Arr<NO>& y) {
+        if constexpr (kUniform) Tick::tick(x, y, s, prm_uni);
+        else Tick::tick(x, y, s, prm_reg);
+    };
+
+    if (lane == 0) {
+        if (kNumBuf > 0) {
+            for (int i = 0; i < S; ++i) mbar_init(&bars[i], 1);
+            fence_barrier_init();
+        }
+#pragma unroll
+        for (int k = 0; k < NI; ++k)
+            if (kBufMask & (1u << k)) prefetch_tmap(&a.in_map[k]);
+#pragma unroll
+        for (int o = 0; o < NO; ++o) prefetch_tmap(&a.out_map[o]);
+    }
+    __syncwarp();
+
+    const int n_tiles = a.warm_tiles + a.seg_tiles;
+
+    auto tile_t0 = [&](int i) {
+        return i < a.warm_tiles ? a.seg_len - (a.warm_tiles - i) * kTileT : (i - a.warm_tiles) * kTileT;
+    };
+    auto issue_load = [&](int i) {                     // lane 0 only
+        if (kNumBuf == 0) return;
+        const int slot = i % S;
+        const int t0 = tile_t0(i);
+        const int p0 = i < a.warm_tiles ? -1 : 0;      // warm-up reads the tail of the previous segment
+        mbar_expect_tx(&bars[slot], kNumBuf * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < NI; ++k) {
+            if (!(kBufMask & (1u << k))) continue;
+            void* dst = my + (size_t)(slot * NT + k) * kTileBytes;
+            if (kInterleaved) tma_load_2d(dst, &a.in_map[k], c0, t0, &bars[slot]);
+            else tma_load_3d(dst, &a.in_map[k], t0, p0, c0, &bars[slot]);
+        }
+    };
+
+    if (lane == 0) {
+        const int pre = n_tiles < S - 1 ? n_tiles : S - 1;
+        for (int i = 0; i < pre; ++i) issue_load(i);
+    }
+
+    for (int i = 0; i < n_tiles; ++i) {
+        const int slot = i % S;
+        const bool warm = i < a.warm_tiles;
+        const int t0 = tile_t0(i);
+        const int n_valid = warm ? kTileT : (a.seg_len - t0 < kTileT ? a.seg_len - t0 : kTileT);
+        const bool active = ch_ok && (!warm || p > 0);
+        unsigned char* base = my + (size_t)slot * NT * kTileBytes;
+
+        if (kNumBuf > 0) mbar_wait(&bars[slot], (unsigned)((i / S) & 1));
+
+        // absolute stream index of this lane's first sample in the tile (dirac synthesis)
+        const long long t_abs0 = a.stream_pos + (long long)(warm ? p - 1 : p) * a.seg_len + t0;
+
+        if (active) {
+            if (!kInterleaved) {
+                // row `lane`, 16-byte chunk j lives at chunk (j ^ (lane & 7)) of the row (SWIZZLE_128B)
+                const unsigned row = (unsigned)lane * 128u;
+                const unsigned sw = (unsigned)(lane & 7);
+                if (n_valid == kTileT) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const unsigned off = row + (((unsigned)j ^ sw) << 4);
+                        float4 xv[NI > 0 ? NI : 1];
+                        float4 yv[NO > 0 ? NO : 1];
+#pragma unroll
+                        for (int k = 0; k < NI; ++k) {
+                            if (kBufMask & (1u << k)) {
+                                xv[k] = *reinterpret_cast<const float4*>(base + k * kTileBytes + off);
+                            } else {
+                                const bool dirac = (a.dirac_mask >> k) & 1u;
+                                const long long tt = t_abs0 + 4 * j;
+                                xv[k].x = (dirac && tt == 0) ? 1.f : 0.f;
+                                xv[k].y = (dirac && tt + 1 == 0) ? 1.f : 0.f;
+                                xv[k].z = (dirac && tt + 2 == 0) ? 1.f : 0.f;
+                                xv[k].w = (dirac && tt + 3 == 0) ? 1.f : 0.f;
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            Arr<NI> x;
+                            Arr<NO> y;
+#pragma unroll
+                            for (int k = 0; k < NI; ++k)
+                                x[k] = q == 0 ? xv[k].x : q == 1 ? xv[k].y : q == 2 ? xv[k].z : xv[k].w;
+                            run_tick(x, y);
+#pragma unroll
+                            for (int o = 0; o < NO; ++o) {
+                                if (q == 0) yv[o].x = y[o];
+                                else if (q == 1) yv[o].y = y[o];
+                                else if (q == 2) yv[o].z = y[o];
+                                else yv[o].w = y[o];
+                            }
+                        }
+                        if (!warm) {
+#pragma unroll
+                            for (int o = 0; o < NO; ++o)
+                                *reinterpret_cast<float4*>(base + o * kTileBytes + off) = yv[o];
+                        }
+                    }
+                } else {
+                    // last, partial tile of the block: TMA zero-filled the tail on load and clips it
+                    // on store; only the state has to be protected
+                    for (int t = 0; t < n_valid; ++t) {
+                        const unsigned off = row + ((((unsigned)t >> 2) ^ sw) << 4) + ((unsigned)t & 3u) * 4u;
+                        Arr<NI> x;
+                        Arr<NO> y;
+#pragma unroll
+                        for (int k = 0; k < NI; ++k) {
+                            if (kBufMask & (1u << k)) x[k] = *reinterpret_cast<const float*>(base + k * kTileBytes + off);
+                            else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
+                        }
+                        run_tick(x, y);
+#pragma unroll
+                        for (int o = 0; o < NO; ++o) *reinterpret_cast<float*>(base + o * kTileBytes + off) = y[o];
+                    }
+                }
+            } else {
+                // interleaved frames: tile is [32 samples][32 channels], lane = channel column
+                float* tile = reinterpret_cast<float*>(base);
+                if (n_valid == kTileT) {
+#pragma unroll 8
+                    for (int t = 0; t < kTileT; ++t) {
+                        Arr<NI> x;
+                        Arr<NO> y;
+#pragma unroll
+                        for (int k = 0; k < NI; ++k) {
+                            if (kBufMask & (1u << k)) x[k] = tile[k * (kTileBytes / 4) + t * 32 + lane];
+                            else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
+                        }
+                        run_tick(x, y);
+#pragma unroll
+                        for (int o = 0; o < NO; ++o) tile[o * (kTileBytes / 4) + t * 32 + lane] = y[o];
+                    }
+                } else {
+                    for (int t = 0; t < n_valid; ++t) {
+                        Arr<NI> x;
+                        Arr<NO> y;
+#pragma unroll
+                        for (int k = 0; k < NI; ++k) {
+                            if (kBufMask & (1u << k)) x[k] = tile[k * (kTileBytes / 4) + t * 32 + lane];
+                            else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
+                        }
+                        run_tick(x, y);
+#pragma unroll
+                        for (int o = 0; o < NO; ++o) tile[o * (kTileBytes / 4) + t * 32 + lane] = y[o];
+                    }
+                }
+            }
+        }
+
+        if (!warm) {
+            fence_proxy_async();                       // generic-proxy writes -> visible to TMA
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int o = 0; o < NO; ++o) {
+                    if (kInterleaved) tma_store_2d(&a.out_map[o], c0, t0, base + o * kTileBytes);
+                    else tma_store_3d(&a.out_map[o], t0, 0, c0, base + o * kTileBytes);
+                }
+                tma_commit();
+            }
+        } else {
+            __syncwarp();
+        }
+
+        // refill the slot that tile i-1 used: its store (committed one iteration ago) must have
+        // finished reading smem
+        const int nxt = i + S - 1;
+        if (lane == 0 && nxt < n_tiles) {
+            tma_wait_read<1>();
+            issue_load(nxt);
+        }
+    }
+
+    if (lane == 0) tma_wait_all<0>();                  // smem must outlive the last stores
+
+    // ---- state back to HBM: the lane that evaluated the last segment owns the final state ----
+    if (ch_ok && p == P - 1) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) a.state[(long long)a.state_row[j] * a.ch_stride + ch] = s[j];
+    }
+}
+
+}  // namespace zgk

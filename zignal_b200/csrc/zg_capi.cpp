@@ -1,0 +1,174 @@
+// zignal-b200 :: host half of the C ABI (analysis, compile, host voice).  Device half: zg_runtime.cu
+#include <cstring>
+
+#include "zg_internal.hpp"
+
+namespace zg {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+int fail(int status, const std::string& msg) {
+    g_last_error = msg;
+    return status;
+}
+
+}  // namespace zg
+
+using namespace zg;
+
+std::shared_ptr<const Ir> zg_graph::ir_for(const std::vector<Dtype>& sig) const {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = irs.find(sig);
+    if (it != irs.end()) return it->second;
+    // lines are numbered by tree position only, so every signature shares one state layout
+    auto ir = std::make_shared<const Ir>(lower(*canonical, sig));
+    if (ir->n_state != ir_f32.n_state) throw Error("state layout differs between signatures (internal)");
+    irs.emplace(sig, ir);
+    return ir;
+}
+
+// Runs f, mapping exceptions to status codes.
+template <class F>
+static int guarded(F&& f) {
+    try {
+        return f();
+    } catch (const Error& e) {
+        std::string m = e.what();
+        return fail(m.rfind("flowz parse error", 0) == 0 ? ZG_ERR_PARSE : ZG_ERR_GRAPH, m);
+    } catch (const std::exception& e) {
+        return fail(ZG_ERR_INTERNAL, e.what());
+    } catch (...) {
+        return fail(ZG_ERR_INTERNAL, "unknown exception");
+    }
+}
+
+extern "C" {
+
+const char* zg_last_error(void) { return g_last_error.c_str(); }
+const char* zg_version(void) { return "zignal-b200 0.1 (sm_100a)"; }
+
+int zg_expr_arity(const char* expr, int* n_in, int* n_out) {
+    if (!expr) return fail(ZG_ERR_ARG, "expr is NULL");
+    return guarded([&] {
+        ExprP e = parse(expr);
+        if (n_in) *n_in = input_arity(*e);
+        if (n_out) *n_out = output_arity(*e);
+        return (int)ZG_OK;
+    });
+}
+
+int zg_expr_delays(const char* expr, int which, int* delays, int capacity, int* count) {
+    if (!expr || !count) return fail(ZG_ERR_ARG, "NULL argument");
+    return guarded([&] {
+        ExprP e = parse(expr);
+        std::vector<int> d = which == 0 ? max_input_delays(*e) : min_input_delays(*e);
+        *count = (int)d.size();
+        for (int i = 0; i < (int)d.size() && i < capacity; ++i) delays[i] = d[i];
+        return (int)ZG_OK;
+    });
+}
+
+int zg_expr_canonical(const char* expr, char* buf, size_t capacity) {
+    if (!expr || !buf || capacity == 0) return fail(ZG_ERR_ARG, "NULL argument");
+    return guarded([&] {
+        std::string s = to_string(*make_canonical(parse(expr)));
+        if (s.size() + 1 > capacity) return fail(ZG_ERR_ARG, "buffer too small");
+        std::memcpy(buf, s.c_str(), s.size() + 1);
+        return (int)ZG_OK;
+    });
+}
+
+int zg_graph_compile(const char* expr, zg_graph** out) {
+    if (!expr || !out) return fail(ZG_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    return guarded([&] {
+        auto g = std::make_unique<zg_graph>();
+        g->text = expr;
+        g->user = parse(expr);
+        g->n_in = input_arity(*g->user);
+        g->n_out = output_arity(*g->user);
+        if (g->n_in > ZG_MAX_WIRES || g->n_out > ZG_MAX_WIRES)
+            return fail(ZG_ERR_UNSUPPORTED, "more than ZG_MAX_WIRES inputs or outputs");
+        g->canonical = canonical_with_front(g->user);
+        g->ir_f32 = lower(*g->canonical, std::vector<Dtype>(g->n_in, Dtype::F32));
+        if (g->ir_f32.n_out != g->n_out) return fail(ZG_ERR_INTERNAL, "output arity mismatch after lowering");
+        g->canonical_str = to_string(*g->canonical);
+        g->dump_str = g->ir_f32.dump();
+        *out = g.release();
+        return (int)ZG_OK;
+    });
+}
+
+void zg_graph_destroy(zg_graph* g) { delete g; }
+
+int zg_graph_get_info(const zg_graph* g, zg_graph_info* info) {
+    if (!g || !info) return fail(ZG_ERR_ARG, "NULL argument");
+    info->n_in = g->n_in;
+    info->n_out = g->n_out;
+    info->n_params = g->ir_f32.n_params;
+    info->n_state = g->ir_f32.n_state;
+    info->n_lines = (int)g->ir_f32.lines.size();
+    info->n_nodes = (int)g->ir_f32.nodes.size();
+    info->all_f32 = g->ir_f32.all_f32() ? 1 : 0;
+    return ZG_OK;
+}
+
+const char* zg_graph_canonical(const zg_graph* g) { return g ? g->canonical_str.c_str() : ""; }
+const char* zg_graph_dump(const zg_graph* g) { return g ? g->dump_str.c_str() : ""; }
+
+int zg_voice_create(const zg_graph* g, zg_voice** out) {
+    if (!g || !out) return fail(ZG_ERR_ARG, "NULL argument");
+    auto v = new zg_voice();
+    v->g = g;
+    v->state.assign(g->ir_f32.n_state, 0.f);
+    v->params.assign(g->ir_f32.n_params, 0.f);
+    *out = v;
+    return ZG_OK;
+}
+
+int zg_voice_clone(const zg_voice* v, zg_voice** out) {
+    if (!v || !out) return fail(ZG_ERR_ARG, "NULL argument");
+    *out = new zg_voice(*v);
+    return ZG_OK;
+}
+
+void zg_voice_destroy(zg_voice* v) { delete v; }
+
+int zg_voice_tick(zg_voice* v, const double* in, const int* in_dtypes, double* out, int* out_dtypes) {
+    if (!v || !out || (v->g->n_in > 0 && !in)) return fail(ZG_ERR_ARG, "NULL argument");
+    return guarded([&] {
+        const zg_graph* g = v->g;
+        const Ir* ir = &g->ir_f32;
+        std::shared_ptr<const Ir> keep;
+        if (in_dtypes) {
+            std::vector<Dtype> sig(g->n_in);
+            bool f32 = true;
+            for (int i = 0; i < g->n_in; ++i) {
+                if (in_dtypes[i] < 0 || in_dtypes[i] > 2) return fail(ZG_ERR_ARG, "bad dtype");
+                sig[i] = (Dtype)in_dtypes[i];
+                f32 = f32 && sig[i] == Dtype::F32;
+            }
+            if (!f32) { keep = g->ir_for(sig); ir = keep.get(); }
+        }
+        host_tick(*ir, v->state.data(), v->params.data(), in, out);
+        if (out_dtypes)
+            for (int o = 0; o < ir->n_out; ++o) out_dtypes[o] = (int)ir->nodes[ir->outs[o]].dtype;
+        return (int)ZG_OK;
+    });
+}
+
+int zg_voice_set_param(zg_voice* v, int index, float value) {
+    if (!v || index < 0 || index >= (int)v->params.size()) return fail(ZG_ERR_ARG, "bad parameter index");
+    v->params[index] = value;
+    return ZG_OK;
+}
+
+int zg_voice_state(zg_voice* v, float** state, int* n_state) {
+    if (!v || !state || !n_state) return fail(ZG_ERR_ARG, "NULL argument");
+    *state = v->state.data();
+    *n_state = (int)v->state.size();
+    return ZG_OK;
+}
+
+}  // extern "C"

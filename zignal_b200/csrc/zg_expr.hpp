@@ -1,0 +1,86 @@
+// zignal-b200 :: expression layer (host, C++17, no Boost)
+//
+// Run-time restatement of the flowz expression grammar and of its static analyses.  The reference
+// does all of this with Boost.Proto at C++ compile time; here the tree is a run-time value so that
+// the same code serves the C ABI, the C++ EDSL shim (include/flowz/flowz.hpp) and the Python tests.
+//
+// Reference behaviour mirrored (all paths relative to /root/reference):
+//   grammar / building blocks        flowz/flowz.hpp:68-102   (placeholders, _k[_n], |= | , ~, bfb)
+//   input_arity / output_arity       flowz/flowz.hpp:162-246
+//   max/min_input_delays             flowz/flowz.hpp:286-506
+//   make_front / add_front_panel     flowz/flowz.hpp:261-277
+//   make_canonical and friends       flowz/flowz.hpp:794-935
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace zg {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+enum class Dtype : uint8_t { I32 = 0, F32 = 1, F64 = 2 };
+
+enum class Op : uint8_t {
+    Placeholder,  // _k                       (k >= 1)
+    Delay,        // _k[_n]  /  _k[-n]        (k >= 1, n >= 1)
+    Const,        // literal terminal         (dtype, value)
+    Param,        // std::ref(float) terminal (param index) -- scalar or per-channel at run time
+    Neg, Add, Sub, Mul, Div,  // leaf arithmetic, evaluated with C++ built-in operator semantics
+    Seq,          // L |= R   (also spelled L >> R)
+    Par,          // L | R    input-splitting parallel
+    Chan,         // (L , R)  fan-out
+    Fb,           // ~x       unary feedback (user facing; removed by canonicalisation)
+    Bfb           // binary_feedback(L = promise, R = future)  (private node)
+};
+
+struct Expr;
+using ExprP = std::shared_ptr<const Expr>;
+
+struct Expr {
+    Op op;
+    int k = 0;            // placeholder index / param index
+    int n = 0;            // delay
+    Dtype dtype = Dtype::F32;  // Const only
+    double value = 0;     // Const only (already rounded to dtype)
+    std::vector<ExprP> ch;
+};
+
+ExprP placeholder(int k);
+ExprP delay(int k, int n);
+ExprP constant(Dtype dt, double v);
+ExprP param(int idx);
+ExprP unary(Op op, ExprP a);
+ExprP binary(Op op, ExprP a, ExprP b);
+
+bool is_terminal(const Expr& e);
+bool is_arith(const Expr& e);
+
+// ---- text form -------------------------------------------------------------------------------
+// parse():  C++ operator precedence (postfix [] > unary - ~ > * / > + - > >> > | > |= (right
+// assoc) > ,).  Literals: 2 (int), 0.5 (double), 0.5f (float), hex floats, $k (parameter k),
+// bfb(L, R) builds the private binary feedback node, front(n) builds make_front<n>().
+ExprP parse(const std::string& text);
+std::string to_string(const Expr& e);       // fully parenthesised, round-trips through parse()
+bool same_structure(const Expr& a, const Expr& b);
+
+// ---- static analysis -------------------------------------------------------------------------
+int input_arity(const Expr& e);
+int output_arity(const Expr& e);
+std::vector<int> max_input_delays(const Expr& e);
+std::vector<int> min_input_delays(const Expr& e);   // -1 = wire unused
+int n_params(const Expr& e);                        // 1 + highest $k used, 0 if none
+
+// ---- canonicalisation ------------------------------------------------------------------------
+ExprP make_front(int n);
+ExprP add_front_panel(ExprP e);
+ExprP make_canonical(ExprP e);                      // replaces every ~x by bfb(promise, future)
+// compile(): front panel + canonical form.  arity 0 is accepted as an extension (the reference has
+// no make_front<0>, TODO.md:65): the expression is canonicalised without a front panel.
+ExprP canonical_with_front(ExprP e);
+
+}  // namespace zg

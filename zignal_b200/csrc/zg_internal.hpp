@@ -1,0 +1,52 @@
+// zignal-b200 :: objects behind the opaque C handles
+#pragma once
+#include <array>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/zignal_b200.h"
+#include "zg_ir.hpp"
+
+struct zg_graph {
+    std::string text;
+    zg::ExprP user;
+    zg::ExprP canonical;
+    int n_in = 0, n_out = 0;
+    zg::Ir ir_f32;                 // the tick program for fp32 inputs (device path + float ticks)
+    std::string canonical_str, dump_str;
+    mutable std::mutex mu;
+    mutable std::map<std::vector<zg::Dtype>, std::shared_ptr<const zg::Ir>> irs;
+
+    std::shared_ptr<const zg::Ir> ir_for(const std::vector<zg::Dtype>& sig) const;
+};
+
+struct zg_voice {
+    const zg_graph* g;
+    std::vector<float> state;
+    std::vector<float> params;
+};
+
+namespace zg {
+void set_last_error(const std::string& msg);
+int fail(int status, const std::string& msg);
+
+// CUDA tick-functor source for one IR (zg_codegen.cpp)
+std::string generate_tick_source(const Ir& ir, bool exact, const std::string& struct_name);
+
+// ---- prebuilt-kernel recognisers (zg_match.cpp) ----
+constexpr int kMaxBiquadSections = 8;
+struct BiquadCoef {
+    bool is_param = false;
+    int param = -1;      // $index when is_param
+    float value = 0.f;   // literal otherwise
+};
+struct BiquadMatch {
+    int sections = 0;
+    std::array<BiquadCoef, 5> coef[kMaxBiquadSections];   // b0 b1 b2 a1 a2 per section
+    std::vector<int> signal_line;                         // line of signal k (0 = input, k = out of section k)
+};
+bool match_df1_cascade(const Ir& ir, BiquadMatch& m);
+}  // namespace zg

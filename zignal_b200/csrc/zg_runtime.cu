@@ -1,0 +1,749 @@
+// zignal-b200 :: device half of the C ABI -- plans, kernel selection, NVRTC specialisation, launches.
+//
+// There is no CPU fallback in this file: every zg_process() is a kernel launch on the plan's B200,
+// and every failure (no device, no driver, NVRTC missing, bad architecture) is returned as
+// ZG_ERR_CUDA with the reason in zg_last_error().
+//
+// Kernel selection at plan time:
+//   K1  tick program is a cascade of direct-form-1 biquads (zg_match.cpp)  -> prebuilt kernel
+//       zg_biquad_df1<SECTIONS, exact, interleaved, uniform> compiled by nvcc into this library;
+//   K2  anything else -> the same hand-written streaming skeleton (kernels/zg_stream.cuh) with the
+//       straight-line tick body generated from the graph (zg_codegen.cpp), compiled once per plan
+//       with NVRTC for sm_100a.
+#include <cuda.h>            // driver API *types* only; entry points come from cudaGetDriverEntryPoint
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+#include "kernels/zg_biquad.cuh"
+#include "zg_internal.hpp"
+
+extern const char* const zg_stream_cuh_source;   // kernels/zg_stream.cuh as text (generated at build time)
+
+using namespace zg;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// driver API + NVRTC, resolved lazily (the library must load on a machine without libcuda)
+// ------------------------------------------------------------------------------------------------
+
+struct Driver {
+    decltype(&cuTensorMapEncodeTiled) tensorMapEncodeTiled = nullptr;
+    decltype(&cuModuleLoadData) moduleLoadData = nullptr;
+    decltype(&cuModuleUnload) moduleUnload = nullptr;
+    decltype(&cuModuleGetFunction) moduleGetFunction = nullptr;
+    decltype(&cuFuncSetAttribute) funcSetAttribute = nullptr;
+    decltype(&cuFuncGetAttribute) funcGetAttribute = nullptr;
+    decltype(&cuLaunchKernel) launchKernel = nullptr;
+    decltype(&cuGetErrorString) getErrorString = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+template <class F>
+bool drv_sym(const char* name, F& f, std::string& why) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    cudaError_t e = cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+        why = std::string("CUDA driver entry point ") + name + " unavailable: " +
+              (e != cudaSuccess ? cudaGetErrorString(e) : "symbol not found");
+        (void)cudaGetLastError();
+        return false;
+    }
+    f = reinterpret_cast<F>(p);
+    return true;
+}
+
+Driver& driver() {
+    static Driver d = [] {
+        Driver r;
+        r.ok = drv_sym("cuTensorMapEncodeTiled", r.tensorMapEncodeTiled, r.why) &&
+               drv_sym("cuModuleLoadData", r.moduleLoadData, r.why) &&
+               drv_sym("cuModuleUnload", r.moduleUnload, r.why) &&
+               drv_sym("cuModuleGetFunction", r.moduleGetFunction, r.why) &&
+               drv_sym("cuFuncSetAttribute", r.funcSetAttribute, r.why) &&
+               drv_sym("cuFuncGetAttribute", r.funcGetAttribute, r.why) &&
+               drv_sym("cuLaunchKernel", r.launchKernel, r.why) &&
+               drv_sym("cuGetErrorString", r.getErrorString, r.why);
+        return r;
+    }();
+    return d;
+}
+
+std::string cu_err(CUresult r) {
+    const char* s = nullptr;
+    if (driver().getErrorString) driver().getErrorString(r, &s);
+    return s ? s : ("CUresult " + std::to_string((int)r));
+}
+
+// NVRTC through dlopen: only plans that need a generated kernel touch it.
+struct Nvrtc {
+    void* lib = nullptr;
+    int (*createProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*destroyProgram)(void**) = nullptr;
+    int (*compileProgram)(void*, int, const char* const*) = nullptr;
+    int (*getCUBINSize)(void*, size_t*) = nullptr;
+    int (*getCUBIN)(void*, char*) = nullptr;
+    int (*getProgramLogSize)(void*, size_t*) = nullptr;
+    int (*getProgramLog)(void*, char*) = nullptr;
+    const char* (*getErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+Nvrtc& nvrtc() {
+    static Nvrtc n = [] {
+        Nvrtc r;
+        const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+        for (const char* nm : names) {
+            r.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (r.lib) break;
+        }
+        if (!r.lib) {
+            r.why = std::string("cannot load libnvrtc.so.12 (needed to specialise the kernel for this graph): ") + dlerror();
+            return r;
+        }
+        auto sym = [&](const char* s) { return dlsym(r.lib, s); };
+        r.createProgram = (decltype(r.createProgram))sym("nvrtcCreateProgram");
+        r.destroyProgram = (decltype(r.destroyProgram))sym("nvrtcDestroyProgram");
+        r.compileProgram = (decltype(r.compileProgram))sym("nvrtcCompileProgram");
+        r.getCUBINSize = (decltype(r.getCUBINSize))sym("nvrtcGetCUBINSize");
+        r.getCUBIN = (decltype(r.getCUBIN))sym("nvrtcGetCUBIN");
+        r.getProgramLogSize = (decltype(r.getProgramLogSize))sym("nvrtcGetProgramLogSize");
+        r.getProgramLog = (decltype(r.getProgramLog))sym("nvrtcGetProgramLog");
+        r.getErrorString = (decltype(r.getErrorString))sym("nvrtcGetErrorString");
+        r.ok = r.createProgram && r.destroyProgram && r.compileProgram && r.getCUBINSize && r.getCUBIN &&
+               r.getProgramLogSize && r.getProgramLog && r.getErrorString;
+        if (!r.ok) r.why = "libnvrtc is missing expected symbols";
+        return r;
+    }();
+    return n;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    (void)cudaGetLastError();
+    return fail(ZG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define ZG_CUDA(call)                                        \
+    do {                                                     \
+        cudaError_t e_ = (call);                             \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// prebuilt kernels (K1)
+// ------------------------------------------------------------------------------------------------
+
+template <class Tick, bool kInterleaved, bool kUniform>
+__global__ void __launch_bounds__(512, 1) zg_stream_kernel(const __grid_constant__ zgk::StreamArgs a) {
+    zgk::stream_block<Tick, kInterleaved, kUniform>(a);
+}
+
+using KernelPtr = void (*)(zgk::StreamArgs);
+
+template <int S>
+KernelPtr biquad_kernel(bool exact, bool interleaved, bool uniform) {
+#define ZG_PICK(E, I, U) \
+    if (exact == E && interleaved == I && uniform == U) \
+        return (KernelPtr)zg_stream_kernel<zgk::BiquadDf1Cascade<S, E>, I, U>;
+    ZG_PICK(false, false, false) ZG_PICK(false, false, true) ZG_PICK(false, true, false) ZG_PICK(false, true, true)
+    ZG_PICK(true, false, false) ZG_PICK(true, false, true) ZG_PICK(true, true, false) ZG_PICK(true, true, true)
+#undef ZG_PICK
+    return nullptr;
+}
+
+KernelPtr biquad_kernel_for(int sections, bool exact, bool interleaved, bool uniform) {
+    switch (sections) {
+        case 1: return biquad_kernel<1>(exact, interleaved, uniform);
+        case 2: return biquad_kernel<2>(exact, interleaved, uniform);
+        case 3: return biquad_kernel<3>(exact, interleaved, uniform);
+        case 4: return biquad_kernel<4>(exact, interleaved, uniform);
+        case 5: return biquad_kernel<5>(exact, interleaved, uniform);
+        case 6: return biquad_kernel<6>(exact, interleaved, uniform);
+        case 7: return biquad_kernel<7>(exact, interleaved, uniform);
+        case 8: return biquad_kernel<8>(exact, interleaved, uniform);
+    }
+    return nullptr;
+}
+
+struct Variant {            // one compiled kernel of a plan
+    bool ready = false;
+    KernelPtr prebuilt = nullptr;
+    CUmodule module = nullptr;
+    CUfunction function = nullptr;
+    int regs = 0;
+    int max_smem_set = 0;
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// the plan
+// ------------------------------------------------------------------------------------------------
+
+struct zg_plan {
+    Ir ir;                                  // private copy: the plan outlives nothing it points to
+    zg_plan_opts opts{};
+    int64_t C = 0, ch_stride = 0;
+    bool exact = false, interleaved = false;
+    unsigned synth_mask = 0, dirac_mask = 0;
+    int n_buf_in = 0;
+
+    bool is_biquad = false;
+    BiquadMatch bq;
+    int kernel_n_state = 0, kernel_n_param = 0;   // as the kernel sees them
+    std::vector<int> state_row;                   // kernel slot -> row of d_state
+
+    Variant variant[2];                     // [uniform]
+    std::string kernel_name;
+
+    float* d_state = nullptr;               // [n_state][ch_stride]
+    float* d_params = nullptr;              // [kernel_n_param][ch_stride]
+    std::vector<std::vector<float>> h_params;   // per graph parameter: size 1 (scalar) or C
+    bool params_dirty = true;
+    bool uniform_now = true;
+    float uparams[zgk::kMaxUniform] = {};
+
+    int64_t stream_pos = 0;
+    int launches = 0;
+    int last_smem = 0, last_threads = 0, last_stages = 0;
+    int sm_count = 148;
+    int max_smem_optin = 227 * 1024;
+
+    // staging for zg_process_host
+    float* d_stage = nullptr;
+    size_t d_stage_floats = 0;
+    cudaStream_t own_stream = nullptr;
+
+    ~zg_plan() {
+        if (opts.device >= 0) cudaSetDevice(opts.device);
+        for (auto& v : variant)
+            if (v.module && driver().moduleUnload) driver().moduleUnload(v.module);
+        if (d_state) cudaFree(d_state);
+        if (d_params) cudaFree(d_params);
+        if (d_stage) cudaFree(d_stage);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+};
+
+namespace {
+
+// ---- NVRTC specialisation (K2) -----------------------------------------------------------------
+
+std::string jit_source(const Ir& ir, bool exact, bool interleaved, bool uniform, unsigned synth_mask) {
+    std::ostringstream src;
+    src << "#define ZG_SYNTH_MASK " << synth_mask << "u\n";
+    src << zg_stream_cuh_source << "\n";
+    src << generate_tick_source(ir, exact, "ZgTick") << "\n";
+    src << "extern \"C\" __global__ void __launch_bounds__(512, 1) zg_graph_kernel("
+           "const __grid_constant__ zgk::StreamArgs a) {\n"
+           "    zgk::stream_block<ZgTick, "
+        << (interleaved ? "true" : "false") << ", " << (uniform ? "true" : "false") << ">(a);\n}\n";
+    return src.str();
+}
+
+// source -> sm_100a cubin.  Needs libnvrtc only (no device, no driver).
+int jit_cubin(const std::string& text, bool exact, std::vector<char>& cubin) {
+    Nvrtc& n = nvrtc();
+    if (!n.ok) return fail(ZG_ERR_CUDA, n.why);
+    void* prog = nullptr;
+    int r = n.createProgram(&prog, text.c_str(), "zg_graph_kernel.cu", 0, nullptr, nullptr);
+    if (r != 0) return fail(ZG_ERR_CUDA, std::string("nvrtcCreateProgram: ") + n.getErrorString(r));
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--generate-line-info",
+                          exact ? "--fmad=false" : "--fmad=true"};
+    r = n.compileProgram(prog, 4, opts);
+    if (r != 0) {
+        size_t ls = 0;
+        n.getProgramLogSize(prog, &ls);
+        std::string log(ls, '\0');
+        if (ls) n.getProgramLog(prog, &log[0]);
+        n.destroyProgram(&prog);
+        return fail(ZG_ERR_CUDA, std::string("NVRTC could not compile the kernel for this graph: ") +
+                                     n.getErrorString(r) + "\n" + log);
+    }
+    size_t cs = 0;
+    n.getCUBINSize(prog, &cs);
+    cubin.resize(cs);
+    n.getCUBIN(prog, cubin.data());
+    n.destroyProgram(&prog);
+    return ZG_OK;
+}
+
+int jit_compile(zg_plan* p, bool uniform, Variant& v) {
+    Driver& d = driver();
+    if (!d.ok) return fail(ZG_ERR_CUDA, d.why);
+    std::vector<char> cubin;
+    int st = jit_cubin(jit_source(p->ir, p->exact, p->interleaved, uniform, p->synth_mask), p->exact, cubin);
+    if (st != ZG_OK) return st;
+    CUresult cr = d.moduleLoadData(&v.module, cubin.data());
+    if (cr != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuModuleLoadData: " + cu_err(cr));
+    cr = d.moduleGetFunction(&v.function, v.module, "zg_graph_kernel");
+    if (cr != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuModuleGetFunction: " + cu_err(cr));
+    d.funcGetAttribute(&v.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, v.function);
+    v.ready = true;
+    return ZG_OK;
+}
+
+int get_variant(zg_plan* p, bool uniform, Variant*& out) {
+    Variant& v = p->variant[uniform ? 1 : 0];
+    out = &v;
+    if (v.ready) return ZG_OK;
+    if (p->is_biquad && !p->opts.force_jit) {
+        v.prebuilt = biquad_kernel_for(p->bq.sections, p->exact, p->interleaved, uniform);
+        if (!v.prebuilt) return fail(ZG_ERR_INTERNAL, "no prebuilt biquad kernel for this section count");
+        cudaFuncAttributes fa;
+        ZG_CUDA(cudaFuncGetAttributes(&fa, (const void*)v.prebuilt));
+        v.regs = fa.numRegs;
+        v.ready = true;
+        return ZG_OK;
+    }
+    return jit_compile(p, uniform, v);
+}
+
+// ---- parameters ------------------------------------------------------------------------------------
+
+// value of kernel parameter slot j for channel c (c = -1: the scalar)
+int sync_params(zg_plan* p) {
+    if (!p->params_dirty) return ZG_OK;
+    const int NP = p->kernel_n_param;
+    bool uniform = NP <= zgk::kMaxUniform;
+    for (auto& h : p->h_params) uniform = uniform && h.size() == 1;
+    // kernel slot j -> (graph parameter | literal)
+    auto slot_src = [&](int j, int& param, float& lit) {
+        if (p->is_biquad && !p->opts.force_jit) {
+            const BiquadCoef& c = p->bq.coef[j / 5][j % 5];
+            param = c.is_param ? c.param : -1;
+            lit = c.value;
+        } else {
+            param = j;
+            lit = 0.f;
+        }
+    };
+    if (uniform) {
+        for (int j = 0; j < NP; ++j) {
+            int prm; float lit;
+            slot_src(j, prm, lit);
+            p->uparams[j] = prm >= 0 ? p->h_params[prm][0] : lit;
+        }
+    } else if (NP > 0) {
+        std::vector<float> host((size_t)NP * p->ch_stride, 0.f);
+        for (int j = 0; j < NP; ++j) {
+            int prm; float lit;
+            slot_src(j, prm, lit);
+            float* row = host.data() + (size_t)j * p->ch_stride;
+            if (prm < 0) std::fill(row, row + p->C, lit);
+            else if (p->h_params[prm].size() == 1) std::fill(row, row + p->C, p->h_params[prm][0]);
+            else std::copy(p->h_params[prm].begin(), p->h_params[prm].end(), row);
+        }
+        if (!p->d_params) ZG_CUDA(cudaMalloc(&p->d_params, host.size() * sizeof(float)));
+        ZG_CUDA(cudaMemcpy(p->d_params, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    p->uniform_now = uniform;
+    p->params_dirty = false;
+    return ZG_OK;
+}
+
+// ---- tensor maps ---------------------------------------------------------------------------------------
+
+int encode_map(zg_plan* p, zgk::TensorMap* out, const void* base, int64_t T, int64_t ld, int P) {
+    Driver& d = driver();
+    CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(out);
+    CUresult r;
+    if (p->interleaved) {
+        // [T][ld] frames: dim0 = channel (contiguous), dim1 = sample
+        cuuint64_t dims[2] = {(cuuint64_t)p->C, (cuuint64_t)T};
+        cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+        cuuint32_t box[2] = {32, 32};
+        cuuint32_t es[2] = {1, 1};
+        r = d.tensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides,
+                                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        // [C][ld] rows cut into P segments: dim0 = sample inside the segment, dim1 = segment, dim2 = channel
+        const int64_t seg = T / P;
+        cuuint64_t dims[3] = {(cuuint64_t)seg, (cuuint64_t)P, (cuuint64_t)p->C};
+        cuuint64_t strides[2] = {(cuuint64_t)(P > 1 ? seg : ld) * 4, (cuuint64_t)ld * 4};
+        cuuint32_t box[3] = {32, (cuuint32_t)P, (cuuint32_t)(32 / P)};
+        cuuint32_t es[3] = {1, 1, 1};
+        r = d.tensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides,
+                                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuTensorMapEncodeTiled: " + cu_err(r));
+    return ZG_OK;
+}
+
+// ---- launch geometry ---------------------------------------------------------------------------------
+//
+// All warps of the launch should be resident at once (one wave) and spread evenly over the SMs:
+// a CTA is `wpc` warps, every warp owns S stages of NT tiles of 4 KB.  Shared memory, not
+// registers, is what limits residency (the skeleton keeps 1 KB of slack to align the tiles).
+struct Geometry {
+    int wpc, grid, stages, smem;
+};
+
+Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs) {
+    Geometry g{};
+    const int64_t per_sm = (n_warps + p->sm_count - 1) / p->sm_count;
+    const int reg_warps = std::max(1, 65536 / (32 * std::max(regs, 32)));   // warps/SM the register file allows
+    int wpc = (int)std::min<int64_t>({per_sm, 16, (int64_t)reg_warps});
+    wpc = std::max(wpc, 1);
+    const int budget = p->max_smem_optin - 1024 /*alignment slack*/ - 16 * 8 * 8 /*barriers*/;
+    int S = budget / (wpc * NT * zgk::kTileBytes);
+    while (S < 3 && wpc > 1) {            // too many wires for that many warps: fewer warps per CTA
+        --wpc;
+        S = budget / (wpc * NT * zgk::kTileBytes);
+    }
+    S = std::min(S, 8);
+    S = std::max(S, 2);
+    g.wpc = wpc;
+    g.stages = S;
+    g.grid = (int)((n_warps + wpc - 1) / wpc);
+    g.smem = wpc * S * NT * zgk::kTileBytes + 1024 + wpc * S * 8;
+    return g;
+}
+
+int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out,
+           cudaStream_t stream) {
+    Driver& d = driver();
+    if (!d.ok) return fail(ZG_ERR_CUDA, d.why);
+    int st = sync_params(p);
+    if (st != ZG_OK) return st;
+    Variant* v = nullptr;
+    st = get_variant(p, p->uniform_now, v);
+    if (st != ZG_OK) return st;
+
+    const int P = 1;                                   // time split: see DESIGN.md (not enabled yet)
+    zgk::StreamArgs a;
+    std::memset(&a, 0, sizeof a);
+    for (int k = 0; k < p->ir.n_in; ++k) {
+        if (p->synth_mask & (1u << k)) continue;
+        st = encode_map(p, &a.in_map[k], in[k], T, ld_in, P);
+        if (st != ZG_OK) return st;
+    }
+    for (int o = 0; o < p->ir.n_out; ++o) {
+        st = encode_map(p, &a.out_map[o], out[o], T, ld_out, P);
+        if (st != ZG_OK) return st;
+    }
+    a.state = p->d_state;
+    a.params = p->d_params;
+    a.ch_stride = p->ch_stride;
+    a.stream_pos = p->stream_pos;
+    a.channels = (int)p->C;
+    a.seg_len = (int)(T / P);
+    a.seg_tiles = (a.seg_len + zgk::kTileT - 1) / zgk::kTileT;
+    a.lanes_p = P;
+    a.log2_p = 0;
+    a.warm_tiles = 0;
+    a.dirac_mask = p->dirac_mask;
+    for (int j = 0; j < p->kernel_n_state; ++j) a.state_row[j] = p->state_row[j];
+    if (p->uniform_now) std::memcpy(a.uparams, p->uparams, sizeof(float) * std::min(p->kernel_n_param, zgk::kMaxUniform));
+
+    const int NT = std::max(1, std::max(p->n_buf_in, p->ir.n_out));
+    const int64_t n_warps = (p->C * P + 31) / 32;
+    Geometry g = choose_geometry(p, n_warps, NT, v->regs);
+    a.stages = g.stages;
+
+    if (g.smem > v->max_smem_set) {
+        if (v->prebuilt) {
+            ZG_CUDA(cudaFuncSetAttribute((const void*)v->prebuilt, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
+        } else {
+            CUresult cr = d.funcSetAttribute(v->function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, g.smem);
+            if (cr != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuFuncSetAttribute(max dynamic smem): " + cu_err(cr));
+        }
+        v->max_smem_set = g.smem;
+    }
+    if (v->prebuilt) {
+        void* args[] = {&a};
+        ZG_CUDA(cudaLaunchKernel((const void*)v->prebuilt, dim3(g.grid), dim3(g.wpc * 32), args, g.smem, stream));
+    } else {
+        void* args[] = {&a};
+        CUresult cr = d.launchKernel(v->function, g.grid, 1, 1, g.wpc * 32, 1, 1, g.smem, (CUstream)stream, args, nullptr);
+        if (cr != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuLaunchKernel: " + cu_err(cr));
+    }
+    p->stream_pos += T;
+    p->launches += 1;
+    p->last_smem = g.smem;
+    p->last_threads = g.wpc * 32;
+    p->last_stages = g.stages;
+    return ZG_OK;
+}
+
+int check_io(const zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out) {
+    if (T < 0) return fail(ZG_ERR_ARG, "n_samples < 0");
+    if (T > 0x7fffffffLL) return fail(ZG_ERR_ARG, "n_samples too large for one block");
+    const int64_t min_ld = p->interleaved ? p->C : T;
+    if (p->n_buf_in > 0 && (ld_in < min_ld || ld_in % 4)) return fail(ZG_ERR_ARG, "ld_in too small or not a multiple of 4");
+    if (ld_out < min_ld || ld_out % 4) return fail(ZG_ERR_ARG, "ld_out too small or not a multiple of 4");
+    if (p->n_buf_in > 0 && !in) return fail(ZG_ERR_ARG, "in is NULL");
+    if (!out) return fail(ZG_ERR_ARG, "out is NULL");
+    for (int k = 0; k < p->ir.n_in; ++k) {
+        if (p->synth_mask & (1u << k)) continue;
+        if (!in[k] || ((uintptr_t)in[k] & 15)) return fail(ZG_ERR_ARG, "input buffer NULL or not 16-byte aligned");
+    }
+    for (int o = 0; o < p->ir.n_out; ++o)
+        if (!out[o] || ((uintptr_t)out[o] & 15)) return fail(ZG_ERR_ARG, "output buffer NULL or not 16-byte aligned");
+    return ZG_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int zg_graph_kernel_compile(const zg_graph* g, const zg_plan_opts* opts, int uniform_params, int want_cubin,
+                            char* buf, size_t capacity, size_t* size) {
+    if (!g || !opts || !size) return fail(ZG_ERR_ARG, "NULL argument");
+    const Ir& ir = g->ir_f32;
+    if (!ir.all_f32()) return fail(ZG_ERR_UNSUPPORTED, "the device path evaluates fp32 graphs only");
+    if (ir.n_state > zgk::kMaxState) return fail(ZG_ERR_UNSUPPORTED, "too much delay state for the register-resident kernel");
+    unsigned synth = 0;
+    for (int k = 0; k < ir.n_in; ++k)
+        if (opts->input_kind[k] != ZG_IN_BUFFER) synth |= 1u << k;
+    const bool exact = opts->mode == ZG_MODE_EXACT;
+    std::string text = jit_source(ir, exact, opts->layout == ZG_INTERLEAVED, uniform_params != 0, synth);
+    std::vector<char> cubin;
+    const char* data = text.data();
+    size_t n = text.size();
+    if (want_cubin) {
+        int st = jit_cubin(text, exact, cubin);
+        if (st != ZG_OK) return st;
+        data = cubin.data();
+        n = cubin.size();
+    }
+    *size = n;
+    if (buf) {
+        if (capacity < n) return fail(ZG_ERR_ARG, "buffer too small");
+        std::memcpy(buf, data, n);
+    }
+    return ZG_OK;
+}
+
+void zg_plan_opts_default(zg_plan_opts* o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof *o);
+    o->device = 0;
+    o->channels = 1;
+    o->mode = ZG_MODE_FAST;
+    o->layout = ZG_PLANAR;
+    o->io_dtype = ZG_F32;
+    o->time_split = 0;
+}
+
+int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
+    if (!g || !opts || !out) return fail(ZG_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (opts->channels < 1 || opts->channels > 0x7fffffe0LL) return fail(ZG_ERR_ARG, "channels out of range");
+    if (opts->io_dtype != ZG_F32) return fail(ZG_ERR_UNSUPPORTED, "only fp32 sample buffers are supported");
+    if (opts->mode != ZG_MODE_EXACT && opts->mode != ZG_MODE_FAST) return fail(ZG_ERR_ARG, "bad mode");
+    if (opts->layout != ZG_PLANAR && opts->layout != ZG_INTERLEAVED) return fail(ZG_ERR_ARG, "bad layout");
+    const Ir& ir = g->ir_f32;
+    if (!ir.all_f32())
+        return fail(ZG_ERR_UNSUPPORTED,
+                    "the device path evaluates fp32 graphs only; this graph has int or double terminals "
+                    "(tick it on the host with zg_voice_tick)");
+    if (ir.n_out < 1) return fail(ZG_ERR_UNSUPPORTED, "graph has no outputs");
+    if (ir.n_state > zgk::kMaxState)
+        return fail(ZG_ERR_UNSUPPORTED, "graph keeps " + std::to_string(ir.n_state) +
+                                            " floats of delay state per channel; the register-resident kernels take at most " +
+                                            std::to_string(zgk::kMaxState));
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(ZG_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                     " (zignal-b200 has no CPU fallback for block evaluation)");
+    }
+    if (opts->device < 0 || opts->device >= ndev) return fail(ZG_ERR_ARG, "bad device ordinal");
+    ZG_CUDA(cudaSetDevice(opts->device));
+    ZG_CUDA(cudaFree(nullptr));
+    cudaDeviceProp prop;
+    ZG_CUDA(cudaGetDeviceProperties(&prop, opts->device));
+    if (prop.major != 10)
+        return fail(ZG_ERR_CUDA, std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) +
+                                     std::to_string(prop.minor) + "); this library contains sm_100a code only");
+    if (!driver().ok) return fail(ZG_ERR_CUDA, driver().why);
+
+    auto p = std::make_unique<zg_plan>();
+    p->ir = ir;
+    p->opts = *opts;
+    p->C = opts->channels;
+    p->ch_stride = (p->C + 31) / 32 * 32;
+    p->exact = opts->mode == ZG_MODE_EXACT;
+    p->interleaved = opts->layout == ZG_INTERLEAVED;
+    p->sm_count = prop.multiProcessorCount;
+    p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    for (int k = 0; k < ir.n_in; ++k) {
+        int kind = opts->input_kind[k];
+        if (kind == ZG_IN_DIRAC) { p->synth_mask |= 1u << k; p->dirac_mask |= 1u << k; }
+        else if (kind == ZG_IN_ZERO) p->synth_mask |= 1u << k;
+        else if (kind != ZG_IN_BUFFER) return fail(ZG_ERR_ARG, "bad input_kind");
+        else p->n_buf_in += 1;
+    }
+
+    p->is_biquad = match_df1_cascade(ir, p->bq) && p->synth_mask == 0;
+    if (p->is_biquad && !opts->force_jit) {
+        const int S = p->bq.sections;
+        p->kernel_n_state = 2 * (S + 1);
+        p->kernel_n_param = 5 * S;
+        p->state_row.resize(p->kernel_n_state);
+        for (int k = 0; k <= S; ++k) {
+            const IrLine& l = ir.lines[p->bq.signal_line[k]];
+            p->state_row[2 * k] = l.offset;          // two ticks ago
+            p->state_row[2 * k + 1] = l.offset + 1;  // one tick ago
+        }
+        char nm[96];
+        std::snprintf(nm, sizeof nm, "zg_biquad_df1<%d,%s,%s>", S, p->exact ? "exact" : "fma",
+                      p->interleaved ? "interleaved" : "planar");
+        p->kernel_name = nm;
+    } else {
+        p->kernel_n_state = ir.n_state;
+        p->kernel_n_param = ir.n_params;
+        p->state_row.resize(ir.n_state);
+        for (int j = 0; j < ir.n_state; ++j) p->state_row[j] = j;
+        p->kernel_name = std::string("zg_graph_kernel<jit,") + (p->exact ? "exact," : "fma,") +
+                         (p->interleaved ? "interleaved>" : "planar>");
+    }
+
+    const size_t state_floats = (size_t)std::max(ir.n_state, 1) * p->ch_stride;
+    ZG_CUDA(cudaMalloc(&p->d_state, state_floats * sizeof(float)));
+    ZG_CUDA(cudaMemset(p->d_state, 0, state_floats * sizeof(float)));
+    p->h_params.assign(ir.n_params, std::vector<float>(1, 0.f));
+    p->params_dirty = true;
+
+    // compile / pick the kernel now so that plan creation is where build errors surface
+    int st = sync_params(p.get());
+    if (st != ZG_OK) return st;
+    Variant* v = nullptr;
+    st = get_variant(p.get(), p->uniform_now, v);
+    if (st != ZG_OK) return st;
+    *out = p.release();
+    return ZG_OK;
+}
+
+void zg_plan_destroy(zg_plan* p) { delete p; }
+
+int zg_plan_get_info(const zg_plan* p, zg_plan_info* info) {
+    if (!p || !info) return fail(ZG_ERR_ARG, "NULL argument");
+    std::memset(info, 0, sizeof *info);
+    std::snprintf(info->kernel, sizeof info->kernel, "%s", p->kernel_name.c_str());
+    const Variant& v = p->variant[p->uniform_now ? 1 : 0];
+    info->jit = v.prebuilt ? 0 : 1;
+    info->lanes_per_channel = 1;
+    info->warmup_samples = 0;
+    info->regs_per_thread = v.regs;
+    info->smem_bytes = p->last_smem;
+    info->launches = p->launches;
+    info->threads_per_cta = p->last_threads;
+    info->stages = p->last_stages;
+    info->uniform_params = p->uniform_now ? 1 : 0;
+    return ZG_OK;
+}
+
+int zg_process(zg_plan* p, const void* const* in, void* const* out, int64_t n_samples, int64_t ld_in,
+               int64_t ld_out, void* stream) {
+    if (!p) return fail(ZG_ERR_ARG, "plan is NULL");
+    int st = check_io(p, in, out, n_samples, ld_in, ld_out);
+    if (st != ZG_OK) return st;
+    if (n_samples == 0) return ZG_OK;
+    ZG_CUDA(cudaSetDevice(p->opts.device));
+    return launch(p, in, out, n_samples, ld_in, ld_out, (cudaStream_t)stream);
+}
+
+int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t n_samples, int64_t ld_in,
+                    int64_t ld_out) {
+    if (!p) return fail(ZG_ERR_ARG, "plan is NULL");
+    if (n_samples < 0) return fail(ZG_ERR_ARG, "n_samples < 0");
+    if (n_samples == 0) return ZG_OK;
+    ZG_CUDA(cudaSetDevice(p->opts.device));
+    if (!p->own_stream) ZG_CUDA(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+    // device staging: same shape as the host buffers, rows padded to a multiple of 4 floats
+    const int64_t rows = p->interleaved ? n_samples : p->C;
+    const int64_t cols = p->interleaved ? p->C : n_samples;
+    const int64_t ld = (cols + 3) / 4 * 4;
+    if ((p->n_buf_in > 0 && ld_in < cols) || ld_out < cols) return fail(ZG_ERR_ARG, "leading dimension too small");
+    const size_t per_buf = (size_t)rows * ld;
+    const size_t need = per_buf * (p->n_buf_in + p->ir.n_out);
+    if (need > p->d_stage_floats) {
+        if (p->d_stage) cudaFree(p->d_stage);
+        p->d_stage = nullptr;
+        p->d_stage_floats = 0;
+        ZG_CUDA(cudaMalloc(&p->d_stage, need * sizeof(float)));
+        p->d_stage_floats = need;
+    }
+    const void* d_in[ZG_MAX_WIRES] = {};
+    void* d_out[ZG_MAX_WIRES] = {};
+    size_t slot = 0;
+    for (int k = 0; k < p->ir.n_in; ++k) {
+        if (p->synth_mask & (1u << k)) continue;
+        if (!in || !in[k]) return fail(ZG_ERR_ARG, "input buffer is NULL");
+        float* dst = p->d_stage + slot++ * per_buf;
+        ZG_CUDA(cudaMemcpy2DAsync(dst, ld * 4, in[k], ld_in * 4, cols * 4, rows, cudaMemcpyHostToDevice, p->own_stream));
+        d_in[k] = dst;
+    }
+    for (int o = 0; o < p->ir.n_out; ++o) {
+        if (!out || !out[o]) return fail(ZG_ERR_ARG, "output buffer is NULL");
+        d_out[o] = p->d_stage + slot++ * per_buf;
+    }
+    int st = check_io(p, d_in, d_out, n_samples, ld, ld);
+    if (st != ZG_OK) return st;
+    st = launch(p, d_in, d_out, n_samples, ld, ld, p->own_stream);
+    if (st != ZG_OK) return st;
+    for (int o = 0; o < p->ir.n_out; ++o)
+        ZG_CUDA(cudaMemcpy2DAsync(out[o], ld_out * 4, d_out[o], ld * 4, cols * 4, rows, cudaMemcpyDeviceToHost, p->own_stream));
+    ZG_CUDA(cudaStreamSynchronize(p->own_stream));
+    return ZG_OK;
+}
+
+int zg_state_reset(zg_plan* p) {
+    if (!p) return fail(ZG_ERR_ARG, "plan is NULL");
+    ZG_CUDA(cudaSetDevice(p->opts.device));
+    ZG_CUDA(cudaDeviceSynchronize());
+    ZG_CUDA(cudaMemset(p->d_state, 0, (size_t)std::max(p->ir.n_state, 1) * p->ch_stride * sizeof(float)));
+    p->stream_pos = 0;
+    return ZG_OK;
+}
+
+int zg_state_get(zg_plan* p, float* host, size_t n_floats) {
+    if (!p || !host) return fail(ZG_ERR_ARG, "NULL argument");
+    if (n_floats != (size_t)p->ir.n_state * p->C) return fail(ZG_ERR_ARG, "expected n_state * channels floats");
+    if (n_floats == 0) return ZG_OK;
+    ZG_CUDA(cudaSetDevice(p->opts.device));
+    ZG_CUDA(cudaDeviceSynchronize());
+    ZG_CUDA(cudaMemcpy2D(host, p->C * 4, p->d_state, p->ch_stride * 4, p->C * 4, p->ir.n_state, cudaMemcpyDeviceToHost));
+    return ZG_OK;
+}
+
+int zg_state_set(zg_plan* p, const float* host, size_t n_floats) {
+    if (!p || !host) return fail(ZG_ERR_ARG, "NULL argument");
+    if (n_floats != (size_t)p->ir.n_state * p->C) return fail(ZG_ERR_ARG, "expected n_state * channels floats");
+    if (n_floats == 0) return ZG_OK;
+    ZG_CUDA(cudaSetDevice(p->opts.device));
+    ZG_CUDA(cudaDeviceSynchronize());
+    ZG_CUDA(cudaMemcpy2D(p->d_state, p->ch_stride * 4, host, p->C * 4, p->C * 4, p->ir.n_state, cudaMemcpyHostToDevice));
+    return ZG_OK;
+}
+
+int zg_param_set(zg_plan* p, int index, const float* host_values, int64_t n) {
+    if (!p || !host_values) return fail(ZG_ERR_ARG, "NULL argument");
+    if (index < 0 || index >= (int)p->h_params.size()) return fail(ZG_ERR_ARG, "bad parameter index");
+    if (n != 1 && n != p->C) return fail(ZG_ERR_ARG, "parameter needs 1 value or one per channel");
+    ZG_CUDA(cudaSetDevice(p->opts.device));
+    ZG_CUDA(cudaDeviceSynchronize());      // a launch in flight may still be reading d_params
+    p->h_params[index].assign(host_values, host_values + n);
+    p->params_dirty = true;
+    return ZG_OK;
+}
+
+}  // extern "C"
