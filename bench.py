@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- Msamples/s of the N-channel biquad chain on 1..8 B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ns|c2] [--coef uniform|per-channel]
+    python bench.py --impl reference ...      # the reference's own CPU loop on the host cores
+    (N > 1: launched by torch.distributed.run, one rank per GPU)
+
+A step = one pass of the hot path (one zg_process() = ONE kernel launch per rank) over one block of
+synthetic input: `ns` = 65 536 channels x 8192 samples per GPU (the north star's target shape,
+SURVEY.md 8d), `c2` = 4096 x 65 536 (BASELINE configs[1]); 4 direct-form-1 biquad sections in series,
+the reference's own graph spelling (test/benchmark.cpp:25-33), stable RBJ low-pass coefficients.
+Channels are independent, so N GPUs = N x the channels (weak scaling), no data-path collective.
+
+  value     whole-job Msamples/s, inputs resident in HBM, CUDA events on the launching stream
+  e2e       same metric through zg_process_host(): pinned host buffers, H2D + kernel + D2H timed
+  roofline  algorithmic bytes (8 B per sample: 4 in + 4 out) / average launch time vs measured HBM peak
+  cpu_baseline  the reference's hand-written biquad loop (oracle/_ref, all host threads), bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+SECTIONS = 4
+WORKLOADS = {
+    # name: (channels per GPU, samples per block)
+    "ns": (65536, 8192),
+    "c2": (4096, 65536),
+}
+BYTES_PER_SAMPLE = 8          # fp32 in + fp32 out; state/coefficients amortise to < 0.1 %
+
+
+def _peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic(workload):
+    """dram bytes per launch from the committed `ncu --set full` capture of the same kernel, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(workload)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """SM clock + throttle reasons during the timed region (NVML, ~2 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---- the reference arm / cpu baseline: the reference's own loop on the host cores ---------------------
+
+def _ref_lib():
+    so = os.path.join(ROOT, "oracle", "_ref", "libzg_ref.so")
+    if os.path.exists(so):
+        return ctypes.CDLL(so)
+    return None
+
+
+def cpu_reference_rate(target_seconds=12.0, samples=8192):
+    """Times `SECTIONS` hand-written DF1 biquads in series per channel (the reference's make_custom,
+    test/benchmark.cpp:35-47, compiled where it lies into oracle/_ref) on all host threads, on a bounded
+    sample of the workload.  Falls back to the oracle's emitted C tick ("port") if _ref is absent."""
+    import numpy as np
+    import flowz_oracle as fo
+    cores = os.cpu_count() or 1
+    lib = _ref_lib()
+    P = ctypes.POINTER(ctypes.c_float)
+
+    def run_ref(C):
+        x = fo.noise(C, samples, seed=0) * np.float32(0.01)
+        y = np.empty_like(x)
+        t0 = time.perf_counter()
+        rc = lib.zg_ref_df1_chain(SECTIONS, x.ctypes.data_as(P), y.ctypes.data_as(P), ctypes.c_long(C), ctypes.c_long(samples))
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        return dt
+
+    port = None
+
+    def run_port(C):
+        nonlocal port
+        x = fo.noise(C, samples, seed=0)
+        port = fo.COracle(fo.biquad_cascade(SECTIONS), C)
+        t0 = time.perf_counter()
+        port.process([x])
+        return time.perf_counter() - t0
+
+    run, kind = (run_ref, "reference") if lib is not None else (run_port, "port")
+    C = 64 * cores
+    dt = run(C)                                   # calibration (also warms the threads up)
+    rate = C * samples / dt
+    C = int(max(cores, min(rate * target_seconds / samples, 262144)))
+    dt = run(C)
+    return {"value": C * samples / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": kind,
+            "sample": f"{C} channels x {samples} samples x {SECTIONS} DF1 sections, {dt:.1f} s, "
+                      f"{'reference make_custom loop (coefficients of test/benchmark.cpp:18-23)' if kind == 'reference' else 'oracle C tick'}, "
+                      f"OpenMP over channels"}, (C, dt)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    C_w, T_w = WORKLOADS[args.workload]
+    # each step = a bounded sample of the workload; size it once so the whole run ends in minutes
+    base, (C, dt) = cpu_reference_rate(target_seconds=2.0, samples=min(T_w, 8192))
+    import numpy as np
+    import flowz_oracle as fo
+    lib = _ref_lib()
+    P = ctypes.POINTER(ctypes.c_float)
+    samples = min(T_w, 8192)
+    x = fo.noise(C, samples, seed=0) * np.float32(0.01)
+    y = np.empty_like(x)
+
+    def step():
+        if lib is not None:
+            lib.zg_ref_df1_chain(SECTIONS, x.ctypes.data_as(P), y.ctypes.data_as(P), ctypes.c_long(C), ctypes.c_long(samples))
+        else:
+            fo.COracle(fo.biquad_cascade(SECTIONS), C).process([x])
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = C * samples * args.steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": "Msamples/s, N-channel 4-section biquad chain", "value": value,
+        "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {C_w} channels x {T_w} samples x {SECTIONS} DF1 biquad sections, fp32 planar",
+                   "step_sample": f"{C} channels x {samples} samples per step on the host"},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": base["cores"], "kind": base["kind"],
+                         "sample": base["sample"]},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm ---------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import zignal_b200 as zg
+    import flowz_oracle as fo      # workload helpers only (graph text, coefficients); nothing is computed by it here
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    C, T = WORKLOADS[args.workload]
+    if args.coef == "uniform":
+        graph = zg.compile(fo.biquad_cascade(SECTIONS))
+        params = []
+    else:
+        graph = zg.compile(fo.biquad_cascade_params(SECTIONS))
+        c = np.arange(C, dtype=np.float64) + rank * C
+        params = []
+        for k in range(SECTIONS):
+            per = np.array([fo.rbj_lowpass(440.0 * 2 ** k * (1.0 + ci / (C * world))) for ci in c], np.float32)
+            params += [per[:, j].copy() for j in range(5)]
+    mode = zg.MODE_EXACT if args.mode == "exact" else zg.MODE_FAST
+    plan = graph.plan(channels=C, device=local, mode=mode,
+                      layout=zg.INTERLEAVED if args.layout == "interleaved" else zg.PLANAR)
+    for i, p in enumerate(params):
+        plan.set_param(i, p)
+
+    shape = (T, C) if args.layout == "interleaved" else (C, T)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.rand(shape, generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    y = torch.empty_like(x)
+
+    for _ in range(max(args.warmup, 3)):
+        plan.process([x], [y])
+    barrier()
+    l0 = plan.info().launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            plan.process([x], [y])
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = plan.info().launches - l0
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * C * T / (ms_per_step * 1e-3) / 1e6
+    info = plan.info()
+
+    # ---- e2e: host buffers through zg_process_host (H2D + kernel + D2H inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty(shape, dtype=torch.float32).pin_memory()
+        hy = torch.empty(shape, dtype=torch.float32).pin_memory()
+        hx.copy_(x)
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        plan.process_host([hx], [hy])                       # warm-up (allocates the device staging)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.process_host([hx], [hy])
+            _ = float(hy[0, 0])                              # the result is read on the host
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * C * T * e2e_steps / dt / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(C * T * 4), "d2h_bytes_per_step": int(C * T * 4), "steps": e2e_steps,
+               "ms_per_step": dt / e2e_steps * 1e3, "api": "zg_process_host (pinned host buffers)"}
+        del hx, hy
+
+    # ---- a spot check of the timed output against the oracle (the checker, not the thing measured) ----
+    parity = None
+    if rank == 0 and args.coef == "uniform" and args.layout == "planar":
+        idx = [0, 1, C // 2, C - 1]
+        ref = fo.COracle(fo.biquad_cascade(SECTIONS), len(idx)).process([x[idx].cpu().numpy()])[0]
+        got = y[idx].cpu().numpy()
+        den = np.abs(ref).max(axis=1)
+        parity = {"max_block_rel_err": float((np.abs(got.astype(np.float64) - ref).max(axis=1) / den).max()),
+                  "bit_identical": bool(np.array_equal(got, ref)), "channels_checked": idx}
+
+    if rank == 0:
+        peak, peak_src = _peak_hbm()
+        achieved = BYTES_PER_SAMPLE * C * T / (ms_per_step * 1e-3) / 1e9       # per GPU, per launch
+        line = {
+            "metric": "Msamples/s, N-channel 4-section biquad chain", "value": value, "unit": "Msamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {C} channels x {T} samples per GPU x {SECTIONS} DF1 biquad sections "
+                                   f"(flowz `fwd |= bwd` x{SECTIONS}), fp32 {args.layout}",
+                       "coefficients": args.coef, "mode": args.mode, "parallelism": f"channel-shard x{world}",
+                       "l2": f"inputs larger than L2 ({C * T * 4 / 2**20:.0f} MiB in + same out per GPU per step)",
+                       "kernel": info.kernel.decode(), "threads_per_cta": info.threads_per_cta,
+                       "stages": info.stages, "smem_bytes": info.smem_bytes, "regs": info.regs_per_thread},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": _traffic(args.workload), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * C * T},
+            "clocks": clk.summary(),
+            "gpu_launches": launches,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if parity is not None:
+            line["parity_spot_check"] = parity
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"], _ = cpu_reference_rate()
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ns", choices=sorted(WORKLOADS))
+    ap.add_argument("--coef", default="uniform", choices=["uniform", "per-channel"])
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--layout", default="planar", choices=["planar", "interleaved"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,71 @@
+"""The C ABI boundary: the library loads, exports every symbol include/zignal_b200.h declares, and
+fails loudly (never silently on a CPU) when there is no B200.  CPU only; no compute calls."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import flowz_oracle as fo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "zignal_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(zg_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(zg):
+    names = _declared()
+    assert len(names) >= 25
+    lib = ctypes.CDLL(zg.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/zignal_b200.h but not exported"
+    assert sorted(zg.EXPORTED) == names           # and the Python binding covers the whole header
+
+
+def test_library_has_sm100a_kernels_and_tma():
+    so = os.path.join(ROOT, "zignal_b200", "libzignal_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    assert "UTMALDG" in sass and "UTMASTG" in sass          # TMA loads and stores
+    assert "FFMA" in sass and "LDS.128" in sass
+
+
+def test_no_gpu_is_a_loud_error(zg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    g = zg.compile(fo.biquad_cascade(4))
+    with pytest.raises(zg.ZgError) as e:
+        g.plan(channels=64)
+    assert e.value.status == zg.ZG_ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+def test_generated_kernels_compile_for_sm100a(zg, mode, layout):
+    """NVRTC needs no device: every BASELINE graph's specialised kernel must build offline."""
+    kw = dict(mode=zg.MODE_EXACT if mode == "exact" else zg.MODE_FAST,
+              layout=zg.PLANAR if layout == "planar" else zg.INTERLEAVED)
+    graphs = ["~(_2 + 0.9f*_1[_1])",
+              "~(0x1.fcp0f*_1[_1] - _1[_2] + _2) |= ~(_2 + 0.9f*_1[_1])",
+              fo.biquad_cascade(4), fo.biquad_cascade_params(2),
+              "(_1 | _1[_1]) |= ~(_2 + _3 + 0.25f*_1[_2])"]
+    for expr in graphs:
+        g = zg.compile(expr)
+        for uniform in (True, False):
+            cubin = g.kernel(cubin=True, uniform_params=uniform, **kw)
+            assert cubin[:4] == b"\x7fELF" and len(cubin) > 4096
+
+
+def test_exact_mode_source_has_no_contractable_arithmetic(zg):
+    src = zg.compile(fo.biquad_cascade(1)).kernel(mode=zg.MODE_EXACT).decode()
+    tick = src[src.index("struct ZgTick"):]
+    assert "__fmul_rn" in tick and "__fadd_rn" in tick
+    assert not re.search(r"v\d+ [*+] v\d+", tick)

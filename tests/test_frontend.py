@@ -1,0 +1,124 @@
+"""The product's host side (parser, static analysis, canonical split, lowering, host voice) against
+the reference's own vectors and against the oracle.  CPU only."""
+import numpy as np
+import pytest
+
+import flowz_oracle as fo
+import reference_vectors as rv
+
+
+def _norm(zg, text):
+    # canonical() is the identity on trees without '~': use it as parse -> print normalisation
+    return zg.canonical(text)
+
+
+@pytest.mark.parametrize("expr,left,right,line", rv.CANONICAL_SPLITS, ids=[f"tests.cpp:{c[3]}" for c in rv.CANONICAL_SPLITS])
+def test_canonical_split(zg, expr, left, right, line):
+    assert zg.canonical(expr) == _norm(zg, f"bfb({left} , {right})")
+    # and the product's printer agrees with the oracle's on the same tree
+    assert zg.canonical(expr) == _norm(zg, str(fo.make_canonical(fo.parse(expr))))
+
+
+@pytest.mark.parametrize("expr,n_in,n_out,delays,line", rv.CANONICAL_ARITY)
+def test_canonical_arity(zg, expr, n_in, n_out, delays, line):
+    c = zg.canonical(expr)
+    assert zg.arity(c) == (n_in, n_out)
+    assert zg.delays(c) == delays
+
+
+@pytest.mark.parametrize("expr,n_in,n_out,ins,outs,line", rv.WIRES_AROUND)
+def test_wires_around_boxes(zg, expr, n_in, n_out, ins, outs, line):
+    assert zg.arity(expr) == (n_in, n_out)
+    assert zg.compile(expr).voice()(*ins) == outs
+
+
+@pytest.mark.parametrize("expr,steps,line", rv.TICKS, ids=[f"{c[0]}@{c[2]}" for c in rv.TICKS])
+def test_known_answer_ticks(zg, expr, steps, line):
+    v = zg.compile(expr).voice()
+    for ins, outs in steps:
+        got = v(*ins)
+        assert got == outs
+        assert all(isinstance(g, int) for g in got) or "[" in expr   # ints stay ints unless they went through a float line
+
+
+def test_series_and_delay_spellings_of_the_prototypes(zg):
+    # north star: `>>` and `_1[-n]` (experimental_steps/wires_mono_only.cpp:37, delay_expression.cpp:99)
+    assert zg.canonical("_1 >> _1[-1]") == zg.canonical("_1 |= _1[_1]")
+    assert zg.canonical("~(_2 + 0.5f*_1[-1]) >> _1[-2]") == zg.canonical("~(_2 + 0.5f*_1[_1]) |= _1[_2]")
+    # >> is left associative and binds tighter than | and |=
+    assert zg.canonical("_1 >> _1 >> _1") == zg.canonical("(_1 |= _1) |= _1")
+
+
+def test_clone_copies_state(zg):
+    v = zg.compile("~(_1[_1] + _2)").voice()
+    v(5)
+    w = v.clone()                          # flowz.hpp:1206-1207: copying the callable copies state_
+    assert v(1) == (6,) and w(10) == (15,)
+
+
+def test_std_ref_parameter_modulation(zg):
+    # flowz/README.md:42-63: ~( std::ref(a)*_1[_1] + 0.1*_2 ), a *= 0.9f per sample; 0.1 is a double
+    g = zg.compile("~($0*_1[_1] + 0.1*_2)")
+    v = g.voice()
+    o = fo.Oracle("~($0*_1[_1] + 0.1*_2)", params=[0.0])
+    a = np.float32(0.9)
+    for t in range(10):
+        x = 1.0 if t == 0 else 0.0
+        v.set_param(0, float(a))
+        o.backend.params[0] = a
+        (dt, want), = o.tick(x)
+        got, = v(x)
+        assert dt == fo.F64 and got == float(want[0])
+        a = np.float32(a * np.float32(0.9))
+
+
+GRAPHS = [
+    "~(_2 + 0.9f*_1[_1])",                                             # BASELINE config 1
+    "~(0x1.fcp0f*_1[_1] - _1[_2] + _2) |= ~(_2 + 0.9f*_1[_1])",        # config 3: osc >> one-pole
+    "_1 |= (_1[_1] , _1[_3]) |= _1 - _2",
+    "(_1 , _1[_2]) |= (_1 | 0.5f*_1) |= _1*_2",
+    "(_1 | _1[_1]) |= ~(_2 + _3 + 0.25f*_1[_2])",
+    "~( (_2 + 0.3f*_1[_1]) |= (0.5f*_1 + 0.25f*_1[_1]) )",
+    "_1 / (_2*_2 + 1.5f) - -_1[_1]",
+]
+
+
+@pytest.mark.parametrize("expr", GRAPHS + [rv.bench_graphs()[k] for k in (1, 2, 3, 4)] + [fo.biquad_cascade(4)])
+def test_host_voice_equals_oracle(zg, expr):
+    g = zg.compile(expr)
+    o = fo.Oracle(expr)
+    assert (g.n_in, g.n_out) == (o.n_in, o.n_out)
+    assert g.canonical == zg.canonical(str(o.canonical))     # same tree (printer-normalised)
+    x = fo.noise(g.n_in, 400, seed=11)
+    v = g.voice()
+    for t in range(400):
+        want = o.tick(*[x[i, t] for i in range(g.n_in)])
+        got = v(*[float(x[i, t]) for i in range(g.n_in)])
+        for (dt, w), y in zip(want, got):
+            assert np.float32(y) == w[0] or (np.isnan(y) and np.isnan(w[0])), (expr, t)
+
+
+def test_line_sharing_removes_duplicate_state(zg):
+    # DF2: the reference keeps two copies of the u line; the tick program keeps one
+    g = zg.compile(rv.bench_graphs()[2])
+    assert g.n_state == 2
+    g4 = zg.compile(fo.biquad_cascade(4))
+    assert (g4.n_state, g4.n_lines) == (10, 5)
+
+
+@pytest.mark.parametrize("expr", ["_1 +", "_0", "_1[_0]", "~(_1 + _2)", "(_1 |= _1) + _1", "foo", "_1 |= |= _1"])
+def test_errors_are_reported_not_thrown(zg, expr):
+    with pytest.raises(zg.ZgError) as e:
+        zg.compile(expr)
+    assert e.value.status in (zg.ZG_ERR_PARSE, zg.ZG_ERR_GRAPH)
+
+
+def test_mono_one_pole_1024_samples_on_cpu(zg):
+    """BASELINE config 0: y = x + a*_1[-1] over 1024 samples, compile() plumbing without a GPU."""
+    a = np.float32(0.9)
+    v = zg.compile("~(_2 + 0.9f*_1[-1])").voice()
+    x = fo.noise(1, 1024, seed=2)[0]
+    y1 = np.float32(0)
+    for t in range(1024):
+        y1 = np.float32(x[t] + np.float32(a * y1))
+        assert np.float32(v(float(x[t]))[0]) == y1
