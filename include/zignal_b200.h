@@ -146,6 +146,7 @@ typedef struct zg_plan_info {
     int threads_per_cta;  /* geometry of the last launch                                        */
     int stages;           /* TMA pipeline depth per warp of the last launch                     */
     int uniform_params;   /* 1 = all parameters are scalars and travel in the constant bank     */
+    int boxes;            /* 4 KB boxes (32 channels x 32 samples) per wire per pipeline stage  */
 } zg_plan_info;
 int zg_plan_get_info(const zg_plan* p, zg_plan_info* info);
 

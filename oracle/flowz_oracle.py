@@ -724,8 +724,26 @@ def biquad_df1(b0, b1, b2, a1, a2) -> str:
 
 
 def biquad_cascade(sections: int = 4) -> str:
-    """`sections` stable RBJ low-pass DF1 sections in series, f = 440 * 2^k Hz."""
-    return " |= ".join(biquad_df1(*rbj_lowpass(440.0 * 2 ** k)) for k in range(sections))
+    """`sections` stable RBJ low-pass DF1 sections in series, f = 440 * 2^k Hz; the
+    octaves wrap after six sections so that every cutoff stays below Nyquist (22 050 Hz)."""
+    return " |= ".join(biquad_df1(*rbj_lowpass(440.0 * 2 ** (k % 6))) for k in range(sections))
+
+
+def biquad_cascade_f64(x: np.ndarray, sections: int = 4) -> np.ndarray:
+    """The same cascade evaluated in float64 (direct form 1, same fp32 coefficients): the yardstick
+    for how far fp32 rounding alone moves the reference's own output (tests of the FMA mode)."""
+    y = np.asarray(x, np.float64)
+    for k in range(sections):
+        b0, b1, b2, a1, a2 = (float(v) for v in rbj_lowpass(440.0 * 2 ** (k % 6)))
+        x1 = x2 = y1 = y2 = np.zeros(y.shape[0])
+        out = np.empty_like(y)
+        for t in range(y.shape[1]):
+            xt = y[:, t]
+            yt = ((b0 * xt + b1 * x1) + b2 * x2 + a1 * y1) + a2 * y2
+            x2, x1, y2, y1 = x1, xt, y1, yt
+            out[:, t] = yt
+        y = out
+    return y
 
 
 def biquad_cascade_params(sections: int = 4) -> str:

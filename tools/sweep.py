@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Tuning sweep (GPU box only): kernel-only Msamples/s of the biquad cascade for combinations of the
+ZG_TUNE_* launch-geometry overrides, modes, layouts and workloads.  Prints one JSON line per point.
+
+    python tools/sweep.py [--workload ns] [--iters 20] [--points "mode=exact,fast;boxes=1,2;wpc=0;stages=0"]
+"""
+import argparse, itertools, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import torch
+import zignal_b200 as zg
+import flowz_oracle as fo
+
+WORK = {"ns": (65536, 8192), "c2": (4096, 65536), "mid": (16384, 16384)}
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="ns")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--sections", type=int, default=4)
+    ap.add_argument("--points", default="mode=exact,fast;boxes=1,2;wpc=0;stages=0;layout=planar;coef=uniform")
+    a = ap.parse_args()
+    axes = {}
+    for part in a.points.split(";"):
+        k, v = part.split("=")
+        axes[k] = v.split(",")
+    for k, d in (("mode", ["exact"]), ("boxes", ["0"]), ("wpc", ["0"]), ("stages", ["0"]), ("layout", ["planar"]), ("coef", ["uniform"])):
+        axes.setdefault(k, d)
+    C, T = WORK[a.workload]
+    x = torch.rand((C, T), device="cuda") * 2 - 1
+    y = torch.empty_like(x)
+    xi, yi = None, None
+    keys = list(axes)
+    for combo in itertools.product(*[axes[k] for k in keys]):
+        pt = dict(zip(keys, combo))
+        for env, k in (("ZG_TUNE_BOXES", "boxes"), ("ZG_TUNE_WPC", "wpc"), ("ZG_TUNE_STAGES", "stages")):
+            if pt[k] != "0": os.environ[env] = pt[k]
+            else: os.environ.pop(env, None)
+        inter = pt["layout"] == "interleaved"
+        if inter and xi is None:
+            xi = x.t().contiguous(); yi = torch.empty_like(xi)
+        if pt["coef"] == "uniform":
+            g = zg.compile(fo.biquad_cascade(a.sections))
+        else:
+            g = zg.compile(fo.biquad_cascade_params(a.sections))
+        try:
+            plan = g.plan(channels=C, mode=zg.MODE_EXACT if pt["mode"] == "exact" else zg.MODE_FAST,
+                          layout=zg.INTERLEAVED if inter else zg.PLANAR)
+            if pt["coef"] != "uniform":
+                import numpy as np
+                for k in range(a.sections):
+                    co = fo.rbj_lowpass(440.0 * 2 ** k)
+                    for j in range(5):
+                        plan.set_param(5 * k + j, np.full(C, co[j], np.float32))
+            bi, bo = ([xi], [yi]) if inter else ([x], [y])
+            for _ in range(3): plan.process(bi, bo)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.iters): plan.process(bi, bo)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / a.iters
+            info = plan.info()
+            pt.update(ms=round(ms, 4), msamples=round(C * T / ms / 1e3), gbs=round(8 * C * T / ms / 1e6),
+                      threads=info.threads_per_cta, stages_used=info.stages, boxes_used=info.boxes, smem=info.smem_bytes,
+                      regs=info.regs_per_thread)
+        except Exception as e:
+            pt["error"] = str(e)[:200]
+        print(json.dumps(pt), flush=True)
+
+if __name__ == "__main__":
+    main()

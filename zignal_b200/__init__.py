@@ -48,7 +48,7 @@ class PlanInfo(C.Structure):
     _fields_ = [("kernel", C.c_char * 96), ("jit", C.c_int), ("lanes_per_channel", C.c_int),
                 ("warmup_samples", C.c_int), ("regs_per_thread", C.c_int), ("smem_bytes", C.c_int),
                 ("launches", C.c_int), ("threads_per_cta", C.c_int), ("stages", C.c_int),
-                ("uniform_params", C.c_int)]
+                ("uniform_params", C.c_int), ("boxes", C.c_int)]
 
 
 def _load() -> C.CDLL:

@@ -6,22 +6,20 @@
 // independent voices at once.
 //
 // Design (B200):
-//   * one LANE per virtual lane v = (channel c, time segment p).  P = 1: lane per channel.  P > 1
-//     ("time split", fast mode, linear graphs with decaying state only): the block is cut into P
-//     segments per channel, lane p evaluates segment p after warming its state up on the W samples
-//     before its segment (outputs discarded), which restores the state to within the tolerance
-//     verified at plan time.  Lane 0 of a channel starts from the true stored state.
+//   * one LANE per channel: the recurrence of a voice is serial in time, voices are independent.
 //   * all delay-line state and per-channel parameters stay in REGISTERS for the whole block; state
 //     is read from HBM once at block start and written once at block end ([n_state][channels]).
-//   * samples move HBM -> smem -> HBM with TMA (cp.async.bulk.tensor) in tiles of 32 lanes x 32
+//   * samples move HBM -> smem -> HBM with TMA (cp.async.bulk.tensor) in boxes of 32 lanes x 32
 //     samples (4 KB, rows of 128 B, hardware SWIZZLE_128B).  With that swizzle a lane reads/writes
 //     its own row 16 bytes at a time (LDS.128/STS.128) and every quarter-warp covers all 32 banks:
 //     conflict free without padding.  Outputs overwrite the consumed inputs in place and the same
-//     tile is stored back with TMA, so a stage costs 4 KB per wire.
+//     box is stored back with TMA, so a box costs 4 KB per wire.  A pipeline stage ("tile") is
+//     `boxes` consecutive boxes in time whose loads / stores are issued back to back, so that HBM
+//     sees 128*boxes contiguous bytes per channel row at a time (DRAM page locality).
 //   * every WARP runs its own pipeline (own stages, own mbarriers, lane 0 issues the TMA): no
 //     __syncthreads anywhere; S stages = 1 computing, 1 draining its store, S-2 loads in flight.
-//   * grid = one warp per 32 virtual lanes; CTAs are 1..4 warps, sized by the host so that the
-//     resident warps per SM divide the work evenly (148 SMs).
+//   * grid = one warp per 32 channels; the host sizes CTAs so that all warps are resident at once and
+//     spread evenly over the 148 SMs.
 #pragma once
 
 namespace zgk {
@@ -35,18 +33,15 @@ constexpr int kMaxState = 64;       // state floats per channel a register-resid
 constexpr int kMaxUniform = 64;     // uniform parameters passed by value
 
 struct StreamArgs {
-    TensorMap in_map[kMaxWires];    // planar: 3-D {seg_len, P, C}; interleaved: 2-D {C, T}
+    TensorMap in_map[kMaxWires];    // planar: 2-D {T, C}; interleaved: 2-D {C, T}; box 32 x 32
     TensorMap out_map[kMaxWires];
     float* state;                   // [n_state][ch_stride]
     const float* params;            // [n_params][ch_stride]
     long long ch_stride;
     long long stream_pos;           // absolute index of sample 0 of this block (dirac inputs)
     int channels;
-    int seg_len;                    // samples per lane = n_samples / P
-    int seg_tiles;                  // ceil(seg_len / 32)
-    int lanes_p;                    // P (power of two <= 32)
-    int log2_p;
-    int warm_tiles;                 // W / 32
+    int n_samples;                  // samples in this block
+    int boxes;                      // NB: boxes (of 32 samples) per pipeline stage
     int stages;                     // S >= 2
     unsigned dirac_mask;            // synthesised input k is a dirac (else zeros)
     int state_row[kMaxState];       // row of state slot j inside `state` (prebuilt ticks use their
@@ -82,25 +77,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "}\n" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* map, int x, int y, int z,
-                                            unsigned long long* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z),
-        "r"(smem_u32(bar))
-        : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(void* dst, const TensorMap* map, int x, int y,
                                             unsigned long long* bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
         : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const TensorMap* map, int x, int y, int z, const void* src) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
-                 "r"(x), "r"(y), "r"(z), "r"(smem_u32(src))
-                 : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const TensorMap* map, int x, int y, const void* src) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
@@ -148,7 +130,7 @@ __host__ __device__ constexpr int popcount_u32(unsigned v) { return v == 0 ? 0 :
 template <class Tick, bool kInterleaved, bool kUniform>
 __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     constexpr int NI = Tick::N_IN, NO = Tick::N_OUT, NS = Tick::N_STATE, NP = Tick::N_PARAM;
-    constexpr int NT = (NI > NO ? NI : NO) > 0 ? (NI > NO ? NI : NO) : 1;   // tiles per stage
+    constexpr int NT = (NI > NO ? NI : NO) > 0 ? (NI > NO ? NI : NO) : 1;   // wires per stage
     constexpr unsigned kAllIn = NI > 0 ? ((1u << NI) - 1u) : 0u;
     constexpr unsigned kBufMask = kAllIn & ~Tick::SYNTH_MASK;
     constexpr int kNumBuf = popcount_u32(kBufMask);
@@ -159,37 +141,36 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     const int warp = threadIdx.x >> 5;
     const int warps_per_cta = blockDim.x >> 5;
     const int S = a.stages;
-    const int P = kInterleaved ? 1 : a.lanes_p;
-    const int lg = kInterleaved ? 0 : a.log2_p;
+    const int NB = a.boxes;
+    const int tile_t = NB * kTileT;
     const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
-    const long long c0ll = gw * (32 >> lg);
+    const long long c0ll = gw * 32;
     if (c0ll >= a.channels) return;                    // warp-uniform
     const int c0 = (int)c0ll;
-    const int p = lane & (P - 1);
-    const int ch = c0 + (lane >> lg);
+    const int ch = c0 + lane;
     const bool ch_ok = ch < a.channels;
 
     // SWIZZLE_128B works on 1024-byte atoms of the shared address: align the tile area explicitly
     // (the host reserves the slack) instead of trusting the placement of dynamic shared memory
     unsigned char* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-    unsigned char* my = tiles + (size_t)warp * S * NT * kTileBytes;
+    const unsigned wire_bytes = (unsigned)NB * kTileBytes;          // one wire of one stage
+    const unsigned stage_bytes = (unsigned)NT * wire_bytes;
+    unsigned char* my = tiles + (size_t)warp * S * stage_bytes;
     unsigned long long* bars =
-        reinterpret_cast<unsigned long long*>(tiles + (size_t)warps_per_cta * S * NT * kTileBytes) + warp * S;
+        reinterpret_cast<unsigned long long*>(tiles + (size_t)warps_per_cta * S * stage_bytes) + warp * S;
 
     // ---- state and parameters into registers ----
     static_assert(NS <= kMaxState, "too much state for a register-resident tick");
     static_assert(!kUniform || NP <= kMaxUniform, "too many uniform parameters");
     Arr<NS> s;
 #pragma unroll
-    for (int j = 0; j < NS; ++j)
-        s[j] = (ch_ok && p == 0) ? a.state[(long long)a.state_row[j] * a.ch_stride + ch] : 0.f;
+    for (int j = 0; j < NS; ++j) s[j] = ch_ok ? a.state[(long long)a.state_row[j] * a.ch_stride + ch] : 0.f;
     Arr<kUniform ? 0 : NP> prm_reg;
     if (!kUniform) {
 #pragma unroll
         for (int j = 0; j < NP; ++j) prm_reg[j] = ch_ok ? a.params[(long long)j * a.ch_stride + ch] : 0.f;
     }
     const UniformParams prm_uni{a.uparams};
-    // `prm` is whichever of the two this instantiation uses
     auto run_tick = [&](const Arr<NI>& x, Arr<NO>& y) {
         if constexpr (kUniform) Tick::tick(x, y, s, prm_uni);
         else Tick::tick(x, y, s, prm_reg);
@@ -208,23 +189,26 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     }
     __syncwarp();
 
-    const int n_tiles = a.warm_tiles + a.seg_tiles;
+    const int n_tiles = (a.n_samples + tile_t - 1) / tile_t;
 
-    auto tile_t0 = [&](int i) {
-        return i < a.warm_tiles ? a.seg_len - (a.warm_tiles - i) * kTileT : (i - a.warm_tiles) * kTileT;
+    auto boxes_in_tile = [&](int t0) {                 // boxes of tile at t0 that hold samples
+        const int left = (a.n_samples - t0 + kTileT - 1) / kTileT;
+        return left < NB ? left : NB;
     };
     auto issue_load = [&](int i) {                     // lane 0 only
         if (kNumBuf == 0) return;
         const int slot = i % S;
-        const int t0 = tile_t0(i);
-        const int p0 = i < a.warm_tiles ? -1 : 0;      // warm-up reads the tail of the previous segment
-        mbar_expect_tx(&bars[slot], kNumBuf * kTileBytes);
+        const int t0 = i * tile_t;
+        const int nb = boxes_in_tile(t0);
+        mbar_expect_tx(&bars[slot], (unsigned)(nb * kNumBuf * kTileBytes));
 #pragma unroll
         for (int k = 0; k < NI; ++k) {
             if (!(kBufMask & (1u << k))) continue;
-            void* dst = my + (size_t)(slot * NT + k) * kTileBytes;
-            if (kInterleaved) tma_load_2d(dst, &a.in_map[k], c0, t0, &bars[slot]);
-            else tma_load_3d(dst, &a.in_map[k], t0, p0, c0, &bars[slot]);
+            unsigned char* dst = my + (size_t)slot * stage_bytes + (size_t)k * wire_bytes;
+            for (int b = 0; b < nb; ++b) {
+                if (kInterleaved) tma_load_2d(dst + b * kTileBytes, &a.in_map[k], c0, t0 + b * kTileT, &bars[slot]);
+                else tma_load_2d(dst + b * kTileBytes, &a.in_map[k], t0 + b * kTileT, c0, &bars[slot]);
+            }
         }
     };
 
@@ -235,142 +219,143 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
 
     for (int i = 0; i < n_tiles; ++i) {
         const int slot = i % S;
-        const bool warm = i < a.warm_tiles;
-        const int t0 = tile_t0(i);
-        const int n_valid = warm ? kTileT : (a.seg_len - t0 < kTileT ? a.seg_len - t0 : kTileT);
-        const bool active = ch_ok && (!warm || p > 0);
-        unsigned char* base = my + (size_t)slot * NT * kTileBytes;
+        const int t0 = i * tile_t;
+        const int nb = boxes_in_tile(t0);
+        unsigned char* stage = my + (size_t)slot * stage_bytes;
 
         if (kNumBuf > 0) mbar_wait(&bars[slot], (unsigned)((i / S) & 1));
 
-        // absolute stream index of this lane's first sample in the tile (dirac synthesis)
-        const long long t_abs0 = a.stream_pos + (long long)(warm ? p - 1 : p) * a.seg_len + t0;
+        if (ch_ok) {
+#pragma unroll 1
+            for (int b = 0; b < nb; ++b) {
+                const int tb0 = t0 + b * kTileT;
+                const int n_valid = a.n_samples - tb0 < kTileT ? a.n_samples - tb0 : kTileT;
+                unsigned char* base = stage + b * kTileBytes;      // wire k of this box: base + k * wire_bytes
+                // absolute stream index of the first sample of the box (dirac synthesis)
+                const long long t_abs0 = a.stream_pos + tb0;
 
-        if (active) {
-            if (!kInterleaved) {
-                // row `lane`, 16-byte chunk j lives at chunk (j ^ (lane & 7)) of the row (SWIZZLE_128B)
-                const unsigned row = (unsigned)lane * 128u;
-                const unsigned sw = (unsigned)(lane & 7);
-                if (n_valid == kTileT) {
+                if (!kInterleaved) {
+                    // row `lane`, 16-byte chunk j lives at chunk (j ^ (lane & 7)) of the row (SWIZZLE_128B)
+                    const unsigned row = (unsigned)lane * 128u;
+                    const unsigned sw = (unsigned)(lane & 7);
+                    if (n_valid == kTileT) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const unsigned off = row + (((unsigned)j ^ sw) << 4);
-                        float4 xv[NI > 0 ? NI : 1];
-                        float4 yv[NO > 0 ? NO : 1];
+                        for (int j = 0; j < 8; ++j) {
+                            const unsigned off = row + (((unsigned)j ^ sw) << 4);
+                            float4 xv[NI > 0 ? NI : 1];
+                            float4 yv[NO > 0 ? NO : 1];
 #pragma unroll
-                        for (int k = 0; k < NI; ++k) {
-                            if (kBufMask & (1u << k)) {
-                                xv[k] = *reinterpret_cast<const float4*>(base + k * kTileBytes + off);
-                            } else {
-                                const bool dirac = (a.dirac_mask >> k) & 1u;
-                                const long long tt = t_abs0 + 4 * j;
-                                xv[k].x = (dirac && tt == 0) ? 1.f : 0.f;
-                                xv[k].y = (dirac && tt + 1 == 0) ? 1.f : 0.f;
-                                xv[k].z = (dirac && tt + 2 == 0) ? 1.f : 0.f;
-                                xv[k].w = (dirac && tt + 3 == 0) ? 1.f : 0.f;
+                            for (int k = 0; k < NI; ++k) {
+                                if (kBufMask & (1u << k)) {
+                                    xv[k] = *reinterpret_cast<const float4*>(base + k * wire_bytes + off);
+                                } else {
+                                    const bool dirac = (a.dirac_mask >> k) & 1u;
+                                    const long long tt = t_abs0 + 4 * j;
+                                    xv[k].x = (dirac && tt == 0) ? 1.f : 0.f;
+                                    xv[k].y = (dirac && tt + 1 == 0) ? 1.f : 0.f;
+                                    xv[k].z = (dirac && tt + 2 == 0) ? 1.f : 0.f;
+                                    xv[k].w = (dirac && tt + 3 == 0) ? 1.f : 0.f;
+                                }
                             }
-                        }
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
+                            for (int q = 0; q < 4; ++q) {
+                                Arr<NI> x;
+                                Arr<NO> y;
+#pragma unroll
+                                for (int k = 0; k < NI; ++k)
+                                    x[k] = q == 0 ? xv[k].x : q == 1 ? xv[k].y : q == 2 ? xv[k].z : xv[k].w;
+                                run_tick(x, y);
+#pragma unroll
+                                for (int o = 0; o < NO; ++o) {
+                                    if (q == 0) yv[o].x = y[o];
+                                    else if (q == 1) yv[o].y = y[o];
+                                    else if (q == 2) yv[o].z = y[o];
+                                    else yv[o].w = y[o];
+                                }
+                            }
+#pragma unroll
+                            for (int o = 0; o < NO; ++o)
+                                *reinterpret_cast<float4*>(base + o * wire_bytes + off) = yv[o];
+                        }
+                    } else {
+                        // last, partial box of the block: TMA zero-filled the tail on load and clips it
+                        // on store; only the state has to be protected
+                        for (int t = 0; t < n_valid; ++t) {
+                            const unsigned off = row + ((((unsigned)t >> 2) ^ sw) << 4) + ((unsigned)t & 3u) * 4u;
                             Arr<NI> x;
                             Arr<NO> y;
 #pragma unroll
-                            for (int k = 0; k < NI; ++k)
-                                x[k] = q == 0 ? xv[k].x : q == 1 ? xv[k].y : q == 2 ? xv[k].z : xv[k].w;
+                            for (int k = 0; k < NI; ++k) {
+                                if (kBufMask & (1u << k)) x[k] = *reinterpret_cast<const float*>(base + k * wire_bytes + off);
+                                else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
+                            }
                             run_tick(x, y);
 #pragma unroll
-                            for (int o = 0; o < NO; ++o) {
-                                if (q == 0) yv[o].x = y[o];
-                                else if (q == 1) yv[o].y = y[o];
-                                else if (q == 2) yv[o].z = y[o];
-                                else yv[o].w = y[o];
-                            }
-                        }
-                        if (!warm) {
-#pragma unroll
-                            for (int o = 0; o < NO; ++o)
-                                *reinterpret_cast<float4*>(base + o * kTileBytes + off) = yv[o];
+                            for (int o = 0; o < NO; ++o) *reinterpret_cast<float*>(base + o * wire_bytes + off) = y[o];
                         }
                     }
                 } else {
-                    // last, partial tile of the block: TMA zero-filled the tail on load and clips it
-                    // on store; only the state has to be protected
-                    for (int t = 0; t < n_valid; ++t) {
-                        const unsigned off = row + ((((unsigned)t >> 2) ^ sw) << 4) + ((unsigned)t & 3u) * 4u;
-                        Arr<NI> x;
-                        Arr<NO> y;
-#pragma unroll
-                        for (int k = 0; k < NI; ++k) {
-                            if (kBufMask & (1u << k)) x[k] = *reinterpret_cast<const float*>(base + k * kTileBytes + off);
-                            else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
-                        }
-                        run_tick(x, y);
-#pragma unroll
-                        for (int o = 0; o < NO; ++o) *reinterpret_cast<float*>(base + o * kTileBytes + off) = y[o];
-                    }
-                }
-            } else {
-                // interleaved frames: tile is [32 samples][32 channels], lane = channel column
-                float* tile = reinterpret_cast<float*>(base);
-                if (n_valid == kTileT) {
+                    // interleaved frames: box is [32 samples][32 channels], lane = channel column
+                    float* box = reinterpret_cast<float*>(base);
+                    const unsigned wire_f = wire_bytes / 4;
+                    if (n_valid == kTileT) {
 #pragma unroll 8
-                    for (int t = 0; t < kTileT; ++t) {
-                        Arr<NI> x;
-                        Arr<NO> y;
+                        for (int t = 0; t < kTileT; ++t) {
+                            Arr<NI> x;
+                            Arr<NO> y;
 #pragma unroll
-                        for (int k = 0; k < NI; ++k) {
-                            if (kBufMask & (1u << k)) x[k] = tile[k * (kTileBytes / 4) + t * 32 + lane];
-                            else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
+                            for (int k = 0; k < NI; ++k) {
+                                if (kBufMask & (1u << k)) x[k] = box[k * wire_f + t * 32 + lane];
+                                else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
+                            }
+                            run_tick(x, y);
+#pragma unroll
+                            for (int o = 0; o < NO; ++o) box[o * wire_f + t * 32 + lane] = y[o];
                         }
-                        run_tick(x, y);
+                    } else {
+                        for (int t = 0; t < n_valid; ++t) {
+                            Arr<NI> x;
+                            Arr<NO> y;
 #pragma unroll
-                        for (int o = 0; o < NO; ++o) tile[o * (kTileBytes / 4) + t * 32 + lane] = y[o];
-                    }
-                } else {
-                    for (int t = 0; t < n_valid; ++t) {
-                        Arr<NI> x;
-                        Arr<NO> y;
+                            for (int k = 0; k < NI; ++k) {
+                                if (kBufMask & (1u << k)) x[k] = box[k * wire_f + t * 32 + lane];
+                                else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
+                            }
+                            run_tick(x, y);
 #pragma unroll
-                        for (int k = 0; k < NI; ++k) {
-                            if (kBufMask & (1u << k)) x[k] = tile[k * (kTileBytes / 4) + t * 32 + lane];
-                            else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
+                            for (int o = 0; o < NO; ++o) box[o * wire_f + t * 32 + lane] = y[o];
                         }
-                        run_tick(x, y);
-#pragma unroll
-                        for (int o = 0; o < NO; ++o) tile[o * (kTileBytes / 4) + t * 32 + lane] = y[o];
                     }
                 }
             }
         }
 
-        if (!warm) {
-            fence_proxy_async();                       // generic-proxy writes -> visible to TMA
-            __syncwarp();
-            if (lane == 0) {
+        fence_proxy_async();                           // generic-proxy writes -> visible to TMA
+        __syncwarp();
+        if (lane == 0) {
 #pragma unroll
-                for (int o = 0; o < NO; ++o) {
-                    if (kInterleaved) tma_store_2d(&a.out_map[o], c0, t0, base + o * kTileBytes);
-                    else tma_store_3d(&a.out_map[o], t0, 0, c0, base + o * kTileBytes);
+            for (int o = 0; o < NO; ++o) {
+                for (int b = 0; b < nb; ++b) {
+                    const unsigned char* src = stage + (size_t)o * wire_bytes + b * kTileBytes;
+                    if (kInterleaved) tma_store_2d(&a.out_map[o], c0, t0 + b * kTileT, src);
+                    else tma_store_2d(&a.out_map[o], t0 + b * kTileT, c0, src);
                 }
-                tma_commit();
             }
-        } else {
-            __syncwarp();
-        }
-
-        // refill the slot that tile i-1 used: its store (committed one iteration ago) must have
-        // finished reading smem
-        const int nxt = i + S - 1;
-        if (lane == 0 && nxt < n_tiles) {
-            tma_wait_read<1>();
-            issue_load(nxt);
+            tma_commit();
+            // refill the slot that tile i-1 used: its store (committed one iteration ago) must have
+            // finished reading smem
+            const int nxt = i + S - 1;
+            if (nxt < n_tiles) {
+                tma_wait_read<1>();
+                issue_load(nxt);
+            }
         }
     }
 
     if (lane == 0) tma_wait_all<0>();                  // smem must outlive the last stores
 
-    // ---- state back to HBM: the lane that evaluated the last segment owns the final state ----
-    if (ch_ok && p == P - 1) {
+    // ---- state back to HBM ----
+    if (ch_ok) {
 #pragma unroll
         for (int j = 0; j < NS; ++j) a.state[(long long)a.state_row[j] * a.ch_stride + ch] = s[j];
     }

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -213,7 +214,7 @@ struct zg_plan {
 
     int64_t stream_pos = 0;
     int launches = 0;
-    int last_smem = 0, last_threads = 0, last_stages = 0;
+    int last_smem = 0, last_threads = 0, last_stages = 0, last_boxes = 0;
     int sm_count = 148;
     int max_smem_optin = 227 * 1024;
 
@@ -352,30 +353,19 @@ int sync_params(zg_plan* p) {
 
 // ---- tensor maps ---------------------------------------------------------------------------------------
 
-int encode_map(zg_plan* p, zgk::TensorMap* out, const void* base, int64_t T, int64_t ld, int P) {
+int encode_map(zg_plan* p, zgk::TensorMap* out, const void* base, int64_t T, int64_t ld) {
     Driver& d = driver();
     CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(out);
-    CUresult r;
-    if (p->interleaved) {
-        // [T][ld] frames: dim0 = channel (contiguous), dim1 = sample
-        cuuint64_t dims[2] = {(cuuint64_t)p->C, (cuuint64_t)T};
-        cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-        cuuint32_t box[2] = {32, 32};
-        cuuint32_t es[2] = {1, 1};
-        r = d.tensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides,
-                                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    } else {
-        // [C][ld] rows cut into P segments: dim0 = sample inside the segment, dim1 = segment, dim2 = channel
-        const int64_t seg = T / P;
-        cuuint64_t dims[3] = {(cuuint64_t)seg, (cuuint64_t)P, (cuuint64_t)p->C};
-        cuuint64_t strides[2] = {(cuuint64_t)(P > 1 ? seg : ld) * 4, (cuuint64_t)ld * 4};
-        cuuint32_t box[3] = {32, (cuuint32_t)P, (cuuint32_t)(32 / P)};
-        cuuint32_t es[3] = {1, 1, 1};
-        r = d.tensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides,
-                                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    }
+    // planar  [C][ld]: dim0 = sample (contiguous), dim1 = channel; rows of a box are swizzled (128B)
+    // interleaved [T][ld] frames: dim0 = channel (contiguous), dim1 = sample
+    cuuint64_t dims[2] = {(cuuint64_t)(p->interleaved ? p->C : T), (cuuint64_t)(p->interleaved ? T : p->C)};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = d.tensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides,
+                                        box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        p->interleaved ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuTensorMapEncodeTiled: " + cu_err(r));
     return ZG_OK;
 }
@@ -383,30 +373,46 @@ int encode_map(zg_plan* p, zgk::TensorMap* out, const void* base, int64_t T, int
 // ---- launch geometry ---------------------------------------------------------------------------------
 //
 // All warps of the launch should be resident at once (one wave) and spread evenly over the SMs:
-// a CTA is `wpc` warps, every warp owns S stages of NT tiles of 4 KB.  Shared memory, not
+// a CTA is `wpc` warps, every warp owns S stages of NT wires x NB boxes of 4 KB.  Shared memory, not
 // registers, is what limits residency (the skeleton keeps 1 KB of slack to align the tiles).
+// ZG_TUNE_WPC / ZG_TUNE_STAGES / ZG_TUNE_BOXES override the choice (tuning experiments only).
 struct Geometry {
-    int wpc, grid, stages, smem;
+    int wpc, grid, stages, boxes, smem;
 };
 
-Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs) {
+int tune_env(const char* name) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : 0;
+}
+
+Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, int64_t T) {
     Geometry g{};
     const int64_t per_sm = (n_warps + p->sm_count - 1) / p->sm_count;
     const int reg_warps = std::max(1, 65536 / (32 * std::max(regs, 32)));   // warps/SM the register file allows
     int wpc = (int)std::min<int64_t>({per_sm, 16, (int64_t)reg_warps});
     wpc = std::max(wpc, 1);
+    if (int w = tune_env("ZG_TUNE_WPC")) wpc = std::min(std::max(w, 1), 16);
     const int budget = p->max_smem_optin - 1024 /*alignment slack*/ - 16 * 8 * 8 /*barriers*/;
-    int S = budget / (wpc * NT * zgk::kTileBytes);
-    while (S < 3 && wpc > 1) {            // too many wires for that many warps: fewer warps per CTA
+    // boxes per stage: 2 (256 contiguous bytes per channel row in flight together) when that still
+    // leaves 3 stages, else 1
+    int NB = 2;
+    if (int b = tune_env("ZG_TUNE_BOXES")) NB = std::min(std::max(b, 1), 8);
+    NB = (int)std::min<int64_t>(NB, std::max<int64_t>(1, (T + zgk::kTileT - 1) / zgk::kTileT));
+    auto stages_for = [&](int w, int nb) { return budget / (w * NT * nb * zgk::kTileBytes); };
+    while (NB > 1 && stages_for(wpc, NB) < 2) --NB;
+    int S = stages_for(wpc, NB);
+    while (S < 2 && wpc > 1) {            // too many wires for that many warps: fewer warps per CTA
         --wpc;
-        S = budget / (wpc * NT * zgk::kTileBytes);
+        S = stages_for(wpc, NB);
     }
     S = std::min(S, 8);
+    if (int st = tune_env("ZG_TUNE_STAGES")) S = std::min(std::max(st, 2), S);
     S = std::max(S, 2);
     g.wpc = wpc;
     g.stages = S;
+    g.boxes = NB;
     g.grid = (int)((n_warps + wpc - 1) / wpc);
-    g.smem = wpc * S * NT * zgk::kTileBytes + 1024 + wpc * S * 8;
+    g.smem = wpc * S * NT * NB * zgk::kTileBytes + 1024 + wpc * S * 8;
     return g;
 }
 
@@ -420,16 +426,15 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     st = get_variant(p, p->uniform_now, v);
     if (st != ZG_OK) return st;
 
-    const int P = 1;                                   // time split: see DESIGN.md (not enabled yet)
     zgk::StreamArgs a;
     std::memset(&a, 0, sizeof a);
     for (int k = 0; k < p->ir.n_in; ++k) {
         if (p->synth_mask & (1u << k)) continue;
-        st = encode_map(p, &a.in_map[k], in[k], T, ld_in, P);
+        st = encode_map(p, &a.in_map[k], in[k], T, ld_in);
         if (st != ZG_OK) return st;
     }
     for (int o = 0; o < p->ir.n_out; ++o) {
-        st = encode_map(p, &a.out_map[o], out[o], T, ld_out, P);
+        st = encode_map(p, &a.out_map[o], out[o], T, ld_out);
         if (st != ZG_OK) return st;
     }
     a.state = p->d_state;
@@ -437,19 +442,16 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     a.ch_stride = p->ch_stride;
     a.stream_pos = p->stream_pos;
     a.channels = (int)p->C;
-    a.seg_len = (int)(T / P);
-    a.seg_tiles = (a.seg_len + zgk::kTileT - 1) / zgk::kTileT;
-    a.lanes_p = P;
-    a.log2_p = 0;
-    a.warm_tiles = 0;
+    a.n_samples = (int)T;
     a.dirac_mask = p->dirac_mask;
     for (int j = 0; j < p->kernel_n_state; ++j) a.state_row[j] = p->state_row[j];
     if (p->uniform_now) std::memcpy(a.uparams, p->uparams, sizeof(float) * std::min(p->kernel_n_param, zgk::kMaxUniform));
 
     const int NT = std::max(1, std::max(p->n_buf_in, p->ir.n_out));
-    const int64_t n_warps = (p->C * P + 31) / 32;
-    Geometry g = choose_geometry(p, n_warps, NT, v->regs);
+    const int64_t n_warps = (p->C + 31) / 32;
+    Geometry g = choose_geometry(p, n_warps, NT, v->regs, T);
     a.stages = g.stages;
+    a.boxes = g.boxes;
 
     if (g.smem > v->max_smem_set) {
         if (v->prebuilt) {
@@ -473,6 +475,7 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     p->last_smem = g.smem;
     p->last_threads = g.wpc * 32;
     p->last_stages = g.stages;
+    p->last_boxes = g.boxes;
     return ZG_OK;
 }
 
@@ -647,6 +650,7 @@ int zg_plan_get_info(const zg_plan* p, zg_plan_info* info) {
     info->launches = p->launches;
     info->threads_per_cta = p->last_threads;
     info->stages = p->last_stages;
+    info->boxes = p->last_boxes;
     info->uniform_params = p->uniform_now ? 1 : 0;
     return ZG_OK;
 }
