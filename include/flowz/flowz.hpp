@@ -423,7 +423,7 @@ public:
     }
 
     // B200 block evaluator for `channels` independent voices of this graph (state starts at zero).
-    block_evaluator on_device(int64_t channels, int mode = ZG_MODE_FAST, int device = 0) const {
+    block_evaluator on_device(int64_t channels, int mode = ZG_MODE_EXACT, int device = 0) const {
         zg_plan_opts o;
         zg_plan_opts_default(&o);
         o.device = device; o.channels = channels; o.mode = mode;

@@ -96,7 +96,7 @@ int zg_voice_state(zg_voice* v, float** state, int* n_state);
 typedef enum zg_mode {
     ZG_MODE_EXACT = 0, /* separately rounded mul/add, lane per channel: bit-identical to the x86
                           non-FMA build of the reference (CMakeLists.txt:17-19)                 */
-    ZG_MODE_FAST = 1   /* FMA contraction (+ verified time-split when enabled): <= 1e-5 block-relative */
+    ZG_MODE_FAST = 1   /* FMA contraction: rounds differently from the reference   */
 } zg_mode;
 
 typedef enum zg_layout {
@@ -118,9 +118,10 @@ typedef struct zg_plan_opts {
     int mode;             /* zg_mode                                                            */
     int layout;           /* zg_layout                                                          */
     int io_dtype;         /* ZG_F32 (bf16 storage: see DESIGN.md, later round)                  */
-    int time_split;       /* FAST mode only: 0 = off, 1 = auto (use P>1 lanes per channel when the
-                             graph is linear, its state decays and there are too few channels to
-                             fill the GPU), >1 = force P (must be 2,4,8,16 or 32)                 */
+    int lanes_per_channel;/* 0 = auto; 1 = one lane per channel; S = S lanes per channel, lane k evaluating
+                             section k of an S-section biquad cascade as a systolic pipeline (same
+                             arithmetic, bit-identical in EXACT mode; planar layout, S = 2 or 4).  Auto
+                             picks S when there are too few channels to fill the GPU with one lane each */
     int input_kind[ZG_MAX_WIRES];
     int force_jit;        /* 1 = never use the prebuilt biquad kernels (tests)                  */
     int reserved[7];
@@ -138,8 +139,8 @@ void zg_plan_destroy(zg_plan* p);
 typedef struct zg_plan_info {
     char kernel[96];      /* name of the kernel this plan launches                              */
     int jit;              /* 1 = specialised with NVRTC at plan time, 0 = prebuilt in the library */
-    int lanes_per_channel;/* P of the time split (1 = lane per channel)                         */
-    int warmup_samples;   /* W of the time split                                                */
+    int lanes_per_channel;/* lanes that evaluate one channel (1, or the section count: see zg_plan_opts) */
+    int host_chunks;      /* row chunks the last zg_process_host call streamed its block in         */
     int regs_per_thread;
     int smem_bytes;
     int launches;         /* kernels launched by this plan so far                               */

@@ -40,17 +40,17 @@ def _torch():
 
 
 def _to_dev(x):
-    torch = _torch()
-    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    import zignal_b200
+    return zignal_b200.to_block(x)          # row pitch padded to a multiple of 4 floats when needed
 
 
-def _run(zg, expr, x, mode, layout="planar", force_jit=False, params=None, blocks=None, input_kind=None):
+def _run(zg, expr, x, mode, layout="planar", force_jit=False, params=None, blocks=None, input_kind=None, lanes=1):
     """x: [n_in][C, T] numpy.  Returns [n_out][C, T] numpy, plan."""
     torch = _torch()
     g = zg.compile(expr)
     C, T = x[0].shape if len(x) else (None, None)
     plan = g.plan(channels=C, mode=mode, layout=zg.PLANAR if layout == "planar" else zg.INTERLEAVED,
-                  force_jit=force_jit, input_kind=input_kind)
+                  force_jit=force_jit, input_kind=input_kind, lanes_per_channel=lanes)
     for i, p in enumerate(params or []):
         plan.set_param(i, p)
     outs = [[] for _ in range(g.n_out)]
@@ -144,8 +144,8 @@ def test_streaming_blocks_equal_one_block(zg):
     x = [fo.noise(C, T, seed=6)]
     expr = fo.biquad_cascade(4)
     whole, _ = _run(zg, expr, x, zg.MODE_EXACT)
-    parts, plan = _run(zg, expr, x, zg.MODE_EXACT, blocks=[4, 32, 28, 1000, 984])
-    assert plan.info().launches == 5
+    parts, plan = _run(zg, expr, x, zg.MODE_EXACT, blocks=[4, 31, 29, 1, 999, 984])
+    assert plan.info().launches == 6
     assert np.array_equal(whole[0], parts[0])
 
 
@@ -167,6 +167,69 @@ def test_state_get_set_reset(zg):
     p3.reset()
     assert np.abs(p3.get_state()).max() == 0
     assert np.array_equal(p3.process([_to_dev(x[:, :T])])[0].cpu().numpy(), y_full[:, :T])
+
+
+# ---- K1b: section-parallel biquad cascade (S lanes per channel) ---------------------------------
+
+@pytest.mark.parametrize("sections", [2, 4])
+@pytest.mark.parametrize("C,T", [(1, 4), (8, 31), (9, 64), (70, 257), (96, 1000), (33, 4100), (520, 8192)])
+def test_biquad_lanes_exact_is_bit_identical(zg, sections, C, T):
+    x = [fo.noise(C, T, seed=100 + sections)]
+    expr = fo.biquad_cascade(sections)
+    ys, plan = _run(zg, expr, x, zg.MODE_EXACT, lanes=sections)
+    info = plan.info()
+    assert info.lanes_per_channel == sections and b"zg_biquad_df1_lanes" in info.kernel and info.launches == 1
+    assert np.array_equal(ys[0], _oracle(expr, x)[0])
+
+
+def test_biquad_lanes_auto_selected_for_few_channels(zg):
+    g = zg.compile(fo.biquad_cascade(4))
+    assert g.plan(channels=4096).info().lanes_per_channel == 4          # BASELINE configs[1]
+    assert g.plan(channels=65536).info().lanes_per_channel == 1         # north-star shape
+    assert g.plan(channels=4096, layout=zg.INTERLEAVED).info().lanes_per_channel == 1
+    assert zg.compile(fo.biquad_cascade(3)).plan(channels=64).info().lanes_per_channel == 1
+    with pytest.raises(zg.ZgError) as e:
+        zg.compile(fo.biquad_cascade(3)).plan(channels=64, lanes_per_channel=4)
+    assert e.value.status == zg.ZG_ERR_UNSUPPORTED
+
+
+def test_biquad_lanes_streaming_and_state_interchange(zg):
+    """ragged blocks continue bit for bit; the state rows written by one kernel are read by the other"""
+    C, T = 40, 3000
+    x = [fo.noise(C, T, seed=77)]
+    expr = fo.biquad_cascade(4)
+    ref = _oracle(expr, x)[0]
+    parts, plan = _run(zg, expr, x, zg.MODE_EXACT, lanes=4, blocks=[5, 1, 250, 7, 1024, 1713])
+    assert plan.info().launches == 6
+    assert np.array_equal(parts[0], ref)
+    g = zg.compile(expr)
+    a = g.plan(channels=C, lanes_per_channel=4)
+    b = g.plan(channels=C, lanes_per_channel=1)
+    y1 = a.process([_to_dev(x[0][:, :1001])])[0].cpu().numpy()
+    b.set_state(a.get_state())
+    y2 = b.process([_to_dev(x[0][:, 1001:2000])])[0].cpu().numpy()
+    a.set_state(b.get_state())
+    y3 = a.process([_to_dev(x[0][:, 2000:])])[0].cpu().numpy()
+    assert np.array_equal(np.concatenate([y1, y2, y3], axis=1), ref)
+
+
+def test_biquad_lanes_per_channel_coefficients_and_fast_mode(zg):
+    C, T, S = 100, 2048, 4
+    x = [fo.noise(C, T, seed=5)]
+    params = []
+    for k in range(S):
+        per_ch = np.array([fo.rbj_lowpass(440.0 * 2 ** k * (1 + c / C)) for c in range(C)], np.float32)
+        params += [per_ch[:, j].copy() for j in range(5)]
+    expr = fo.biquad_cascade_params(S)
+    ys, plan = _run(zg, expr, x, zg.MODE_EXACT, params=params, lanes=4)
+    assert plan.info().uniform_params == 0 and plan.info().lanes_per_channel == 4
+    assert np.array_equal(ys[0], _oracle(expr, x, params)[0])
+    # FMA mode: same association as the lane-per-channel kernel -> the two agree bit for bit
+    e4 = fo.biquad_cascade(4)
+    f4, _ = _run(zg, e4, x, zg.MODE_FAST, lanes=4)
+    f1, _ = _run(zg, e4, x, zg.MODE_FAST, lanes=1)
+    assert np.array_equal(f4[0], f1[0])
+    _check_fast_biquad(f4[0], _oracle(e4, x)[0], x[0], 4)
 
 
 # ---- K2: generated tick (NVRTC) -----------------------------------------------------------------
@@ -197,7 +260,10 @@ def test_generated_kernel_exact_is_bit_identical(zg, expr, layout):
         assert np.array_equal(y, r, equal_nan=True)
 
 
-@pytest.mark.parametrize("expr", GENERIC[:6] + GENERIC[8:])
+# GENERIC[1] (the oscillator) is left out on purpose: its poles sit ON the unit circle, rounding
+# differences grow linearly with time, and FMA-vs-non-FMA exceeds 1e-5 within ~1000 samples (measured
+# 2e-5 at 2048).  Marginally stable graphs have to run in EXACT mode.
+@pytest.mark.parametrize("expr", GENERIC[:1] + GENERIC[2:6] + GENERIC[8:])
 def test_generated_kernel_fast_within_tolerance(zg, expr):
     g = zg.compile(expr)
     C, T = 64, 2048
@@ -333,6 +399,10 @@ def test_full_size_config2_4096x65536(zg):
     expr = fo.biquad_cascade(4)
     gen = torch.Generator(device="cuda").manual_seed(1)
     x = torch.rand((C, T), generator=gen, device="cuda") * 2 - 1
-    y = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT).process([x])[0]
+    plan = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT)
+    y = plan.process([x])[0]
+    assert plan.info().lanes_per_channel == 4            # too few channels for a lane each: K1b
     idx = [0, 5, 4095]
     assert np.array_equal(y[idx].cpu().numpy(), _oracle(expr, [x[idx].cpu().numpy()])[0])
+    y1 = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, lanes_per_channel=1).process([x])[0]
+    assert torch.equal(y, y1)                            # both kernels, every channel, bit for bit

@@ -11,7 +11,7 @@ import torch
 import zignal_b200 as zg
 import flowz_oracle as fo
 
-WORK = {"ns": (65536, 8192), "c2": (4096, 65536), "mid": (16384, 16384)}
+WORK = {"ns": (65536, 8192), "c2": (4096, 65536), "mid": (16384, 16384), "c32k": (32768, 8192), "c8k": (8192, 32768)}
 
 def main():
     ap = argparse.ArgumentParser()
@@ -24,7 +24,7 @@ def main():
     for part in a.points.split(";"):
         k, v = part.split("=")
         axes[k] = v.split(",")
-    for k, d in (("mode", ["exact"]), ("boxes", ["0"]), ("wpc", ["0"]), ("stages", ["0"]), ("layout", ["planar"]), ("coef", ["uniform"])):
+    for k, d in (("mode", ["exact"]), ("boxes", ["0"]), ("wpc", ["0"]), ("stages", ["0"]), ("layout", ["planar"]), ("coef", ["uniform"]), ("lanes", ["0"])):
         axes.setdefault(k, d)
     C, T = WORK[a.workload]
     x = torch.rand((C, T), device="cuda") * 2 - 1
@@ -45,7 +45,7 @@ def main():
             g = zg.compile(fo.biquad_cascade_params(a.sections))
         try:
             plan = g.plan(channels=C, mode=zg.MODE_EXACT if pt["mode"] == "exact" else zg.MODE_FAST,
-                          layout=zg.INTERLEAVED if inter else zg.PLANAR)
+                          layout=zg.INTERLEAVED if inter else zg.PLANAR, lanes_per_channel=int(pt["lanes"]))
             if pt["coef"] != "uniform":
                 import numpy as np
                 for k in range(a.sections):
@@ -62,7 +62,7 @@ def main():
             ms = e0.elapsed_time(e1) / a.iters
             info = plan.info()
             pt.update(ms=round(ms, 4), msamples=round(C * T / ms / 1e3), gbs=round(8 * C * T / ms / 1e6),
-                      threads=info.threads_per_cta, stages_used=info.stages, boxes_used=info.boxes, smem=info.smem_bytes,
+                      threads=info.threads_per_cta, stages_used=info.stages, boxes_used=info.boxes, smem=info.smem_bytes, lanes_used=info.lanes_per_channel,
                       regs=info.regs_per_thread)
         except Exception as e:
             pt["error"] = str(e)[:200]

@@ -40,13 +40,13 @@ class GraphInfo(C.Structure):
 
 class PlanOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("channels", C.c_int64), ("mode", C.c_int), ("layout", C.c_int),
-                ("io_dtype", C.c_int), ("time_split", C.c_int), ("input_kind", C.c_int * MAX_WIRES),
+                ("io_dtype", C.c_int), ("lanes_per_channel", C.c_int), ("input_kind", C.c_int * MAX_WIRES),
                 ("force_jit", C.c_int), ("reserved", C.c_int * 7)]
 
 
 class PlanInfo(C.Structure):
     _fields_ = [("kernel", C.c_char * 96), ("jit", C.c_int), ("lanes_per_channel", C.c_int),
-                ("warmup_samples", C.c_int), ("regs_per_thread", C.c_int), ("smem_bytes", C.c_int),
+                ("host_chunks", C.c_int), ("regs_per_thread", C.c_int), ("smem_bytes", C.c_int),
                 ("launches", C.c_int), ("threads_per_cta", C.c_int), ("stages", C.c_int),
                 ("uniform_params", C.c_int), ("boxes", C.c_int)]
 
@@ -226,15 +226,33 @@ class Voice:
         return [p[i] for i in range(n.value)]
 
 
-def _opts(channels: int, device: int = 0, mode: int = MODE_FAST, layout: int = PLANAR,
-          input_kind: Optional[Sequence[int]] = None, time_split: int = 0, force_jit: bool = False) -> PlanOpts:
+def _opts(channels: int, device: int = 0, mode: int = MODE_EXACT, layout: int = PLANAR,
+          input_kind: Optional[Sequence[int]] = None, lanes_per_channel: int = 0, force_jit: bool = False) -> PlanOpts:
     o = PlanOpts()
     lib.zg_plan_opts_default(C.byref(o))
     o.device, o.channels, o.mode, o.layout = device, channels, mode, layout
-    o.time_split, o.force_jit = time_split, int(force_jit)
+    o.lanes_per_channel, o.force_jit = lanes_per_channel, int(force_jit)
     for i, k in enumerate(input_kind or []):
         o.input_kind[i] = k
     return o
+
+
+def empty_block(rows: int, cols: int, device=None):
+    """float32 CUDA buffer [rows, cols] whose row pitch is a multiple of 4 floats (16 bytes), as the
+    TMA tensor maps behind zg_process require; a view into a padded allocation when cols % 4 != 0."""
+    import torch
+    ld = (cols + 3) // 4 * 4
+    return torch.empty((rows, ld), dtype=torch.float32, device=device or "cuda")[:, :cols]
+
+
+def to_block(array, device=None):
+    """Host [rows, cols] float32 data -> device buffer with a legal pitch (see empty_block)."""
+    import numpy as np
+    import torch
+    a = torch.from_numpy(np.ascontiguousarray(array, np.float32))
+    out = empty_block(a.shape[0], a.shape[1], device)
+    out.copy_(a)
+    return out
 
 
 class Plan:
@@ -287,7 +305,7 @@ class Plan:
         shape = (n_samples, self.channels) if self.interleaved else (self.channels, n_samples)
         dev = torch.device("cuda", self.opts.device)
         if outputs is None:
-            outputs = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(self.graph.n_out)]
+            outputs = [empty_block(shape[0], shape[1], dev) for _ in range(self.graph.n_out)]
         for t in [t for t in ins if t is not None] + list(outputs):
             if t.dtype != torch.float32 or not t.is_cuda or t.stride(1) != 1 or tuple(t.shape) != shape:
                 raise TypeError(f"buffers must be float32 CUDA tensors of shape {shape} with unit inner stride")

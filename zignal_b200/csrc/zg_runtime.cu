@@ -21,6 +21,7 @@
 #include <sstream>
 
 #include "kernels/zg_biquad.cuh"
+#include "kernels/zg_biquad_lanes.cuh"
 #include "zg_internal.hpp"
 
 extern const char* const zg_stream_cuh_source;   // kernels/zg_stream.cuh as text (generated at build time)
@@ -147,7 +148,21 @@ __global__ void __launch_bounds__(512, 1) zg_stream_kernel(const __grid_constant
     zgk::stream_block<Tick, kInterleaved, kUniform>(a);
 }
 
+template <int S, bool kExact, bool kUniform>
+__global__ void __launch_bounds__(512, 1) zg_biquad_lanes_kernel(const __grid_constant__ zgk::StreamArgs a) {
+    zgk::biquad_lanes_block<S, kExact, kUniform>(a);
+}
+
 using KernelPtr = void (*)(zgk::StreamArgs);
+
+KernelPtr biquad_lanes_kernel_for(int sections, bool exact, bool uniform) {
+#define ZG_PICK(S, E, U) \
+    if (sections == S && exact == E && uniform == U) return (KernelPtr)zg_biquad_lanes_kernel<S, E, U>;
+    ZG_PICK(2, false, false) ZG_PICK(2, false, true) ZG_PICK(2, true, false) ZG_PICK(2, true, true)
+    ZG_PICK(4, false, false) ZG_PICK(4, false, true) ZG_PICK(4, true, false) ZG_PICK(4, true, true)
+#undef ZG_PICK
+    return nullptr;
+}
 
 template <int S>
 KernelPtr biquad_kernel(bool exact, bool interleaved, bool uniform) {
@@ -198,6 +213,7 @@ struct zg_plan {
     int n_buf_in = 0;
 
     bool is_biquad = false;
+    int lanes = 1;                          // lanes per channel (K1b when > 1)
     BiquadMatch bq;
     int kernel_n_state = 0, kernel_n_param = 0;   // as the kernel sees them
     std::vector<int> state_row;                   // kernel slot -> row of d_state
@@ -221,7 +237,10 @@ struct zg_plan {
     // staging for zg_process_host
     float* d_stage = nullptr;
     size_t d_stage_floats = 0;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr;      // kernels of zg_process_host
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    std::vector<cudaEvent_t> events;        // [2 * chunk]: input landed, kernel done
+    int last_host_chunks = 0;
 
     ~zg_plan() {
         if (opts.device >= 0) cudaSetDevice(opts.device);
@@ -231,6 +250,9 @@ struct zg_plan {
         if (d_params) cudaFree(d_params);
         if (d_stage) cudaFree(d_stage);
         if (own_stream) cudaStreamDestroy(own_stream);
+        if (h2d_stream) cudaStreamDestroy(h2d_stream);
+        if (d2h_stream) cudaStreamDestroy(d2h_stream);
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
     }
 };
 
@@ -297,7 +319,8 @@ int get_variant(zg_plan* p, bool uniform, Variant*& out) {
     out = &v;
     if (v.ready) return ZG_OK;
     if (p->is_biquad && !p->opts.force_jit) {
-        v.prebuilt = biquad_kernel_for(p->bq.sections, p->exact, p->interleaved, uniform);
+        v.prebuilt = p->lanes > 1 ? biquad_lanes_kernel_for(p->bq.sections, p->exact, uniform)
+                                  : biquad_kernel_for(p->bq.sections, p->exact, p->interleaved, uniform);
         if (!v.prebuilt) return fail(ZG_ERR_INTERNAL, "no prebuilt biquad kernel for this section count");
         cudaFuncAttributes fa;
         ZG_CUDA(cudaFuncGetAttributes(&fa, (const void*)v.prebuilt));
@@ -353,14 +376,14 @@ int sync_params(zg_plan* p) {
 
 // ---- tensor maps ---------------------------------------------------------------------------------------
 
-int encode_map(zg_plan* p, zgk::TensorMap* out, const void* base, int64_t T, int64_t ld) {
+int encode_map(zg_plan* p, zgk::TensorMap* out, const void* base, int64_t C, int64_t T, int64_t ld, int box_rows) {
     Driver& d = driver();
     CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(out);
     // planar  [C][ld]: dim0 = sample (contiguous), dim1 = channel; rows of a box are swizzled (128B)
     // interleaved [T][ld] frames: dim0 = channel (contiguous), dim1 = sample
-    cuuint64_t dims[2] = {(cuuint64_t)(p->interleaved ? p->C : T), (cuuint64_t)(p->interleaved ? T : p->C)};
+    cuuint64_t dims[2] = {(cuuint64_t)(p->interleaved ? C : T), (cuuint64_t)(p->interleaved ? T : C)};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {32, 32};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = d.tensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides,
                                         box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -416,8 +439,35 @@ Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, in
     return g;
 }
 
+// K1b: a box is (32 / lanes) channels x 32 samples; tiles are long in time (the pipeline fills and
+// drains once per tile) and three stages deep.
+Geometry choose_geometry_lanes(const zg_plan* p, int64_t n_warps, int regs, int64_t T) {
+    Geometry g{};
+    const int box_bytes = (32 / p->lanes) * 128;
+    const int64_t per_sm = (n_warps + p->sm_count - 1) / p->sm_count;
+    const int reg_warps = std::max(1, 65536 / (32 * std::max(regs, 32)));
+    int wpc = (int)std::max<int64_t>(1, std::min<int64_t>({per_sm, 16, (int64_t)reg_warps}));
+    if (int w = tune_env("ZG_TUNE_WPC")) wpc = std::min(std::max(w, 1), 16);
+    const int budget = p->max_smem_optin - 1024 - 16 * 8 * 8;
+    int S = 3;
+    if (int st = tune_env("ZG_TUNE_STAGES")) S = std::min(std::max(st, 2), 8);
+    int NB = 16;
+    if (int b = tune_env("ZG_TUNE_BOXES")) NB = std::min(std::max(b, 1), 32);
+    NB = (int)std::min<int64_t>(NB, std::max<int64_t>(1, (T + zgk::kTileT - 1) / zgk::kTileT));
+    while (NB > 1 && wpc * S * NB * box_bytes > budget) NB /= 2;
+    while (wpc > 1 && wpc * S * NB * box_bytes > budget) --wpc;
+    g.wpc = wpc;
+    g.stages = S;
+    g.boxes = NB;
+    g.grid = (int)((n_warps + wpc - 1) / wpc);
+    g.smem = wpc * S * NB * box_bytes + 1024 + wpc * S * 8;
+    return g;
+}
+
+// One kernel launch over channels [c_begin, c_begin + c_count) of the plan; in/out point at the first
+// of those channels.  `advance` = this launch ends the block (the stream position moves on by T).
 int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out,
-           cudaStream_t stream) {
+           cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance) {
     Driver& d = driver();
     if (!d.ok) return fail(ZG_ERR_CUDA, d.why);
     int st = sync_params(p);
@@ -430,26 +480,27 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     std::memset(&a, 0, sizeof a);
     for (int k = 0; k < p->ir.n_in; ++k) {
         if (p->synth_mask & (1u << k)) continue;
-        st = encode_map(p, &a.in_map[k], in[k], T, ld_in);
+        st = encode_map(p, &a.in_map[k], in[k], c_count, T, ld_in, 32 / p->lanes);
         if (st != ZG_OK) return st;
     }
     for (int o = 0; o < p->ir.n_out; ++o) {
-        st = encode_map(p, &a.out_map[o], out[o], T, ld_out);
+        st = encode_map(p, &a.out_map[o], out[o], c_count, T, ld_out, 32 / p->lanes);
         if (st != ZG_OK) return st;
     }
-    a.state = p->d_state;
-    a.params = p->d_params;
+    a.state = p->d_state + c_begin;
+    a.params = p->d_params ? p->d_params + c_begin : nullptr;
     a.ch_stride = p->ch_stride;
     a.stream_pos = p->stream_pos;
-    a.channels = (int)p->C;
+    a.channels = (int)c_count;
     a.n_samples = (int)T;
     a.dirac_mask = p->dirac_mask;
     for (int j = 0; j < p->kernel_n_state; ++j) a.state_row[j] = p->state_row[j];
     if (p->uniform_now) std::memcpy(a.uparams, p->uparams, sizeof(float) * std::min(p->kernel_n_param, zgk::kMaxUniform));
 
     const int NT = std::max(1, std::max(p->n_buf_in, p->ir.n_out));
-    const int64_t n_warps = (p->C + 31) / 32;
-    Geometry g = choose_geometry(p, n_warps, NT, v->regs, T);
+    const int cpw = 32 / p->lanes;                     // channels per warp
+    const int64_t n_warps = (c_count + cpw - 1) / cpw;
+    Geometry g = p->lanes > 1 ? choose_geometry_lanes(p, n_warps, v->regs, T) : choose_geometry(p, n_warps, NT, v->regs, T);
     a.stages = g.stages;
     a.boxes = g.boxes;
 
@@ -470,7 +521,7 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
         CUresult cr = d.launchKernel(v->function, g.grid, 1, 1, g.wpc * 32, 1, 1, g.smem, (CUstream)stream, args, nullptr);
         if (cr != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuLaunchKernel: " + cu_err(cr));
     }
-    p->stream_pos += T;
+    if (advance) p->stream_pos += T;
     p->launches += 1;
     p->last_smem = g.smem;
     p->last_threads = g.wpc * 32;
@@ -537,10 +588,10 @@ void zg_plan_opts_default(zg_plan_opts* o) {
     std::memset(o, 0, sizeof *o);
     o->device = 0;
     o->channels = 1;
-    o->mode = ZG_MODE_FAST;
+    o->mode = ZG_MODE_EXACT;
     o->layout = ZG_PLANAR;
     o->io_dtype = ZG_F32;
-    o->time_split = 0;
+    o->lanes_per_channel = 0;
 }
 
 int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
@@ -596,6 +647,16 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     }
 
     p->is_biquad = match_df1_cascade(ir, p->bq) && p->synth_mask == 0;
+    const int want_lanes = tune_env("ZG_TUNE_LANES") ? tune_env("ZG_TUNE_LANES") : opts->lanes_per_channel;
+    if (want_lanes < 0 || (want_lanes > 1 && !(p->is_biquad && !opts->force_jit && !p->interleaved &&
+                                               want_lanes == p->bq.sections && (want_lanes == 2 || want_lanes == 4))))
+        return fail(ZG_ERR_UNSUPPORTED,
+                    "lanes_per_channel > 1 needs a planar biquad cascade of exactly that many (2 or 4) sections");
+    if (p->is_biquad && !opts->force_jit && !p->interleaved && (p->bq.sections == 2 || p->bq.sections == 4)) {
+        // one lane per channel leaves SM schedulers idle below ~2 warps per scheduler: spread the sections
+        const bool too_few = (p->C + 31) / 32 < (int64_t)p->sm_count * 4;
+        if (want_lanes > 1 || (want_lanes == 0 && too_few)) p->lanes = p->bq.sections;
+    }
     if (p->is_biquad && !opts->force_jit) {
         const int S = p->bq.sections;
         p->kernel_n_state = 2 * (S + 1);
@@ -607,8 +668,11 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
             p->state_row[2 * k + 1] = l.offset + 1;  // one tick ago
         }
         char nm[96];
-        std::snprintf(nm, sizeof nm, "zg_biquad_df1<%d,%s,%s>", S, p->exact ? "exact" : "fma",
-                      p->interleaved ? "interleaved" : "planar");
+        if (p->lanes > 1)
+            std::snprintf(nm, sizeof nm, "zg_biquad_df1_lanes<%d,%s,planar>", S, p->exact ? "exact" : "fma");
+        else
+            std::snprintf(nm, sizeof nm, "zg_biquad_df1<%d,%s,%s>", S, p->exact ? "exact" : "fma",
+                          p->interleaved ? "interleaved" : "planar");
         p->kernel_name = nm;
     } else {
         p->kernel_n_state = ir.n_state;
@@ -643,8 +707,8 @@ int zg_plan_get_info(const zg_plan* p, zg_plan_info* info) {
     std::snprintf(info->kernel, sizeof info->kernel, "%s", p->kernel_name.c_str());
     const Variant& v = p->variant[p->uniform_now ? 1 : 0];
     info->jit = v.prebuilt ? 0 : 1;
-    info->lanes_per_channel = 1;
-    info->warmup_samples = 0;
+    info->lanes_per_channel = p->lanes;
+    info->host_chunks = p->last_host_chunks;
     info->regs_per_thread = v.regs;
     info->smem_bytes = p->last_smem;
     info->launches = p->launches;
@@ -662,7 +726,7 @@ int zg_process(zg_plan* p, const void* const* in, void* const* out, int64_t n_sa
     if (st != ZG_OK) return st;
     if (n_samples == 0) return ZG_OK;
     ZG_CUDA(cudaSetDevice(p->opts.device));
-    return launch(p, in, out, n_samples, ld_in, ld_out, (cudaStream_t)stream);
+    return launch(p, in, out, n_samples, ld_in, ld_out, (cudaStream_t)stream, 0, p->C, true);
 }
 
 int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t n_samples, int64_t ld_in,
@@ -672,6 +736,8 @@ int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t
     if (n_samples == 0) return ZG_OK;
     ZG_CUDA(cudaSetDevice(p->opts.device));
     if (!p->own_stream) ZG_CUDA(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+    if (!p->h2d_stream) ZG_CUDA(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
+    if (!p->d2h_stream) ZG_CUDA(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
     // device staging: same shape as the host buffers, rows padded to a multiple of 4 floats
     const int64_t rows = p->interleaved ? n_samples : p->C;
     const int64_t cols = p->interleaved ? p->C : n_samples;
@@ -686,26 +752,70 @@ int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t
         ZG_CUDA(cudaMalloc(&p->d_stage, need * sizeof(float)));
         p->d_stage_floats = need;
     }
-    const void* d_in[ZG_MAX_WIRES] = {};
-    void* d_out[ZG_MAX_WIRES] = {};
+    float* d_in[ZG_MAX_WIRES] = {};
+    float* d_out[ZG_MAX_WIRES] = {};
     size_t slot = 0;
     for (int k = 0; k < p->ir.n_in; ++k) {
         if (p->synth_mask & (1u << k)) continue;
         if (!in || !in[k]) return fail(ZG_ERR_ARG, "input buffer is NULL");
-        float* dst = p->d_stage + slot++ * per_buf;
-        ZG_CUDA(cudaMemcpy2DAsync(dst, ld * 4, in[k], ld_in * 4, cols * 4, rows, cudaMemcpyHostToDevice, p->own_stream));
-        d_in[k] = dst;
+        d_in[k] = p->d_stage + slot++ * per_buf;
     }
     for (int o = 0; o < p->ir.n_out; ++o) {
         if (!out || !out[o]) return fail(ZG_ERR_ARG, "output buffer is NULL");
         d_out[o] = p->d_stage + slot++ * per_buf;
     }
-    int st = check_io(p, d_in, d_out, n_samples, ld, ld);
-    if (st != ZG_OK) return st;
-    st = launch(p, d_in, d_out, n_samples, ld, ld, p->own_stream);
-    if (st != ZG_OK) return st;
-    for (int o = 0; o < p->ir.n_out; ++o)
-        ZG_CUDA(cudaMemcpy2DAsync(out[o], ld_out * 4, d_out[o], ld * 4, cols * 4, rows, cudaMemcpyDeviceToHost, p->own_stream));
+    {
+        const void* ci[ZG_MAX_WIRES];
+        void* co[ZG_MAX_WIRES];
+        for (int k = 0; k < ZG_MAX_WIRES; ++k) { ci[k] = d_in[k]; co[k] = d_out[k]; }
+        int st = check_io(p, ci, co, n_samples, ld, ld);
+        if (st != ZG_OK) return st;
+    }
+
+    // The block is cut into row chunks (planar: channel ranges, independent; interleaved: time ranges,
+    // launched in order, state carried in HBM) and streamed: H2D of chunk k+1, the kernel of chunk k
+    // and D2H of chunk k-1 overlap on three streams, so a PCIe-bound call costs one direction, not two.
+    const int64_t row_bytes = cols * 4 * std::max(1, std::max(p->n_buf_in, p->ir.n_out));
+    int64_t n_chunks = std::min<int64_t>(16, (rows * row_bytes) / (32ll << 20));
+    if (int c = tune_env("ZG_TUNE_HOST_CHUNKS")) n_chunks = c;
+    n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, rows / 32));
+    int64_t chunk_rows = (rows + n_chunks - 1) / n_chunks;
+    chunk_rows = (chunk_rows + 31) / 32 * 32;
+    n_chunks = (rows + chunk_rows - 1) / chunk_rows;
+    while ((int64_t)p->events.size() < 2 * n_chunks) {
+        cudaEvent_t e;
+        ZG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p->events.push_back(e);
+    }
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int64_t r0 = c * chunk_rows, nr = std::min(chunk_rows, rows - r0);
+        for (int k = 0; k < p->ir.n_in; ++k) {
+            if (!d_in[k]) continue;
+            ZG_CUDA(cudaMemcpy2DAsync(d_in[k] + r0 * ld, ld * 4, (const float*)in[k] + r0 * ld_in, ld_in * 4, cols * 4, nr,
+                                      cudaMemcpyHostToDevice, p->h2d_stream));
+        }
+        ZG_CUDA(cudaEventRecord(p->events[2 * c], p->h2d_stream));
+        ZG_CUDA(cudaStreamWaitEvent(p->own_stream, p->events[2 * c], 0));
+        const void* ci[ZG_MAX_WIRES] = {};
+        void* co[ZG_MAX_WIRES] = {};
+        for (int k = 0; k < ZG_MAX_WIRES; ++k) {
+            ci[k] = d_in[k] ? d_in[k] + r0 * ld : nullptr;
+            co[k] = d_out[k] ? d_out[k] + r0 * ld : nullptr;
+        }
+        int st = p->interleaved ? launch(p, ci, co, nr, ld, ld, p->own_stream, 0, p->C, true)
+                                : launch(p, ci, co, n_samples, ld, ld, p->own_stream, r0, nr, c + 1 == n_chunks);
+        if (st != ZG_OK) {
+            cudaDeviceSynchronize();
+            return st;
+        }
+        ZG_CUDA(cudaEventRecord(p->events[2 * c + 1], p->own_stream));
+        ZG_CUDA(cudaStreamWaitEvent(p->d2h_stream, p->events[2 * c + 1], 0));
+        for (int o = 0; o < p->ir.n_out; ++o)
+            ZG_CUDA(cudaMemcpy2DAsync((float*)out[o] + r0 * ld_out, ld_out * 4, d_out[o] + r0 * ld, ld * 4, cols * 4, nr,
+                                      cudaMemcpyDeviceToHost, p->d2h_stream));
+    }
+    p->last_host_chunks = (int)n_chunks;
+    ZG_CUDA(cudaStreamSynchronize(p->d2h_stream));
     ZG_CUDA(cudaStreamSynchronize(p->own_stream));
     return ZG_OK;
 }
