@@ -15,6 +15,8 @@ Channels are independent, so N GPUs = N x the channels (weak scaling), no data-p
   e2e       same metric through zg_process_host(): pinned host buffers, H2D + kernel + D2H timed
   roofline  algorithmic bytes (8 B per sample: 4 in + 4 out) / average launch time vs measured HBM peak
   cpu_baseline  the reference's hand-written biquad loop (oracle/_ref, all host threads), bounded sample
+  also      the other biquad shape (c2 when the headline is ns and vice versa), device-resident, same rules
+Default mode is EXACT: bit-identical to the reference's x86 build, checked on sampled channels.
 """
 from __future__ import annotations
 
@@ -37,6 +39,12 @@ WORKLOADS = {
     "c2": (4096, 65536),
 }
 BYTES_PER_SAMPLE = 8          # fp32 in + fp32 out; state/coefficients amortise to < 0.1 %
+
+
+def workload_string(name, layout="planar"):
+    C, T = WORKLOADS[name]
+    return (f"{name}: {C} channels x {T} samples per GPU x {SECTIONS} DF1 biquad sections "
+            f"(flowz `fwd |= bwd` x{SECTIONS}), fp32 {layout}")
 
 
 def _peak_hbm():
@@ -194,7 +202,7 @@ def run_reference_arm(args):
         "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {C_w} channels x {T_w} samples x {SECTIONS} DF1 biquad sections, fp32 planar",
+        "config": {"workload": workload_string(args.workload),
                    "step_sample": f"{C} channels x {samples} samples per step on the host"},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": base["cores"], "kind": base["kind"],
                          "sample": base["sample"]},
@@ -229,47 +237,50 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    C, T = WORKLOADS[args.workload]
-    if args.coef == "uniform":
-        graph = zg.compile(fo.biquad_cascade(SECTIONS))
-        params = []
-    else:
-        graph = zg.compile(fo.biquad_cascade_params(SECTIONS))
-        c = np.arange(C, dtype=np.float64) + rank * C
-        params = []
-        for k in range(SECTIONS):
-            per = np.array([fo.rbj_lowpass(440.0 * 2 ** k * (1.0 + ci / (C * world))) for ci in c], np.float32)
-            params += [per[:, j].copy() for j in range(5)]
-    mode = zg.MODE_EXACT if args.mode == "exact" else zg.MODE_FAST
-    plan = graph.plan(channels=C, device=local, mode=mode,
-                      layout=zg.INTERLEAVED if args.layout == "interleaved" else zg.PLANAR)
-    for i, p in enumerate(params):
-        plan.set_param(i, p)
-
-    shape = (T, C) if args.layout == "interleaved" else (C, T)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = torch.rand(shape, generator=gen, device=dev, dtype=torch.float32) * 2 - 1
-    y = torch.empty_like(x)
-
-    for _ in range(max(args.warmup, 3)):
-        plan.process([x], [y])
-    barrier()
-    l0 = plan.info().launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
+    def device_rate(workload):
+        """K launches of one zg_process() each between CUDA events; returns the plan, buffers and timing."""
+        C, T = WORKLOADS[workload]
+        if args.coef == "uniform":
+            graph = zg.compile(fo.biquad_cascade(SECTIONS))
+            params = []
+        else:
+            graph = zg.compile(fo.biquad_cascade_params(SECTIONS))
+            c = np.arange(C, dtype=np.float64) + rank * C
+            params = []
+            for k in range(SECTIONS):
+                per = np.array([fo.rbj_lowpass(440.0 * 2 ** k * (1.0 + ci / (C * world))) for ci in c], np.float32)
+                params += [per[:, j].copy() for j in range(5)]
+        mode = zg.MODE_EXACT if args.mode == "exact" else zg.MODE_FAST
+        plan = graph.plan(channels=C, device=local, mode=mode,
+                          layout=zg.INTERLEAVED if args.layout == "interleaved" else zg.PLANAR)
+        for i, p in enumerate(params):
+            plan.set_param(i, p)
+        shape = (T, C) if args.layout == "interleaved" else (C, T)
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        x = torch.rand(shape, generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+        y = torch.empty_like(x)
+        for _ in range(max(args.warmup, 3)):
             plan.process([x], [y])
-        e1.record()
         barrier()
-    ms = e0.elapsed_time(e1)
-    launches = plan.info().launches - l0
-    if dist is not None:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
+        l0 = plan.info().launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                plan.process([x], [y])
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1)
+        launches = plan.info().launches - l0
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return plan, x, y, shape, ms / args.steps, launches, clk
+
+    C, T = WORKLOADS[args.workload]
+    plan, x, y, shape, ms_per_step, launches, clk = device_rate(args.workload)
     value = world * C * T / (ms_per_step * 1e-3) / 1e6
     info = plan.info()
 
@@ -310,6 +321,22 @@ def run_ours(args):
         parity = {"max_block_rel_err": float((np.abs(got.astype(np.float64) - ref).max(axis=1) / den).max()),
                   "bit_identical": bool(np.array_equal(got, ref)), "channels_checked": idx}
 
+    # ---- the other biquad configuration (BASELINE configs[1] vs the north-star shape), same timing rules ----
+    also = None
+    if not args.no_also:
+        other = "c2" if args.workload == "ns" else "ns"
+        del x, y
+        torch.cuda.empty_cache()
+        Co, To = WORKLOADS[other]
+        plan_o, xo, yo, _, ms_o, _, _ = device_rate(other)
+        io = plan_o.info()
+        also = {other: {"workload": workload_string(other, args.layout),
+                        "value": world * Co * To / (ms_o * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_o,
+                        "roofline_frac": BYTES_PER_SAMPLE * Co * To / (ms_o * 1e-3) / 1e9 / _peak_hbm()[0],
+                        "kernel": io.kernel.decode(), "lanes_per_channel": io.lanes_per_channel,
+                        "traffic": _traffic(other)}}
+        del plan_o, xo, yo
+
     if rank == 0:
         peak, peak_src = _peak_hbm()
         achieved = BYTES_PER_SAMPLE * C * T / (ms_per_step * 1e-3) / 1e9       # per GPU, per launch
@@ -317,11 +344,11 @@ def run_ours(args):
             "metric": "Msamples/s, N-channel 4-section biquad chain", "value": value, "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {C} channels x {T} samples per GPU x {SECTIONS} DF1 biquad sections "
-                                   f"(flowz `fwd |= bwd` x{SECTIONS}), fp32 {args.layout}",
+            "config": {"workload": workload_string(args.workload, args.layout),
                        "coefficients": args.coef, "mode": args.mode, "parallelism": f"channel-shard x{world}",
                        "l2": f"inputs larger than L2 ({C * T * 4 / 2**20:.0f} MiB in + same out per GPU per step)",
-                       "kernel": info.kernel.decode(), "threads_per_cta": info.threads_per_cta,
+                       "kernel": info.kernel.decode(), "lanes_per_channel": info.lanes_per_channel,
+                       "threads_per_cta": info.threads_per_cta,
                        "stages": info.stages, "boxes": info.boxes, "smem_bytes": info.smem_bytes, "regs": info.regs_per_thread},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _traffic(args.workload), "peak_source": peak_src,
@@ -333,6 +360,8 @@ def run_ours(args):
             line["e2e"] = e2e
         if parity is not None:
             line["parity_spot_check"] = parity
+        if also is not None:
+            line["also"] = also
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"], _ = cpu_reference_rate()
         print(json.dumps(line), flush=True)
@@ -354,6 +383,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the second workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -8,29 +8,47 @@
 //
 //     lane = channel_in_warp * S + sec            32/S channels per warp, S x as many warps
 //
-// The cascade becomes a systolic pipeline in time, advancing in GROUPS of four samples: in group g
-// lane `sec` evaluates samples 4(g-sec) .. 4(g-sec)+3.  Its inputs are the four outputs lane sec-1
-// produced one group earlier, handed over with __shfl_up; a whole group (>= 4 x 12 cycles of the
-// lane's own recurrence) lies between producing a value and consuming it, so the shuffle latency
-// (~25 cycles + the feed-forward half of the section) never sits on the critical path -- with a skew
-// of one or two samples it does, and the warp runs at half speed (measured).  Every lane performs
-// exactly the operations of its section in exactly the reference's association, so EXACT mode stays
+// The cascade becomes a systolic pipeline in time, advancing in GROUPS of four samples: in iteration
+// g lane `sec` evaluates samples 4c .. 4c+3 of chunk c = g - 2*sec.  Values travel between
+// neighbouring lanes through a 512-byte per-warp exchange buffer in shared memory: at the end of an
+// iteration every lane stores its four outputs with ONE STS.128 -- the last lane of a channel into the
+// output tile, the others into their exchange slot -- and at the start of the next iteration every
+// lane issues ONE LDS.128 -- the first lane of a channel from the input tile, the others from the
+// slot of the lane below -- whose result it consumes one iteration later.  Two iterations (>= 100
+// cycles) therefore lie between producing a value and needing it, so neither the shared-memory
+// round trip nor the feed-forward half of the next section is ever on the critical path, which is the
+// lane's own 12-cycle recurrence (a shuffle-based hand-over with a skew of 1-4 samples measured 2-3x
+// slower: its latency lands on the path all lanes of the warp share).  Every lane performs exactly
+// the operations of its section in exactly the reference's association, so EXACT mode stays
 // bit-identical to the oracle -- only the *order in time* in which independent sections are evaluated
 // changes, which no result depends on.
 //
-// A tile (NB boxes of [32/S channels x 32 samples], 128-byte rows, SWIZZLE_128B) is self-contained:
-// the pipeline fills at its start and drains at its end (S-1 extra groups per tile, ~2 % at 512
-// samples), so between tiles the registers hold the plain delay-line state and the state rows in HBM
-// are interchangeable with the lane-per-channel kernel's.  Groups in which some lane is outside the
-// tile run predicated ("slow" groups); the steady state in between is one LDS.128 (lane 0 of a
-// channel reads chunk g), four unpredicated ticks, four shuffles and one STS.128 (lane S-1 overwrites
-// chunk g-(S-1) in place -- read S-1 groups earlier, so no hazard).
+// A tile (NB boxes of [32/S channels x 32 samples], 128-byte rows, SWIZZLE_128B; one 3-D TMA
+// operation per tile and direction) is self-contained: the pipeline fills at its start and drains at
+// its end (2(S-1) extra iterations per tile, < 5 % at 512 samples), so between tiles the registers
+// hold the plain delay-line state and the state rows in HBM are interchangeable with the
+// lane-per-channel kernel's.  Iterations in which some lane is outside the tile run predicated
+// ("slow"); the steady state in between is one LDS.128, four unpredicated ticks and one STS.128.
 #pragma once
 #include <type_traits>
 
 #include "zg_stream.cuh"
 
 namespace zgk {
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* map, int x, int y, int z,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z),
+        "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const TensorMap* map, int x, int y, int z, const void* src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
+                 "r"(x), "r"(y), "r"(z), "r"(smem_u32(src))
+                 : "memory");
+}
 
 template <bool kExact>
 struct Df1Lane {
@@ -50,11 +68,17 @@ struct Df1Lane {
     }
 };
 
+constexpr int kLanesXbufBytes = 512;         // exchange buffer per warp: 32 lanes x 16 bytes
+
+// in_map[0] / out_map[0]: 2-D {T, C}, box {32, 32/S}        (ragged last tile, box by box)
+// in_map[1] / out_map[1]: 3-D {32, C, T/32} over the full 32-sample boxes, box {32, 32/S, NB}
 template <int S, bool kExact, bool kUniform>
 __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
     static_assert(S == 2 || S == 4, "lanes per channel: 2 or 4 (the box must span whole swizzle atoms)");
     constexpr int CPW = 32 / S;              // channels per warp
     constexpr int kBoxBytes = CPW * 128;
+    constexpr int LAG = 2;                   // iterations between neighbouring sections
+    constexpr int DRAIN = LAG * (S - 1);     // iterations until the last section has caught up (< 8)
 
     extern __shared__ __align__(1024) unsigned char smem[];
 
@@ -77,8 +101,11 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
     unsigned char* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     const unsigned stage_bytes = (unsigned)NB * kBoxBytes;
     unsigned char* my = tiles + (size_t)warp * St * stage_bytes;
-    unsigned long long* bars =
-        reinterpret_cast<unsigned long long*>(tiles + (size_t)warps_per_cta * St * stage_bytes) + warp * St;
+    unsigned char* xbuf = tiles + (size_t)warps_per_cta * St * stage_bytes + (size_t)warp * kLanesXbufBytes;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+                                   tiles + (size_t)warps_per_cta * (St * stage_bytes + kLanesXbufBytes)) + warp * St;
+    unsigned char* const x_in = xbuf + (lane > 0 ? lane - 1 : 0) * 16;   // what the lane below stored
+    unsigned char* const x_out = xbuf + lane * 16;
 
     // ---- this lane's section: coefficients and delay-line state ----
     // kernel slots as in zg_biquad.cuh: state 2k / 2k+1 = signal k two / one tick ago, params 5k..5k+4
@@ -99,21 +126,42 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
         fence_barrier_init();
         prefetch_tmap(&a.in_map[0]);
         prefetch_tmap(&a.out_map[0]);
+        if (a.flags & 1) {
+            prefetch_tmap(&a.in_map[1]);
+            prefetch_tmap(&a.out_map[1]);
+        }
     }
+    *reinterpret_cast<float4*>(x_out) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 
     const int n_tiles = (a.n_samples + tile_t - 1) / tile_t;
-    auto boxes_in_tile = [&](int t0) {
-        const int left = (a.n_samples - t0 + kTileT - 1) / kTileT;
-        return left < NB ? left : NB;
+    const int full_boxes = a.n_samples >> 5;           // boxes of the block without a ragged tail
+    const bool ragged = (a.n_samples & 31) != 0;
+    const bool have3d = (a.flags & 1) != 0;
+    // tile i: boxes [i*NB, i*NB + nbf) are full; `rag` = the block's ragged box follows them in this tile
+    auto tile_shape = [&](int i, int& nbf, bool& rag) {
+        const int b0 = i * NB;
+        nbf = full_boxes - b0;
+        nbf = nbf < 0 ? 0 : (nbf > NB ? NB : nbf);
+        rag = ragged && full_boxes >= b0 && full_boxes < b0 + NB;
+        if (!have3d) {                                 // no whole-tile map: every box goes on its own
+            if (!rag) nbf -= 1;
+            rag = true;
+        }
     };
     auto issue_load = [&](int i) {                     // lane 0 only
         const int slot = i % St;
-        const int t0 = i * tile_t;
-        const int nb = boxes_in_tile(t0);
-        mbar_expect_tx(&bars[slot], (unsigned)(nb * kBoxBytes));
+        int nbf; bool rag;
+        tile_shape(i, nbf, rag);
         unsigned char* dst = my + (size_t)slot * stage_bytes;
-        for (int b = 0; b < nb; ++b) tma_load_2d(dst + b * kBoxBytes, &a.in_map[0], t0 + b * kTileT, c0, &bars[slot]);
+        if (!rag) {                                    // one operation; boxes past the end are zero-filled
+            mbar_expect_tx(&bars[slot], (unsigned)(NB * kBoxBytes));
+            tma_load_3d(dst, &a.in_map[1], 0, c0, i * NB, &bars[slot]);
+        } else {
+            mbar_expect_tx(&bars[slot], (unsigned)((nbf + 1) * kBoxBytes));
+            for (int b = 0; b <= nbf; ++b)
+                tma_load_2d(dst + b * kBoxBytes, &a.in_map[0], (i * NB + b) * kTileT, c0, &bars[slot]);
+        }
     };
     if (lane == 0) {
         const int pre = n_tiles < St - 1 ? n_tiles : St - 1;
@@ -122,7 +170,7 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
 
     // row `cl` of every box; 16-byte chunk j of the row lives at chunk j ^ (cl & 7)   (SWIZZLE_128B).
     // The eight chunk offsets of this lane never change: keep them in registers so that the steady
-    // state addresses shared memory as [uniform box base + off[j]] with no per-access arithmetic.
+    // state addresses shared memory with no per-access arithmetic.
     unsigned off[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) off[j] = (unsigned)cl * 128u + ((((unsigned)j) ^ (unsigned)(cl & 7)) << 4);
@@ -130,96 +178,103 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
     for (int i = 0; i < n_tiles; ++i) {
         const int slot = i % St;
         const int t0 = i * tile_t;
-        const int nb = boxes_in_tile(t0);
         const int nt = a.n_samples - t0 < tile_t ? a.n_samples - t0 : tile_t;
         unsigned char* stage = my + (size_t)slot * stage_bytes;
-        auto sample_ptr = [&](int t) {                 // slow groups only
-            const unsigned g = (unsigned)t >> 2;
-            return reinterpret_cast<float*>(stage + (g >> 3) * kBoxBytes + (unsigned)cl * 128u +
-                                            (((g & 7u) ^ (unsigned)(cl & 7)) << 4) + ((unsigned)t & 3u) * 4u);
+        auto chunk_ptr = [&](int c) {                  // chunk c of the tile, this lane's channel
+            return stage + ((unsigned)c >> 3) * kBoxBytes + (unsigned)cl * 128u +
+                   ((((unsigned)c & 7u) ^ (unsigned)(cl & 7)) << 4);
         };
 
         mbar_wait(&bars[slot], (unsigned)((i / St) & 1));
 
-        float r[4] = {0.f, 0.f, 0.f, 0.f};             // outputs of lane sec-1 for the samples of this group
-        auto slow_group = [&](int g) {                 // predicated: lanes may be outside the tile
+        // `nxt` = the four inputs of the NEXT iteration, loaded one iteration ahead
+        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (first) nxt = *reinterpret_cast<const float4*>(chunk_ptr(0));
+
+        auto slow_iter = [&](int g) {                  // predicated: lanes may be outside the tile
+            const float4 cur = nxt;
+            __syncwarp();
+            if (!first) nxt = *reinterpret_cast<const float4*>(x_in);
+            else if (g + 1 < NB * 8) nxt = *reinterpret_cast<const float4*>(chunk_ptr(g + 1));
+            const int c = g - LAG * sec;
             float o[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int m = 4 * (g - sec) + q;
+                const int m = 4 * c + q;
                 const bool act = ch_ok && m >= 0 && m < nt;
-                float in = r[q];
-                if (first && act) in = *sample_ptr(m);
-                const float y = f.eval(in);
-                if (act) f.push(in, y);
-                if (last && act) *sample_ptr(m) = y;
-                o[q] = y;
+                const float in = q == 0 ? cur.x : q == 1 ? cur.y : q == 2 ? cur.z : cur.w;
+                o[q] = f.eval(in);
+                if (act) f.push(in, o[q]);
+                if (last && act) reinterpret_cast<float*>(chunk_ptr(c))[q] = o[q];
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) r[q] = __shfl_up_sync(0xffffffffu, o[q], 1);
+            if (!last) *reinterpret_cast<float4*>(x_out) = make_float4(o[0], o[1], o[2], o[3]);
         };
-        // steady state: chunk j of the box at `box` in, chunk j-(S-1) (possibly of the box before) out
-        // (the input chunk was loaded one group ahead: a warp alone on its scheduler cannot hide LDS latency)
-        float4 xcur = make_float4(0.f, 0.f, 0.f, 0.f);
-        auto fast_group = [&](unsigned char* box, auto jc, bool more) {
+        // steady state, iteration 8*box + j: chunk j of `box` in (for the next iteration: chunk j+1),
+        // chunk j - DRAIN (possibly of the box before) out
+        auto fast_iter = [&](unsigned char* box, auto jc, bool more) {
             constexpr int j = decltype(jc)::value;
-            constexpr int jo = (j - (S - 1) + 8) & 7;
-            constexpr int back = (j - (S - 1)) < 0 ? kBoxBytes : 0;
-            const float4 xv = xcur;
-            if (j < 7) xcur = *reinterpret_cast<const float4*>(box + off[(j + 1) & 7]);
-            else if (more) xcur = *reinterpret_cast<const float4*>(box + kBoxBytes + off[0]);
+            constexpr int jo = (j - DRAIN + 8) & 7;
+            constexpr int back = (j - DRAIN) < 0 ? kBoxBytes : 0;
+            const float4 cur = nxt;
+            __syncwarp();
+            const unsigned char* src = x_in;
+            if (first) src = j < 7 ? box + off[(j + 1) & 7] : (more ? box + kBoxBytes + off[0] : x_in);
+            nxt = *reinterpret_cast<const float4*>(src);
             float o[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float xq = q == 0 ? xv.x : q == 1 ? xv.y : q == 2 ? xv.z : xv.w;
-                const float in = first ? xq : r[q];
+                const float in = q == 0 ? cur.x : q == 1 ? cur.y : q == 2 ? cur.z : cur.w;
                 o[q] = f.eval(in);
                 f.push(in, o[q]);
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) r[q] = __shfl_up_sync(0xffffffffu, o[q], 1);
-            if (last) *reinterpret_cast<float4*>(box - back + off[jo]) = make_float4(o[0], o[1], o[2], o[3]);
+            unsigned char* dst = last ? box - back + off[jo] : x_out;
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
         };
 
-        const int nfull = nt >> 5;                     // boxes without a ragged tail
-        const int total = (nt + 3) / 4 + (S - 1);      // groups until the last lane has drained
+        const int nfull = nt >> 5;                     // boxes of this tile without a ragged tail
+        const int total = (nt + 3) / 4 + DRAIN;        // iterations until the last lane has drained
         if (nfull >= 1) {
-            for (int g = 0; g < S - 1; ++g) slow_group(g);
-            // rest of box 0: every lane is inside the tile from group S-1 on
-            xcur = *reinterpret_cast<const float4*>(stage + off[S - 1]);
-            if constexpr (S - 1 <= 1) fast_group(stage, std::integral_constant<int, 1>{}, true);
-            if constexpr (S - 1 <= 2) fast_group(stage, std::integral_constant<int, 2>{}, true);
-            fast_group(stage, std::integral_constant<int, 3>{}, true);
-            fast_group(stage, std::integral_constant<int, 4>{}, true);
-            fast_group(stage, std::integral_constant<int, 5>{}, true);
-            fast_group(stage, std::integral_constant<int, 6>{}, true);
-            fast_group(stage, std::integral_constant<int, 7>{}, nfull > 1);
+            for (int g = 0; g < DRAIN; ++g) slow_iter(g);
+            // rest of box 0: every lane is inside the tile from iteration DRAIN on
+            if constexpr (DRAIN <= 2) fast_iter(stage, std::integral_constant<int, 2>{}, true);
+            if constexpr (DRAIN <= 2) fast_iter(stage, std::integral_constant<int, 3>{}, true);
+            if constexpr (DRAIN <= 2) fast_iter(stage, std::integral_constant<int, 4>{}, true);
+            if constexpr (DRAIN <= 2) fast_iter(stage, std::integral_constant<int, 5>{}, true);
+            fast_iter(stage, std::integral_constant<int, 6>{}, true);
+            fast_iter(stage, std::integral_constant<int, 7>{}, nt > 32);
 #pragma unroll 1
             for (int b = 1; b < nfull; ++b) {
                 unsigned char* box = stage + (unsigned)b * kBoxBytes;
-                fast_group(box, std::integral_constant<int, 0>{}, true);
-                fast_group(box, std::integral_constant<int, 1>{}, true);
-                fast_group(box, std::integral_constant<int, 2>{}, true);
-                fast_group(box, std::integral_constant<int, 3>{}, true);
-                fast_group(box, std::integral_constant<int, 4>{}, true);
-                fast_group(box, std::integral_constant<int, 5>{}, true);
-                fast_group(box, std::integral_constant<int, 6>{}, true);
-                fast_group(box, std::integral_constant<int, 7>{}, b + 1 < nfull);
+                fast_iter(box, std::integral_constant<int, 0>{}, true);
+                fast_iter(box, std::integral_constant<int, 1>{}, true);
+                fast_iter(box, std::integral_constant<int, 2>{}, true);
+                fast_iter(box, std::integral_constant<int, 3>{}, true);
+                fast_iter(box, std::integral_constant<int, 4>{}, true);
+                fast_iter(box, std::integral_constant<int, 5>{}, true);
+                fast_iter(box, std::integral_constant<int, 6>{}, true);
+                fast_iter(box, std::integral_constant<int, 7>{}, nt > 32 * (b + 1));
             }
-            for (int g = nfull * 8; g < total; ++g) slow_group(g);
+            for (int g = nfull * 8; g < total; ++g) slow_iter(g);
         } else {
-            for (int g = 0; g < total; ++g) slow_group(g);
+            for (int g = 0; g < total; ++g) slow_iter(g);
         }
 
         fence_proxy_async();                           // generic-proxy writes -> visible to TMA
         __syncwarp();
         if (lane == 0) {
-            for (int b = 0; b < nb; ++b) tma_store_2d(&a.out_map[0], t0 + b * kTileT, c0, stage + b * kBoxBytes);
+            int nbf; bool rag;
+            tile_shape(i, nbf, rag);
+            if (!rag) {
+                tma_store_3d(&a.out_map[1], 0, c0, i * NB, stage);      // boxes past the end are clipped
+            } else {
+                for (int b = 0; b <= nbf; ++b)
+                    tma_store_2d(&a.out_map[0], (i * NB + b) * kTileT, c0, stage + b * kBoxBytes);
+            }
             tma_commit();
-            const int nxt = i + St - 1;
-            if (nxt < n_tiles) {
+            const int nxt_tile = i + St - 1;
+            if (nxt_tile < n_tiles) {
                 tma_wait_read<1>();                    // the slot of tile i-1: its store has left smem
-                issue_load(nxt);
+                issue_load(nxt_tile);
             }
         }
     }

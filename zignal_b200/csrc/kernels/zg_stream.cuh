@@ -43,6 +43,7 @@ struct StreamArgs {
     int n_samples;                  // samples in this block
     int boxes;                      // NB: boxes (of 32 samples) per pipeline stage
     int stages;                     // S >= 2
+    int flags;                      // bit 0: in_map[1] / out_map[1] hold the 3-D whole-tile maps (K1b)
     unsigned dirac_mask;            // synthesised input k is a dirac (else zeros)
     int state_row[kMaxState];       // row of state slot j inside `state` (prebuilt ticks use their
                                     // own slot order; generated ticks use the identity)

@@ -393,6 +393,24 @@ int encode_map(zg_plan* p, zgk::TensorMap* out, const void* base, int64_t C, int
     return ZG_OK;
 }
 
+// K1b whole-tile map: the planar [C][ld] buffer seen as {32 samples, C channels, T/32 boxes} (strides
+// ld*4 and 128 bytes), box {32, rows, NB}: one TMA operation moves NB consecutive boxes of `rows`
+// channels and lays them out in shared memory box after box, exactly like NB single-box operations.
+// Only the full 32-sample boxes are covered (a ragged tail goes through the 2-D map, which clips at T).
+bool encode_map_tile3d(zgk::TensorMap* out, const void* base, int64_t C, int64_t T, int64_t ld, int box_rows, int NB) {
+    Driver& d = driver();
+    if (T < 32) return false;
+    cuuint64_t dims[3] = {32, (cuuint64_t)C, (cuuint64_t)(T / 32)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)NB};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = d.tensorMapEncodeTiled(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                                        const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;       // a driver that rejects the stride order: the kernel moves box by box
+}
+
 // ---- launch geometry ---------------------------------------------------------------------------------
 //
 // All warps of the launch should be resident at once (one wave) and spread evenly over the SMs:
@@ -454,13 +472,14 @@ Geometry choose_geometry_lanes(const zg_plan* p, int64_t n_warps, int regs, int6
     int NB = 16;
     if (int b = tune_env("ZG_TUNE_BOXES")) NB = std::min(std::max(b, 1), 32);
     NB = (int)std::min<int64_t>(NB, std::max<int64_t>(1, (T + zgk::kTileT - 1) / zgk::kTileT));
-    while (NB > 1 && wpc * S * NB * box_bytes > budget) NB /= 2;
-    while (wpc > 1 && wpc * S * NB * box_bytes > budget) --wpc;
+    auto need = [&](int w, int nb) { return w * (S * nb * box_bytes + zgk::kLanesXbufBytes); };
+    while (NB > 1 && need(wpc, NB) > budget) NB /= 2;
+    while (wpc > 1 && need(wpc, NB) > budget) --wpc;
     g.wpc = wpc;
     g.stages = S;
     g.boxes = NB;
     g.grid = (int)((n_warps + wpc - 1) / wpc);
-    g.smem = wpc * S * NB * box_bytes + 1024 + wpc * S * 8;
+    g.smem = need(wpc, NB) + 1024 + wpc * S * 8;
     return g;
 }
 
@@ -503,6 +522,11 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     Geometry g = p->lanes > 1 ? choose_geometry_lanes(p, n_warps, v->regs, T) : choose_geometry(p, n_warps, NT, v->regs, T);
     a.stages = g.stages;
     a.boxes = g.boxes;
+    if (p->lanes > 1 && !tune_env("ZG_TUNE_NO3D")) {
+        const bool ok = encode_map_tile3d(&a.in_map[1], in[0], c_count, T, ld_in, cpw, g.boxes) &&
+                        encode_map_tile3d(&a.out_map[1], out[0], c_count, T, ld_out, cpw, g.boxes);
+        a.flags = ok ? 1 : 0;
+    }
 
     if (g.smem > v->max_smem_set) {
         if (v->prebuilt) {
