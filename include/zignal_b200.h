@@ -79,6 +79,13 @@ int zg_graph_get_info(const zg_graph* g, zg_graph_info* info);
 /* canonical expression / SSA dump; valid until the graph is destroyed (print_state stand-in) */
 const char* zg_graph_canonical(const zg_graph* g);
 const char* zg_graph_dump(const zg_graph* g);
+/* Which device kernel family the tick program is recognised as (planar layout, buffer inputs):
+ *   "biquad_df1:<S>"  S direct-form-1 sections in series, test/benchmark.cpp:25-33  -> prebuilt K1 / K1b
+ *   "fir:<N>"         c0*_1 + c1*_1[_1] + ... + c(N-1)*_1[_(N-1)], summed left to right -> prebuilt K3
+ *   "generated"       any other fp32 graph: tick body generated from the SSA, NVRTC         -> K2
+ *   "host-only"       int / double terminals: zg_voice_tick only
+ * Pure host analysis (no device).                                                              */
+int zg_graph_kernel_class(const zg_graph* g, char* buf, size_t capacity);
 
 /* ---- host voice: stateful_lambda (flowz.hpp:1181-1230) ----------------------------------------
  * zg_voice_tick is operator()(args...) for exactly n_in arguments; in_dtypes[i] says what C++

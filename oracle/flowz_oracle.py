@@ -691,8 +691,8 @@ def noise(channels: int, samples: int, seed: int = 0) -> np.ndarray:
     """x[c,t] ~ U(-1,1) from a counter hash of (seed, c, t): identical wherever it is generated."""
     c = np.arange(channels, dtype=np.uint64)[:, None]
     t = np.arange(samples, dtype=np.uint64)[None, :]
-    h = (c * np.uint64(0x9E3779B97F4A7C15) + t * np.uint64(0xC2B2AE3D27D4EB4F)
-         + np.uint64(seed) * np.uint64(0x165667B19E3779F9)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    sd = np.uint64((int(seed) * 0x165667B19E3779F9) & 0xFFFFFFFFFFFFFFFF)      # wraps, like the uint64 product
+    h = (c * np.uint64(0x9E3779B97F4A7C15) + t * np.uint64(0xC2B2AE3D27D4EB4F) + sd) & np.uint64(0xFFFFFFFFFFFFFFFF)
     h ^= h >> np.uint64(33); h *= np.uint64(0xFF51AFD7ED558CCD)
     h ^= h >> np.uint64(33); h *= np.uint64(0xC4CEB9FE1A85EC53)
     h ^= h >> np.uint64(33)
@@ -753,3 +753,39 @@ def biquad_cascade_params(sections: int = 4) -> str:
         p = 5 * k
         parts.append(f"(${p}*_1 + ${p+1}*_1[_1] + ${p+2}*_1[_2] |= ~(_2 + ${p+3}*_1[_1] + ${p+4}*_1[_2]))")
     return " |= ".join(parts)
+
+
+# ---- FIR (BASELINE configs[3]; SURVEY.md 8d: windowed-sinc taps shared by all channels) ----------
+
+def fir_taps(n: int = 256, cutoff: float = 0.25) -> np.ndarray:
+    """n-tap Hamming-windowed sinc low-pass (cutoff in cycles/sample * 2), DC gain ~ 1, fp32."""
+    k = np.arange(n, dtype=np.float64) - (n - 1) / 2.0
+    h = np.sinc(k * cutoff) * np.hamming(n) if n > 1 else np.ones(1)
+    return (h / h.sum()).astype(np.float32)
+
+
+def fir_expr(taps: Sequence[float]) -> str:
+    """c0*_1 + c1*_1[_1] + ... in the reference's spelling (flowz.hpp:84-85 delays, :769-772 arithmetic);
+    C++ associates the sum to the left."""
+    return " + ".join(f"{lit(c)}*_1" if k == 0 else f"{lit(c)}*_1[_{k}]" for k, c in enumerate(taps))
+
+
+def fir_expr_params(n: int) -> str:
+    """Same FIR with every tap a run-time parameter $0..$(n-1)."""
+    return " + ".join(f"${k}*_1" if k == 0 else f"${k}*_1[_{k}]" for k in range(n))
+
+
+def fir_direct(x: np.ndarray, taps: Sequence[float], history: Optional[np.ndarray] = None) -> np.ndarray:
+    """What the tick of fir_expr(taps) computes, vectorised over the block: every product and every sum
+    rounded to fp32 separately, summed in tap order (numpy float32 arithmetic does exactly that).
+    `history` = [C][n-1] samples before the block (the delay line, oldest first), zeros if None.
+    Checked against the tick-by-tick oracles in tests/test_oracle_golden.py."""
+    x = np.asarray(x, np.float32)
+    C_, T = x.shape
+    n = len(taps)
+    h = np.zeros((C_, n - 1), np.float32) if history is None else np.asarray(history, np.float32)
+    ext = np.concatenate([h, x], axis=1)
+    acc = np.float32(taps[0]) * ext[:, n - 1:n - 1 + T]
+    for k in range(1, n):
+        acc = acc + np.float32(taps[k]) * ext[:, n - 1 - k:n - 1 - k + T]
+    return acc

@@ -363,6 +363,130 @@ def test_argument_errors(zg):
     assert e.value.status == zg.ZG_ERR_UNSUPPORTED
 
 
+# ---- K3: dense FIR (BASELINE configs[3]) -----------------------------------------------------------
+
+@pytest.mark.parametrize("n_taps,C,T", [(256, 64, 1024), (256, 33, 700), (2, 32, 64), (17, 40, 100), (33, 5, 31),
+                                        (100, 64, 4096), (255, 32, 513), (257, 32, 640), (512, 96, 2048)])
+def test_fir_exact_is_bit_identical(zg, n_taps, C, T):
+    h = fo.fir_taps(n_taps)
+    expr = fo.fir_expr(h)
+    x = fo.noise(C, T, seed=n_taps + C)
+    ys, plan = _run(zg, expr, [x], zg.MODE_EXACT)
+    assert plan.info().kernel.decode().startswith(f"zg_fir<{n_taps} taps,exact") and plan.info().jit == 0
+    assert np.array_equal(ys[0], fo.fir_direct(x, h))
+    if C * T <= 64 * 1024:                                   # and the tick-by-tick oracle itself
+        assert np.array_equal(ys[0], _oracle(expr, [x])[0])
+
+
+def test_fir_fast_within_tolerance(zg):
+    h = fo.fir_taps(256)
+    x = fo.noise(64, 2048, seed=5)
+    ys, _ = _run(zg, fo.fir_expr(h), [x], zg.MODE_FAST)
+    ref = fo.fir_direct(x, h)
+    err = _rel_err(ys[0], ref)
+    assert 0 < err <= TOL, err
+
+
+def test_fir_streaming_blocks_and_state(zg):
+    """Ragged block lengths (shorter than the delay line, not multiples of the 32-sample box) continue
+    exactly like consecutive ticks; the delay line is visible through zg_state_get in the oracle's
+    slot order (oldest first, rotate_push_back flowz.hpp:130-148)."""
+    h = fo.fir_taps(256)
+    expr = fo.fir_expr(h)
+    C, T = 40, 1500
+    x = fo.noise(C, T, seed=9)
+    ys, plan = _run(zg, expr, [x], zg.MODE_EXACT, blocks=[7, 100, 33, 255, 256, 1, 848])
+    assert np.array_equal(ys[0], fo.fir_direct(x, h))
+    st = plan.get_state()                                     # [255][C]
+    assert np.array_equal(st, x[:, -255:].T)
+    # set_state: a plan started from that delay line continues the stream
+    x2 = fo.noise(C, 300, seed=10)
+    plan2 = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT)
+    plan2.set_state(st)
+    y2 = plan2.process([_to_dev(x2)])[0].cpu().numpy()
+    assert np.array_equal(y2, fo.fir_direct(x2, h, history=x[:, -255:]))
+    plan2.reset()
+    y3 = plan2.process([_to_dev(x2)])[0].cpu().numpy()
+    assert np.array_equal(y3, fo.fir_direct(x2, h))
+
+
+def test_fir_time_segments_for_few_channels(zg):
+    """Few channel groups: the block is cut into time segments (a FIR has no recurrence); the segment
+    that ends the block writes the delay line."""
+    h = fo.fir_taps(256)
+    C, T = 64, 16384
+    x = fo.noise(C, T, seed=11)
+    ys, plan = _run(zg, fo.fir_expr(h), [x], zg.MODE_EXACT, blocks=[T // 2, T // 2])
+    assert plan.info().launches == 2
+    assert np.array_equal(ys[0], fo.fir_direct(x, h))
+    assert np.array_equal(plan.get_state(), x[:, -255:].T)
+
+
+def test_fir_taps_as_parameters(zg):
+    n = 48
+    h = fo.fir_taps(n)
+    x = fo.noise(64, 512, seed=12)
+    ys, _ = _run(zg, fo.fir_expr_params(n), [x], zg.MODE_EXACT, params=[float(v) for v in h])
+    assert np.array_equal(ys[0], fo.fir_direct(x, h))
+    g = zg.compile(fo.fir_expr_params(n))
+    plan = g.plan(channels=64)
+    plan.set_param(3, np.linspace(0, 1, 64, dtype=np.float32))      # per-channel tap: not this kernel
+    with pytest.raises(zg.ZgError) as e:
+        plan.process([_to_dev(x)])
+    assert e.value.status == zg.ZG_ERR_UNSUPPORTED
+
+
+def test_fir_delay_indexing_integer_ramp(zg):
+    """Unit taps on an integer ramp: every output is an exactly representable integer sum."""
+    n = 40
+    x = np.tile(np.arange(1, 201, dtype=np.float32), (32, 1))
+    ys, _ = _run(zg, fo.fir_expr(np.ones(n, np.float32)), [x], zg.MODE_FAST)
+    c = np.concatenate([np.zeros(1), np.cumsum(x[0].astype(np.float64))])
+    t = np.arange(200)
+    want = c[t + 1] - c[np.maximum(t + 1 - n, 0)]
+    assert np.array_equal(ys[0], np.tile(want.astype(np.float32), (32, 1)))
+
+
+def test_fir_process_host_and_long_delay_errors(zg):
+    h = fo.fir_taps(64)
+    x = fo.noise(2048, 4096, seed=13)
+    plan = zg.compile(fo.fir_expr(h)).plan(channels=2048)
+    y = plan.process_host([x])[0]
+    assert np.array_equal(y, fo.fir_direct(x, h))
+    with pytest.raises(zg.ZgError) as e:                      # long delay line that is not a dense FIR
+        zg.compile("_1[_100] + 0.5f*_1").plan(channels=8)
+    assert e.value.status == zg.ZG_ERR_UNSUPPORTED
+    with pytest.raises(zg.ZgError) as e:
+        zg.compile(fo.fir_expr(fo.fir_taps(256))).plan(channels=8, layout=zg.INTERLEAVED)
+    assert e.value.status == zg.ZG_ERR_UNSUPPORTED
+
+
+def test_full_size_config4_fir256_32768_channels(zg):
+    """BASELINE configs[3] at full size: 32 768 channels x 256 taps (T = 2048 here keeps the host-side
+    check quick; the kernel path is the same for any T).  Properties: sampled channels bit-identical
+    to the oracle, identical inputs give identical channels, two half blocks equal one block,
+    linearity in FAST mode."""
+    torch = _torch()
+    C, T = 32768, 2048
+    h = fo.fir_taps(256)
+    g = zg.compile(fo.fir_expr(h))
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.rand((C, T), generator=gen, device="cuda") * 2 - 1
+    x[1::2] = x[0::2]
+    plan = g.plan(channels=C, mode=zg.MODE_EXACT)
+    y = plan.process([x])[0]
+    torch.cuda.synchronize()
+    assert torch.equal(y[0::2], y[1::2])
+    idx = [0, 1, 31, 32, 4097, 32766, 32767]
+    assert np.array_equal(y[idx].cpu().numpy(), fo.fir_direct(x[idx].cpu().numpy(), h))
+    plan2 = g.plan(channels=C, mode=zg.MODE_EXACT)
+    ya = plan2.process([x[:, :T // 2]])[0]
+    yb = plan2.process([x[:, T // 2:]])[0]
+    assert torch.equal(torch.cat([ya, yb], dim=1), y)
+    yf = g.plan(channels=C, mode=zg.MODE_FAST).process([x])[0]
+    assert _rel_err(yf[idx].cpu().numpy(), y[idx].cpu().numpy()) <= TOL
+
+
 # ---- size-independent properties at BASELINE sizes ---------------------------------------------------
 
 def test_full_size_properties_65536_channels(zg):

@@ -1,0 +1,52 @@
+"""Host-side recognisers (zg_graph_kernel_class, zg_match.cpp): which device kernel family a tick
+program is routed to.  A graph is only routed to a prebuilt kernel when its lowered arithmetic is
+exactly the kernel's, association included; everything else must fall through to the generated
+kernel.  CPU only.  Also pins the vectorised FIR oracle against the tick-by-tick oracles."""
+import numpy as np
+import pytest
+
+import flowz_oracle as fo
+
+
+@pytest.mark.parametrize("expr,want", [
+    (fo.fir_expr(fo.fir_taps(256)), "fir:256"),
+    (fo.fir_expr(fo.fir_taps(2)), "fir:2"),
+    (fo.fir_expr_params(7), "fir:7"),
+    ("_1[_1]*0.5f + 0.25f*_1", "generated"),                          # taps out of order
+    ("0.5f*_1 + 0.25f*_1[_2]", "generated"),                          # sparse
+    ("0.5f*_1 + (0.25f*_1[_1] + 0.125f*_1[_2])", "generated"),        # right-associated sub-sum
+    ("0.5f*_1 + 0.25f*_1[_1] - 0.125f*_1[_2]", "generated"),          # a difference is not a sum
+    ("0.5f*_1", "generated"),
+    (fo.biquad_cascade(4), "biquad_df1:4"),
+    (fo.biquad_cascade_params(2), "biquad_df1:2"),
+    (fo.biquad_cascade(9), "generated"),                              # more sections than prebuilt
+    ("~(_2 + 0.9f*_1[_1])", "generated"),
+    ("_1 + 1", "host-only"),
+    ("0.5*_1", "host-only"),
+])
+def test_kernel_class(zg, expr, want):
+    assert zg.compile(expr).kernel_class() == want
+
+
+def test_fir_accepts_both_delay_spellings_and_operand_orders(zg):
+    assert zg.compile("0.5f*_1 + _1[-1]*0.25f + 0.125f*_1[_2]").kernel_class() == "fir:3"
+    assert zg.compile("_1*0.5f >> 1.0f*_1 + 0.25f*_1[-1]").kernel_class() == "generated"
+
+
+@pytest.mark.parametrize("n", [2, 5, 16, 33, 256])
+def test_vectorised_fir_oracle_equals_tick_oracles(zg, n):
+    """fir_direct (used for the large GPU parity cases) == the emitted-C tick oracle == the numpy tick
+    oracle == the library's own host voice, bit for bit."""
+    h = fo.fir_taps(n)
+    expr = fo.fir_expr(h)
+    x = fo.noise(3, 300, seed=n)
+    want = fo.fir_direct(x, h)
+    assert np.array_equal(fo.COracle(expr, 3).process([x])[0], want)
+    if n <= 33:
+        assert np.array_equal(fo.Oracle(expr, 3).process([x])[0], want)
+    v = zg.compile(expr).voice()
+    got = np.array([v.tick(np.float32(s))[0] for s in x[1, :64]], np.float32)
+    assert np.array_equal(got, want[1, :64])
+    # with history: continuing a stream
+    assert np.array_equal(fo.fir_direct(x[:, 100:], h, history=np.concatenate(
+        [np.zeros((3, max(0, n - 1 - 100)), np.float32), x[:, max(0, 100 - (n - 1)):100]], axis=1)), want[:, 100:])

@@ -69,6 +69,7 @@ def _load() -> C.CDLL:
         "zg_graph_get_info": (ci, [vp, P(GraphInfo)]),
         "zg_graph_canonical": (cp, [vp]),
         "zg_graph_dump": (cp, [vp]),
+        "zg_graph_kernel_class": (ci, [vp, C.c_char_p, sz]),
         "zg_voice_create": (ci, [vp, P(vp)]),
         "zg_voice_clone": (ci, [vp, P(vp)]),
         "zg_voice_destroy": (None, [vp]),
@@ -95,7 +96,7 @@ def _load() -> C.CDLL:
 
 lib = _load()
 EXPORTED = ["zg_last_error", "zg_version", "zg_expr_arity", "zg_expr_delays", "zg_expr_canonical",
-            "zg_graph_compile", "zg_graph_destroy", "zg_graph_get_info", "zg_graph_canonical", "zg_graph_dump",
+            "zg_graph_compile", "zg_graph_destroy", "zg_graph_get_info", "zg_graph_canonical", "zg_graph_dump", "zg_graph_kernel_class",
             "zg_voice_create", "zg_voice_clone", "zg_voice_destroy", "zg_voice_tick", "zg_voice_set_param",
             "zg_voice_state", "zg_plan_opts_default", "zg_graph_kernel_compile", "zg_plan_create",
             "zg_plan_destroy", "zg_plan_get_info", "zg_process", "zg_process_host", "zg_state_reset",
@@ -158,6 +159,12 @@ class Graph:
 
     def dump(self) -> str:
         return lib.zg_graph_dump(self._h).decode()
+
+    def kernel_class(self) -> str:
+        """'biquad_df1:<S>' | 'fir:<N>' | 'generated' | 'host-only' (zg_graph_kernel_class)."""
+        buf = C.create_string_buffer(64)
+        _check(lib.zg_graph_kernel_class(self._h, buf, len(buf)))
+        return buf.value.decode()
 
     def voice(self) -> "Voice":
         return Voice(self)

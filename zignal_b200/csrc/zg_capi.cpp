@@ -117,6 +117,20 @@ int zg_graph_get_info(const zg_graph* g, zg_graph_info* info) {
 const char* zg_graph_canonical(const zg_graph* g) { return g ? g->canonical_str.c_str() : ""; }
 const char* zg_graph_dump(const zg_graph* g) { return g ? g->dump_str.c_str() : ""; }
 
+int zg_graph_kernel_class(const zg_graph* g, char* buf, size_t capacity) {
+    if (!g || !buf || capacity == 0) return fail(ZG_ERR_ARG, "NULL argument");
+    std::string s;
+    BiquadMatch bq;
+    FirMatch fir;
+    if (!g->ir_f32.all_f32()) s = "host-only";
+    else if (match_fir(g->ir_f32, fir)) s = "fir:" + std::to_string(fir.taps.size());
+    else if (match_df1_cascade(g->ir_f32, bq)) s = "biquad_df1:" + std::to_string(bq.sections);
+    else s = "generated";
+    if (s.size() + 1 > capacity) return fail(ZG_ERR_ARG, "buffer too small");
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return ZG_OK;
+}
+
 int zg_voice_create(const zg_graph* g, zg_voice** out) {
     if (!g || !out) return fail(ZG_ERR_ARG, "NULL argument");
     auto v = new zg_voice();

@@ -49,4 +49,11 @@ struct BiquadMatch {
     std::vector<int> signal_line;                         // line of signal k (0 = input, k = out of section k)
 };
 bool match_df1_cascade(const Ir& ir, BiquadMatch& m);
+
+// out = ((c0*x + c1*x[-1]) + c2*x[-2]) + ... + c(N-1)*x[-(N-1)]: a dense FIR summed left to right, the
+// association of the C++ parse tree of `c0*_1 + c1*_1[_1] + ...` (BASELINE configs[3])
+struct FirMatch {
+    std::vector<BiquadCoef> taps;    // taps[k] multiplies the input delayed by k samples
+};
+bool match_fir(const Ir& ir, FirMatch& m);
 }  // namespace zg

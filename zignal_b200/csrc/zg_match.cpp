@@ -118,4 +118,46 @@ bool match_df1_cascade(const Ir& ir, BiquadMatch& m) {
     return true;
 }
 
+// match_fir(): a single-input, single-output sum of N >= 2 terms coef * x[-k], k = 0..N-1 in that
+// order, associated to the left.  The kernel (kernels/zg_fir.cuh) adds the products in exactly this
+// order, so EXACT mode stays bit-identical; any other spelling (sparse taps, another order, a
+// bracketed sub-sum) is NOT re-associated to fit -- it falls through to the generated kernel.
+bool match_fir(const Ir& ir, FirMatch& m) {
+    if (ir.n_in != 1 || ir.n_out != 1 || !ir.all_f32() || ir.lines.size() != 1) return false;
+    const IrLine& line = ir.lines[0];
+    if (line.src < 0 || ir.nodes[line.src].op != IrOp::In || ir.nodes[line.src].a != 0) return false;
+    std::vector<std::pair<int, BiquadCoef>> rev;      // (delay, coef), last term first
+    int id = ir.outs[0];
+    auto term = [&](int t, int& delay, BiquadCoef& c) {
+        int other;
+        if (!match_scaled(ir, t, c, other)) return false;
+        const IrNode& o = ir.nodes[other];
+        if (o.op == IrOp::In && o.a == 0) { delay = 0; return true; }
+        if (o.op == IrOp::DRead && o.a == 0) { delay = o.b; return true; }
+        return false;
+    };
+    for (;;) {
+        const IrNode& n = ir.nodes[id];
+        int delay;
+        BiquadCoef c;
+        if (n.op == IrOp::Add && n.dtype == Dtype::F32) {
+            if (!term(n.b, delay, c)) return false;
+            rev.push_back({delay, c});
+            id = n.a;
+            continue;
+        }
+        if (!term(id, delay, c)) return false;
+        rev.push_back({delay, c});
+        break;
+    }
+    const int N = (int)rev.size();
+    if (N < 2 || line.depth != N - 1 || ir.n_state != N - 1) return false;
+    m.taps.resize(N);
+    for (int k = 0; k < N; ++k) {
+        if (rev[N - 1 - k].first != k) return false;
+        m.taps[k] = rev[N - 1 - k].second;
+    }
+    return true;
+}
+
 }  // namespace zg

@@ -22,6 +22,7 @@
 
 #include "kernels/zg_biquad.cuh"
 #include "kernels/zg_biquad_lanes.cuh"
+#include "kernels/zg_fir.cuh"
 #include "zg_internal.hpp"
 
 extern const char* const zg_stream_cuh_source;   // kernels/zg_stream.cuh as text (generated at build time)
@@ -153,6 +154,11 @@ __global__ void __launch_bounds__(512, 1) zg_biquad_lanes_kernel(const __grid_co
     zgk::biquad_lanes_block<S, kExact, kUniform>(a);
 }
 
+template <bool kExact>
+__global__ void __launch_bounds__(512, 1) zg_fir_kernel(const __grid_constant__ zgk::FirArgs a) {
+    zgk::fir_block<kExact>(a);
+}
+
 using KernelPtr = void (*)(zgk::StreamArgs);
 
 KernelPtr biquad_lanes_kernel_for(int sections, bool exact, bool uniform) {
@@ -218,6 +224,13 @@ struct zg_plan {
     int kernel_n_state = 0, kernel_n_param = 0;   // as the kernel sees them
     std::vector<int> state_row;                   // kernel slot -> row of d_state
 
+    bool is_fir = false;                    // K3: dense FIR (kernels/zg_fir.cuh)
+    FirMatch fir;
+    float* d_taps = nullptr;                // [n_taps]
+    float* d_state_alt = nullptr;           // K3 ping-pongs the delay line between two buffers
+    int fir_regs = 0;
+    int last_grid = 0;
+
     Variant variant[2];                     // [uniform]
     std::string kernel_name;
 
@@ -247,6 +260,8 @@ struct zg_plan {
         for (auto& v : variant)
             if (v.module && driver().moduleUnload) driver().moduleUnload(v.module);
         if (d_state) cudaFree(d_state);
+        if (d_state_alt) cudaFree(d_state_alt);
+        if (d_taps) cudaFree(d_taps);
         if (d_params) cudaFree(d_params);
         if (d_stage) cudaFree(d_stage);
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -318,6 +333,13 @@ int get_variant(zg_plan* p, bool uniform, Variant*& out) {
     Variant& v = p->variant[uniform ? 1 : 0];
     out = &v;
     if (v.ready) return ZG_OK;
+    if (p->is_fir) {
+        cudaFuncAttributes fa;
+        ZG_CUDA(cudaFuncGetAttributes(&fa, p->exact ? (const void*)zg_fir_kernel<true> : (const void*)zg_fir_kernel<false>));
+        v.regs = fa.numRegs;
+        v.ready = true;
+        return ZG_OK;
+    }
     if (p->is_biquad && !p->opts.force_jit) {
         v.prebuilt = p->lanes > 1 ? biquad_lanes_kernel_for(p->bq.sections, p->exact, uniform)
                                   : biquad_kernel_for(p->bq.sections, p->exact, p->interleaved, uniform);
@@ -336,6 +358,22 @@ int get_variant(zg_plan* p, bool uniform, Variant*& out) {
 // value of kernel parameter slot j for channel c (c = -1: the scalar)
 int sync_params(zg_plan* p) {
     if (!p->params_dirty) return ZG_OK;
+    if (p->is_fir) {
+        // taps are shared by all channels: literals, or scalar $k parameters
+        std::vector<float> taps(p->fir.taps.size());
+        for (size_t k = 0; k < taps.size(); ++k) {
+            const BiquadCoef& c = p->fir.taps[k];
+            if (c.is_param && p->h_params[c.param].size() != 1)
+                return fail(ZG_ERR_UNSUPPORTED, "the FIR kernel shares its taps between channels: $" +
+                                                    std::to_string(c.param) + " must be a scalar");
+            taps[k] = c.is_param ? p->h_params[c.param][0] : c.value;
+        }
+        if (!p->d_taps) ZG_CUDA(cudaMalloc(&p->d_taps, taps.size() * sizeof(float)));
+        ZG_CUDA(cudaMemcpy(p->d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+        p->uniform_now = true;
+        p->params_dirty = false;
+        return ZG_OK;
+    }
     const int NP = p->kernel_n_param;
     bool uniform = NP <= zgk::kMaxUniform;
     for (auto& h : p->h_params) uniform = uniform && h.size() == 1;
@@ -485,12 +523,16 @@ Geometry choose_geometry_lanes(const zg_plan* p, int64_t n_warps, int regs, int6
 
 // One kernel launch over channels [c_begin, c_begin + c_count) of the plan; in/out point at the first
 // of those channels.  `advance` = this launch ends the block (the stream position moves on by T).
+int launch_fir(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out,
+               cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance);
+
 int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out,
            cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance) {
     Driver& d = driver();
     if (!d.ok) return fail(ZG_ERR_CUDA, d.why);
     int st = sync_params(p);
     if (st != ZG_OK) return st;
+    if (p->is_fir) return launch_fir(p, in, out, T, ld_in, ld_out, stream, c_begin, c_count, advance);
     Variant* v = nullptr;
     st = get_variant(p, p->uniform_now, v);
     if (st != ZG_OK) return st;
@@ -551,6 +593,70 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     p->last_threads = g.wpc * 32;
     p->last_stages = g.stages;
     p->last_boxes = g.boxes;
+    return ZG_OK;
+}
+
+// K3 geometry: W warps per CTA (one 32-sample box each per step), ring of H + 2W input boxes, 2 output
+// boxes per warp; time is cut into segments when there are fewer channel groups than ~2 CTAs per SM.
+int launch_fir(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out,
+               cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance) {
+    const int N = (int)p->fir.taps.size();
+    const int H = (N - 1 + 31) / 32;
+    const int n_taps_pad = (N + 15) / 16 * 16;
+    const int fixed = 1024 /*alignment slack*/ + n_taps_pad * 4 + 64 /*barriers*/ + H * zgk::kTileBytes;
+    int W = (p->max_smem_optin - fixed) / (4 * zgk::kTileBytes);
+    int want = 8;
+    if (int w = tune_env("ZG_TUNE_WPC")) want = w;
+    W = std::min({W, want, 16});
+    if (W < 1) return fail(ZG_ERR_UNSUPPORTED, "FIR has too many taps for the shared-memory ring");
+    const int64_t total_boxes = (T + zgk::kTileT - 1) / zgk::kTileT;
+    W = (int)std::max<int64_t>(1, std::min<int64_t>(W, total_boxes));
+    const int NR = H + 2 * W;
+    const int64_t groups = (c_count + 31) / 32;
+    int64_t n_segs = std::max<int64_t>(1, (2 * (int64_t)p->sm_count + groups - 1) / groups);
+    if (int sg = tune_env("ZG_TUNE_SEGS")) n_segs = sg;
+    const int64_t min_seg = ((std::max(H, 4 * W) + W - 1) / W) * W;          // >= H, whole steps, worth a prologue
+    int64_t seg_boxes = (total_boxes + n_segs - 1) / n_segs;
+    seg_boxes = std::max<int64_t>(min_seg, (seg_boxes + W - 1) / W * W);
+    n_segs = (total_boxes + seg_boxes - 1) / seg_boxes;
+    if (groups * n_segs > 0x7fffffffLL) return fail(ZG_ERR_ARG, "block too large for one launch");
+
+    zgk::FirArgs a;
+    std::memset(&a, 0, sizeof a);
+    int st = encode_map(p, &a.in_map, in[0], c_count, T, ld_in, 32);
+    if (st != ZG_OK) return st;
+    st = encode_map(p, &a.out_map, out[0], c_count, T, ld_out, 32);
+    if (st != ZG_OK) return st;
+    a.state_in = p->d_state + c_begin;
+    a.state_out = p->d_state_alt + c_begin;
+    a.taps = p->d_taps;
+    a.ch_stride = p->ch_stride;
+    a.channels = (int)c_count;
+    a.n_samples = (int)T;
+    a.n_taps = N;
+    a.hist_boxes = H;
+    a.ring_boxes = NR;
+    a.seg_boxes = (int)seg_boxes;
+    a.n_segs = (int)n_segs;
+    const int smem = fixed + (NR - H + 2 * W) * zgk::kTileBytes;
+    const void* fn = p->exact ? (const void*)zg_fir_kernel<true> : (const void*)zg_fir_kernel<false>;
+    Variant& v = p->variant[1];
+    if (smem > v.max_smem_set) {
+        ZG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        v.max_smem_set = smem;
+    }
+    void* args[] = {&a};
+    ZG_CUDA(cudaLaunchKernel(fn, dim3((unsigned)(groups * n_segs)), dim3(W * 32), args, smem, stream));
+    if (advance) {
+        std::swap(p->d_state, p->d_state_alt);      // stream order: the next launch reads what this one wrote
+        p->stream_pos += T;
+    }
+    p->launches += 1;
+    p->last_smem = smem;
+    p->last_threads = W * 32;
+    p->last_stages = NR;
+    p->last_boxes = (int)seg_boxes;
+    p->last_grid = (int)(groups * n_segs);
     return ZG_OK;
 }
 
@@ -631,10 +737,15 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
                     "the device path evaluates fp32 graphs only; this graph has int or double terminals "
                     "(tick it on the host with zg_voice_tick)");
     if (ir.n_out < 1) return fail(ZG_ERR_UNSUPPORTED, "graph has no outputs");
-    if (ir.n_state > zgk::kMaxState)
+    FirMatch fir;
+    bool any_synth = false;
+    for (int k = 0; k < ir.n_in; ++k) any_synth = any_synth || opts->input_kind[k] != ZG_IN_BUFFER;
+    const bool is_fir = !opts->force_jit && !any_synth && opts->layout == ZG_PLANAR && match_fir(ir, fir);
+    if (!is_fir && ir.n_state > zgk::kMaxState)
         return fail(ZG_ERR_UNSUPPORTED, "graph keeps " + std::to_string(ir.n_state) +
                                             " floats of delay state per channel; the register-resident kernels take at most " +
-                                            std::to_string(zgk::kMaxState));
+                                            std::to_string(zgk::kMaxState) +
+                                            " (longer delay lines: only the dense FIR form c0*_1 + c1*_1[_1] + ..., planar layout)");
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -670,7 +781,9 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
         else p->n_buf_in += 1;
     }
 
-    p->is_biquad = match_df1_cascade(ir, p->bq) && p->synth_mask == 0;
+    p->is_fir = is_fir;
+    if (is_fir) p->fir = fir;
+    p->is_biquad = !is_fir && match_df1_cascade(ir, p->bq) && p->synth_mask == 0;
     const int want_lanes = tune_env("ZG_TUNE_LANES") ? tune_env("ZG_TUNE_LANES") : opts->lanes_per_channel;
     if (want_lanes < 0 || (want_lanes > 1 && !(p->is_biquad && !opts->force_jit && !p->interleaved &&
                                                want_lanes == p->bq.sections && (want_lanes == 2 || want_lanes == 4))))
@@ -681,7 +794,11 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
         const bool too_few = (p->C + 31) / 32 < (int64_t)p->sm_count * 4;
         if (want_lanes > 1 || (want_lanes == 0 && too_few)) p->lanes = p->bq.sections;
     }
-    if (p->is_biquad && !opts->force_jit) {
+    if (p->is_fir) {
+        p->kernel_n_state = ir.n_state;
+        p->kernel_n_param = 0;
+        p->kernel_name = "zg_fir<" + std::to_string(fir.taps.size()) + (p->exact ? " taps,exact,planar>" : " taps,fma,planar>");
+    } else if (p->is_biquad && !opts->force_jit) {
         const int S = p->bq.sections;
         p->kernel_n_state = 2 * (S + 1);
         p->kernel_n_param = 5 * S;
@@ -710,6 +827,10 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     const size_t state_floats = (size_t)std::max(ir.n_state, 1) * p->ch_stride;
     ZG_CUDA(cudaMalloc(&p->d_state, state_floats * sizeof(float)));
     ZG_CUDA(cudaMemset(p->d_state, 0, state_floats * sizeof(float)));
+    if (p->is_fir) {
+        ZG_CUDA(cudaMalloc(&p->d_state_alt, state_floats * sizeof(float)));
+        ZG_CUDA(cudaMemset(p->d_state_alt, 0, state_floats * sizeof(float)));
+    }
     p->h_params.assign(ir.n_params, std::vector<float>(1, 0.f));
     p->params_dirty = true;
 
@@ -730,7 +851,7 @@ int zg_plan_get_info(const zg_plan* p, zg_plan_info* info) {
     std::memset(info, 0, sizeof *info);
     std::snprintf(info->kernel, sizeof info->kernel, "%s", p->kernel_name.c_str());
     const Variant& v = p->variant[p->uniform_now ? 1 : 0];
-    info->jit = v.prebuilt ? 0 : 1;
+    info->jit = (v.prebuilt || p->is_fir) ? 0 : 1;
     info->lanes_per_channel = p->lanes;
     info->host_chunks = p->last_host_chunks;
     info->regs_per_thread = v.regs;
