@@ -43,7 +43,7 @@ typedef enum zg_status {
     ZG_ERR_INTERNAL = -6
 } zg_status;
 
-typedef enum zg_dtype { ZG_I32 = 0, ZG_F32 = 1, ZG_F64 = 2 } zg_dtype;
+typedef enum zg_dtype { ZG_I32 = 0, ZG_F32 = 1, ZG_F64 = 2, ZG_BF16 = 3 /* sample storage only */ } zg_dtype;
 
 typedef struct zg_graph zg_graph; /* immutable, shareable between threads        */
 typedef struct zg_voice zg_voice; /* one voice on the host: state_ of stateful_lambda */
@@ -124,7 +124,9 @@ typedef struct zg_plan_opts {
     int64_t channels;     /* C: independent voices evaluated by this plan                       */
     int mode;             /* zg_mode                                                            */
     int layout;           /* zg_layout                                                          */
-    int io_dtype;         /* ZG_F32 (bf16 storage: see DESIGN.md, later round)                  */
+    int io_dtype;         /* sample storage in HBM: ZG_F32, or ZG_BF16 (state, parameters and all
+                             arithmetic stay fp32; outputs are rounded to nearest even; generated
+                             kernel only: no K1b / FIR)                                            */
     int lanes_per_channel;/* 0 = auto; 1 = one lane per channel; S = S lanes per channel, lane k evaluating
                              section k of an S-section biquad cascade as a systolic pipeline (same
                              arithmetic, bit-identical in EXACT mode; planar layout, S = 2 or 4).  Auto
@@ -158,9 +160,9 @@ typedef struct zg_plan_info {
 } zg_plan_info;
 int zg_plan_get_info(const zg_plan* p, zg_plan_info* info);
 
-/* One block of n_samples for all channels.  in[i] / out[j] are DEVICE pointers to fp32 buffers in
- * the plan's layout; ld is the leading dimension in elements (planar: >= n_samples, multiple of 4;
- * interleaved: >= channels, multiple of 4).  Buffers must be 16-byte aligned.  Asynchronous on
+/* One block of n_samples for all channels.  in[i] / out[j] are DEVICE pointers to sample buffers
+ * (io_dtype) in the plan's layout; ld is the leading dimension in elements (planar: >= n_samples,
+ * interleaved: >= channels; a multiple of 16 bytes).  Buffers must be 16-byte aligned.  Asynchronous on
  * `stream` (a cudaStream_t, may be NULL).  Consecutive calls continue the stream exactly like
  * consecutive ticks: state is read at block start and written back at block end.               */
 int zg_process(zg_plan* p, const void* const* in, void* const* out, int64_t n_samples,

@@ -789,3 +789,36 @@ def fir_direct(x: np.ndarray, taps: Sequence[float], history: Optional[np.ndarra
     for k in range(1, n):
         acc = acc + np.float32(taps[k]) * ext[:, n - 1 - k:n - 1 - k + T]
     return acc
+
+
+# ---- bf16 sample storage (BASELINE configs[4]) and the polyphonic voice graph -----------------------
+
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    """fp32 -> nearest-even bf16 -> fp32 (finite inputs): what storing a sample as bf16 does."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    r = (u + np.uint64(0x7FFF) + ((u >> np.uint64(16)) & np.uint64(1))) & np.uint64(0xFFFF0000)
+    return r.astype(np.uint32).view(np.float32).reshape(np.shape(x))
+
+
+def bf16_bits(x: np.ndarray) -> np.ndarray:
+    """the 16 stored bits of bf16_round(x)"""
+    return (bf16_round(x).view(np.uint32) >> np.uint32(16)).astype(np.uint16)
+
+
+def osc_expr(f: float = 440.0, sr: float = 44100.0) -> str:
+    """Recursive sine oscillator y = k*y1 - y2 + x, dirac-excited (flowz has no sin, TODO.md:4;
+    zero-input graphs do not compile, TODO.md:65); k = 2 cos(2 pi f / sr)."""
+    return f"~({lit(2.0 * np.cos(2.0 * np.pi * f / sr))}*_1[_1] - _1[_2] + _2)"
+
+
+def osc_lp_expr(f: float = 440.0, a: float = 0.9) -> str:
+    """BASELINE configs[2]: sine oscillator >> one-pole low-pass."""
+    return f"{osc_expr(f)} |= ~(_2 + {lit(a)}*_1[_1])"
+
+
+def poly_voice_expr(f: float = 440.0, g: float = 0.25) -> str:
+    """BASELINE configs[4]: osc >> biquad >> (biquad inside a unit-delayed feedback
+    loop of gain g):  osc |= (fwd|=bwd) |= ~( (_2 + g*_1[_1]) |= (fwd|=bwd) )."""
+    bq1 = biquad_df1(*rbj_lowpass(1760.0))
+    bq2 = biquad_df1(*rbj_lowpass(3520.0))
+    return f"{osc_expr(f)} |= {bq1} |= ~((_2 + {lit(g)}*_1[_1]) |= {bq2})"

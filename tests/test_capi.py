@@ -69,3 +69,17 @@ def test_exact_mode_source_has_no_contractable_arithmetic(zg):
     tick = src[src.index("struct ZgTick"):]
     assert "__fmul_rn" in tick and "__fadd_rn" in tick
     assert not re.search(r"v\d+ [*+] v\d+", tick)
+
+
+def test_bf16_storage_kernels_compile_for_sm100a(zg):
+    """BASELINE configs[4]: the polyphonic voice chain with bf16 sample storage and a synthesised dirac
+    input; the kernel converts with cvt.rn.bf16x2.f32 (F2FP in SASS) and keeps fp32 arithmetic."""
+    g = zg.compile(fo.poly_voice_expr())
+    for layout in (zg.PLANAR, zg.INTERLEAVED):
+        cubin = g.kernel(cubin=True, io_dtype=zg.BF16, layout=layout, input_kind=[zg.IN_DIRAC])
+        assert cubin[:4] == b"\x7fELF"
+    src = g.kernel(io_dtype=zg.BF16).decode()
+    assert "stream_block<ZgTick, false, true, 2>" in src
+    with pytest.raises(zg.ZgError) as e:
+        g.kernel(io_dtype=zg.I32)
+    assert e.value.status == zg.ZG_ERR_ARG

@@ -487,6 +487,100 @@ def test_full_size_config4_fir256_32768_channels(zg):
     assert _rel_err(yf[idx].cpu().numpy(), y[idx].cpu().numpy()) <= TOL
 
 
+# ---- bf16 sample storage (BASELINE configs[4]) ------------------------------------------------------
+# Bar: compare after rounding the oracle's fp32 output to bf16, <= 1 bf16 ulp.  EXACT mode
+# does better: inputs are bf16-representable, arithmetic and state are fp32 exactly as the oracle's, the
+# store rounds to nearest even -> the stored 16 bits are identical.
+
+def _run_bf16(zg, expr, x, mode, layout="planar", blocks=None, input_kind=None, n_samples=None, channels=None):
+    """x: [n_in][C, T] fp32 (rounded to bf16 on the way in).  Returns [n_out] uint16 arrays [C, T]."""
+    torch = _torch()
+    import zignal_b200
+    g = zg.compile(expr)
+    C, T = (x[0].shape if x and x[0] is not None else (channels, n_samples))
+    plan = g.plan(channels=C, mode=mode, layout=zg.PLANAR if layout == "planar" else zg.INTERLEAVED,
+                  io_dtype=zg.BF16, input_kind=input_kind)
+    assert b"bf16" in plan.info().kernel
+    outs = [[] for _ in range(g.n_out)]
+    t0 = 0
+    for n in (blocks or [T]):
+        ins = []
+        for k in range(g.n_in):
+            if input_kind and input_kind[k] != zg.IN_BUFFER:
+                ins.append(None)
+                continue
+            xb = x[k][:, t0:t0 + n]
+            ins.append(zignal_b200.to_block(xb.T if layout == "interleaved" else xb, dtype=torch.bfloat16))
+        ys = plan.process(ins, n_samples=n)
+        torch.cuda.synchronize()
+        for o, y in zip(outs, ys):
+            y = y.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+            o.append(y.T if layout == "interleaved" else y)
+        t0 += n
+    return [np.concatenate(o, axis=1) for o in outs], plan
+
+
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+@pytest.mark.parametrize("C,T", [(64, 1024), (33, 100), (1, 7), (40, 4100)])
+def test_bf16_storage_exact_mode_stores_identical_bits(zg, layout, C, T):
+    expr = fo.biquad_cascade(2)
+    x = fo.noise(C, T, seed=C * 7 + T)
+    ys, _ = _run_bf16(zg, expr, [x], zg.MODE_EXACT, layout)
+    ref = _oracle(expr, [fo.bf16_round(x)])[0]
+    assert np.array_equal(ys[0], fo.bf16_bits(ref))
+
+
+@pytest.mark.parametrize("expr", ["(_1 | _1[_1]) |= ~(_2 + _3 + 0.25f*_1[_2])",          # two inputs
+                                  "_1 |= (_1[_1] , 0.5f*_1[_2] , _1)"])                    # three outputs
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+def test_bf16_storage_streaming_and_multi_wire(zg, expr, layout):
+    g = zg.compile(expr)
+    x = [fo.noise(48, 900, seed=21 + k) for k in range(g.n_in)]
+    ys, _ = _run_bf16(zg, expr, x, zg.MODE_EXACT, layout, blocks=[64, 1, 100, 735])
+    ref = _oracle(expr, [fo.bf16_round(v) for v in x])
+    assert len(ys) == g.n_out
+    for y, r in zip(ys, ref):
+        assert np.array_equal(y, fo.bf16_bits(r))
+
+
+def test_bf16_polyphonic_voice_chain(zg):
+    """BASELINE configs[4]'s graph: osc >> biquad >> (biquad in a feedback loop), dirac-excited (input
+    synthesised in the kernel: no HBM read), bf16 output.  FAST mode within 1 bf16 ulp."""
+    expr = fo.poly_voice_expr()
+    C, T = 256, 2048
+    d = np.zeros((C, T), np.float32); d[:, 0] = 1
+    ref = _oracle(expr, [d])[0]
+    ys, plan = _run_bf16(zg, expr, [None], zg.MODE_EXACT, input_kind=[zg.IN_DIRAC], n_samples=T, channels=C,
+                         blocks=[1000, 1048])
+    assert np.array_equal(ys[0], fo.bf16_bits(ref))
+    yf, _ = _run_bf16(zg, expr, [None], zg.MODE_FAST, input_kind=[zg.IN_DIRAC], n_samples=T, channels=C)
+    got = (yf[0].astype(np.uint32) << 16).view(np.float32)
+    ulp = np.maximum(np.abs(fo.bf16_round(ref)), 2.0 ** -126) * 2.0 ** -7          # >= 1 bf16 ulp of the value
+    # the oscillator is marginally stable (DESIGN.md 5): FMA rounding drifts, so the bar is block-relative
+    assert np.abs(got - ref).max() <= np.abs(ref).max() * 2.0 ** -7, np.abs(got - ref).max()
+    assert np.all(np.abs(got - fo.bf16_round(ref)) <= ulp)
+
+
+def test_bf16_process_host(zg):
+    torch = _torch()
+    expr = fo.biquad_cascade(4)
+    C, T = 512, 1000
+    x = fo.noise(C, T, seed=31)
+    xh = torch.from_numpy(x).to(torch.bfloat16)
+    y = zg.compile(expr).plan(channels=C, io_dtype=zg.BF16).process_host([xh])[0]
+    ref = _oracle(expr, [fo.bf16_round(x)])[0]
+    assert np.array_equal(y.view(torch.int16).numpy().view(np.uint16), fo.bf16_bits(ref))
+
+
+def test_bf16_unsupported_kernels_say_so(zg):
+    with pytest.raises(zg.ZgError) as e:
+        zg.compile(fo.biquad_cascade(4)).plan(channels=64, io_dtype=zg.BF16, lanes_per_channel=4)
+    assert e.value.status == zg.ZG_ERR_UNSUPPORTED
+    with pytest.raises(zg.ZgError) as e:
+        zg.compile(fo.fir_expr(fo.fir_taps(256))).plan(channels=64, io_dtype=zg.BF16)
+    assert e.value.status == zg.ZG_ERR_UNSUPPORTED
+
+
 # ---- size-independent properties at BASELINE sizes ---------------------------------------------------
 
 def test_full_size_properties_65536_channels(zg):

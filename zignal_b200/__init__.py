@@ -26,6 +26,7 @@ MODE_EXACT, MODE_FAST = 0, 1
 PLANAR, INTERLEAVED = 0, 1
 IN_BUFFER, IN_DIRAC, IN_ZERO = 0, 1, 2
 MAX_WIRES = 8
+I32, F32, F64, BF16 = 0, 1, 2, 3            # zg_dtype (BF16: sample storage only)
 
 
 class ZgError(RuntimeError):
@@ -150,7 +151,7 @@ class Graph:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:                 # (module globals are gone at interpreter shutdown)
             lib.zg_graph_destroy(h)
 
     @property
@@ -199,7 +200,7 @@ class Voice:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:
             lib.zg_voice_destroy(h)
 
     def clone(self) -> "Voice":
@@ -234,30 +235,34 @@ class Voice:
 
 
 def _opts(channels: int, device: int = 0, mode: int = MODE_EXACT, layout: int = PLANAR,
-          input_kind: Optional[Sequence[int]] = None, lanes_per_channel: int = 0, force_jit: bool = False) -> PlanOpts:
+          input_kind: Optional[Sequence[int]] = None, lanes_per_channel: int = 0, force_jit: bool = False,
+          io_dtype: int = 1) -> PlanOpts:
     o = PlanOpts()
     lib.zg_plan_opts_default(C.byref(o))
-    o.device, o.channels, o.mode, o.layout = device, channels, mode, layout
+    o.device, o.channels, o.mode, o.layout, o.io_dtype = device, channels, mode, layout, io_dtype
     o.lanes_per_channel, o.force_jit = lanes_per_channel, int(force_jit)
     for i, k in enumerate(input_kind or []):
         o.input_kind[i] = k
     return o
 
 
-def empty_block(rows: int, cols: int, device=None):
-    """float32 CUDA buffer [rows, cols] whose row pitch is a multiple of 4 floats (16 bytes), as the
-    TMA tensor maps behind zg_process require; a view into a padded allocation when cols % 4 != 0."""
+def empty_block(rows: int, cols: int, device=None, dtype=None):
+    """CUDA sample buffer [rows, cols] (float32, or bfloat16) whose row pitch is a multiple of 16 bytes,
+    as the TMA tensor maps behind zg_process require; a view into a padded allocation otherwise."""
     import torch
-    ld = (cols + 3) // 4 * 4
-    return torch.empty((rows, ld), dtype=torch.float32, device=device or "cuda")[:, :cols]
+    dtype = dtype or torch.float32
+    m = 16 // torch.empty((), dtype=dtype).element_size()
+    ld = (cols + m - 1) // m * m
+    return torch.empty((rows, ld), dtype=dtype, device=device or "cuda")[:, :cols]
 
 
-def to_block(array, device=None):
-    """Host [rows, cols] float32 data -> device buffer with a legal pitch (see empty_block)."""
+def to_block(array, device=None, dtype=None):
+    """Host [rows, cols] float32 data -> device buffer with a legal pitch (see empty_block); with
+    dtype=torch.bfloat16 the samples are rounded to nearest even on the way."""
     import numpy as np
     import torch
     a = torch.from_numpy(np.ascontiguousarray(array, np.float32))
-    out = empty_block(a.shape[0], a.shape[1], device)
+    out = empty_block(a.shape[0], a.shape[1], device, dtype)
     out.copy_(a)
     return out
 
@@ -278,7 +283,7 @@ class Plan:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:
             lib.zg_plan_destroy(h)
 
     @property
@@ -311,12 +316,13 @@ class Plan:
             n_samples = ref.shape[0] if self.interleaved else ref.shape[1]
         shape = (n_samples, self.channels) if self.interleaved else (self.channels, n_samples)
         dev = torch.device("cuda", self.opts.device)
+        dt = torch.bfloat16 if self.opts.io_dtype == BF16 else torch.float32
         if outputs is None:
-            outputs = [empty_block(shape[0], shape[1], dev) for _ in range(self.graph.n_out)]
+            outputs = [empty_block(shape[0], shape[1], dev, dt) for _ in range(self.graph.n_out)]
         for t in [t for t in ins if t is not None] + list(outputs):
-            if t.dtype != torch.float32 or not t.is_cuda or t.stride(1) != 1 or tuple(t.shape) != shape:
-                raise TypeError(f"buffers must be float32 CUDA tensors of shape {shape} with unit inner stride")
-        ld_in = ref.stride(0) if ref is not None else (shape[1] + 3) // 4 * 4
+            if t.dtype != dt or not t.is_cuda or t.stride(1) != 1 or tuple(t.shape) != shape:
+                raise TypeError(f"buffers must be {dt} CUDA tensors of shape {shape} with unit inner stride")
+        ld_in = ref.stride(0) if ref is not None else (shape[1] + 7) // 8 * 8
         in_ptrs = [t.data_ptr() if t is not None else None for t in ins]
         out_ptrs = [t.data_ptr() for t in outputs]
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -326,12 +332,19 @@ class Plan:
     def process_host(self, inputs, outputs=None, n_samples: Optional[int] = None):
         """Same with host arrays (numpy float32 or CPU torch tensors): H2D, kernel, D2H, synchronise."""
         import numpy as np
+        bf16 = self.opts.io_dtype == BF16                       # bf16 blocks: CPU torch.bfloat16 tensors
         ins = [None if x is None else (x if hasattr(x, "data_ptr") else np.ascontiguousarray(x, np.float32)) for x in inputs]
         ref = next((t for t in ins if t is not None), None)
         if n_samples is None:
             n_samples = ref.shape[0] if self.interleaved else ref.shape[1]
         shape = (n_samples, self.channels) if self.interleaved else (self.channels, n_samples)
-        if outputs is None:
+        if bf16:
+            import torch
+            if any(t is not None and not (hasattr(t, "data_ptr") and t.dtype == torch.bfloat16) for t in ins):
+                raise TypeError("a bf16 plan takes torch.bfloat16 host tensors")
+            if outputs is None:
+                outputs = [torch.empty(shape, dtype=torch.bfloat16) for _ in range(self.graph.n_out)]
+        elif outputs is None:
             outputs = [np.empty(shape, np.float32) for _ in range(self.graph.n_out)]
 
         def ptr(a):

@@ -20,6 +20,9 @@
 //     __syncthreads anywhere; S stages = 1 computing, 1 draining its store, S-2 loads in flight.
 //   * grid = one warp per 32 channels; the host sizes CTAs so that all warps are resident at once and
 //     spread evenly over the 148 SMs.
+//   * sample storage in HBM is fp32 or bf16 (kIo = bytes per sample); state, parameters and all
+//     arithmetic are fp32 either way.  A planar box row is always 128 bytes (32 fp32 / 64 bf16 samples),
+//     a 16-byte chunk is 4 / 8 ticks; bf16 outputs are rounded to nearest even (cvt.rn.bf16x2.f32).
 #pragma once
 
 namespace zgk {
@@ -27,8 +30,12 @@ namespace zgk {
 struct alignas(64) TensorMap { unsigned long long opaque[16]; };   // CUtensorMap, 128 bytes
 
 constexpr int kMaxWires = 8;
-constexpr int kTileT = 32;          // samples per tile row (128 bytes of fp32)
+constexpr int kTileT = 32;          // samples per fp32 box row (128 bytes)
 constexpr int kTileBytes = 4096;    // 32 rows x 128 bytes
+// box geometry for a sample size of `io` bytes: planar boxes are 32 channel rows of 128 bytes,
+// interleaved boxes are 32 frames of 32 channels
+__host__ __device__ constexpr int box_samples(bool interleaved, int io) { return interleaved ? 32 : 128 / io; }
+__host__ __device__ constexpr int box_bytes(bool interleaved, int io) { return interleaved ? 1024 * io : 4096; }
 constexpr int kMaxState = 64;       // state floats per channel a register-resident tick may keep
 constexpr int kMaxUniform = 64;     // uniform parameters passed by value
 
@@ -106,6 +113,45 @@ __device__ __forceinline__ void prefetch_tmap(const TensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// ---- sample storage <-> fp32 ---------------------------------------------------------------------
+template <int kIo> struct Io;
+template <> struct Io<4> {
+    static constexpr int kPerChunk = 4;                       // samples per 16-byte chunk
+    typedef float Elem;
+    static __device__ __forceinline__ void unpack(const uint4& v, float (&f)[4]) {
+        f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&f)[4]) {
+        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    }
+    static __device__ __forceinline__ float load(const void* p) { return *reinterpret_cast<const float*>(p); }
+    static __device__ __forceinline__ void store(void* p, float v) { *reinterpret_cast<float*>(p) = v; }
+};
+template <> struct Io<2> {                                    // bf16: the upper 16 bits of an fp32
+    static constexpr int kPerChunk = 8;
+    typedef unsigned short Elem;
+    static __device__ __forceinline__ unsigned pack2(float lo, float hi) {
+        unsigned r;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+        return r;
+    }
+    static __device__ __forceinline__ void unpack(const uint4& v, float (&f)[8]) {
+        f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+        f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+        f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+        f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {
+        return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    }
+    static __device__ __forceinline__ float load(const void* p) {
+        return __uint_as_float((unsigned)*reinterpret_cast<const unsigned short*>(p) << 16);
+    }
+    static __device__ __forceinline__ void store(void* p, float v) {
+        *reinterpret_cast<unsigned short*>(p) = (unsigned short)(pack2(v, 0.f) & 0xffffu);
+    }
+};
+
 template <int N>
 struct Arr {                       // zero-length-safe register array
     float v[N > 0 ? N : 1];
@@ -128,8 +174,12 @@ __host__ __device__ constexpr int popcount_u32(unsigned v) { return v == 0 ? 0 :
 //   template <class P>                            // P = Arr<N_PARAM> or UniformParams
 //   static __device__ void tick(const Arr<N_IN>& x, Arr<N_OUT>& y, Arr<N_STATE>& s, const P& p);
 
-template <class Tick, bool kInterleaved, bool kUniform>
+template <class Tick, bool kInterleaved, bool kUniform, int kIo = 4>
 __device__ __forceinline__ void stream_block(const StreamArgs& a) {
+    typedef Io<kIo> IO;
+    constexpr int VPC = IO::kPerChunk;                         // ticks per 16-byte chunk
+    constexpr int BT = box_samples(kInterleaved, kIo);        // samples per box
+    constexpr int BB = box_bytes(kInterleaved, kIo);          // bytes per box
     constexpr int NI = Tick::N_IN, NO = Tick::N_OUT, NS = Tick::N_STATE, NP = Tick::N_PARAM;
     constexpr int NT = (NI > NO ? NI : NO) > 0 ? (NI > NO ? NI : NO) : 1;   // wires per stage
     constexpr unsigned kAllIn = NI > 0 ? ((1u << NI) - 1u) : 0u;
@@ -143,7 +193,7 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     const int warps_per_cta = blockDim.x >> 5;
     const int S = a.stages;
     const int NB = a.boxes;
-    const int tile_t = NB * kTileT;
+    const int tile_t = NB * BT;
     const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
     const long long c0ll = gw * 32;
     if (c0ll >= a.channels) return;                    // warp-uniform
@@ -154,7 +204,7 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     // SWIZZLE_128B works on 1024-byte atoms of the shared address: align the tile area explicitly
     // (the host reserves the slack) instead of trusting the placement of dynamic shared memory
     unsigned char* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-    const unsigned wire_bytes = (unsigned)NB * kTileBytes;          // one wire of one stage
+    const unsigned wire_bytes = (unsigned)NB * BB;                  // one wire of one stage
     const unsigned stage_bytes = (unsigned)NT * wire_bytes;
     unsigned char* my = tiles + (size_t)warp * S * stage_bytes;
     unsigned long long* bars =
@@ -193,7 +243,7 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     const int n_tiles = (a.n_samples + tile_t - 1) / tile_t;
 
     auto boxes_in_tile = [&](int t0) {                 // boxes of tile at t0 that hold samples
-        const int left = (a.n_samples - t0 + kTileT - 1) / kTileT;
+        const int left = (a.n_samples - t0 + BT - 1) / BT;
         return left < NB ? left : NB;
     };
     auto issue_load = [&](int i) {                     // lane 0 only
@@ -201,14 +251,14 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
         const int slot = i % S;
         const int t0 = i * tile_t;
         const int nb = boxes_in_tile(t0);
-        mbar_expect_tx(&bars[slot], (unsigned)(nb * kNumBuf * kTileBytes));
+        mbar_expect_tx(&bars[slot], (unsigned)(nb * kNumBuf * BB));
 #pragma unroll
         for (int k = 0; k < NI; ++k) {
             if (!(kBufMask & (1u << k))) continue;
             unsigned char* dst = my + (size_t)slot * stage_bytes + (size_t)k * wire_bytes;
             for (int b = 0; b < nb; ++b) {
-                if (kInterleaved) tma_load_2d(dst + b * kTileBytes, &a.in_map[k], c0, t0 + b * kTileT, &bars[slot]);
-                else tma_load_2d(dst + b * kTileBytes, &a.in_map[k], t0 + b * kTileT, c0, &bars[slot]);
+                if (kInterleaved) tma_load_2d(dst + b * BB, &a.in_map[k], c0, t0 + b * BT, &bars[slot]);
+                else tma_load_2d(dst + b * BB, &a.in_map[k], t0 + b * BT, c0, &bars[slot]);
             }
         }
     };
@@ -229,9 +279,9 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
         if (ch_ok) {
 #pragma unroll 1
             for (int b = 0; b < nb; ++b) {
-                const int tb0 = t0 + b * kTileT;
-                const int n_valid = a.n_samples - tb0 < kTileT ? a.n_samples - tb0 : kTileT;
-                unsigned char* base = stage + b * kTileBytes;      // wire k of this box: base + k * wire_bytes
+                const int tb0 = t0 + b * BT;
+                const int n_valid = a.n_samples - tb0 < BT ? a.n_samples - tb0 : BT;
+                unsigned char* base = stage + b * BB;              // wire k of this box: base + k * wire_bytes
                 // absolute stream index of the first sample of the box (dirac synthesis)
                 const long long t_abs0 = a.stream_pos + tb0;
 
@@ -239,89 +289,81 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                     // row `lane`, 16-byte chunk j lives at chunk (j ^ (lane & 7)) of the row (SWIZZLE_128B)
                     const unsigned row = (unsigned)lane * 128u;
                     const unsigned sw = (unsigned)(lane & 7);
-                    if (n_valid == kTileT) {
+                    if (n_valid == BT) {
                         // the chunk of step j+1 is loaded before the ticks of step j: the LDS latency
                         // overlaps arithmetic instead of stalling the warp (3-4 warps per scheduler)
-                        float4 xn[NI > 0 ? NI : 1];
+                        uint4 xn[NI > 0 ? NI : 1];
 #pragma unroll
                         for (int k = 0; k < NI; ++k)
                             if (kBufMask & (1u << k))
-                                xn[k] = *reinterpret_cast<const float4*>(base + k * wire_bytes + row + (sw << 4));
+                                xn[k] = *reinterpret_cast<const uint4*>(base + k * wire_bytes + row + (sw << 4));
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const unsigned off = row + (((unsigned)j ^ sw) << 4);
-                            float4 xv[NI > 0 ? NI : 1];
-                            float4 yv[NO > 0 ? NO : 1];
+                            float xv[NI > 0 ? NI : 1][VPC];
+                            float yv[NO > 0 ? NO : 1][VPC];
 #pragma unroll
                             for (int k = 0; k < NI; ++k) {
                                 if (kBufMask & (1u << k)) {
-                                    xv[k] = xn[k];
+                                    IO::unpack(xn[k], xv[k]);
                                     if (j < 7)
-                                        xn[k] = *reinterpret_cast<const float4*>(base + k * wire_bytes + row +
-                                                                                 (((unsigned)(j + 1) ^ sw) << 4));
+                                        xn[k] = *reinterpret_cast<const uint4*>(base + k * wire_bytes + row +
+                                                                                (((unsigned)(j + 1) ^ sw) << 4));
                                 } else {
                                     const bool dirac = (a.dirac_mask >> k) & 1u;
-                                    const long long tt = t_abs0 + 4 * j;
-                                    xv[k].x = (dirac && tt == 0) ? 1.f : 0.f;
-                                    xv[k].y = (dirac && tt + 1 == 0) ? 1.f : 0.f;
-                                    xv[k].z = (dirac && tt + 2 == 0) ? 1.f : 0.f;
-                                    xv[k].w = (dirac && tt + 3 == 0) ? 1.f : 0.f;
+                                    const long long tt = t_abs0 + VPC * j;
+#pragma unroll
+                                    for (int q = 0; q < VPC; ++q) xv[k][q] = (dirac && tt + q == 0) ? 1.f : 0.f;
                                 }
                             }
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
+                            for (int q = 0; q < VPC; ++q) {
                                 Arr<NI> x;
                                 Arr<NO> y;
 #pragma unroll
-                                for (int k = 0; k < NI; ++k)
-                                    x[k] = q == 0 ? xv[k].x : q == 1 ? xv[k].y : q == 2 ? xv[k].z : xv[k].w;
+                                for (int k = 0; k < NI; ++k) x[k] = xv[k][q];
                                 run_tick(x, y);
 #pragma unroll
-                                for (int o = 0; o < NO; ++o) {
-                                    if (q == 0) yv[o].x = y[o];
-                                    else if (q == 1) yv[o].y = y[o];
-                                    else if (q == 2) yv[o].z = y[o];
-                                    else yv[o].w = y[o];
-                                }
+                                for (int o = 0; o < NO; ++o) yv[o][q] = y[o];
                             }
 #pragma unroll
                             for (int o = 0; o < NO; ++o)
-                                *reinterpret_cast<float4*>(base + o * wire_bytes + off) = yv[o];
+                                *reinterpret_cast<uint4*>(base + o * wire_bytes + off) = IO::pack(yv[o]);
                         }
                     } else {
                         // last, partial box of the block: TMA zero-filled the tail on load and clips it
                         // on store; only the state has to be protected
                         for (int t = 0; t < n_valid; ++t) {
-                            const unsigned off = row + ((((unsigned)t >> 2) ^ sw) << 4) + ((unsigned)t & 3u) * 4u;
+                            const unsigned off = row + ((((unsigned)t / VPC) ^ sw) << 4) + ((unsigned)t % VPC) * kIo;
                             Arr<NI> x;
                             Arr<NO> y;
 #pragma unroll
                             for (int k = 0; k < NI; ++k) {
-                                if (kBufMask & (1u << k)) x[k] = *reinterpret_cast<const float*>(base + k * wire_bytes + off);
+                                if (kBufMask & (1u << k)) x[k] = IO::load(base + k * wire_bytes + off);
                                 else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
                             }
                             run_tick(x, y);
 #pragma unroll
-                            for (int o = 0; o < NO; ++o) *reinterpret_cast<float*>(base + o * wire_bytes + off) = y[o];
+                            for (int o = 0; o < NO; ++o) IO::store(base + o * wire_bytes + off, y[o]);
                         }
                     }
                 } else {
                     // interleaved frames: box is [32 samples][32 channels], lane = channel column
-                    float* box = reinterpret_cast<float*>(base);
-                    const unsigned wire_f = wire_bytes / 4;
-                    if (n_valid == kTileT) {
+                    typename IO::Elem* box = reinterpret_cast<typename IO::Elem*>(base);
+                    const unsigned wire_f = wire_bytes / kIo;
+                    if (n_valid == BT) {
 #pragma unroll 8
-                        for (int t = 0; t < kTileT; ++t) {
+                        for (int t = 0; t < BT; ++t) {
                             Arr<NI> x;
                             Arr<NO> y;
 #pragma unroll
                             for (int k = 0; k < NI; ++k) {
-                                if (kBufMask & (1u << k)) x[k] = box[k * wire_f + t * 32 + lane];
+                                if (kBufMask & (1u << k)) x[k] = IO::load(&box[k * wire_f + t * 32 + lane]);
                                 else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
                             }
                             run_tick(x, y);
 #pragma unroll
-                            for (int o = 0; o < NO; ++o) box[o * wire_f + t * 32 + lane] = y[o];
+                            for (int o = 0; o < NO; ++o) IO::store(&box[o * wire_f + t * 32 + lane], y[o]);
                         }
                     } else {
                         for (int t = 0; t < n_valid; ++t) {
@@ -329,12 +371,12 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                             Arr<NO> y;
 #pragma unroll
                             for (int k = 0; k < NI; ++k) {
-                                if (kBufMask & (1u << k)) x[k] = box[k * wire_f + t * 32 + lane];
+                                if (kBufMask & (1u << k)) x[k] = IO::load(&box[k * wire_f + t * 32 + lane]);
                                 else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
                             }
                             run_tick(x, y);
 #pragma unroll
-                            for (int o = 0; o < NO; ++o) box[o * wire_f + t * 32 + lane] = y[o];
+                            for (int o = 0; o < NO; ++o) IO::store(&box[o * wire_f + t * 32 + lane], y[o]);
                         }
                     }
                 }
@@ -347,9 +389,9 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
 #pragma unroll
             for (int o = 0; o < NO; ++o) {
                 for (int b = 0; b < nb; ++b) {
-                    const unsigned char* src = stage + (size_t)o * wire_bytes + b * kTileBytes;
-                    if (kInterleaved) tma_store_2d(&a.out_map[o], c0, t0 + b * kTileT, src);
-                    else tma_store_2d(&a.out_map[o], t0 + b * kTileT, c0, src);
+                    const unsigned char* src = stage + (size_t)o * wire_bytes + b * BB;
+                    if (kInterleaved) tma_store_2d(&a.out_map[o], c0, t0 + b * BT, src);
+                    else tma_store_2d(&a.out_map[o], t0 + b * BT, c0, src);
                 }
             }
             tma_commit();

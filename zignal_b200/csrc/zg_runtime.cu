@@ -215,6 +215,7 @@ struct zg_plan {
     zg_plan_opts opts{};
     int64_t C = 0, ch_stride = 0;
     bool exact = false, interleaved = false;
+    int io = 4;                             // bytes per sample in HBM: 4 = fp32, 2 = bf16
     unsigned synth_mask = 0, dirac_mask = 0;
     int n_buf_in = 0;
 
@@ -248,8 +249,8 @@ struct zg_plan {
     int max_smem_optin = 227 * 1024;
 
     // staging for zg_process_host
-    float* d_stage = nullptr;
-    size_t d_stage_floats = 0;
+    unsigned char* d_stage = nullptr;
+    size_t d_stage_bytes = 0;
     cudaStream_t own_stream = nullptr;      // kernels of zg_process_host
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> events;        // [2 * chunk]: input landed, kernel done
@@ -275,7 +276,7 @@ namespace {
 
 // ---- NVRTC specialisation (K2) -----------------------------------------------------------------
 
-std::string jit_source(const Ir& ir, bool exact, bool interleaved, bool uniform, unsigned synth_mask) {
+std::string jit_source(const Ir& ir, bool exact, bool interleaved, bool uniform, unsigned synth_mask, int io) {
     std::ostringstream src;
     src << "#define ZG_SYNTH_MASK " << synth_mask << "u\n";
     src << zg_stream_cuh_source << "\n";
@@ -283,7 +284,7 @@ std::string jit_source(const Ir& ir, bool exact, bool interleaved, bool uniform,
     src << "extern \"C\" __global__ void __launch_bounds__(512, 1) zg_graph_kernel("
            "const __grid_constant__ zgk::StreamArgs a) {\n"
            "    zgk::stream_block<ZgTick, "
-        << (interleaved ? "true" : "false") << ", " << (uniform ? "true" : "false") << ">(a);\n}\n";
+        << (interleaved ? "true" : "false") << ", " << (uniform ? "true" : "false") << ", " << io << ">(a);\n}\n";
     return src.str();
 }
 
@@ -318,7 +319,7 @@ int jit_compile(zg_plan* p, bool uniform, Variant& v) {
     Driver& d = driver();
     if (!d.ok) return fail(ZG_ERR_CUDA, d.why);
     std::vector<char> cubin;
-    int st = jit_cubin(jit_source(p->ir, p->exact, p->interleaved, uniform, p->synth_mask), p->exact, cubin);
+    int st = jit_cubin(jit_source(p->ir, p->exact, p->interleaved, uniform, p->synth_mask, p->io), p->exact, cubin);
     if (st != ZG_OK) return st;
     CUresult cr = d.moduleLoadData(&v.module, cubin.data());
     if (cr != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuModuleLoadData: " + cu_err(cr));
@@ -420,10 +421,12 @@ int encode_map(zg_plan* p, zgk::TensorMap* out, const void* base, int64_t C, int
     // planar  [C][ld]: dim0 = sample (contiguous), dim1 = channel; rows of a box are swizzled (128B)
     // interleaved [T][ld] frames: dim0 = channel (contiguous), dim1 = sample
     cuuint64_t dims[2] = {(cuuint64_t)(p->interleaved ? C : T), (cuuint64_t)(p->interleaved ? T : C)};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * p->io};
+    // planar rows are 128 bytes of samples (32 fp32 / 64 bf16); interleaved rows are 32 channels
+    cuuint32_t box[2] = {(cuuint32_t)(p->interleaved ? 32 : 128 / p->io), (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = d.tensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides,
+    CUresult r = d.tensorMapEncodeTiled(tm, p->io == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                                        const_cast<void*>(base), dims, strides,
                                         box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                         p->interleaved ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -466,6 +469,7 @@ int tune_env(const char* name) {
 
 Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, int64_t T) {
     Geometry g{};
+    const int BT = zgk::box_samples(p->interleaved, p->io), BB = zgk::box_bytes(p->interleaved, p->io);
     const int64_t per_sm = (n_warps + p->sm_count - 1) / p->sm_count;
     const int reg_warps = std::max(1, 65536 / (32 * std::max(regs, 32)));   // warps/SM the register file allows
     int wpc = (int)std::min<int64_t>({per_sm, 16, (int64_t)reg_warps});
@@ -476,8 +480,8 @@ Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, in
     // leaves 3 stages, else 1
     int NB = 2;
     if (int b = tune_env("ZG_TUNE_BOXES")) NB = std::min(std::max(b, 1), 8);
-    NB = (int)std::min<int64_t>(NB, std::max<int64_t>(1, (T + zgk::kTileT - 1) / zgk::kTileT));
-    auto stages_for = [&](int w, int nb) { return budget / (w * NT * nb * zgk::kTileBytes); };
+    NB = (int)std::min<int64_t>(NB, std::max<int64_t>(1, (T + BT - 1) / BT));
+    auto stages_for = [&](int w, int nb) { return budget / (w * NT * nb * BB); };
     while (NB > 1 && stages_for(wpc, NB) < 2) --NB;
     int S = stages_for(wpc, NB);
     while (S < 2 && wpc > 1) {            // too many wires for that many warps: fewer warps per CTA
@@ -491,7 +495,7 @@ Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, in
     g.stages = S;
     g.boxes = NB;
     g.grid = (int)((n_warps + wpc - 1) / wpc);
-    g.smem = wpc * S * NT * NB * zgk::kTileBytes + 1024 + wpc * S * 8;
+    g.smem = wpc * S * NT * NB * BB + 1024 + wpc * S * 8;
     return g;
 }
 
@@ -664,8 +668,9 @@ int check_io(const zg_plan* p, const void* const* in, void* const* out, int64_t 
     if (T < 0) return fail(ZG_ERR_ARG, "n_samples < 0");
     if (T > 0x7fffffffLL) return fail(ZG_ERR_ARG, "n_samples too large for one block");
     const int64_t min_ld = p->interleaved ? p->C : T;
-    if (p->n_buf_in > 0 && (ld_in < min_ld || ld_in % 4)) return fail(ZG_ERR_ARG, "ld_in too small or not a multiple of 4");
-    if (ld_out < min_ld || ld_out % 4) return fail(ZG_ERR_ARG, "ld_out too small or not a multiple of 4");
+    const int ldm = 16 / p->io;                  // rows must start 16-byte aligned (TMA global strides)
+    if (p->n_buf_in > 0 && (ld_in < min_ld || ld_in % ldm)) return fail(ZG_ERR_ARG, "ld_in too small or not a multiple of 16 bytes");
+    if (ld_out < min_ld || ld_out % ldm) return fail(ZG_ERR_ARG, "ld_out too small or not a multiple of 16 bytes");
     if (p->n_buf_in > 0 && !in) return fail(ZG_ERR_ARG, "in is NULL");
     if (!out) return fail(ZG_ERR_ARG, "out is NULL");
     for (int k = 0; k < p->ir.n_in; ++k) {
@@ -695,7 +700,9 @@ int zg_graph_kernel_compile(const zg_graph* g, const zg_plan_opts* opts, int uni
     for (int k = 0; k < ir.n_in; ++k)
         if (opts->input_kind[k] != ZG_IN_BUFFER) synth |= 1u << k;
     const bool exact = opts->mode == ZG_MODE_EXACT;
-    std::string text = jit_source(ir, exact, opts->layout == ZG_INTERLEAVED, uniform_params != 0, synth);
+    if (opts->io_dtype != ZG_F32 && opts->io_dtype != ZG_BF16) return fail(ZG_ERR_ARG, "io_dtype must be ZG_F32 or ZG_BF16");
+    std::string text = jit_source(ir, exact, opts->layout == ZG_INTERLEAVED, uniform_params != 0, synth,
+                                  opts->io_dtype == ZG_BF16 ? 2 : 4);
     std::vector<char> cubin;
     const char* data = text.data();
     size_t n = text.size();
@@ -728,7 +735,8 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     if (!g || !opts || !out) return fail(ZG_ERR_ARG, "NULL argument");
     *out = nullptr;
     if (opts->channels < 1 || opts->channels > 0x7fffffe0LL) return fail(ZG_ERR_ARG, "channels out of range");
-    if (opts->io_dtype != ZG_F32) return fail(ZG_ERR_UNSUPPORTED, "only fp32 sample buffers are supported");
+    if (opts->io_dtype != ZG_F32 && opts->io_dtype != ZG_BF16) return fail(ZG_ERR_ARG, "io_dtype must be ZG_F32 or ZG_BF16");
+    const bool bf16 = opts->io_dtype == ZG_BF16;
     if (opts->mode != ZG_MODE_EXACT && opts->mode != ZG_MODE_FAST) return fail(ZG_ERR_ARG, "bad mode");
     if (opts->layout != ZG_PLANAR && opts->layout != ZG_INTERLEAVED) return fail(ZG_ERR_ARG, "bad layout");
     const Ir& ir = g->ir_f32;
@@ -740,7 +748,7 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     FirMatch fir;
     bool any_synth = false;
     for (int k = 0; k < ir.n_in; ++k) any_synth = any_synth || opts->input_kind[k] != ZG_IN_BUFFER;
-    const bool is_fir = !opts->force_jit && !any_synth && opts->layout == ZG_PLANAR && match_fir(ir, fir);
+    const bool is_fir = !opts->force_jit && !any_synth && opts->layout == ZG_PLANAR && !bf16 && match_fir(ir, fir);
     if (!is_fir && ir.n_state > zgk::kMaxState)
         return fail(ZG_ERR_UNSUPPORTED, "graph keeps " + std::to_string(ir.n_state) +
                                             " floats of delay state per channel; the register-resident kernels take at most " +
@@ -771,6 +779,7 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     p->ch_stride = (p->C + 31) / 32 * 32;
     p->exact = opts->mode == ZG_MODE_EXACT;
     p->interleaved = opts->layout == ZG_INTERLEAVED;
+    p->io = bf16 ? 2 : 4;
     p->sm_count = prop.multiProcessorCount;
     p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     for (int k = 0; k < ir.n_in; ++k) {
@@ -783,7 +792,9 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
 
     p->is_fir = is_fir;
     if (is_fir) p->fir = fir;
-    p->is_biquad = !is_fir && match_df1_cascade(ir, p->bq) && p->synth_mask == 0;
+    // bf16 storage runs the generated kernel (the prebuilt ones are instantiated for fp32 storage only;
+    // the generated tick of a biquad cascade is the same arithmetic, tests/test_gpu_parity.py)
+    p->is_biquad = !is_fir && !bf16 && match_df1_cascade(ir, p->bq) && p->synth_mask == 0;
     const int want_lanes = tune_env("ZG_TUNE_LANES") ? tune_env("ZG_TUNE_LANES") : opts->lanes_per_channel;
     if (want_lanes < 0 || (want_lanes > 1 && !(p->is_biquad && !opts->force_jit && !p->interleaved &&
                                                want_lanes == p->bq.sections && (want_lanes == 2 || want_lanes == 4))))
@@ -821,7 +832,7 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
         p->state_row.resize(ir.n_state);
         for (int j = 0; j < ir.n_state; ++j) p->state_row[j] = j;
         p->kernel_name = std::string("zg_graph_kernel<jit,") + (p->exact ? "exact," : "fma,") +
-                         (p->interleaved ? "interleaved>" : "planar>");
+                         (p->interleaved ? "interleaved" : "planar") + (bf16 ? ",bf16>" : ">");
     }
 
     const size_t state_floats = (size_t)std::max(ir.n_state, 1) * p->ch_stride;
@@ -886,19 +897,21 @@ int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t
     // device staging: same shape as the host buffers, rows padded to a multiple of 4 floats
     const int64_t rows = p->interleaved ? n_samples : p->C;
     const int64_t cols = p->interleaved ? p->C : n_samples;
-    const int64_t ld = (cols + 3) / 4 * 4;
+    const int es = p->io;                                   // bytes per sample
+    const int ldm = 16 / es;
+    const int64_t ld = (cols + ldm - 1) / ldm * ldm;
     if ((p->n_buf_in > 0 && ld_in < cols) || ld_out < cols) return fail(ZG_ERR_ARG, "leading dimension too small");
-    const size_t per_buf = (size_t)rows * ld;
+    const size_t per_buf = (size_t)rows * ld * es;          // bytes
     const size_t need = per_buf * (p->n_buf_in + p->ir.n_out);
-    if (need > p->d_stage_floats) {
+    if (need > p->d_stage_bytes) {
         if (p->d_stage) cudaFree(p->d_stage);
         p->d_stage = nullptr;
-        p->d_stage_floats = 0;
-        ZG_CUDA(cudaMalloc(&p->d_stage, need * sizeof(float)));
-        p->d_stage_floats = need;
+        p->d_stage_bytes = 0;
+        ZG_CUDA(cudaMalloc(&p->d_stage, need));
+        p->d_stage_bytes = need;
     }
-    float* d_in[ZG_MAX_WIRES] = {};
-    float* d_out[ZG_MAX_WIRES] = {};
+    unsigned char* d_in[ZG_MAX_WIRES] = {};
+    unsigned char* d_out[ZG_MAX_WIRES] = {};
     size_t slot = 0;
     for (int k = 0; k < p->ir.n_in; ++k) {
         if (p->synth_mask & (1u << k)) continue;
@@ -920,7 +933,7 @@ int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t
     // The block is cut into row chunks (planar: channel ranges, independent; interleaved: time ranges,
     // launched in order, state carried in HBM) and streamed: H2D of chunk k+1, the kernel of chunk k
     // and D2H of chunk k-1 overlap on three streams, so a PCIe-bound call costs one direction, not two.
-    const int64_t row_bytes = cols * 4 * std::max(1, std::max(p->n_buf_in, p->ir.n_out));
+    const int64_t row_bytes = cols * es * std::max(1, std::max(p->n_buf_in, p->ir.n_out));
     int64_t n_chunks = std::min<int64_t>(16, (rows * row_bytes) / (32ll << 20));
     if (int c = tune_env("ZG_TUNE_HOST_CHUNKS")) n_chunks = c;
     n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, rows / 32));
@@ -936,16 +949,16 @@ int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t
         const int64_t r0 = c * chunk_rows, nr = std::min(chunk_rows, rows - r0);
         for (int k = 0; k < p->ir.n_in; ++k) {
             if (!d_in[k]) continue;
-            ZG_CUDA(cudaMemcpy2DAsync(d_in[k] + r0 * ld, ld * 4, (const float*)in[k] + r0 * ld_in, ld_in * 4, cols * 4, nr,
-                                      cudaMemcpyHostToDevice, p->h2d_stream));
+            ZG_CUDA(cudaMemcpy2DAsync(d_in[k] + r0 * ld * es, ld * es, (const unsigned char*)in[k] + r0 * ld_in * es,
+                                      ld_in * es, cols * es, nr, cudaMemcpyHostToDevice, p->h2d_stream));
         }
         ZG_CUDA(cudaEventRecord(p->events[2 * c], p->h2d_stream));
         ZG_CUDA(cudaStreamWaitEvent(p->own_stream, p->events[2 * c], 0));
         const void* ci[ZG_MAX_WIRES] = {};
         void* co[ZG_MAX_WIRES] = {};
         for (int k = 0; k < ZG_MAX_WIRES; ++k) {
-            ci[k] = d_in[k] ? d_in[k] + r0 * ld : nullptr;
-            co[k] = d_out[k] ? d_out[k] + r0 * ld : nullptr;
+            ci[k] = d_in[k] ? d_in[k] + r0 * ld * es : nullptr;
+            co[k] = d_out[k] ? d_out[k] + r0 * ld * es : nullptr;
         }
         int st = p->interleaved ? launch(p, ci, co, nr, ld, ld, p->own_stream, 0, p->C, true)
                                 : launch(p, ci, co, n_samples, ld, ld, p->own_stream, r0, nr, c + 1 == n_chunks);
@@ -956,8 +969,8 @@ int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t
         ZG_CUDA(cudaEventRecord(p->events[2 * c + 1], p->own_stream));
         ZG_CUDA(cudaStreamWaitEvent(p->d2h_stream, p->events[2 * c + 1], 0));
         for (int o = 0; o < p->ir.n_out; ++o)
-            ZG_CUDA(cudaMemcpy2DAsync((float*)out[o] + r0 * ld_out, ld_out * 4, d_out[o] + r0 * ld, ld * 4, cols * 4, nr,
-                                      cudaMemcpyDeviceToHost, p->d2h_stream));
+            ZG_CUDA(cudaMemcpy2DAsync((unsigned char*)out[o] + r0 * ld_out * es, ld_out * es, d_out[o] + r0 * ld * es, ld * es,
+                                      cols * es, nr, cudaMemcpyDeviceToHost, p->d2h_stream));
     }
     p->last_host_chunks = (int)n_chunks;
     ZG_CUDA(cudaStreamSynchronize(p->d2h_stream));
