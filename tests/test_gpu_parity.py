@@ -555,10 +555,12 @@ def test_bf16_polyphonic_voice_chain(zg):
     assert np.array_equal(ys[0], fo.bf16_bits(ref))
     yf, _ = _run_bf16(zg, expr, [None], zg.MODE_FAST, input_kind=[zg.IN_DIRAC], n_samples=T, channels=C)
     got = (yf[0].astype(np.uint32) << 16).view(np.float32)
-    ulp = np.maximum(np.abs(fo.bf16_round(ref)), 2.0 ** -126) * 2.0 ** -7          # >= 1 bf16 ulp of the value
-    # the oscillator is marginally stable: FMA rounding drifts, so the bar is block-relative
-    assert np.abs(got - ref).max() <= np.abs(ref).max() * 2.0 ** -7, np.abs(got - ref).max()
-    assert np.all(np.abs(got - fo.bf16_round(ref)) <= ulp)
+    # FAST rounds differently, and the oscillator is marginally stable: its error is relative
+    # to the block's amplitude, not to each sample (near a zero crossing one ulp of the sample is tiny).
+    # Bar: within one bf16 ulp of the block's largest value, and most stored samples identical.
+    ulp_max = 2.0 ** (np.floor(np.log2(np.abs(ref).max())) - 7)
+    assert np.abs(got - fo.bf16_round(ref)).max() <= ulp_max
+    assert np.mean(yf[0] == fo.bf16_bits(ref)) > 0.9
 
 
 def test_bf16_process_host(zg):

@@ -68,17 +68,19 @@ struct Df1Lane {
     }
 };
 
-constexpr int kLanesXbufBytes = 512;         // exchange buffer per warp: 32 lanes x 16 bytes
+constexpr int kLanesXbufBytes = 1024;        // exchange buffer per warp: 2 chunks x 32 lanes x 16 bytes
 
 // in_map[0] / out_map[0]: 2-D {T, C}, box {32, 32/S}        (ragged last tile, box by box)
 // in_map[1] / out_map[1]: 3-D {32, C, T/32} over the full 32-sample boxes, box {32, 32/S, NB}
-template <int S, bool kExact, bool kUniform>
+template <int S, bool kExact, bool kUniform, int CH = 1>
 __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
+    static_assert(CH == 1 || CH == 2, "16-byte chunks (of four samples) per iteration");
     static_assert(S == 2 || S == 4, "lanes per channel: 2 or 4 (the box must span whole swizzle atoms)");
     constexpr int CPW = 32 / S;              // channels per warp
     constexpr int kBoxBytes = CPW * 128;
     constexpr int LAG = 2;                   // iterations between neighbouring sections
-    constexpr int DRAIN = LAG * (S - 1);     // iterations until the last section has caught up (< 8)
+    constexpr int DRAIN = LAG * (S - 1);     // iterations until the last section has caught up
+    constexpr int IPB = 8 / CH;              // iterations per 32-sample box
 
     extern __shared__ __align__(1024) unsigned char smem[];
 
@@ -104,6 +106,8 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
     unsigned char* xbuf = tiles + (size_t)warps_per_cta * St * stage_bytes + (size_t)warp * kLanesXbufBytes;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(
                                    tiles + (size_t)warps_per_cta * (St * stage_bytes + kLanesXbufBytes)) + warp * St;
+    // exchange buffer: CH arrays of 32 x 16 bytes (array u = chunk u of the iteration), so that the 32
+    // lanes of one STS.128 / LDS.128 touch 512 contiguous bytes
     unsigned char* const x_in = xbuf + (lane > 0 ? lane - 1 : 0) * 16;   // what the lane below stored
     unsigned char* const x_out = xbuf + lane * 16;
 
@@ -131,7 +135,8 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
             prefetch_tmap(&a.out_map[1]);
         }
     }
-    *reinterpret_cast<float4*>(x_out) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < CH; ++u) *reinterpret_cast<float4*>(x_out + u * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 
     const int n_tiles = (a.n_samples + tile_t - 1) / tile_t;
@@ -187,74 +192,93 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
 
         mbar_wait(&bars[slot], (unsigned)((i / St) & 1));
 
-        // `nxt` = the four inputs of the NEXT iteration, loaded one iteration ahead
-        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (first) nxt = *reinterpret_cast<const float4*>(chunk_ptr(0));
+        // `nxt` = the 4*CH inputs of the NEXT iteration, loaded one iteration ahead
+        float4 nxt[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            nxt[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (first) nxt[u] = *reinterpret_cast<const float4*>(chunk_ptr(u));
+        }
 
         auto slow_iter = [&](int g) {                  // predicated: lanes may be outside the tile
-            const float4 cur = nxt;
-            __syncwarp();
-            if (!first) nxt = *reinterpret_cast<const float4*>(x_in);
-            else if (g + 1 < NB * 8) nxt = *reinterpret_cast<const float4*>(chunk_ptr(g + 1));
-            const int c = g - LAG * sec;
-            float o[4];
+            float4 cur[CH];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int m = 4 * c + q;
-                const bool act = ch_ok && m >= 0 && m < nt;
-                const float in = q == 0 ? cur.x : q == 1 ? cur.y : q == 2 ? cur.z : cur.w;
-                o[q] = f.eval(in);
-                if (act) f.push(in, o[q]);
-                if (last && act) reinterpret_cast<float*>(chunk_ptr(c))[q] = o[q];
+            for (int u = 0; u < CH; ++u) cur[u] = nxt[u];
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                if (!first) nxt[u] = *reinterpret_cast<const float4*>(x_in + u * 512);
+                else if (CH * (g + 1) + u < NB * 8) nxt[u] = *reinterpret_cast<const float4*>(chunk_ptr(CH * (g + 1) + u));
             }
-            if (!last) *reinterpret_cast<float4*>(x_out) = make_float4(o[0], o[1], o[2], o[3]);
+            const int c = g - LAG * sec;               // this lane's position, in iterations
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                float o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int m = 4 * (CH * c + u) + q;
+                    const bool act = ch_ok && m >= 0 && m < nt;
+                    const float in = q == 0 ? cur[u].x : q == 1 ? cur[u].y : q == 2 ? cur[u].z : cur[u].w;
+                    o[q] = f.eval(in);
+                    if (act) f.push(in, o[q]);
+                    if (last && act) reinterpret_cast<float*>(chunk_ptr(CH * c + u))[q] = o[q];
+                }
+                if (!last) *reinterpret_cast<float4*>(x_out + u * 512) = make_float4(o[0], o[1], o[2], o[3]);
+            }
         };
-        // steady state, iteration 8*box + j: chunk j of `box` in (for the next iteration: chunk j+1),
-        // chunk j - DRAIN (possibly of the box before) out
+        // steady state, iteration IPB*box + j: chunks CH*j .. CH*j+CH-1 of `box` in (loaded one iteration
+        // ahead: those of iteration j+1), the chunks of iteration j - DRAIN (one or two boxes back) out
         auto fast_iter = [&](unsigned char* box, auto jc, bool more) {
             constexpr int j = decltype(jc)::value;
-            constexpr int jo = (j - DRAIN + 8) & 7;
-            constexpr int back = (j - DRAIN) < 0 ? kBoxBytes : 0;
-            const float4 cur = nxt;
-            __syncwarp();
-            const unsigned char* src = x_in;
-            if (first) src = j < 7 ? box + off[(j + 1) & 7] : (more ? box + kBoxBytes + off[0] : x_in);
-            nxt = *reinterpret_cast<const float4*>(src);
-            float o[4];
+            constexpr int back = (DRAIN - j + IPB - 1) / IPB;                 // boxes back (>= 0)
+            constexpr int jo = (j - DRAIN + 8 * IPB) % IPB;
+            float4 cur[CH];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float in = q == 0 ? cur.x : q == 1 ? cur.y : q == 2 ? cur.z : cur.w;
-                o[q] = f.eval(in);
-                f.push(in, o[q]);
+            for (int u = 0; u < CH; ++u) cur[u] = nxt[u];
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                const unsigned char* src = x_in + u * 512;
+                if (first) src = j < IPB - 1 ? box + off[(CH * (j + 1) + u) & 7] : (more ? box + kBoxBytes + off[u] : x_in + u * 512);
+                nxt[u] = *reinterpret_cast<const float4*>(src);
             }
-            unsigned char* dst = last ? box - back + off[jo] : x_out;
-            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                float o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float in = q == 0 ? cur[u].x : q == 1 ? cur[u].y : q == 2 ? cur[u].z : cur[u].w;
+                    o[q] = f.eval(in);
+                    f.push(in, o[q]);
+                }
+                unsigned char* dst = last ? box - back * kBoxBytes + off[CH * jo + u] : x_out + u * 512;
+                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        };
+        // fast iterations g in [g0, g1) of the tile with compile-time position inside the box
+        auto fast_span = [&](int b, auto j0c, bool more_after_box) {
+            constexpr int j0 = decltype(j0c)::value;
+            unsigned char* box = stage + (unsigned)b * kBoxBytes;
+            if constexpr (j0 <= 0) fast_iter(box, std::integral_constant<int, 0>{}, true);
+            if constexpr (j0 <= 1 && IPB > 1) fast_iter(box, std::integral_constant<int, 1 % IPB>{}, IPB > 2 || more_after_box);
+            if constexpr (j0 <= 2 && IPB > 2) fast_iter(box, std::integral_constant<int, 2 % IPB>{}, true);
+            if constexpr (j0 <= 3 && IPB > 3) fast_iter(box, std::integral_constant<int, 3 % IPB>{}, IPB > 4 || more_after_box);
+            if constexpr (j0 <= 4 && IPB > 4) fast_iter(box, std::integral_constant<int, 4 % IPB>{}, true);
+            if constexpr (j0 <= 5 && IPB > 5) fast_iter(box, std::integral_constant<int, 5 % IPB>{}, true);
+            if constexpr (j0 <= 6 && IPB > 6) fast_iter(box, std::integral_constant<int, 6 % IPB>{}, true);
+            if constexpr (j0 <= 7 && IPB > 7) fast_iter(box, std::integral_constant<int, 7 % IPB>{}, more_after_box);
         };
 
         const int nfull = nt >> 5;                     // boxes of this tile without a ragged tail
-        const int total = (nt + 3) / 4 + DRAIN;        // iterations until the last lane has drained
-        if (nfull >= 1) {
+        const int total = (nt + 4 * CH - 1) / (4 * CH) + DRAIN;   // iterations until the last lane has drained
+        constexpr int HB = (DRAIN + IPB - 1) / IPB;    // boxes the pipeline needs to fill
+        if (nfull >= HB) {
             for (int g = 0; g < DRAIN; ++g) slow_iter(g);
-            // rest of box 0: every lane is inside the tile from iteration DRAIN on
-            if constexpr (DRAIN <= 2) fast_iter(stage, std::integral_constant<int, 2>{}, true);
-            if constexpr (DRAIN <= 2) fast_iter(stage, std::integral_constant<int, 3>{}, true);
-            if constexpr (DRAIN <= 2) fast_iter(stage, std::integral_constant<int, 4>{}, true);
-            if constexpr (DRAIN <= 2) fast_iter(stage, std::integral_constant<int, 5>{}, true);
-            fast_iter(stage, std::integral_constant<int, 6>{}, true);
-            fast_iter(stage, std::integral_constant<int, 7>{}, nt > 32);
+            // rest of box HB-1: every lane is inside the tile from iteration DRAIN on
+            fast_span(HB - 1, std::integral_constant<int, DRAIN % IPB == 0 ? IPB : DRAIN % IPB>{}, nt > 32 * HB);
 #pragma unroll 1
-            for (int b = 1; b < nfull; ++b) {
-                unsigned char* box = stage + (unsigned)b * kBoxBytes;
-                fast_iter(box, std::integral_constant<int, 0>{}, true);
-                fast_iter(box, std::integral_constant<int, 1>{}, true);
-                fast_iter(box, std::integral_constant<int, 2>{}, true);
-                fast_iter(box, std::integral_constant<int, 3>{}, true);
-                fast_iter(box, std::integral_constant<int, 4>{}, true);
-                fast_iter(box, std::integral_constant<int, 5>{}, true);
-                fast_iter(box, std::integral_constant<int, 6>{}, true);
-                fast_iter(box, std::integral_constant<int, 7>{}, nt > 32 * (b + 1));
-            }
-            for (int g = nfull * 8; g < total; ++g) slow_iter(g);
+            for (int b = HB; b < nfull; ++b) fast_span(b, std::integral_constant<int, 0>{}, nt > 32 * (b + 1));
+            for (int g = nfull * IPB; g < total; ++g) slow_iter(g);
         } else {
             for (int g = 0; g < total; ++g) slow_iter(g);
         }

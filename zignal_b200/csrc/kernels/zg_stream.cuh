@@ -97,6 +97,25 @@ __device__ __forceinline__ void tma_store_2d(const TensorMap* map, int x, int y,
                  "r"(x), "r"(y), "r"(smem_u32(src))
                  : "memory");
 }
+// same with an L2 eviction-priority hint (createpolicy): samples are streamed once, they need not stay in L2
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const TensorMap* map, int x, int y,
+                                                 unsigned long long* bar, unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const TensorMap* map, int x, int y, const void* src,
+                                                  unsigned long long policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(map),
+                 "r"(x), "r"(y), "r"(smem_u32(src)), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_wait_read() {
@@ -241,6 +260,9 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     __syncwarp();
 
     const int n_tiles = (a.n_samples + tile_t - 1) / tile_t;
+    // flags bit 2 / bit 3: L2 evict-first hint on the sample loads / stores
+    const bool hint_loads = (a.flags & 4) != 0, hint_stores = (a.flags & 8) != 0;
+    const unsigned long long policy = (a.flags & 12) ? l2_policy_evict_first() : 0ull;
 
     auto boxes_in_tile = [&](int t0) {                 // boxes of tile at t0 that hold samples
         const int left = (a.n_samples - t0 + BT - 1) / BT;
@@ -257,8 +279,9 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
             if (!(kBufMask & (1u << k))) continue;
             unsigned char* dst = my + (size_t)slot * stage_bytes + (size_t)k * wire_bytes;
             for (int b = 0; b < nb; ++b) {
-                if (kInterleaved) tma_load_2d(dst + b * BB, &a.in_map[k], c0, t0 + b * BT, &bars[slot]);
-                else tma_load_2d(dst + b * BB, &a.in_map[k], t0 + b * BT, c0, &bars[slot]);
+                const int cx = kInterleaved ? c0 : t0 + b * BT, cy = kInterleaved ? t0 + b * BT : c0;
+                if (hint_loads) tma_load_2d_hint(dst + b * BB, &a.in_map[k], cx, cy, &bars[slot], policy);
+                else tma_load_2d(dst + b * BB, &a.in_map[k], cx, cy, &bars[slot]);
             }
         }
     };
@@ -267,6 +290,11 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
         const int pre = n_tiles < S - 1 ? n_tiles : S - 1;
         for (int i = 0; i < pre; ++i) issue_load(i);
     }
+    // The slot that tile i-1 used is refilled (tile i+S-1) as soon as the first box of tile i is done:
+    // by then the store of tile i-1 has long read its shared memory, and the load has the rest of the
+    // tile's arithmetic to land -- a warp never waits a full HBM round trip at a tile boundary.
+    // (flags bit 1: refill only after the store of tile i has been issued, the first version.)
+    const bool early_refill = (a.flags & 2) == 0;
 
     for (int i = 0; i < n_tiles; ++i) {
         const int slot = i % S;
@@ -282,6 +310,10 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                 const int tb0 = t0 + b * BT;
                 const int n_valid = a.n_samples - tb0 < BT ? a.n_samples - tb0 : BT;
                 unsigned char* base = stage + b * BB;              // wire k of this box: base + k * wire_bytes
+                if (early_refill && lane == 0 && b == 1 && i + S - 1 < n_tiles) {
+                    tma_wait_read<0>();                            // the store of tile i-1 (the only one pending)
+                    issue_load(i + S - 1);
+                }
                 // absolute stream index of the first sample of the box (dirac synthesis)
                 const long long t_abs0 = a.stream_pos + tb0;
 
@@ -390,15 +422,16 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
             for (int o = 0; o < NO; ++o) {
                 for (int b = 0; b < nb; ++b) {
                     const unsigned char* src = stage + (size_t)o * wire_bytes + b * BB;
-                    if (kInterleaved) tma_store_2d(&a.out_map[o], c0, t0 + b * BT, src);
-                    else tma_store_2d(&a.out_map[o], t0 + b * BT, c0, src);
+                    const int cx = kInterleaved ? c0 : t0 + b * BT, cy = kInterleaved ? t0 + b * BT : c0;
+                    if (hint_stores) tma_store_2d_hint(&a.out_map[o], cx, cy, src, policy);
+                    else tma_store_2d(&a.out_map[o], cx, cy, src);
                 }
             }
             tma_commit();
             // refill the slot that tile i-1 used: its store (committed one iteration ago) must have
             // finished reading smem
             const int nxt = i + S - 1;
-            if (nxt < n_tiles) {
+            if (nxt < n_tiles && !(early_refill && nb > 1)) {
                 tma_wait_read<1>();
                 issue_load(nxt);
             }

@@ -216,6 +216,7 @@ struct zg_plan {
     int64_t C = 0, ch_stride = 0;
     bool exact = false, interleaved = false;
     int io = 4;                             // bytes per sample in HBM: 4 = fp32, 2 = bf16
+    int tick_ops = 0;                       // floating-point instructions per tick (estimate; refill policy)
     unsigned synth_mask = 0, dirac_mask = 0;
     int n_buf_in = 0;
 
@@ -425,11 +426,15 @@ int encode_map(zg_plan* p, zgk::TensorMap* out, const void* base, int64_t C, int
     // planar rows are 128 bytes of samples (32 fp32 / 64 bf16); interleaved rows are 32 channels
     cuuint32_t box[2] = {(cuuint32_t)(p->interleaved ? 32 : 128 / p->io), (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (int t = tune_env("ZG_TUNE_L2PROMO"))
+        promo = t == 1 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : t == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+              : t == 4 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     CUresult r = d.tensorMapEncodeTiled(tm, p->io == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                                         const_cast<void*>(base), dims, strides,
                                         box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                         p->interleaved ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
-                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                        promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuTensorMapEncodeTiled: " + cu_err(r));
     return ZG_OK;
 }
@@ -573,6 +578,14 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
                         encode_map_tile3d(&a.out_map[1], out[0], c_count, T, ld_out, cpw, g.boxes);
         a.flags = ok ? 1 : 0;
     }
+    // K4 refill policy (measured, profiles/r01_sweep_refill.jsonl): a tick with a lot of arithmetic per sample
+    // is bound by instruction issue and gains from refilling a slot in the middle of the next tile (the load
+    // latency hides behind arithmetic); a light tick is bound by HBM and does better when a warp's load and
+    // store requests leave together.  ZG_TUNE_LATE_REFILL=1 / =2 force late / early.
+    bool late = p->tick_ops < 28;
+    if (int t = tune_env("ZG_TUNE_LATE_REFILL")) late = t == 1;
+    if (late) a.flags |= 2;
+    if (int h = tune_env("ZG_TUNE_L2HINT")) a.flags |= (h & 3) << 2;       // 1 = loads, 2 = stores, 3 = both: evict-first
 
     if (g.smem > v->max_smem_set) {
         if (v->prebuilt) {
@@ -835,6 +848,15 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
                          (p->interleaved ? "interleaved" : "planar") + (bf16 ? ",bf16>" : ">");
     }
 
+    {
+        int arith = 0, mul = 0;
+        for (const IrNode& n : ir.nodes) {
+            if (n.op == IrOp::Add || n.op == IrOp::Sub || n.op == IrOp::Mul || n.op == IrOp::Div || n.op == IrOp::Neg) ++arith;
+            if (n.op == IrOp::Mul) ++mul;
+        }
+        // FAST: a product feeding a sum contracts into one FMA (at most one product per sum)
+        p->tick_ops = p->exact ? arith : arith - std::min(mul, arith - mul);
+    }
     const size_t state_floats = (size_t)std::max(ir.n_state, 1) * p->ch_stride;
     ZG_CUDA(cudaMalloc(&p->d_state, state_floats * sizeof(float)));
     ZG_CUDA(cudaMemset(p->d_state, 0, state_floats * sizeof(float)));
