@@ -66,6 +66,16 @@ struct Df1Lane {
     __device__ __forceinline__ void push(float in, float y) {
         x2 = x1; x1 = in; y2 = y1; y1 = y;
     }
+    // push only where `act`; written with selp so that the fill / drain iterations stay branch-free
+    // (as `if (act) push(..)` they compiled to one divergent branch per sample: 5x the steady state)
+    static __device__ __forceinline__ float sel(bool p, float a, float b) {
+        float r;
+        asm("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\nselp.f32 %0, %1, %2, q;\n}" : "=f"(r) : "f"(a), "f"(b), "r"((unsigned)p));
+        return r;
+    }
+    __device__ __forceinline__ void push_if(bool act, float in, float y) {
+        x2 = sel(act, x1, x2); x1 = sel(act, in, x1); y2 = sel(act, y1, y2); y1 = sel(act, y, y1);
+    }
 };
 
 constexpr int kLanesXbufBytes = 1024;        // exchange buffer per warp: 2 chunks x 32 lanes x 16 bytes
@@ -206,9 +216,10 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
             for (int u = 0; u < CH; ++u) cur[u] = nxt[u];
             __syncwarp();
 #pragma unroll
-            for (int u = 0; u < CH; ++u) {
-                if (!first) nxt[u] = *reinterpret_cast<const float4*>(x_in + u * 512);
-                else if (CH * (g + 1) + u < NB * 8) nxt[u] = *reinterpret_cast<const float4*>(chunk_ptr(CH * (g + 1) + u));
+            for (int u = 0; u < CH; ++u) {                       // one LDS per lane, no divergence
+                const unsigned char* src = x_in + u * 512;
+                if (first && CH * (g + 1) + u < NB * 8) src = chunk_ptr(CH * (g + 1) + u);
+                nxt[u] = *reinterpret_cast<const float4*>(src);
             }
             const int c = g - LAG * sec;               // this lane's position, in iterations
 #pragma unroll
@@ -220,28 +231,52 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
                     const bool act = ch_ok && m >= 0 && m < nt;
                     const float in = q == 0 ? cur[u].x : q == 1 ? cur[u].y : q == 2 ? cur[u].z : cur[u].w;
                     o[q] = f.eval(in);
-                    if (act) f.push(in, o[q]);
+                    f.push_if(act, in, o[q]);
                     if (last && act) reinterpret_cast<float*>(chunk_ptr(CH * c + u))[q] = o[q];
                 }
-                if (!last) *reinterpret_cast<float4*>(x_out + u * 512) = make_float4(o[0], o[1], o[2], o[3]);
+                // (the slot of a channel's last lane is read by nobody: the lane above is a first lane)
+                *reinterpret_cast<float4*>(x_out + u * 512) = make_float4(o[0], o[1], o[2], o[3]);
             }
         };
         // steady state, iteration IPB*box + j: chunks CH*j .. CH*j+CH-1 of `box` in (loaded one iteration
-        // ahead: those of iteration j+1), the chunks of iteration j - DRAIN (one or two boxes back) out
-        auto fast_iter = [&](unsigned char* box, auto jc, bool more) {
+        // ahead: those of iteration j+1), the chunks of iteration j - DRAIN (one or two boxes back) out.
+        // Every lane keeps the shared-memory address of each of its IPB loads and stores of a box in
+        // registers: first / last lanes of a channel point into the tile (and move on by one box per box),
+        // the others at their exchange slots (and stay) -- the steady state has no address selection left
+        // and the LDS can issue right after the warp has synchronised.
+        unsigned char* sptr[IPB][CH];
+        unsigned char* dptr[IPB][CH];
+        auto set_ptrs = [&](int b) {
+            unsigned char* box = stage + (unsigned)b * kBoxBytes;
+#pragma unroll
+            for (int j = 0; j < IPB; ++j) {
+                const int back = (DRAIN - j + IPB - 1) / IPB;                 // boxes back (>= 0)
+                const int jo = (j - DRAIN + 8 * IPB) % IPB;
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    // (the last iteration of a box prefetches from the next box; past the tile's last box
+                    // that is some other shared memory of this CTA: read, never used)
+                    sptr[j][u] = first ? (j < IPB - 1 ? box + off[(CH * (j + 1) + u) & 7] : box + kBoxBytes + off[u])
+                                       : x_in + u * 512;
+                    dptr[j][u] = last ? box - back * kBoxBytes + off[CH * jo + u] : x_out + u * 512;
+                }
+            }
+        };
+        const unsigned sinc = first ? (unsigned)kBoxBytes : 0u, dinc = last ? (unsigned)kBoxBytes : 0u;
+        auto next_box = [&]() {
+#pragma unroll
+            for (int j = 0; j < IPB; ++j)
+#pragma unroll
+                for (int u = 0; u < CH; ++u) { sptr[j][u] += sinc; dptr[j][u] += dinc; }
+        };
+        auto fast_iter = [&](auto jc) {
             constexpr int j = decltype(jc)::value;
-            constexpr int back = (DRAIN - j + IPB - 1) / IPB;                 // boxes back (>= 0)
-            constexpr int jo = (j - DRAIN + 8 * IPB) % IPB;
             float4 cur[CH];
 #pragma unroll
             for (int u = 0; u < CH; ++u) cur[u] = nxt[u];
             __syncwarp();
 #pragma unroll
-            for (int u = 0; u < CH; ++u) {
-                const unsigned char* src = x_in + u * 512;
-                if (first) src = j < IPB - 1 ? box + off[(CH * (j + 1) + u) & 7] : (more ? box + kBoxBytes + off[u] : x_in + u * 512);
-                nxt[u] = *reinterpret_cast<const float4*>(src);
-            }
+            for (int u = 0; u < CH; ++u) nxt[u] = *reinterpret_cast<const float4*>(sptr[j][u]);
 #pragma unroll
             for (int u = 0; u < CH; ++u) {
                 float o[4];
@@ -251,22 +286,20 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
                     o[q] = f.eval(in);
                     f.push(in, o[q]);
                 }
-                unsigned char* dst = last ? box - back * kBoxBytes + off[CH * jo + u] : x_out + u * 512;
-                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(dptr[j][u]) = make_float4(o[0], o[1], o[2], o[3]);
             }
         };
-        // fast iterations g in [g0, g1) of the tile with compile-time position inside the box
-        auto fast_span = [&](int b, auto j0c, bool more_after_box) {
+        // iterations j0 .. IPB-1 of the current box (compile-time position inside the box)
+        auto fast_span = [&](auto j0c) {
             constexpr int j0 = decltype(j0c)::value;
-            unsigned char* box = stage + (unsigned)b * kBoxBytes;
-            if constexpr (j0 <= 0) fast_iter(box, std::integral_constant<int, 0>{}, true);
-            if constexpr (j0 <= 1 && IPB > 1) fast_iter(box, std::integral_constant<int, 1 % IPB>{}, IPB > 2 || more_after_box);
-            if constexpr (j0 <= 2 && IPB > 2) fast_iter(box, std::integral_constant<int, 2 % IPB>{}, true);
-            if constexpr (j0 <= 3 && IPB > 3) fast_iter(box, std::integral_constant<int, 3 % IPB>{}, IPB > 4 || more_after_box);
-            if constexpr (j0 <= 4 && IPB > 4) fast_iter(box, std::integral_constant<int, 4 % IPB>{}, true);
-            if constexpr (j0 <= 5 && IPB > 5) fast_iter(box, std::integral_constant<int, 5 % IPB>{}, true);
-            if constexpr (j0 <= 6 && IPB > 6) fast_iter(box, std::integral_constant<int, 6 % IPB>{}, true);
-            if constexpr (j0 <= 7 && IPB > 7) fast_iter(box, std::integral_constant<int, 7 % IPB>{}, more_after_box);
+            if constexpr (j0 <= 0) fast_iter(std::integral_constant<int, 0>{});
+            if constexpr (j0 <= 1 && IPB > 1) fast_iter(std::integral_constant<int, 1 % IPB>{});
+            if constexpr (j0 <= 2 && IPB > 2) fast_iter(std::integral_constant<int, 2 % IPB>{});
+            if constexpr (j0 <= 3 && IPB > 3) fast_iter(std::integral_constant<int, 3 % IPB>{});
+            if constexpr (j0 <= 4 && IPB > 4) fast_iter(std::integral_constant<int, 4 % IPB>{});
+            if constexpr (j0 <= 5 && IPB > 5) fast_iter(std::integral_constant<int, 5 % IPB>{});
+            if constexpr (j0 <= 6 && IPB > 6) fast_iter(std::integral_constant<int, 6 % IPB>{});
+            if constexpr (j0 <= 7 && IPB > 7) fast_iter(std::integral_constant<int, 7 % IPB>{});
         };
 
         const int nfull = nt >> 5;                     // boxes of this tile without a ragged tail
@@ -275,9 +308,13 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
         if (nfull >= HB) {
             for (int g = 0; g < DRAIN; ++g) slow_iter(g);
             // rest of box HB-1: every lane is inside the tile from iteration DRAIN on
-            fast_span(HB - 1, std::integral_constant<int, DRAIN % IPB == 0 ? IPB : DRAIN % IPB>{}, nt > 32 * HB);
+            set_ptrs(HB - 1);
+            fast_span(std::integral_constant<int, DRAIN % IPB == 0 ? IPB : DRAIN % IPB>{});
 #pragma unroll 1
-            for (int b = HB; b < nfull; ++b) fast_span(b, std::integral_constant<int, 0>{}, nt > 32 * (b + 1));
+            for (int b = HB; b < nfull; ++b) {
+                next_box();
+                fast_span(std::integral_constant<int, 0>{});
+            }
             for (int g = nfull * IPB; g < total; ++g) slow_iter(g);
         } else {
             for (int g = 0; g < total; ++g) slow_iter(g);

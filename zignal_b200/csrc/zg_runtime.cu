@@ -414,6 +414,11 @@ int sync_params(zg_plan* p) {
     return ZG_OK;
 }
 
+int tune_env(const char* name) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : 0;
+}
+
 // ---- tensor maps ---------------------------------------------------------------------------------------
 
 int encode_map(zg_plan* p, zgk::TensorMap* out, const void* base, int64_t C, int64_t T, int64_t ld, int box_rows) {
@@ -466,11 +471,6 @@ bool encode_map_tile3d(zgk::TensorMap* out, const void* base, int64_t C, int64_t
 struct Geometry {
     int wpc, grid, stages, boxes, smem;
 };
-
-int tune_env(const char* name) {
-    const char* v = std::getenv(name);
-    return v && *v ? std::atoi(v) : 0;
-}
 
 Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, int64_t T) {
     Geometry g{};
