@@ -172,7 +172,8 @@ def test_state_get_set_reset(zg):
 # ---- K1b: section-parallel biquad cascade (S lanes per channel) ---------------------------------
 
 @pytest.mark.parametrize("sections", [2, 4])
-@pytest.mark.parametrize("C,T", [(1, 4), (8, 31), (9, 64), (70, 257), (96, 1000), (33, 4100), (520, 8192)])
+@pytest.mark.parametrize("C,T", [(1, 4), (8, 31), (9, 64), (70, 257), (96, 1000), (33, 4100), (520, 8192),
+                                 (40, 1536), (17, 1537), (20000, 2100)])
 def test_biquad_lanes_exact_is_bit_identical(zg, sections, C, T):
     x = [fo.noise(C, T, seed=100 + sections)]
     expr = fo.biquad_cascade(sections)

@@ -78,19 +78,19 @@ struct Df1Lane {
     }
 };
 
-constexpr int kLanesXbufBytes = 1024;        // exchange buffer per warp: 2 chunks x 32 lanes x 16 bytes
+constexpr int kLanesXbufBytes = 512;         // exchange buffer per warp: 32 lanes x 16 bytes
 
 // in_map[0] / out_map[0]: 2-D {T, C}, box {32, 32/S}        (ragged last tile, box by box)
 // in_map[1] / out_map[1]: 3-D {32, C, T/32} over the full 32-sample boxes, box {32, 32/S, NB}
-template <int S, bool kExact, bool kUniform, int CH = 1>
+template <int S, bool kExact, bool kUniform>
 __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
-    static_assert(CH == 1 || CH == 2, "16-byte chunks (of four samples) per iteration");
     static_assert(S == 2 || S == 4, "lanes per channel: 2 or 4 (the box must span whole swizzle atoms)");
     constexpr int CPW = 32 / S;              // channels per warp
     constexpr int kBoxBytes = CPW * 128;
-    constexpr int LAG = 2;                   // iterations between neighbouring sections
+    constexpr int PD = 2;                    // iterations between loading a chunk and evaluating it
+    constexpr int LAG = PD + 1;              // iterations between neighbouring sections
     constexpr int DRAIN = LAG * (S - 1);     // iterations until the last section has caught up
-    constexpr int IPB = 8 / CH;              // iterations per 32-sample box
+    constexpr int HB = (DRAIN + 7) / 8;      // boxes of iterations during which the pipeline fills
 
     extern __shared__ __align__(1024) unsigned char smem[];
 
@@ -112,14 +112,14 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
 
     unsigned char* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     const unsigned stage_bytes = (unsigned)NB * kBoxBytes;
+    // the St stages of a warp are contiguous: a ring of RB = St*NB boxes, global box Bx at (Bx mod RB)
     unsigned char* my = tiles + (size_t)warp * St * stage_bytes;
+    const int RB = St * NB;
     unsigned char* xbuf = tiles + (size_t)warps_per_cta * St * stage_bytes + (size_t)warp * kLanesXbufBytes;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(
                                    tiles + (size_t)warps_per_cta * (St * stage_bytes + kLanesXbufBytes)) + warp * St;
-    // exchange buffer: CH arrays of 32 x 16 bytes (array u = chunk u of the iteration), so that the 32
-    // lanes of one STS.128 / LDS.128 touch 512 contiguous bytes
     unsigned char* const x_in = xbuf + (lane > 0 ? lane - 1 : 0) * 16;   // what the lane below stored
-    unsigned char* const x_out = xbuf + lane * 16;
+    unsigned char* const x_out = xbuf + lane * 16;                       // (a last lane's slot is read by nobody)
 
     // ---- this lane's section: coefficients and delay-line state ----
     // kernel slots as in zg_biquad.cuh: state 2k / 2k+1 = signal k two / one tick ago, params 5k..5k+4
@@ -145,13 +145,17 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
             prefetch_tmap(&a.out_map[1]);
         }
     }
-#pragma unroll
-    for (int u = 0; u < CH; ++u) *reinterpret_cast<float4*>(x_out + u * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(x_out) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 
-    const int n_tiles = (a.n_samples + tile_t - 1) / tile_t;
-    const int full_boxes = a.n_samples >> 5;           // boxes of the block without a ragged tail
-    const bool ragged = (a.n_samples & 31) != 0;
+    const int T = a.n_samples;
+    const int NC = (T + 3) >> 2;                       // 16-byte chunks (of four samples) of the block
+    const int total = NC + DRAIN;                      // iterations: lane `sec` evaluates chunk G - LAG*sec in iteration G
+    const int iter_boxes = (total + 7) >> 3;
+    const int CPT = NB * 8;                            // chunks per tile
+    const int n_tiles = (T + tile_t - 1) / tile_t;
+    const int full_boxes = T >> 5;                     // boxes of the block without a ragged tail
+    const bool ragged = (T & 31) != 0;
     const bool have3d = (a.flags & 1) != 0;
     // tile i: boxes [i*NB, i*NB + nbf) are full; `rag` = the block's ragged box follows them in this tile
     auto tile_shape = [&](int i, int& nbf, bool& rag) {
@@ -178,167 +182,183 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
                 tma_load_2d(dst + b * kBoxBytes, &a.in_map[0], (i * NB + b) * kTileT, c0, &bars[slot]);
         }
     };
+    auto issue_store = [&](int i) {                    // lane 0 only
+        unsigned char* src = my + (size_t)(i % St) * stage_bytes;
+        int nbf; bool rag;
+        tile_shape(i, nbf, rag);
+        if (!rag) {
+            tma_store_3d(&a.out_map[1], 0, c0, i * NB, src);           // boxes past the end are clipped
+        } else {
+            for (int b = 0; b <= nbf; ++b)
+                tma_store_2d(&a.out_map[0], (i * NB + b) * kTileT, c0, src + b * kBoxBytes);
+        }
+        tma_commit();
+    };
     if (lane == 0) {
-        const int pre = n_tiles < St - 1 ? n_tiles : St - 1;
+        const int pre = n_tiles < St ? n_tiles : St;
         for (int i = 0; i < pre; ++i) issue_load(i);
     }
 
-    // row `cl` of every box; 16-byte chunk j of the row lives at chunk j ^ (cl & 7)   (SWIZZLE_128B).
-    // The eight chunk offsets of this lane never change: keep them in registers so that the steady
-    // state addresses shared memory with no per-access arithmetic.
+    // row `cl` of every box; 16-byte chunk j of the row lives at chunk j ^ (cl & 7)   (SWIZZLE_128B)
     unsigned off[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) off[j] = (unsigned)cl * 128u + ((((unsigned)j) ^ (unsigned)(cl & 7)) << 4);
+    auto ring_box = [&](int bx) { return my + (unsigned)(bx % RB) * kBoxBytes; };          // bx >= 0
+    auto chunk_ptr = [&](int c) {                      // chunk c >= 0 of the block, this lane's channel
+        return ring_box(c >> 3) + (unsigned)cl * 128u + ((((unsigned)c & 7u) ^ (unsigned)(cl & 7)) << 4);
+    };
 
-    for (int i = 0; i < n_tiles; ++i) {
-        const int slot = i % St;
-        const int t0 = i * tile_t;
-        const int nt = a.n_samples - t0 < tile_t ? a.n_samples - t0 : tile_t;
-        unsigned char* stage = my + (size_t)slot * stage_bytes;
-        auto chunk_ptr = [&](int c) {                  // chunk c of the tile, this lane's channel
-            return stage + ((unsigned)c >> 3) * kBoxBytes + (unsigned)cl * 128u +
-                   ((((unsigned)c & 7u) ^ (unsigned)(cl & 7)) << 4);
-        };
+    mbar_wait(&bars[0], 0);                            // tile 0
+    // r0 / r1: the inputs of this lane's next two iterations (loaded PD iterations ahead)
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+    if (first) {
+        r0 = *reinterpret_cast<const float4*>(chunk_ptr(0));
+        r1 = *reinterpret_cast<const float4*>(chunk_ptr(1));
+    }
 
-        mbar_wait(&bars[slot], (unsigned)((i / St) & 1));
-
-        // `nxt` = the 4*CH inputs of the NEXT iteration, loaded one iteration ahead
-        float4 nxt[CH];
+    // fill, drain and ragged ends: any lane may be outside the block (predicated, branch-free, dynamic addresses)
+    auto slow_iter = [&](int g) {
+        const float4 cur = r0;
+        r0 = r1;
+        __syncwarp();
+        const unsigned char* src = x_in;
+        if (first && g + PD < n_tiles * CPT) src = chunk_ptr(g + PD);
+        r1 = *reinterpret_cast<const float4*>(src);
+        const int c = g - LAG * sec;                   // this lane's chunk
+        float* dst = reinterpret_cast<float*>(chunk_ptr(c > 0 ? c : 0));
+        float o[4];
 #pragma unroll
-        for (int u = 0; u < CH; ++u) {
-            nxt[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (first) nxt[u] = *reinterpret_cast<const float4*>(chunk_ptr(u));
+        for (int q = 0; q < 4; ++q) {
+            const bool act = ch_ok && c >= 0 && 4 * c + q < T;
+            const float in = q == 0 ? cur.x : q == 1 ? cur.y : q == 2 ? cur.z : cur.w;
+            o[q] = f.eval(in);
+            f.push_if(act, in, o[q]);
+            if (last && act) dst[q] = o[q];
         }
+        *reinterpret_cast<float4*>(x_out) = make_float4(o[0], o[1], o[2], o[3]);
+    };
 
-        auto slow_iter = [&](int g) {                  // predicated: lanes may be outside the tile
-            float4 cur[CH];
+    // Steady state.  Every lane keeps the shared-memory address of each of its 8 loads and 8 stores of a
+    // box of iterations in registers: first / last lanes of a channel point into the ring (and move on by
+    // one box per box), the others at their exchange slots (and stay), so an iteration is one LDS.128, four
+    // ticks and one STS.128 with no address arithmetic.  In iteration 8B + j a first lane loads chunk
+    // 8B + j + PD, a last lane stores chunk 8B + j - DRAIN.
+    unsigned char* sptr[8];
+    unsigned char* dptr[8];
+    int bmod = 0;                                      // B mod RB, kept incrementally (no division in the loop)
+    const unsigned sinc = first ? (unsigned)kBoxBytes : 0u, dinc = last ? (unsigned)kBoxBytes : 0u;
+    auto set_ptrs_prev = [&]() {                       // the table of box B (ring position bmod), minus one step
+        unsigned char* rb[4];                          // ring boxes B-2 .. B+1
 #pragma unroll
-            for (int u = 0; u < CH; ++u) cur[u] = nxt[u];
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < CH; ++u) {                       // one LDS per lane, no divergence
-                const unsigned char* src = x_in + u * 512;
-                if (first && CH * (g + 1) + u < NB * 8) src = chunk_ptr(CH * (g + 1) + u);
-                nxt[u] = *reinterpret_cast<const float4*>(src);
-            }
-            const int c = g - LAG * sec;               // this lane's position, in iterations
-#pragma unroll
-            for (int u = 0; u < CH; ++u) {
-                float o[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int m = 4 * (CH * c + u) + q;
-                    const bool act = ch_ok && m >= 0 && m < nt;
-                    const float in = q == 0 ? cur[u].x : q == 1 ? cur[u].y : q == 2 ? cur[u].z : cur[u].w;
-                    o[q] = f.eval(in);
-                    f.push_if(act, in, o[q]);
-                    if (last && act) reinterpret_cast<float*>(chunk_ptr(CH * c + u))[q] = o[q];
-                }
-                // (the slot of a channel's last lane is read by nobody: the lane above is a first lane)
-                *reinterpret_cast<float4*>(x_out + u * 512) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-        };
-        // steady state, iteration IPB*box + j: chunks CH*j .. CH*j+CH-1 of `box` in (loaded one iteration
-        // ahead: those of iteration j+1), the chunks of iteration j - DRAIN (one or two boxes back) out.
-        // Every lane keeps the shared-memory address of each of its IPB loads and stores of a box in
-        // registers: first / last lanes of a channel point into the tile (and move on by one box per box),
-        // the others at their exchange slots (and stay) -- the steady state has no address selection left
-        // and the LDS can issue right after the warp has synchronised.
-        unsigned char* sptr[IPB][CH];
-        unsigned char* dptr[IPB][CH];
-        auto set_ptrs = [&](int b) {
-            unsigned char* box = stage + (unsigned)b * kBoxBytes;
-#pragma unroll
-            for (int j = 0; j < IPB; ++j) {
-                const int back = (DRAIN - j + IPB - 1) / IPB;                 // boxes back (>= 0)
-                const int jo = (j - DRAIN + 8 * IPB) % IPB;
-#pragma unroll
-                for (int u = 0; u < CH; ++u) {
-                    // (the last iteration of a box prefetches from the next box; past the tile's last box
-                    // that is some other shared memory of this CTA: read, never used)
-                    sptr[j][u] = first ? (j < IPB - 1 ? box + off[(CH * (j + 1) + u) & 7] : box + kBoxBytes + off[u])
-                                       : x_in + u * 512;
-                    dptr[j][u] = last ? box - back * kBoxBytes + off[CH * jo + u] : x_out + u * 512;
-                }
-            }
-        };
-        const unsigned sinc = first ? (unsigned)kBoxBytes : 0u, dinc = last ? (unsigned)kBoxBytes : 0u;
-        auto next_box = [&]() {
-#pragma unroll
-            for (int j = 0; j < IPB; ++j)
-#pragma unroll
-                for (int u = 0; u < CH; ++u) { sptr[j][u] += sinc; dptr[j][u] += dinc; }
-        };
-        auto fast_iter = [&](auto jc) {
-            constexpr int j = decltype(jc)::value;
-            float4 cur[CH];
-#pragma unroll
-            for (int u = 0; u < CH; ++u) cur[u] = nxt[u];
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < CH; ++u) nxt[u] = *reinterpret_cast<const float4*>(sptr[j][u]);
-#pragma unroll
-            for (int u = 0; u < CH; ++u) {
-                float o[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float in = q == 0 ? cur[u].x : q == 1 ? cur[u].y : q == 2 ? cur[u].z : cur[u].w;
-                    o[q] = f.eval(in);
-                    f.push(in, o[q]);
-                }
-                *reinterpret_cast<float4*>(dptr[j][u]) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-        };
-        // iterations j0 .. IPB-1 of the current box (compile-time position inside the box)
-        auto fast_span = [&](auto j0c) {
-            constexpr int j0 = decltype(j0c)::value;
-            if constexpr (j0 <= 0) fast_iter(std::integral_constant<int, 0>{});
-            if constexpr (j0 <= 1 && IPB > 1) fast_iter(std::integral_constant<int, 1 % IPB>{});
-            if constexpr (j0 <= 2 && IPB > 2) fast_iter(std::integral_constant<int, 2 % IPB>{});
-            if constexpr (j0 <= 3 && IPB > 3) fast_iter(std::integral_constant<int, 3 % IPB>{});
-            if constexpr (j0 <= 4 && IPB > 4) fast_iter(std::integral_constant<int, 4 % IPB>{});
-            if constexpr (j0 <= 5 && IPB > 5) fast_iter(std::integral_constant<int, 5 % IPB>{});
-            if constexpr (j0 <= 6 && IPB > 6) fast_iter(std::integral_constant<int, 6 % IPB>{});
-            if constexpr (j0 <= 7 && IPB > 7) fast_iter(std::integral_constant<int, 7 % IPB>{});
-        };
-
-        const int nfull = nt >> 5;                     // boxes of this tile without a ragged tail
-        const int total = (nt + 4 * CH - 1) / (4 * CH) + DRAIN;   // iterations until the last lane has drained
-        constexpr int HB = (DRAIN + IPB - 1) / IPB;    // boxes the pipeline needs to fill
-        if (nfull >= HB) {
-            for (int g = 0; g < DRAIN; ++g) slow_iter(g);
-            // rest of box HB-1: every lane is inside the tile from iteration DRAIN on
-            set_ptrs(HB - 1);
-            fast_span(std::integral_constant<int, DRAIN % IPB == 0 ? IPB : DRAIN % IPB>{});
-#pragma unroll 1
-            for (int b = HB; b < nfull; ++b) {
-                next_box();
-                fast_span(std::integral_constant<int, 0>{});
-            }
-            for (int g = nfull * IPB; g < total; ++g) slow_iter(g);
-        } else {
-            for (int g = 0; g < total; ++g) slow_iter(g);
+        for (int d = -2; d <= 1; ++d) {
+            int r = bmod + d;
+            r = r < 0 ? r + RB : (r >= RB ? r - RB : r);
+            rb[d + 2] = my + (unsigned)r * kBoxBytes;
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int back = (DRAIN - j + 7) / 8;                      // boxes back (0 .. 2)
+            const int jo = (j - DRAIN + 64) % 8;
+            sptr[j] = first ? rb[2 + (j + PD) / 8] + off[(j + PD) & 7] - kBoxBytes : x_in;
+            dptr[j] = last ? rb[2 - back] + off[jo] - kBoxBytes : x_out;
+        }
+    };
+    auto fast_iter = [&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const float4 cur = r0;
+        r0 = r1;
+        __syncwarp();
+        r1 = *reinterpret_cast<const float4*>(sptr[j]);
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float in = q == 0 ? cur.x : q == 1 ? cur.y : q == 2 ? cur.z : cur.w;
+            o[q] = f.eval(in);
+            f.push(in, o[q]);
+        }
+        *reinterpret_cast<float4*>(dptr[j]) = make_float4(o[0], o[1], o[2], o[3]);
+    };
 
+    // The pipeline runs through the whole block: tiles only matter to TMA.  Two events per tile, each due
+    // before a known box of iterations; between events the hot loop is a run of boxes with nothing but a
+    // counter:
+    //   store  tile i is complete once the last lane has written its last chunk, DRAIN iterations after its
+    //          last input chunk was read (two boxes into tile i+1).  At the same point the slot of tile i-1,
+    //          stored a whole tile ago, is refilled with tile i-1+St (needs St >= 3: the host sees to it);
+    //   wait   tile i must have landed before box i*NB - 1 (the prefetch of a first lane reaches into it).
+    constexpr int kNever = 0x7fffffff;
+    auto store_box = [&](int i) {                      // first box by which tile i is complete
+        const int end_chunk = (i + 1) * CPT < NC ? (i + 1) * CPT : NC;
+        return ((end_chunk + DRAIN - 1) >> 3) + 1;
+    };
+    int s_tile = 0, s_box = store_box(0);
+    int r_tile = -1;                                   // tile to load into the slot stored at the previous event
+    int w_tile = 2, w_box = n_tiles > 2 ? 2 * NB - 1 : kNever;
+    if (n_tiles > 1) mbar_wait(&bars[1 % St], 0);      // tile 1 (the fill iterations may reach into it)
+    auto do_store = [&]() {
         fence_proxy_async();                           // generic-proxy writes -> visible to TMA
         __syncwarp();
         if (lane == 0) {
-            int nbf; bool rag;
-            tile_shape(i, nbf, rag);
-            if (!rag) {
-                tma_store_3d(&a.out_map[1], 0, c0, i * NB, stage);      // boxes past the end are clipped
+            if (r_tile >= 0) {
+                tma_wait_read<0>();
+                issue_load(r_tile);
+            }
+            issue_store(s_tile);
+        }
+        r_tile = s_tile + St < n_tiles ? s_tile + St : -1;
+        ++s_tile;
+        s_box = s_tile < n_tiles ? store_box(s_tile) : kNever;
+    };
+    bool ptrs_valid = false;
+    int B = 0;
+#pragma unroll 1
+    while (B < iter_boxes) {
+        while (B >= s_box) do_store();
+        while (B >= w_box) {
+            mbar_wait(&bars[w_tile % St], (unsigned)((w_tile / St) & 1));
+            ++w_tile;
+            w_box = w_tile < n_tiles ? w_tile * NB - 1 : kNever;
+        }
+        if (B >= HB && B < full_boxes) {               // every lane is inside the block for all 8 iterations
+            int stop = s_box < w_box ? s_box : w_box;
+            stop = stop < full_boxes ? stop : full_boxes;
+            int n = stop - B;
+            // a pointer table survives a step of one box unless one of the boxes it refers to (B-2 .. B+1)
+            // wraps around the ring: ring positions RB-1, 0, 1, 2 rebuild it
+            if (!ptrs_valid || bmod <= 2 || bmod == RB - 1) {
+                set_ptrs_prev();
+                ptrs_valid = true;
+                n = 1;
             } else {
-                for (int b = 0; b <= nbf; ++b)
-                    tma_store_2d(&a.out_map[0], (i * NB + b) * kTileT, c0, stage + b * kBoxBytes);
+                const int room = RB - 1 - bmod;
+                n = n < room ? n : room;
             }
-            tma_commit();
-            const int nxt_tile = i + St - 1;
-            if (nxt_tile < n_tiles) {
-                tma_wait_read<1>();                    // the slot of tile i-1: its store has left smem
-                issue_load(nxt_tile);
+            B += n;
+            bmod += n;
+            bmod = bmod >= RB ? bmod - RB : bmod;
+#pragma unroll 1
+            for (; n > 0; --n) {                       // the hot loop
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { sptr[j] += sinc; dptr[j] += dinc; }
+                fast_iter(std::integral_constant<int, 0>{});
+                fast_iter(std::integral_constant<int, 1>{});
+                fast_iter(std::integral_constant<int, 2>{});
+                fast_iter(std::integral_constant<int, 3>{});
+                fast_iter(std::integral_constant<int, 4>{});
+                fast_iter(std::integral_constant<int, 5>{});
+                fast_iter(std::integral_constant<int, 6>{});
+                fast_iter(std::integral_constant<int, 7>{});
             }
+        } else {
+            ptrs_valid = false;
+            const int g1 = 8 * B + 8 < total ? 8 * B + 8 : total;
+#pragma unroll 1
+            for (int g = 8 * B; g < g1; ++g) slow_iter(g);
+            ++B;
+            bmod = bmod + 1 == RB ? 0 : bmod + 1;
         }
     }
+    while (s_tile < n_tiles) do_store();               // the tiles that end with the block
 
     if (lane == 0) tma_wait_all<0>();
 

@@ -514,13 +514,19 @@ Geometry choose_geometry_lanes(const zg_plan* p, int64_t n_warps, int regs, int6
     int wpc = (int)std::max<int64_t>(1, std::min<int64_t>({per_sm, 16, (int64_t)reg_warps}));
     if (int w = tune_env("ZG_TUNE_WPC")) wpc = std::min(std::max(w, 1), 16);
     const int budget = p->max_smem_optin - 1024 - 16 * 8 * 8;
-    int S = 3;
-    if (int st = tune_env("ZG_TUNE_STAGES")) S = std::min(std::max(st, 2), 8);
+    int S = 3;                                           // >= 3: a slot is refilled one tile after its store
+    if (int st = tune_env("ZG_TUNE_STAGES")) S = std::min(std::max(st, 3), 8);
     int NB = 16;
     if (int b = tune_env("ZG_TUNE_BOXES")) NB = std::min(std::max(b, 1), 32);
+    // The pipeline of the lanes runs through tile boundaries: the first lane of a channel is DRAIN + PD
+    // iterations ahead of the last one, so a slot can only be refilled a few boxes into the next tile and
+    // the ring (S stages of NB boxes) must be long enough for that: NB >= 8 whenever the block has more tiles
+    // than stages (kernels/zg_biquad_lanes.cuh).  Fewer warps per CTA rather than shorter tiles.
+    const int min_nb = 8;
+    NB = std::max(NB, min_nb);
     NB = (int)std::min<int64_t>(NB, std::max<int64_t>(1, (T + zgk::kTileT - 1) / zgk::kTileT));
     auto need = [&](int w, int nb) { return w * (S * nb * box_bytes + zgk::kLanesXbufBytes); };
-    while (NB > 1 && need(wpc, NB) > budget) NB /= 2;
+    while (NB > min_nb && need(wpc, NB) > budget) NB = std::max(NB / 2, min_nb);
     while (wpc > 1 && need(wpc, NB) > budget) --wpc;
     g.wpc = wpc;
     g.stages = S;
