@@ -66,6 +66,53 @@ struct Df1Lane {
     __device__ __forceinline__ void push(float in, float y) {
         x2 = x1; x1 = in; y2 = y1; y1 = y;
     }
+    // feed-forward half of a tick: (b0*x + b1*xa) + b2*xb, xa / xb = the inputs one / two ticks before x
+    __device__ __forceinline__ float ff(float x, float xa, float xb) const {
+        if (kExact) return __fadd_rn(__fadd_rn(__fmul_rn(b0, x), __fmul_rn(b1, xa)), __fmul_rn(b2, xb));
+        return fmaf(b2, xb, fmaf(b1, xa, b0 * x));
+    }
+    // v[] of the four samples in c, from the plain state (start of a run of steady-state iterations)
+    __device__ __forceinline__ void prime(const float4& c, float (&v)[4]) const {
+        v[0] = ff(c.x, x1, x2); v[1] = ff(c.y, c.x, x1); v[2] = ff(c.z, c.y, c.x); v[3] = ff(c.w, c.z, c.y);
+    }
+    // Four ticks, software-pipelined by one iteration: the feed-forward halves v[] of the samples in c were
+    // computed during the previous iteration; this one runs the recurrence  y = (v + a1*y1) + a2*y2  -- three
+    // dependent 4-cycle instructions per sample, the critical path of the whole kernel -- and computes, in
+    // its shadow, v[] of the NEXT four samples n (their history is c.z, c.w).  Same operations in the same
+    // association as eval(): bit-identical.  The statements are interleaved the way the instruction stream
+    // should be (one recurrence instruction, two independent ones): with a single warp per scheduler
+    // nothing else hides the 4-cycle latency.
+    __device__ __forceinline__ void step4(const float4& c, const float4& n, float (&v)[4], float (&o)[4]) {
+        if (kExact) {
+            float t, s, w0, w1, w2, w3, m;
+            const float p0 = __fmul_rn(a2, y2), p1 = __fmul_rn(a2, y1);
+            t = __fmul_rn(a1, y1);      w0 = __fmul_rn(b0, n.x);  m = __fmul_rn(b1, c.w);
+            s = __fadd_rn(v[0], t);     w0 = __fadd_rn(w0, m);    m = __fmul_rn(b2, c.z);
+            o[0] = __fadd_rn(s, p0);    w0 = __fadd_rn(w0, m);    w1 = __fmul_rn(b0, n.y);
+            t = __fmul_rn(a1, o[0]);    m = __fmul_rn(b1, n.x);   const float p2 = __fmul_rn(a2, o[0]);
+            s = __fadd_rn(v[1], t);     w1 = __fadd_rn(w1, m);    m = __fmul_rn(b2, c.w);
+            o[1] = __fadd_rn(s, p1);    w1 = __fadd_rn(w1, m);    w2 = __fmul_rn(b0, n.z);
+            t = __fmul_rn(a1, o[1]);    m = __fmul_rn(b1, n.y);   const float p3 = __fmul_rn(a2, o[1]);
+            s = __fadd_rn(v[2], t);     w2 = __fadd_rn(w2, m);    m = __fmul_rn(b2, n.x);
+            o[2] = __fadd_rn(s, p2);    w2 = __fadd_rn(w2, m);    w3 = __fmul_rn(b0, n.w);
+            t = __fmul_rn(a1, o[2]);    m = __fmul_rn(b1, n.z);
+            s = __fadd_rn(v[3], t);     w3 = __fadd_rn(w3, m);    m = __fmul_rn(b2, n.y);
+            o[3] = __fadd_rn(s, p3);    w3 = __fadd_rn(w3, m);
+            v[0] = w0; v[1] = w1; v[2] = w2; v[3] = w3;
+        } else {
+            float s, w0, w1, w2, w3;
+            s = fmaf(a1, y1, v[0]);     w0 = b0 * n.x;            w0 = fmaf(b1, c.w, w0);
+            o[0] = fmaf(a2, y2, s);     w0 = fmaf(b2, c.z, w0);   w1 = b0 * n.y;
+            s = fmaf(a1, o[0], v[1]);   w1 = fmaf(b1, n.x, w1);   w1 = fmaf(b2, c.w, w1);
+            o[1] = fmaf(a2, y1, s);     w2 = b0 * n.z;            w2 = fmaf(b1, n.y, w2);
+            s = fmaf(a1, o[1], v[2]);   w2 = fmaf(b2, n.x, w2);   w3 = b0 * n.w;
+            o[2] = fmaf(a2, o[0], s);   w3 = fmaf(b1, n.z, w3);   w3 = fmaf(b2, n.y, w3);
+            s = fmaf(a1, o[2], v[3]);
+            o[3] = fmaf(a2, o[1], s);
+            v[0] = w0; v[1] = w1; v[2] = w2; v[3] = w3;
+        }
+        x2 = c.z; x1 = c.w; y2 = o[2]; y1 = o[3];
+    }
     // push only where `act`; written with selp so that the fill / drain iterations stay branch-free
     // (as `if (act) push(..)` they compiled to one divergent branch per sample: 5x the steady state)
     static __device__ __forceinline__ float sel(bool p, float a, float b) {
@@ -87,7 +134,8 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
     static_assert(S == 2 || S == 4, "lanes per channel: 2 or 4 (the box must span whole swizzle atoms)");
     constexpr int CPW = 32 / S;              // channels per warp
     constexpr int kBoxBytes = CPW * 128;
-    constexpr int PD = 2;                    // iterations between loading a chunk and evaluating it
+    constexpr int PD = 3;                    // iterations between loading a chunk and evaluating it (its
+                                             // feed-forward half is computed one iteration early: step4)
     constexpr int LAG = PD + 1;              // iterations between neighbouring sections
     constexpr int DRAIN = LAG * (S - 1);     // iterations until the last section has caught up
     constexpr int HB = (DRAIN + 7) / 8;      // boxes of iterations during which the pipeline fills
@@ -118,8 +166,24 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
     unsigned char* xbuf = tiles + (size_t)warps_per_cta * St * stage_bytes + (size_t)warp * kLanesXbufBytes;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(
                                    tiles + (size_t)warps_per_cta * (St * stage_bytes + kLanesXbufBytes)) + warp * St;
-    unsigned char* const x_in = xbuf + (lane > 0 ? lane - 1 : 0) * 16;   // what the lane below stored
-    unsigned char* const x_out = xbuf + lane * 16;                       // (a last lane's slot is read by nobody)
+    // Exchange slots.  An LDS.128 / STS.128 is served a quarter-warp (8 lanes x 16 bytes) at a time and is
+    // conflict free iff those 8 accesses fall into 8 different 16-byte bank groups.  In every quarter-warp the
+    // first (last) lanes of its 8/S channels read (write) the tile: rows cl, chunk jj ^ (cl & 7) -- an aligned
+    // block of 8/S bank groups that moves with jj -- while the other lanes read (write) exchange slots.  So
+    // the slots of a quarter-warp live in one 128-byte line and are XOR-ed away from the block the tile
+    // accesses of the same instruction use: `jj` = the chunk index the first lanes load in the iteration
+    // that READS the slot (the last lanes' store of the writing iteration uses the same block: DRAIN - PD - 1
+    // is a multiple of 8).  With plain lane-indexed slots every second wavefront was a bank conflict and the
+    // four warps of an SM kept the shared-memory pipe busy 64 of ~76 cycles per iteration.
+    constexpr int GB = 8 / S;                          // bank groups per block = channels per quarter-warp
+    constexpr int LG = S == 4 ? 1 : 2;                 // log2(GB)
+    static_assert((DRAIN - PD - 1) % 8 == 0, "slot swizzle assumes stores and loads use the same tile block");
+    auto xslot = [&](int wl, int jj) {                 // slot written by lane wl (not a last lane)
+        const int q = wl >> 3, ca = (wl / S) & (GB - 1), sw = wl & (S - 1);
+        const int g0 = GB * (1 + sw) + ca;
+        const int pb = ((jj & 7) >> LG) ^ (q & (S - 1));
+        return xbuf + 128 * q + 16 * (g0 ^ (GB * pb));
+    };
 
     // ---- this lane's section: coefficients and delay-line state ----
     // kernel slots as in zg_biquad.cuh: state 2k / 2k+1 = signal k two / one tick ago, params 5k..5k+4
@@ -145,7 +209,7 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
             prefetch_tmap(&a.out_map[1]);
         }
     }
-    *reinterpret_cast<float4*>(x_out) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(xbuf + lane * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 
     const int T = a.n_samples;
@@ -209,21 +273,23 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
     };
 
     mbar_wait(&bars[0], 0);                            // tile 0
-    // r0 / r1: the inputs of this lane's next two iterations (loaded PD iterations ahead)
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+    // r0 / r1 / r2: the inputs of this lane's next three iterations (loaded PD iterations ahead)
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
     if (first) {
         r0 = *reinterpret_cast<const float4*>(chunk_ptr(0));
         r1 = *reinterpret_cast<const float4*>(chunk_ptr(1));
+        r2 = *reinterpret_cast<const float4*>(chunk_ptr(2));
     }
 
     // fill, drain and ragged ends: any lane may be outside the block (predicated, branch-free, dynamic addresses)
     auto slow_iter = [&](int g) {
         const float4 cur = r0;
         r0 = r1;
+        r1 = r2;
         __syncwarp();
-        const unsigned char* src = x_in;
+        const unsigned char* src = first ? xbuf : xslot(lane - 1, g + PD);
         if (first && g + PD < n_tiles * CPT) src = chunk_ptr(g + PD);
-        r1 = *reinterpret_cast<const float4*>(src);
+        r2 = *reinterpret_cast<const float4*>(src);
         const int c = g - LAG * sec;                   // this lane's chunk
         float* dst = reinterpret_cast<float*>(chunk_ptr(c > 0 ? c : 0));
         float o[4];
@@ -235,7 +301,7 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
             f.push_if(act, in, o[q]);
             if (last && act) dst[q] = o[q];
         }
-        *reinterpret_cast<float4*>(x_out) = make_float4(o[0], o[1], o[2], o[3]);
+        if (!last) *reinterpret_cast<float4*>(xslot(lane, g + 1 + PD)) = make_float4(o[0], o[1], o[2], o[3]);
     };
 
     // Steady state.  Every lane keeps the shared-memory address of each of its 8 loads and 8 stores of a
@@ -259,23 +325,20 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
         for (int j = 0; j < 8; ++j) {
             const int back = (DRAIN - j + 7) / 8;                      // boxes back (0 .. 2)
             const int jo = (j - DRAIN + 64) % 8;
-            sptr[j] = first ? rb[2 + (j + PD) / 8] + off[(j + PD) & 7] - kBoxBytes : x_in;
-            dptr[j] = last ? rb[2 - back] + off[jo] - kBoxBytes : x_out;
+            sptr[j] = first ? rb[2 + (j + PD) / 8] + off[(j + PD) & 7] - kBoxBytes : xslot(lane - 1, j + PD);
+            dptr[j] = last ? rb[2 - back] + off[jo] - kBoxBytes : xslot(lane, j + 1 + PD);
         }
     };
+    float v[4];                                        // feed-forward halves of the samples in r0 (see step4)
     auto fast_iter = [&](auto jc) {
         constexpr int j = decltype(jc)::value;
         const float4 cur = r0;
         r0 = r1;
+        r1 = r2;
         __syncwarp();
-        r1 = *reinterpret_cast<const float4*>(sptr[j]);
+        r2 = *reinterpret_cast<const float4*>(sptr[j]);
         float o[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float in = q == 0 ? cur.x : q == 1 ? cur.y : q == 2 ? cur.z : cur.w;
-            o[q] = f.eval(in);
-            f.push(in, o[q]);
-        }
+        f.step4(cur, r0, v, o);
         *reinterpret_cast<float4*>(dptr[j]) = make_float4(o[0], o[1], o[2], o[3]);
     };
 
@@ -336,6 +399,7 @@ __device__ __forceinline__ void biquad_lanes_block(const StreamArgs& a) {
             B += n;
             bmod += n;
             bmod = bmod >= RB ? bmod - RB : bmod;
+            f.prime(r0, v);
 #pragma unroll 1
             for (; n > 0; --n) {                       // the hot loop
 #pragma unroll
