@@ -122,9 +122,16 @@ class ClockSampler:
 # ---- the reference arm / cpu baseline: the reference's own loop on the host cores ---------------------
 
 def _ref_lib():
+    """oracle/_ref/libzg_ref.so (the reference's benchmark.cpp compiled where it lies), on ALL host threads:
+    torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would silently time one core."""
     so = os.path.join(ROOT, "oracle", "_ref", "libzg_ref.so")
     if os.path.exists(so):
-        return ctypes.CDLL(so)
+        lib = ctypes.CDLL(so)
+        try:
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(os.cpu_count() or 1)
+        except OSError:
+            pass
+        return lib
     return None
 
 
@@ -141,6 +148,7 @@ def cpu_reference_rate(target_seconds=12.0, samples=8192):
     def run_ref(C):
         x = fo.noise(C, samples, seed=0) * np.float32(0.01)
         y = np.empty_like(x)
+        y.fill(1.0)                               # pages touched before the clock starts (np.zeros would map them lazily)
         t0 = time.perf_counter()
         rc = lib.zg_ref_df1_chain(SECTIONS, x.ctypes.data_as(P), y.ctypes.data_as(P), ctypes.c_long(C), ctypes.c_long(samples))
         dt = time.perf_counter() - t0

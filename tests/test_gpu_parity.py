@@ -627,3 +627,41 @@ def test_full_size_config2_4096x65536(zg):
     assert np.array_equal(y[idx].cpu().numpy(), _oracle(expr, [x[idx].cpu().numpy()])[0])
     y1 = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, lanes_per_channel=1).process([x])[0]
     assert torch.equal(y, y1)                            # both kernels, every channel, bit for bit
+
+
+def test_full_size_config5_one_million_voices_bf16(zg):
+    """BASELINE configs[4] at its full voice count on one GPU (1 048 576 voices x 512 samples, bf16 out, dirac
+    input synthesised in the kernel).  Every voice runs the same graph from the same excitation, so all rows
+    must be identical, and equal to the oracle's row bit for bit; a second block continues the stream."""
+    torch = _torch()
+    C, T = 1 << 20, 512
+    expr = fo.poly_voice_expr()
+    plan = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, io_dtype=zg.BF16, input_kind=[zg.IN_DIRAC])
+    y1 = plan.process([None], n_samples=T)[0]
+    y2 = plan.process([None], n_samples=T)[0]
+    torch.cuda.synchronize()
+    y = torch.cat([y1, y2], dim=1).view(torch.int16)
+    assert bool((y == y[0:1]).all())
+    d = np.zeros((1, 2 * T), np.float32); d[0, 0] = 1
+    ref = fo.bf16_bits(_oracle(expr, [d])[0])
+    for c in (0, 12345, C - 1):
+        assert np.array_equal(y[c].cpu().numpy().view(np.uint16), ref[0])
+
+
+def test_sample_rate_parameter_is_just_another_input_wire(zg):
+    """block-rate parameters are `$k` (zg_param_set); a parameter that changes every sample
+    is expressed the way the reference would -- as one more input of the graph (here the feedback gain of a
+    one-pole low-pass: y = x + a(t) * y1)."""
+    expr = "~(_2 + _3*_1[_1])"
+    g = zg.compile(expr)
+    assert (g.n_in, g.n_out) == (2, 1)
+    C, T = 96, 700
+    x = fo.noise(C, T, seed=41)
+    a = (0.5 + 0.45 * fo.noise(C, T, seed=42)).astype(np.float32)          # 0.05 .. 0.95, per channel and sample
+    for mode in (zg.MODE_EXACT, zg.MODE_FAST):
+        ys, _ = _run(zg, expr, [x, a], mode, blocks=[100, 600])
+        ref = _oracle(expr, [x, a])[0]
+        if mode == zg.MODE_EXACT:
+            assert np.array_equal(ys[0], ref)
+        else:
+            assert _rel_err(ys[0], ref) <= TOL

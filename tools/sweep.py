@@ -24,7 +24,7 @@ def main():
     for part in a.points.split(";"):
         k, v = part.split("=")
         axes[k] = v.split(",")
-    for k, d in (("mode", ["exact"]), ("boxes", ["0"]), ("wpc", ["0"]), ("stages", ["0"]), ("layout", ["planar"]), ("coef", ["uniform"]), ("lanes", ["0"]), ("late", ["0"]), ("hint", ["0"]), ("promo", ["0"])):
+    for k, d in (("mode", ["exact"]), ("boxes", ["0"]), ("wpc", ["0"]), ("stages", ["0"]), ("layout", ["planar"]), ("coef", ["uniform"]), ("lanes", ["0"]), ("late", ["0"]), ("hint", ["0"]), ("promo", ["0"]), ("cu", ["0"]), ("jit", ["0"])):
         axes.setdefault(k, d)
     C, T = WORK[a.workload]
     x = torch.rand((C, T), device="cuda") * 2 - 1
@@ -33,7 +33,7 @@ def main():
     keys = list(axes)
     for combo in itertools.product(*[axes[k] for k in keys]):
         pt = dict(zip(keys, combo))
-        for env, k in (("ZG_TUNE_BOXES", "boxes"), ("ZG_TUNE_WPC", "wpc"), ("ZG_TUNE_STAGES", "stages"), ("ZG_TUNE_LATE_REFILL", "late"), ("ZG_TUNE_L2HINT", "hint"), ("ZG_TUNE_L2PROMO", "promo")):
+        for env, k in (("ZG_TUNE_BOXES", "boxes"), ("ZG_TUNE_WPC", "wpc"), ("ZG_TUNE_STAGES", "stages"), ("ZG_TUNE_LATE_REFILL", "late"), ("ZG_TUNE_L2HINT", "hint"), ("ZG_TUNE_L2PROMO", "promo"), ("ZG_TUNE_CHUNK_UNROLL", "cu")):
             if pt[k] != "0": os.environ[env] = pt[k]
             else: os.environ.pop(env, None)
         inter = pt["layout"] == "interleaved"
@@ -45,7 +45,7 @@ def main():
             g = zg.compile(fo.biquad_cascade_params(a.sections))
         try:
             plan = g.plan(channels=C, mode=zg.MODE_EXACT if pt["mode"] == "exact" else zg.MODE_FAST,
-                          layout=zg.INTERLEAVED if inter else zg.PLANAR, lanes_per_channel=int(pt["lanes"]))
+                          layout=zg.INTERLEAVED if inter else zg.PLANAR, lanes_per_channel=int(pt["lanes"]), force_jit=pt["jit"] == "1")
             if pt["coef"] != "uniform":
                 import numpy as np
                 for k in range(a.sections):

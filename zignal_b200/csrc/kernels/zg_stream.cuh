@@ -185,6 +185,14 @@ struct UniformParams {             // view of StreamArgs::uparams (kernel parame
 
 __host__ __device__ constexpr int popcount_u32(unsigned v) { return v == 0 ? 0 : (int)(v & 1u) + popcount_u32(v >> 1); }
 
+// How many of the 8 chunks of a box row are unrolled into one loop body: Tick::CHUNK_UNROLL (8, 4, 2 or 1)
+// if the tick declares it, else all 8.  A 4-section EXACT biquad box is 1200 instructions (19 KB) fully
+// unrolled -- with 14 warps at different places of it the instruction caches miss (ncu: no_instruction).
+template <class T, class = void>
+struct chunk_unroll { static constexpr int value = 8; };
+template <class T>
+struct chunk_unroll<T, decltype((void)T::CHUNK_UNROLL)> { static constexpr int value = T::CHUNK_UNROLL; };
+
 // ---- the streaming loop ---------------------------------------------------------------------------
 //
 // Tick must provide
@@ -329,8 +337,13 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                         for (int k = 0; k < NI; ++k)
                             if (kBufMask & (1u << k))
                                 xn[k] = *reinterpret_cast<const uint4*>(base + k * wire_bytes + row + (sw << 4));
+                        constexpr int CU = chunk_unroll<Tick>::value;
+                        static_assert(CU == 8 || CU == 4 || CU == 2 || CU == 1, "CHUNK_UNROLL must divide 8");
+#pragma unroll 1
+                        for (int h = 0; h < 8; h += CU)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                        for (int jj = 0; jj < CU; ++jj) {
+                            const int j = h + jj;
                             const unsigned off = row + (((unsigned)j ^ sw) << 4);
                             float xv[NI > 0 ? NI : 1][VPC];
                             float yv[NO > 0 ? NO : 1][VPC];

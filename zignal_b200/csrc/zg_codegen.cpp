@@ -4,6 +4,7 @@
 // one tick in SSA order.  It stands in for what the reference gets from template expansion of
 // eval_it (flowz/flowz.hpp:740-774) over the canonical expression.
 #include <cstdio>
+#include <cstdlib>
 #include <sstream>
 
 #include "zg_internal.hpp"
@@ -42,6 +43,16 @@ std::string generate_tick_source(const Ir& ir, bool exact, const std::string& st
     os << "    static constexpr int N_IN = " << ir.n_in << ", N_OUT = " << ir.n_out << ", N_STATE = " << ir.n_state
        << ", N_PARAM = " << ir.n_params << ";\n";
     os << "    static constexpr unsigned SYNTH_MASK = ZG_SYNTH_MASK;\n";
+    {
+        // keep the unrolled loop body of the skeleton around 600 instructions (kernels/zg_stream.cuh)
+        int arith = 0;
+        for (const IrNode& n : ir.nodes)
+            if (n.op == IrOp::Add || n.op == IrOp::Sub || n.op == IrOp::Mul || n.op == IrOp::Div || n.op == IrOp::Neg) ++arith;
+        int cu = 8;
+        while (cu > 1 && arith * 4 * cu > 640) cu /= 2;
+        if (const char* e = std::getenv("ZG_TUNE_CHUNK_UNROLL")) { int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) cu = v; }
+        os << "    static constexpr int CHUNK_UNROLL = " << cu << ";\n";
+    }
     os << "    template <class P>\n"
           "    static __device__ __forceinline__ void tick(const zgk::Arr<N_IN>& x, zgk::Arr<N_OUT>& y,\n"
           "                                                zgk::Arr<N_STATE>& s, const P& p) {\n";
