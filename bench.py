@@ -14,7 +14,10 @@ Channels are independent, so N GPUs = N x the channels (weak scaling), no data-p
   value     whole-job Msamples/s, inputs resident in HBM, CUDA events on the launching stream
   e2e       same metric through zg_process_host(): pinned host buffers, H2D + kernel + D2H timed
   roofline  algorithmic bytes (8 B per sample: 4 in + 4 out) / average launch time vs measured HBM peak
-  cpu_baseline  the reference's hand-written biquad loop (oracle/_ref, all host threads), bounded sample
+  cpu_baseline  the reference's hand-written biquad loop (oracle/_ref, all host threads), bounded sample; this
+            CPU leg is also the only place the arm touches oracle/ (a spot check of the timed kernel's output
+            against the oracle rides along as cpu_baseline.parity_spot_check); graphs and coefficients of
+            the GPU legs come from zignal_b200/workloads.py
   also      the other biquad shape (c2 when the headline is ns and vice versa), device-resident, same rules
 Default mode is EXACT: bit-identical to the reference's x86 build, checked on sampled channels.
 """
@@ -222,7 +225,7 @@ def run_reference_arm(args):
 
 # ---- the other BASELINE configs (parity-tested in tests/; timed here for the record, not the headline) ----
 
-def other_configs(zg, fo, torch, dev, local, world, rank, args, barrier, dist):
+def other_configs(zg, wl, torch, dev, local, world, rank, args, barrier, dist):
     """configs[2] osc >> one-pole LP (65 536 voices, source-only: 4 B/sample written), configs[3] 256-tap FIR
     x 32 768 channels (8 B/sample, but bound by FP32 issue: 511 instructions per sample in EXACT mode),
     configs[4] polyphonic chain, bf16 storage, 131 072 voices per GPU (2 B/sample written).  Same timing
@@ -232,12 +235,12 @@ def other_configs(zg, fo, torch, dev, local, world, rank, args, barrier, dist):
     steps = max(3, min(args.steps, 10))
     out = {}
     cases = [
-        ("c3", "configs[2]: 65536-voice sine osc >> one-pole LP, dirac-excited, fp32 out", fo.osc_lp_expr(), 65536, 16384,
+        ("c3", "configs[2]: 65536-voice sine osc >> one-pole LP, dirac-excited, fp32 out", wl.osc_lp_expr(), 65536, 16384,
          dict(input_kind=[zg.IN_DIRAC]), None, torch.float32, 4, None),
-        ("c4", "configs[3]: 256-tap FIR x 32768 channels x 8192 samples, fp32", fo.fir_expr(fo.fir_taps(256)), 32768, 8192,
+        ("c4", "configs[3]: 256-tap FIR x 32768 channels x 8192 samples, fp32", wl.fir_expr(wl.fir_taps(256)), 32768, 8192,
          dict(), torch.float32, torch.float32, 8, 511 if args.mode == "exact" else 256),
         ("c5", "configs[4]: polyphonic chain osc >> biquad >> (biquad ~ feedback), 131072 voices per GPU x 4096 samples, "
-               "bf16 out, dirac-excited", fo.poly_voice_expr(), 131072, 4096,
+               "bf16 out, dirac-excited", wl.poly_voice_expr(), 131072, 4096,
          dict(input_kind=[zg.IN_DIRAC], io_dtype=zg.BF16), None, torch.bfloat16, 2, None),
     ]
     for name, desc, expr, C, T, kw, in_dt, out_dt, bytes_per_sample, instr_per_sample in cases:
@@ -283,7 +286,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import zignal_b200 as zg
-    import flowz_oracle as fo      # workload helpers only (graph text, coefficients); nothing is computed by it here
+    from zignal_b200 import workloads as wl      # graph text + coefficients; nothing under oracle/ is touched by this arm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -306,14 +309,14 @@ def run_ours(args):
         """K launches of one zg_process() each between CUDA events; returns the plan, buffers and timing."""
         C, T = WORKLOADS[workload]
         if args.coef == "uniform":
-            graph = zg.compile(fo.biquad_cascade(SECTIONS))
+            graph = zg.compile(wl.biquad_cascade(SECTIONS))
             params = []
         else:
-            graph = zg.compile(fo.biquad_cascade_params(SECTIONS))
+            graph = zg.compile(wl.biquad_cascade_params(SECTIONS))
             c = np.arange(C, dtype=np.float64) + rank * C
             params = []
             for k in range(SECTIONS):
-                per = np.array([fo.rbj_lowpass(440.0 * 2 ** k * (1.0 + ci / (C * world))) for ci in c], np.float32)
+                per = np.array([wl.rbj_lowpass(440.0 * 2 ** k * (1.0 + ci / (C * world))) for ci in c], np.float32)
                 params += [per[:, j].copy() for j in range(5)]
         mode = zg.MODE_EXACT if args.mode == "exact" else zg.MODE_FAST
         plan = graph.plan(channels=C, device=local, mode=mode,
@@ -373,9 +376,11 @@ def run_ours(args):
                "ms_per_step": dt / e2e_steps * 1e3, "api": "zg_process_host (pinned host buffers)"}
         del hx, hy
 
-    # ---- a spot check of the timed output against the oracle (the checker, not the thing measured) ----
+    # ---- CPU leg, part 1 (rank 0, N = 1 only; the one place this arm may execute oracle/): a spot check of the
+    #      timed kernel's output against the oracle -- the checker, not the thing measured ----
     parity = None
-    if rank == 0 and args.coef == "uniform" and args.layout == "planar":
+    if rank == 0 and world == 1 and not args.no_cpu and args.coef == "uniform" and args.layout == "planar":
+        import flowz_oracle as fo
         plan.reset()                                         # the oracle starts from zero state too
         plan.process([x], [y])
         torch.cuda.synchronize()
@@ -402,7 +407,7 @@ def run_ours(args):
                         "traffic": _traffic(other)}}
         del plan_o, xo, yo
         torch.cuda.empty_cache()
-        also.update(other_configs(zg, fo, torch, dev, local, world, rank, args, barrier, dist))
+        also.update(other_configs(zg, wl, torch, dev, local, world, rank, args, barrier, dist))
 
     if rank == 0:
         peak, peak_src = _peak_hbm()
@@ -425,12 +430,12 @@ def run_ours(args):
         }
         if e2e is not None:
             line["e2e"] = e2e
-        if parity is not None:
-            line["parity_spot_check"] = parity
         if also is not None:
             line["also"] = also
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu:                  # CPU leg, part 2: the reference's loop on the host cores
             line["cpu_baseline"], _ = cpu_reference_rate()
+            if parity is not None:
+                line["cpu_baseline"]["parity_spot_check"] = parity
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

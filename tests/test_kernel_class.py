@@ -50,3 +50,18 @@ def test_vectorised_fir_oracle_equals_tick_oracles(zg, n):
     # with history: continuing a stream
     assert np.array_equal(fo.fir_direct(x[:, 100:], h, history=np.concatenate(
         [np.zeros((3, max(0, n - 1 - 100)), np.float32), x[:, max(0, 100 - (n - 1)):100]], axis=1)), want[:, 100:])
+
+
+def test_package_workloads_equal_the_oracles_copies(zg):
+    """bench.py's GPU arm and the tools build their graphs from zignal_b200/workloads.py (nothing under
+    oracle/ is imported there); the oracle keeps its own builders.  Same text, same coefficients."""
+    from zignal_b200 import workloads as wl
+    for n in (1, 2, 4, 8):
+        assert wl.biquad_cascade(n) == fo.biquad_cascade(n)
+        assert wl.biquad_cascade_params(n) == fo.biquad_cascade_params(n)
+    assert wl.osc_lp_expr() == fo.osc_lp_expr() and wl.poly_voice_expr() == fo.poly_voice_expr()
+    for n in (2, 17, 256, 512):
+        assert np.array_equal(np.array(wl.fir_taps(n), np.float32), fo.fir_taps(n))
+        assert wl.fir_expr(wl.fir_taps(n)) == fo.fir_expr(fo.fir_taps(n))
+    for f in (440.0, 3520.0, 440.0 * 1.37):
+        assert wl.rbj_lowpass(f) == tuple(float(v) for v in fo.rbj_lowpass(f))

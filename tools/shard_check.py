@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
 import torch.distributed as dist
 import zignal_b200 as zg
-import flowz_oracle as fo
+from zignal_b200 import workloads as fo
 from zignal_b200.shard import channel_range, scatter_channels, gather_channels
 
 

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
 import zignal_b200 as zg
-import flowz_oracle as fo
+from zignal_b200 import workloads as fo
 
 WORK = {"ns": (65536, 8192), "c2": (4096, 65536), "mid": (16384, 16384), "c32k": (32768, 8192), "c8k": (8192, 32768)}
 

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
 import zignal_b200 as zg
-import flowz_oracle as fo
+from zignal_b200 import workloads as fo
 
 
 def main():

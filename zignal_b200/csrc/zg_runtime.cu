@@ -962,7 +962,9 @@ int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t
     // launched in order, state carried in HBM) and streamed: H2D of chunk k+1, the kernel of chunk k
     // and D2H of chunk k-1 overlap on three streams, so a PCIe-bound call costs one direction, not two.
     const int64_t row_bytes = cols * es * std::max(1, std::max(p->n_buf_in, p->ir.n_out));
-    int64_t n_chunks = std::min<int64_t>(16, (rows * row_bytes) / (32ll << 20));
+    // (the first H2D and the last D2H overlap nothing: 1/n_chunks of each direction is exposed, so many
+    // chunks -- but each still tens of MB, far above the per-copy and per-launch overheads)
+    int64_t n_chunks = std::min<int64_t>(32, (rows * row_bytes) / (32ll << 20));
     if (int c = tune_env("ZG_TUNE_HOST_CHUNKS")) n_chunks = c;
     n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, rows / 32));
     int64_t chunk_rows = (rows + n_chunks - 1) / n_chunks;
