@@ -11,13 +11,15 @@ import torch
 import zignal_b200 as zg
 from zignal_b200 import workloads as fo
 
-WORK = {"ns": (65536, 8192), "c2": (4096, 65536), "mid": (16384, 16384), "c32k": (32768, 8192), "c8k": (8192, 32768)}
+WORK = {"c3": (65536, 16384), "c5": (131072, 4096), "ns": (65536, 8192), "c2": (4096, 65536), "mid": (16384, 16384), "c32k": (32768, 8192), "c8k": (8192, 32768)}
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="ns")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--sections", type=int, default=4)
+    ap.add_argument("--graph", default="biquad", choices=["biquad", "osc", "poly", "copy"],
+                    help="osc = configs[2] (dirac in, fp32 out), poly = configs[4] (dirac in, bf16 out), copy = y = 1.0f*x")
     ap.add_argument("--points", default="mode=exact,fast;boxes=1,2;wpc=0;stages=0;layout=planar;coef=uniform")
     a = ap.parse_args()
     axes = {}
@@ -39,13 +41,22 @@ def main():
         inter = pt["layout"] == "interleaved"
         if inter and xi is None:
             xi = x.t().contiguous(); yi = torch.empty_like(xi)
-        if pt["coef"] == "uniform":
+        extra = {}
+        out_dt, bytes_per_sample, has_in = torch.float32, 8, True
+        if a.graph == "osc":
+            g = zg.compile(fo.osc_lp_expr()); extra = dict(input_kind=[zg.IN_DIRAC]); bytes_per_sample, has_in = 4, False
+        elif a.graph == "poly":
+            g = zg.compile(fo.poly_voice_expr()); extra = dict(input_kind=[zg.IN_DIRAC], io_dtype=zg.BF16)
+            out_dt, bytes_per_sample, has_in = torch.bfloat16, 2, False
+        elif a.graph == "copy":
+            g = zg.compile("0x1p+0f*_1")
+        elif pt["coef"] == "uniform":
             g = zg.compile(fo.biquad_cascade(a.sections))
         else:
             g = zg.compile(fo.biquad_cascade_params(a.sections))
         try:
             plan = g.plan(channels=C, mode=zg.MODE_EXACT if pt["mode"] == "exact" else zg.MODE_FAST,
-                          layout=zg.INTERLEAVED if inter else zg.PLANAR, lanes_per_channel=int(pt["lanes"]), force_jit=pt["jit"] == "1")
+                          layout=zg.INTERLEAVED if inter else zg.PLANAR, lanes_per_channel=int(pt["lanes"]), force_jit=pt["jit"] == "1", **extra)
             if pt["coef"] != "uniform":
                 import numpy as np
                 for k in range(a.sections):
@@ -53,6 +64,10 @@ def main():
                     for j in range(5):
                         plan.set_param(5 * k + j, np.full(C, co[j], np.float32))
             bi, bo = ([xi], [yi]) if inter else ([x], [y])
+            if out_dt != torch.float32: bo = [torch.empty(bo[0].shape, dtype=out_dt, device="cuda")]
+            if not has_in: bi = [None]
+            _proc = plan.process
+            plan.process = lambda i, o: _proc(i, o, n_samples=T)
             for _ in range(3): plan.process(bi, bo)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -61,7 +76,7 @@ def main():
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / a.iters
             info = plan.info()
-            pt.update(ms=round(ms, 4), msamples=round(C * T / ms / 1e3), gbs=round(8 * C * T / ms / 1e6),
+            pt.update(ms=round(ms, 4), msamples=round(C * T / ms / 1e3), gbs=round(bytes_per_sample * C * T / ms / 1e6),
                       threads=info.threads_per_cta, stages_used=info.stages, boxes_used=info.boxes, smem=info.smem_bytes, lanes_used=info.lanes_per_channel,
                       regs=info.regs_per_thread)
         except Exception as e:

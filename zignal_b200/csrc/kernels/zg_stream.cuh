@@ -322,14 +322,17 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                     tma_wait_read<0>();                            // the store of tile i-1 (the only one pending)
                     issue_load(i + S - 1);
                 }
-                // absolute stream index of the first sample of the box (dirac synthesis)
+                // absolute stream index of the first sample of the box (dirac synthesis).  A dirac is 1.0 at
+                // stream position 0 only: the one box that holds it takes the sample-by-sample path below;
+                // everywhere else a synthesised input is the constant 0 (no per-sample compare in the hot loop)
                 const long long t_abs0 = a.stream_pos + tb0;
+                const bool full_box = n_valid == BT && !(Tick::SYNTH_MASK != 0 && a.dirac_mask != 0 && t_abs0 == 0);
 
                 if (!kInterleaved) {
                     // row `lane`, 16-byte chunk j lives at chunk (j ^ (lane & 7)) of the row (SWIZZLE_128B)
                     const unsigned row = (unsigned)lane * 128u;
                     const unsigned sw = (unsigned)(lane & 7);
-                    if (n_valid == BT) {
+                    if (full_box) {
                         // the chunk of step j+1 is loaded before the ticks of step j: the LDS latency
                         // overlaps arithmetic instead of stalling the warp (3-4 warps per scheduler)
                         uint4 xn[NI > 0 ? NI : 1];
@@ -355,10 +358,8 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                                         xn[k] = *reinterpret_cast<const uint4*>(base + k * wire_bytes + row +
                                                                                 (((unsigned)(j + 1) ^ sw) << 4));
                                 } else {
-                                    const bool dirac = (a.dirac_mask >> k) & 1u;
-                                    const long long tt = t_abs0 + VPC * j;
 #pragma unroll
-                                    for (int q = 0; q < VPC; ++q) xv[k][q] = (dirac && tt + q == 0) ? 1.f : 0.f;
+                                    for (int q = 0; q < VPC; ++q) xv[k][q] = 0.f;
                                 }
                             }
 #pragma unroll
@@ -396,7 +397,7 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                     // interleaved frames: box is [32 samples][32 channels], lane = channel column
                     typename IO::Elem* box = reinterpret_cast<typename IO::Elem*>(base);
                     const unsigned wire_f = wire_bytes / kIo;
-                    if (n_valid == BT) {
+                    if (full_box) {
 #pragma unroll 8
                         for (int t = 0; t < BT; ++t) {
                             Arr<NI> x;
@@ -404,7 +405,7 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
 #pragma unroll
                             for (int k = 0; k < NI; ++k) {
                                 if (kBufMask & (1u << k)) x[k] = IO::load(&box[k * wire_f + t * 32 + lane]);
-                                else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
+                                else x[k] = 0.f;
                             }
                             run_tick(x, y);
 #pragma unroll

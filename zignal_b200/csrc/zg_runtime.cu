@@ -216,7 +216,9 @@ struct zg_plan {
     int64_t C = 0, ch_stride = 0;
     bool exact = false, interleaved = false;
     int io = 4;                             // bytes per sample in HBM: 4 = fp32, 2 = bf16
-    int tick_ops = 0;                       // floating-point instructions per tick (estimate; refill policy)
+    int tick_ops = 0;                       // floating-point instructions per tick (estimate)
+    bool light_tick = false;                // < 3.5 such instructions per byte of sample traffic: HBM-bound
+                                            // (refill and geometry policy); else bound by instruction issue
     unsigned synth_mask = 0, dirac_mask = 0;
     int n_buf_in = 0;
 
@@ -479,11 +481,19 @@ Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, in
     const int reg_warps = std::max(1, 65536 / (32 * std::max(regs, 32)));   // warps/SM the register file allows
     int wpc = (int)std::min<int64_t>({per_sm, 16, (int64_t)reg_warps});
     wpc = std::max(wpc, 1);
-    if (int w = tune_env("ZG_TUNE_WPC")) wpc = std::min(std::max(w, 1), 16);
-    const int budget = p->max_smem_optin - 1024 /*alignment slack*/ - 16 * 8 * 8 /*barriers*/;
     // boxes per stage: 2 (256 contiguous bytes per channel row in flight together) when that still
     // leaves 3 stages, else 1
     int NB = 2;
+    // A tick with little arithmetic is bound by HBM, and HBM likes fewer, longer streams: 7 resident warps
+    // per SM with 4 boxes (512 contiguous bytes per channel row) per stage beat 14 x 2 by 3-11 % (copy graph
+    // 5.72 -> 5.87 TB/s, osc >> LP 4.97 -> 5.51, FMA biquad x4 5.53 -> 5.74; profiles/r01_sweep_synth.jsonl).
+    // Arithmetic-heavy ticks are issue-bound and keep all the warps the shared memory allows.
+    if (p->light_tick && per_sm > 7) {
+        wpc = std::min(wpc, 7);
+        NB = 4;
+    }
+    if (int w = tune_env("ZG_TUNE_WPC")) wpc = std::min(std::max(w, 1), 16);
+    const int budget = p->max_smem_optin - 1024 /*alignment slack*/ - 16 * 8 * 8 /*barriers*/;
     if (int b = tune_env("ZG_TUNE_BOXES")) NB = std::min(std::max(b, 1), 8);
     NB = (int)std::min<int64_t>(NB, std::max<int64_t>(1, (T + BT - 1) / BT));
     auto stages_for = [&](int w, int nb) { return budget / (w * NT * nb * BB); };
@@ -588,7 +598,7 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     // is bound by instruction issue and gains from refilling a slot in the middle of the next tile (the load
     // latency hides behind arithmetic); a light tick is bound by HBM and does better when a warp's load and
     // store requests leave together.  ZG_TUNE_LATE_REFILL=1 / =2 force late / early.
-    bool late = p->tick_ops < 28;
+    bool late = p->light_tick;
     if (int t = tune_env("ZG_TUNE_LATE_REFILL")) late = t == 1;
     if (late) a.flags |= 2;
     if (int h = tune_env("ZG_TUNE_L2HINT")) a.flags |= (h & 3) << 2;       // 1 = loads, 2 = stores, 3 = both: evict-first
@@ -862,6 +872,8 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
         }
         // FAST: a product feeding a sum contracts into one FMA (at most one product per sum)
         p->tick_ops = p->exact ? arith : arith - std::min(mul, arith - mul);
+        const int bytes = p->io * std::max(1, p->n_buf_in + ir.n_out);
+        p->light_tick = 2 * p->tick_ops < 7 * bytes;
     }
     const size_t state_floats = (size_t)std::max(ir.n_state, 1) * p->ch_stride;
     ZG_CUDA(cudaMalloc(&p->d_state, state_floats * sizeof(float)));
