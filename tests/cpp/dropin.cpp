@@ -1,0 +1,99 @@
+// A flowz user's program, unchanged in spelling, built against the B200-native library instead of the
+// reference header (andre-bergner/zignal flowz/flowz.hpp).  Used by tests/test_cpp_dropin.py:
+//   ./dropin          host only: compile() + operator() ticks (BASELINE configs[0], runs without a GPU)
+//   ./dropin gpu      additionally: the same graphs as blocks on the B200 through on_device(), which must
+//                     reproduce the per-sample ticks bit for bit (EXACT mode)
+#include <flowz/flowz.hpp>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+static int failures = 0;
+#define CHECK(cond)                                                          \
+    do {                                                                     \
+        if (!(cond)) { std::printf("FAILED %s:%d  %s\n", __FILE__, __LINE__, #cond); ++failures; } \
+    } while (0)
+
+static float noise(unsigned& s) {                       // deterministic input in [-1, 1)
+    s = s * 1664525u + 1013904223u;
+    return (float)((s >> 8) & 0xffffff) / 8388608.0f - 1.0f;
+}
+
+int main(int argc, char** argv) {
+    using namespace flowz;
+    const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
+
+    // ---- BASELINE configs[0]: mono one-pole low-pass y = x + a*y1 over 1024 samples (flowz/README.md) ----
+    auto one_pole = compile(~(_2 + 0.9f * _1[_1]));
+    std::vector<float> x(1024), y_host(1024);
+    unsigned seed = 1;
+    for (auto& v : x) v = noise(seed);
+    float y1 = 0.f;
+    for (int t = 0; t < 1024; ++t) {
+        y_host[t] = std::get<0>(one_pole(x[t]));
+        const float want = x[t] + 0.9f * y1;             // the same arithmetic by hand
+        CHECK(y_host[t] == want);
+        y1 = want;
+    }
+
+    // ---- the reference's benchmark graph: direct-form-1 biquad, fwd |= bwd (test/benchmark.cpp:18-33) ----
+    const float b0 = 0.2f, b1 = 0.4f, b2 = 0.2f, a1 = 0.3f, a2 = -0.1f;
+    auto fwd = b0 * _1 + b1 * _1[_1] + b2 * _1[_2];
+    auto bwd = ~(_2 + a1 * _1[_1] + a2 * _1[_2]);
+    auto biquad = compile(fwd |= bwd);
+    std::vector<float> yb_host(1024);
+    {
+        float x1 = 0, x2 = 0, v1 = 0, v2 = 0;
+        for (int t = 0; t < 1024; ++t) {
+            yb_host[t] = std::get<0>(biquad(x[t]));
+            const float v = (b0 * x[t] + b1 * x1) + b2 * x2;
+            const float w = (v + a1 * v1) + a2 * v2;
+            CHECK(yb_host[t] == w);
+            x2 = x1; x1 = x[t]; v2 = v1; v1 = w;
+        }
+    }
+
+    // ---- std::ref parameters (flowz/README.md:42-63) and state copy (flowz.hpp:1206-1207) ----
+    float gain = 0.5f;
+    auto amp = compile(std::ref(gain) * _1);
+    CHECK(std::get<0>(amp(2.0f)) == 1.0f);
+    gain = 3.0f;
+    CHECK(std::get<0>(amp(2.0f)) == 6.0f);
+    auto fork = one_pole;                                 // continues from the same state, independently
+    CHECK(std::get<0>(fork(0.25f)) == std::get<0>(one_pole(0.25f)));
+
+    if (gpu) {
+        // the same graphs for 96 voices at once; every voice gets the same input, so every row must equal
+        // the host ticks above bit for bit
+        const int64_t C = 96, T = 1024;
+        std::vector<float> in((size_t)C * T), out((size_t)C * T);
+        for (int64_t c = 0; c < C; ++c) std::memcpy(&in[c * T], x.data(), T * sizeof(float));
+        const float* ip[1] = {in.data()};
+        float* op[1] = {out.data()};
+        {
+            auto dev = compile(~(_2 + 0.9f * _1[_1])).on_device(C);
+            dev.process_host(ip, op, 512, T, T);                       // two blocks: state carries over
+            const float* ip2[1] = {in.data() + 512};
+            float* op2[1] = {out.data() + 512};
+            dev.process_host(ip2, op2, 512, T, T);
+            for (int64_t c = 0; c < C; ++c) CHECK(std::memcmp(&out[c * T], y_host.data(), T * sizeof(float)) == 0);
+        }
+        {
+            auto dev = compile(fwd |= bwd).on_device(C);
+            dev.process_host(ip, op, T, T, T);
+            for (int64_t c = 0; c < C; ++c) CHECK(std::memcmp(&out[c * T], yb_host.data(), T * sizeof(float)) == 0);
+            CHECK(std::strstr(dev.info().kernel, "zg_biquad_df1") != nullptr);   // recognised: prebuilt kernel
+        }
+    } else {
+        // without a device the block evaluator must say so, not fall back to a CPU loop
+        bool threw = false;
+        try { (void)one_pole.on_device(8); } catch (const std::exception& e) { threw = std::strstr(e.what(), "no CPU fallback") != nullptr; }
+        if (!threw) std::printf("note: on_device() did not fail -- is a GPU visible?\n");
+    }
+
+    std::printf(failures ? "dropin: %d FAILURES\n" : "dropin ok (%d failures)\n", failures);
+    return failures ? 1 : 0;
+}

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--workload", default="ns")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--sections", type=int, default=4)
+    ap.add_argument("--pad", type=int, default=0, help="extra floats of row pitch (planar buffers)")
     ap.add_argument("--graph", default="biquad", choices=["biquad", "osc", "poly", "copy"],
                     help="osc = configs[2] (dirac in, fp32 out), poly = configs[4] (dirac in, bf16 out), copy = y = 1.0f*x")
     ap.add_argument("--points", default="mode=exact,fast;boxes=1,2;wpc=0;stages=0;layout=planar;coef=uniform")
@@ -29,8 +30,9 @@ def main():
     for k, d in (("mode", ["exact"]), ("boxes", ["0"]), ("wpc", ["0"]), ("stages", ["0"]), ("layout", ["planar"]), ("coef", ["uniform"]), ("lanes", ["0"]), ("late", ["0"]), ("hint", ["0"]), ("promo", ["0"]), ("cu", ["0"]), ("jit", ["0"])):
         axes.setdefault(k, d)
     C, T = WORK[a.workload]
-    x = torch.rand((C, T), device="cuda") * 2 - 1
-    y = torch.empty_like(x)
+    x = torch.empty((C, T + a.pad), device="cuda")[:, :T]
+    x.copy_(torch.rand((C, T), device="cuda") * 2 - 1)
+    y = torch.empty((C, T + a.pad), device="cuda")[:, :T]
     xi, yi = None, None
     keys = list(axes)
     for combo in itertools.product(*[axes[k] for k in keys]):
@@ -76,7 +78,7 @@ def main():
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / a.iters
             info = plan.info()
-            pt.update(ms=round(ms, 4), msamples=round(C * T / ms / 1e3), gbs=round(bytes_per_sample * C * T / ms / 1e6),
+            pt.update(pad=a.pad, ms=round(ms, 4), msamples=round(C * T / ms / 1e3), gbs=round(bytes_per_sample * C * T / ms / 1e6),
                       threads=info.threads_per_cta, stages_used=info.stages, boxes_used=info.boxes, smem=info.smem_bytes, lanes_used=info.lanes_per_channel,
                       regs=info.regs_per_thread)
         except Exception as e:
