@@ -121,6 +121,44 @@ def test_reference_benchmark_graph_df1_dirac(zg, ):
         assert np.array_equal(ys[0][c, :201], g["custom1_dirac"])     # the reference's own hand-written loop
 
 
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+def test_symmetric_and_asymmetric_numerators_take_different_ticks(zg, layout):
+    """EXACT, shared coefficients: sections with b0 == b2 (bit for bit) reuse the product b0*x two ticks later
+    instead of recomputing b2*x2 -- the same operands, so still bit-identical; any other coefficient set runs
+    the nine-instruction tick.  Switching between them by zg_param_set keeps the stream continuous."""
+    S, C, T = 4, 70, 900
+    x = [fo.noise(C, T, seed=61)]
+    expr = fo.biquad_cascade_params(S)
+    sym = [v for k in range(S) for v in fo.rbj_lowpass(440.0 * 2 ** k)]
+    asym = list(sym)
+    asym[2] = np.float32(asym[2] * 1.25)                     # b2 != b0 in the first section
+    for params, tag in ((sym, True), (asym, False)):
+        ys, plan = _run(zg, expr, x, zg.MODE_EXACT, layout, params=[float(v) for v in params])
+        assert (b"+b0=b2" in plan.info().kernel) == tag
+        assert np.array_equal(ys[0], _oracle(expr, x, [float(v) for v in params])[0])
+    # one stream, coefficients changed between blocks: symmetric -> asymmetric -> symmetric
+    g = zg.compile(expr)
+    plan = g.plan(channels=C, mode=zg.MODE_EXACT, layout=zg.PLANAR if layout == "planar" else zg.INTERLEAVED)
+    outs, t0 = [], 0
+    for params, n in ((sym, 300), (asym, 301), (sym, 299)):
+        for i, v in enumerate(params):
+            plan.set_param(i, float(v))
+        xb = x[0][:, t0:t0 + n]
+        yb = plan.process([_to_dev(xb.T if layout == "interleaved" else xb)])[0].cpu().numpy()
+        outs.append(yb.T if layout == "interleaved" else yb)
+        t0 += n
+    # oracle: same schedule (state carried by hand through three oracles sharing a state vector is not exposed;
+    # the C oracle takes per-channel parameters only per run, so compare block by block with explicit states)
+    ref_plan = g.plan(channels=C, mode=zg.MODE_EXACT, force_jit=True)          # generated kernel: no product reuse
+    t0 = 0
+    for k, (params, n) in enumerate(((sym, 300), (asym, 301), (sym, 299))):
+        for i, v in enumerate(params):
+            ref_plan.set_param(i, float(v))
+        yb = ref_plan.process([_to_dev(x[0][:, t0:t0 + n])])[0].cpu().numpy()
+        assert np.array_equal(outs[k], yb)
+        t0 += n
+
+
 def test_per_channel_coefficients(zg):
     C, T, S = 128, 512, 2
     x = [fo.noise(C, T, seed=4)]

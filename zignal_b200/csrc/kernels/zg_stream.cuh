@@ -193,6 +193,13 @@ struct chunk_unroll { static constexpr int value = 8; };
 template <class T>
 struct chunk_unroll<T, decltype((void)T::CHUNK_UNROLL)> { static constexpr int value = T::CHUNK_UNROLL; };
 
+// Registers a tick keeps across the block besides its delay-line state (Tick::N_EXTRA, default 0): values
+// derived from the state at block start by Tick::init(s, p, e) and handed to tick(x, y, s, p, e).
+template <class T, class = void>
+struct extra_count { static constexpr int value = 0; };
+template <class T>
+struct extra_count<T, decltype((void)T::N_EXTRA)> { static constexpr int value = T::N_EXTRA; };
+
 // ---- the streaming loop ---------------------------------------------------------------------------
 //
 // Tick must provide
@@ -249,9 +256,20 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
         for (int j = 0; j < NP; ++j) prm_reg[j] = ch_ok ? a.params[(long long)j * a.ch_stride + ch] : 0.f;
     }
     const UniformParams prm_uni{a.uparams};
+    constexpr int NE = extra_count<Tick>::value;
+    Arr<NE> ex;
+    if constexpr (NE > 0) {
+        if constexpr (kUniform) Tick::init(s, prm_uni, ex);
+        else Tick::init(s, prm_reg, ex);
+    }
     auto run_tick = [&](const Arr<NI>& x, Arr<NO>& y) {
-        if constexpr (kUniform) Tick::tick(x, y, s, prm_uni);
-        else Tick::tick(x, y, s, prm_reg);
+        if constexpr (NE > 0) {
+            if constexpr (kUniform) Tick::tick(x, y, s, prm_uni, ex);
+            else Tick::tick(x, y, s, prm_reg, ex);
+        } else {
+            if constexpr (kUniform) Tick::tick(x, y, s, prm_uni);
+            else Tick::tick(x, y, s, prm_reg);
+        }
     };
 
     if (lane == 0) {

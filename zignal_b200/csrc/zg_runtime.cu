@@ -171,7 +171,11 @@ KernelPtr biquad_lanes_kernel_for(int sections, bool exact, bool uniform) {
 }
 
 template <int S>
-KernelPtr biquad_kernel(bool exact, bool interleaved, bool uniform) {
+KernelPtr biquad_kernel(bool exact, bool interleaved, bool uniform, bool sym) {
+    // b0 == b2 in every section, EXACT, shared coefficients: the product-reusing tick (kernels/zg_biquad.cuh)
+    if (sym && exact && uniform)
+        return interleaved ? (KernelPtr)zg_stream_kernel<zgk::BiquadDf1Cascade<S, true, true>, true, true>
+                           : (KernelPtr)zg_stream_kernel<zgk::BiquadDf1Cascade<S, true, true>, false, true>;
 #define ZG_PICK(E, I, U) \
     if (exact == E && interleaved == I && uniform == U) \
         return (KernelPtr)zg_stream_kernel<zgk::BiquadDf1Cascade<S, E>, I, U>;
@@ -181,16 +185,16 @@ KernelPtr biquad_kernel(bool exact, bool interleaved, bool uniform) {
     return nullptr;
 }
 
-KernelPtr biquad_kernel_for(int sections, bool exact, bool interleaved, bool uniform) {
+KernelPtr biquad_kernel_for(int sections, bool exact, bool interleaved, bool uniform, bool sym) {
     switch (sections) {
-        case 1: return biquad_kernel<1>(exact, interleaved, uniform);
-        case 2: return biquad_kernel<2>(exact, interleaved, uniform);
-        case 3: return biquad_kernel<3>(exact, interleaved, uniform);
-        case 4: return biquad_kernel<4>(exact, interleaved, uniform);
-        case 5: return biquad_kernel<5>(exact, interleaved, uniform);
-        case 6: return biquad_kernel<6>(exact, interleaved, uniform);
-        case 7: return biquad_kernel<7>(exact, interleaved, uniform);
-        case 8: return biquad_kernel<8>(exact, interleaved, uniform);
+        case 1: return biquad_kernel<1>(exact, interleaved, uniform, sym);
+        case 2: return biquad_kernel<2>(exact, interleaved, uniform, sym);
+        case 3: return biquad_kernel<3>(exact, interleaved, uniform, sym);
+        case 4: return biquad_kernel<4>(exact, interleaved, uniform, sym);
+        case 5: return biquad_kernel<5>(exact, interleaved, uniform, sym);
+        case 6: return biquad_kernel<6>(exact, interleaved, uniform, sym);
+        case 7: return biquad_kernel<7>(exact, interleaved, uniform, sym);
+        case 8: return biquad_kernel<8>(exact, interleaved, uniform, sym);
     }
     return nullptr;
 }
@@ -235,7 +239,8 @@ struct zg_plan {
     int fir_regs = 0;
     int last_grid = 0;
 
-    Variant variant[2];                     // [uniform]
+    Variant variant[3];                     // [0] per-channel parameters, [1] uniform, [2] uniform + symmetric biquads
+    bool sym_now = false;                   // K1: every section has b0 == b2 (bit for bit), coefficients uniform
     std::string kernel_name;
 
     float* d_state = nullptr;               // [n_state][ch_stride]
@@ -333,8 +338,20 @@ int jit_compile(zg_plan* p, bool uniform, Variant& v) {
     return ZG_OK;
 }
 
+int tune_env(const char* name) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : 0;
+}
+
+int variant_index(const zg_plan* p) {
+    const bool sym = p->uniform_now && p->sym_now && p->is_biquad && !p->opts.force_jit && p->lanes == 1 && p->exact &&
+                     !tune_env("ZG_TUNE_NO_SYM");
+    return p->uniform_now ? (sym ? 2 : 1) : 0;
+}
+
 int get_variant(zg_plan* p, bool uniform, Variant*& out) {
-    Variant& v = p->variant[uniform ? 1 : 0];
+    const int vi = variant_index(p);
+    Variant& v = p->variant[vi];
     out = &v;
     if (v.ready) return ZG_OK;
     if (p->is_fir) {
@@ -346,7 +363,7 @@ int get_variant(zg_plan* p, bool uniform, Variant*& out) {
     }
     if (p->is_biquad && !p->opts.force_jit) {
         v.prebuilt = p->lanes > 1 ? biquad_lanes_kernel_for(p->bq.sections, p->exact, uniform)
-                                  : biquad_kernel_for(p->bq.sections, p->exact, p->interleaved, uniform);
+                                  : biquad_kernel_for(p->bq.sections, p->exact, p->interleaved, uniform, vi == 2);
         if (!v.prebuilt) return fail(ZG_ERR_INTERNAL, "no prebuilt biquad kernel for this section count");
         cudaFuncAttributes fa;
         ZG_CUDA(cudaFuncGetAttributes(&fa, (const void*)v.prebuilt));
@@ -392,11 +409,18 @@ int sync_params(zg_plan* p) {
             lit = 0.f;
         }
     };
+    p->sym_now = false;
     if (uniform) {
         for (int j = 0; j < NP; ++j) {
             int prm; float lit;
             slot_src(j, prm, lit);
             p->uparams[j] = prm >= 0 ? p->h_params[prm][0] : lit;
+        }
+        if (p->is_biquad && !p->opts.force_jit) {
+            bool sym = true;
+            for (int k = 0; k < p->bq.sections; ++k)
+                sym = sym && std::memcmp(&p->uparams[5 * k], &p->uparams[5 * k + 2], sizeof(float)) == 0;
+            p->sym_now = sym;
         }
     } else if (NP > 0) {
         std::vector<float> host((size_t)NP * p->ch_stride, 0.f);
@@ -414,11 +438,6 @@ int sync_params(zg_plan* p) {
     p->uniform_now = uniform;
     p->params_dirty = false;
     return ZG_OK;
-}
-
-int tune_env(const char* name) {
-    const char* v = std::getenv(name);
-    return v && *v ? std::atoi(v) : 0;
 }
 
 // ---- tensor maps ---------------------------------------------------------------------------------------
@@ -900,8 +919,9 @@ void zg_plan_destroy(zg_plan* p) { delete p; }
 int zg_plan_get_info(const zg_plan* p, zg_plan_info* info) {
     if (!p || !info) return fail(ZG_ERR_ARG, "NULL argument");
     std::memset(info, 0, sizeof *info);
-    std::snprintf(info->kernel, sizeof info->kernel, "%s", p->kernel_name.c_str());
-    const Variant& v = p->variant[p->uniform_now ? 1 : 0];
+    std::snprintf(info->kernel, sizeof info->kernel, "%s%s", p->kernel_name.c_str(),
+                  variant_index(p) == 2 ? "+b0=b2" : "");      // the product-reusing tick (kernels/zg_biquad.cuh)
+    const Variant& v = p->variant[variant_index(p)];
     info->jit = (v.prebuilt || p->is_fir) ? 0 : 1;
     info->lanes_per_channel = p->lanes;
     info->host_chunks = p->last_host_chunks;
