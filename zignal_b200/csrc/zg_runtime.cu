@@ -850,7 +850,9 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
                     "lanes_per_channel > 1 needs a planar biquad cascade of exactly that many (2 or 4) sections");
     if (p->is_biquad && !opts->force_jit && !p->interleaved && (p->bq.sections == 2 || p->bq.sections == 4)) {
         // one lane per channel leaves SM schedulers idle below ~2 warps per scheduler: spread the sections
-        const bool too_few = (p->C + 31) / 32 < (int64_t)p->sm_count * 4;
+        // measured crossover (4 sections, T >= 16k; profiles/r01_sweep_ns_lanes.jsonl): 8192 channels K1b 0.60 ms
+        // vs K1 1.18 ms, 16 384 channels K1b 0.79 vs K1 0.58 -> K1b below ~2.5 warps of channels per SM
+        const bool too_few = (p->C + 31) / 32 < (int64_t)p->sm_count * 5 / 2;
         if (want_lanes > 1 || (want_lanes == 0 && too_few)) p->lanes = p->bq.sections;
     }
     if (p->is_fir) {
