@@ -280,6 +280,25 @@ def other_configs(zg, wl, torch, dev, local, world, rank, args, barrier, dist):
     return out
 
 
+def _bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, before any pinned host buffer is allocated:
+    with one rank per GPU on a two-socket box, host staging memory that sits on the other socket turns the e2e
+    path (H2D + D2H of every block) into cross-socket traffic.  Best effort; silently skipped if NVML or the
+    affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 # ---- our arm ---------------------------------------------------------------------------------------------
 
 def run_ours(args):
@@ -295,6 +314,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    _bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
