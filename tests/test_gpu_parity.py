@@ -703,3 +703,37 @@ def test_sample_rate_parameter_is_just_another_input_wire(zg):
             assert np.array_equal(ys[0], ref)
         else:
             assert _rel_err(ys[0], ref) <= TOL
+
+
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+def test_mixed_buffer_and_synthesised_inputs(zg, layout):
+    """Two inputs, one streamed from HBM and one synthesised in the kernel (dirac / zeros): only the buffer
+    wire gets a TMA pipeline; blocks continue across the dirac's position."""
+    expr = "(_1 | _1[_1]) |= ~(_2 + _3 + 0.25f*_1[_2])"
+    g = zg.compile(expr)
+    assert g.n_in == 2
+    C, T = 45, 500
+    x0 = fo.noise(C, T, seed=71)
+    d = np.zeros((C, T), np.float32); d[:, 0] = 1
+    for kind, second in ((zg.IN_DIRAC, d), (zg.IN_ZERO, np.zeros_like(d))):
+        ys, _ = _run(zg, expr, [x0, second], zg.MODE_EXACT, layout, input_kind=[zg.IN_BUFFER, kind], blocks=[1, 63, 436])
+        assert np.array_equal(ys[0], _oracle(expr, [x0, second])[0])
+
+
+def test_full_size_config3_65536_voice_oscillators(zg):
+    """BASELINE configs[2] at full size: 65 536 voices of osc >> one-pole low-pass, dirac-excited, 16 384 samples.
+    All voices are identical, and equal to the oracle bit for bit (EXACT: a marginally stable oscillator must not
+    be re-rounded); two half blocks continue the stream."""
+    torch = _torch()
+    C, T = 65536, 16384
+    expr = fo.osc_lp_expr()
+    plan = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, input_kind=[zg.IN_DIRAC])
+    ya = plan.process([None], n_samples=T // 2)[0]
+    yb = plan.process([None], n_samples=T // 2)[0]
+    torch.cuda.synchronize()
+    y = torch.cat([ya, yb], dim=1)
+    assert bool((y == y[0:1]).all())
+    d = np.zeros((1, T), np.float32); d[0, 0] = 1
+    ref = _oracle(expr, [d])[0]
+    assert np.array_equal(y[C - 1].cpu().numpy(), ref[0])
+    assert np.abs(ref).max() > 1.0                       # it really oscillates

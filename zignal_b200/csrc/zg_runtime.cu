@@ -507,7 +507,13 @@ Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, in
     // per SM with 4 boxes (512 contiguous bytes per channel row) per stage beat 14 x 2 by 3-11 % (copy graph
     // 5.72 -> 5.87 TB/s, osc >> LP 4.97 -> 5.51, FMA biquad x4 5.53 -> 5.74; profiles/r01_sweep_synth.jsonl).
     // Arithmetic-heavy ticks are issue-bound and keep all the warps the shared memory allows.
-    if (p->light_tick && per_sm > 7) {
+    // Planar blocks keep gaining from that trade up to ~4.25 instructions per byte -- the product-reusing EXACT
+    // 4-section tick (32 instructions / 8 B): 0.791 ms against 0.805-0.845 with 14 x 2; at 8 sections (8 per byte)
+    // or on interleaved frames 14 x 2 is the faster one (profiles/r01_sweep_sym2.jsonl).
+    const int ops = p->tick_ops - (variant_index(p) == 2 ? p->bq.sections : 0);
+    const int bytes = p->io * std::max(1, p->n_buf_in + p->ir.n_out);
+    const bool long_runs = !p->interleaved && 4 * ops < 17 * bytes;
+    if (long_runs && per_sm > 7) {
         wpc = std::min(wpc, 7);
         NB = 4;
     }
@@ -602,7 +608,9 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     for (int j = 0; j < p->kernel_n_state; ++j) a.state_row[j] = p->state_row[j];
     if (p->uniform_now) std::memcpy(a.uparams, p->uparams, sizeof(float) * std::min(p->kernel_n_param, zgk::kMaxUniform));
 
-    const int NT = std::max(1, std::max(p->n_buf_in, p->ir.n_out));
+    // wires per pipeline stage as the kernel lays them out: wire k of a stage belongs to input k / output k
+    // (kernels/zg_stream.cuh: NT = max(N_IN, N_OUT)), whether or not input k is synthesised
+    const int NT = std::max(1, std::max(p->ir.n_in, p->ir.n_out));
     const int cpw = 32 / p->lanes;                     // channels per warp
     const int64_t n_warps = (c_count + cpw - 1) / cpw;
     Geometry g = p->lanes > 1 ? choose_geometry_lanes(p, n_warps, v->regs, T) : choose_geometry(p, n_warps, NT, v->regs, T);
