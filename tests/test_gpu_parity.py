@@ -737,3 +737,35 @@ def test_full_size_config3_65536_voice_oscillators(zg):
     ref = _oracle(expr, [d])[0]
     assert np.array_equal(y[C - 1].cpu().numpy(), ref[0])
     assert np.abs(ref).max() > 1.0                       # it really oscillates
+
+
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+def test_buffer_input_behind_a_synthesised_one(zg, layout):
+    """the buffer wire is input 1, input 0 is synthesised: stage wire k belongs to input k either way"""
+    expr = "(_1 | _1[_1]) |= ~(_2 + _3 + 0.25f*_1[_2])"
+    C, T = 45, 500
+    x1 = fo.noise(C, T, seed=72)
+    d = np.zeros((C, T), np.float32); d[:, 0] = 1
+    ys, _ = _run(zg, expr, [d, x1], zg.MODE_EXACT, layout, input_kind=[zg.IN_DIRAC, zg.IN_BUFFER], blocks=[70, 430])
+    assert np.array_equal(ys[0], _oracle(expr, [d, x1])[0])
+
+
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_six_inputs_two_outputs(zg, layout, dtype):
+    """many wires per stage: the geometry has to give up warps per CTA for shared memory"""
+    expr = "(_1 + _2 + _3 , _4*_5 - _6[_1])"
+    g = zg.compile(expr)
+    assert (g.n_in, g.n_out) == (6, 2)
+    C, T = 200, 300
+    x = [fo.noise(C, T, seed=80 + k) for k in range(6)]
+    if dtype == "f32":
+        ys, _ = _run(zg, expr, x, zg.MODE_EXACT, layout)
+        ref = _oracle(expr, x)
+        for y, r in zip(ys, ref):
+            assert np.array_equal(y, r)
+    else:
+        ys, _ = _run_bf16(zg, expr, x, zg.MODE_EXACT, layout)
+        ref = _oracle(expr, [fo.bf16_round(v) for v in x])
+        for y, r in zip(ys, ref):
+            assert np.array_equal(y, fo.bf16_bits(r))
