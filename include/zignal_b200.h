@@ -178,6 +178,10 @@ int zg_state_get(zg_plan* p, float* host, size_t n_floats);
 int zg_state_set(zg_plan* p, const float* host, size_t n_floats);
 /* $index for all channels: n == 1 broadcasts a scalar, n == channels sets one value per channel */
 int zg_param_set(zg_plan* p, int index, const float* host_values, int64_t n);
+/* Same from DEVICE memory, one value per channel (n == channels): coefficients computed on the GPU -- e.g. RBJ
+ * sections from per-voice f, Q (reactive_equations/reactive_filter_coeff.cpp:16-50) -- never visit the host.
+ * Synchronises the device (the values are copied before the call returns).                               */
+int zg_param_set_device(zg_plan* p, int index, const float* device_values, int64_t n);
 
 #ifdef __cplusplus
 }

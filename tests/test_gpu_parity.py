@@ -769,3 +769,41 @@ def test_six_inputs_two_outputs(zg, layout, dtype):
         ref = _oracle(expr, [fo.bf16_round(v) for v in x])
         for y, r in zip(ys, ref):
             assert np.array_equal(y, fo.bf16_bits(r))
+
+
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_coefficients_computed_on_the_device(zg, lanes):
+    """per-voice RBJ low-pass sections computed on the GPU from per-voice cutoff frequencies
+    (formulae of reactive_equations/reactive_filter_coeff.cpp:16-50, flowz sign convention) and handed to the plan
+    with zg_param_set_device -- no host round trip.  The kernel must use exactly those values: the output equals
+    the oracle fed the same coefficients (read back only for the check), bit for bit."""
+    torch = _torch()
+    S, C, T = 4, 96, 1200
+    expr = fo.biquad_cascade_params(S)
+    g = zg.compile(expr)
+    plan = g.plan(channels=C, mode=zg.MODE_EXACT, lanes_per_channel=lanes)
+    c = torch.arange(C, device="cuda", dtype=torch.float64)
+    coefs = []
+    for k in range(S):
+        f = 440.0 * 2 ** k * (1.0 + c / C)
+        w0 = 2.0 * torch.pi * f / 44100.0
+        alpha = torch.sin(w0) / (2.0 * 0.707)
+        a0 = 1.0 + alpha
+        b1 = (1.0 - torch.cos(w0)) / a0
+        for v in (b1 / 2.0, b1, b1 / 2.0, 2.0 * torch.cos(w0) / a0, -(1.0 - alpha) / a0):
+            coefs.append(v.to(torch.float32).contiguous())
+    for i, v in enumerate(coefs):
+        plan.set_param_device(i, v)
+    x = fo.noise(C, T, seed=91)
+    y = plan.process([_to_dev(x)])[0].cpu().numpy()
+    assert plan.info().uniform_params == 0 and plan.info().lanes_per_channel == lanes
+    params = [v.cpu().numpy() for v in coefs]
+    assert np.array_equal(y, _oracle(expr, [x], params)[0])
+    # a later host-side set of the same parameter replaces the device-side one
+    plan.reset()
+    plan.set_param(0, 0.0)                                   # b0 of the first section := 0 for every voice
+    params[0] = np.zeros(C, np.float32)
+    y2 = plan.process([_to_dev(x)])[0].cpu().numpy()
+    assert np.array_equal(y2, _oracle(expr, [x], params)[0])
+    with pytest.raises(zg.ZgError):
+        plan.set_param_device(0, torch.zeros(C - 1, device="cuda"))

@@ -88,6 +88,7 @@ def _load() -> C.CDLL:
         "zg_state_get": (ci, [vp, P(C.c_float), sz]),
         "zg_state_set": (ci, [vp, P(C.c_float), sz]),
         "zg_param_set": (ci, [vp, ci, P(C.c_float), i64]),
+        "zg_param_set_device": (ci, [vp, ci, vp, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here = header and library disagree
@@ -101,7 +102,7 @@ EXPORTED = ["zg_last_error", "zg_version", "zg_expr_arity", "zg_expr_delays", "z
             "zg_voice_create", "zg_voice_clone", "zg_voice_destroy", "zg_voice_tick", "zg_voice_set_param",
             "zg_voice_state", "zg_plan_opts_default", "zg_graph_kernel_compile", "zg_plan_create",
             "zg_plan_destroy", "zg_plan_get_info", "zg_process", "zg_process_host", "zg_state_reset",
-            "zg_state_get", "zg_state_set", "zg_param_set"]
+            "zg_state_get", "zg_state_set", "zg_param_set", "zg_param_set_device"]
 
 
 def _check(status: int) -> None:
@@ -373,3 +374,10 @@ class Plan:
         import numpy as np
         a = np.ascontiguousarray(np.atleast_1d(values), np.float32)
         _check(lib.zg_param_set(self._h, index, a.ctypes.data_as(C.POINTER(C.c_float)), a.size))
+
+    def set_param_device(self, index: int, values) -> None:
+        """values: float32 CUDA tensor [channels] (e.g. coefficients computed with torch on the device)."""
+        import torch
+        if not (values.is_cuda and values.dtype == torch.float32 and values.is_contiguous()):
+            raise TypeError("set_param_device needs a contiguous float32 CUDA tensor (one value per channel)")
+        _check(lib.zg_param_set_device(self._h, index, C.c_void_p(values.data_ptr()), values.numel()))

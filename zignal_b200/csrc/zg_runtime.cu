@@ -246,6 +246,8 @@ struct zg_plan {
     float* d_state = nullptr;               // [n_state][ch_stride]
     float* d_params = nullptr;              // [kernel_n_param][ch_stride]
     std::vector<std::vector<float>> h_params;   // per graph parameter: size 1 (scalar) or C
+    std::vector<char> param_on_device;          // parameter k was last set from device memory (zg_param_set_device)
+    float* d_user_params = nullptr;             // [n_params][ch_stride]: the device-side values of those
     bool params_dirty = true;
     bool uniform_now = true;
     float uparams[zgk::kMaxUniform] = {};
@@ -272,6 +274,7 @@ struct zg_plan {
         if (d_state_alt) cudaFree(d_state_alt);
         if (d_taps) cudaFree(d_taps);
         if (d_params) cudaFree(d_params);
+        if (d_user_params) cudaFree(d_user_params);
         if (d_stage) cudaFree(d_stage);
         if (own_stream) cudaStreamDestroy(own_stream);
         if (h2d_stream) cudaStreamDestroy(h2d_stream);
@@ -384,7 +387,7 @@ int sync_params(zg_plan* p) {
         std::vector<float> taps(p->fir.taps.size());
         for (size_t k = 0; k < taps.size(); ++k) {
             const BiquadCoef& c = p->fir.taps[k];
-            if (c.is_param && p->h_params[c.param].size() != 1)
+            if (c.is_param && (p->h_params[c.param].size() != 1 || p->param_on_device[c.param]))
                 return fail(ZG_ERR_UNSUPPORTED, "the FIR kernel shares its taps between channels: $" +
                                                     std::to_string(c.param) + " must be a scalar");
             taps[k] = c.is_param ? p->h_params[c.param][0] : c.value;
@@ -398,6 +401,7 @@ int sync_params(zg_plan* p) {
     const int NP = p->kernel_n_param;
     bool uniform = NP <= zgk::kMaxUniform;
     for (auto& h : p->h_params) uniform = uniform && h.size() == 1;
+    for (char d : p->param_on_device) uniform = uniform && !d;
     // kernel slot j -> (graph parameter | literal)
     auto slot_src = [&](int j, int& param, float& lit) {
         if (p->is_biquad && !p->opts.force_jit) {
@@ -429,11 +433,19 @@ int sync_params(zg_plan* p) {
             slot_src(j, prm, lit);
             float* row = host.data() + (size_t)j * p->ch_stride;
             if (prm < 0) std::fill(row, row + p->C, lit);
+            else if (p->param_on_device[prm]) continue;                    // copied device to device below
             else if (p->h_params[prm].size() == 1) std::fill(row, row + p->C, p->h_params[prm][0]);
             else std::copy(p->h_params[prm].begin(), p->h_params[prm].end(), row);
         }
         if (!p->d_params) ZG_CUDA(cudaMalloc(&p->d_params, host.size() * sizeof(float)));
         ZG_CUDA(cudaMemcpy(p->d_params, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+        for (int j = 0; j < NP; ++j) {
+            int prm; float lit;
+            slot_src(j, prm, lit);
+            if (prm >= 0 && p->param_on_device[prm])
+                ZG_CUDA(cudaMemcpy(p->d_params + (size_t)j * p->ch_stride, p->d_user_params + (size_t)prm * p->ch_stride,
+                                   p->C * sizeof(float), cudaMemcpyDeviceToDevice));
+        }
     }
     p->uniform_now = uniform;
     p->params_dirty = false;
@@ -912,6 +924,7 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
         ZG_CUDA(cudaMemset(p->d_state_alt, 0, state_floats * sizeof(float)));
     }
     p->h_params.assign(ir.n_params, std::vector<float>(1, 0.f));
+    p->param_on_device.assign(ir.n_params, 0);
     p->params_dirty = true;
 
     // compile / pick the kernel now so that plan creation is where build errors surface
@@ -1086,6 +1099,25 @@ int zg_param_set(zg_plan* p, int index, const float* host_values, int64_t n) {
     ZG_CUDA(cudaSetDevice(p->opts.device));
     ZG_CUDA(cudaDeviceSynchronize());      // a launch in flight may still be reading d_params
     p->h_params[index].assign(host_values, host_values + n);
+    p->param_on_device[index] = 0;
+    p->params_dirty = true;
+    return ZG_OK;
+}
+
+int zg_param_set_device(zg_plan* p, int index, const float* device_values, int64_t n) {
+    if (!p || !device_values) return fail(ZG_ERR_ARG, "NULL argument");
+    if (index < 0 || index >= (int)p->h_params.size()) return fail(ZG_ERR_ARG, "bad parameter index");
+    if (n != p->C) return fail(ZG_ERR_ARG, "a parameter set from device memory needs one value per channel");
+    ZG_CUDA(cudaSetDevice(p->opts.device));
+    ZG_CUDA(cudaDeviceSynchronize());      // the producer of device_values and any launch still reading d_params
+    if (!p->d_user_params) {
+        const size_t bytes = p->h_params.size() * (size_t)p->ch_stride * sizeof(float);
+        ZG_CUDA(cudaMalloc(&p->d_user_params, bytes));
+        ZG_CUDA(cudaMemset(p->d_user_params, 0, bytes));
+    }
+    ZG_CUDA(cudaMemcpy(p->d_user_params + (size_t)index * p->ch_stride, device_values, p->C * sizeof(float),
+                       cudaMemcpyDeviceToDevice));
+    p->param_on_device[index] = 1;
     p->params_dirty = true;
     return ZG_OK;
 }
