@@ -492,9 +492,9 @@ def test_fir_process_host_and_long_delay_errors(zg):
     plan = zg.compile(fo.fir_expr(h)).plan(channels=2048)
     y = plan.process_host([x])[0]
     assert np.array_equal(y, fo.fir_direct(x, h))
-    with pytest.raises(zg.ZgError) as e:                      # long delay line that is not a dense FIR
-        zg.compile("_1[_100] + 0.5f*_1").plan(channels=8)
-    assert e.value.status == zg.ZG_ERR_UNSUPPORTED
+    # a long delay line that is not a dense FIR runs the generated kernel (the line is a ring in HBM)
+    ys, plan2 = _run(zg, "_1[_100] + 0.5f*_1", [x[:64, :600]], zg.MODE_EXACT)
+    assert plan2.info().jit == 1 and np.array_equal(ys[0], _oracle("_1[_100] + 0.5f*_1", [x[:64, :600]])[0])
     with pytest.raises(zg.ZgError) as e:
         zg.compile(fo.fir_expr(fo.fir_taps(256))).plan(channels=8, layout=zg.INTERLEAVED)
     assert e.value.status == zg.ZG_ERR_UNSUPPORTED
@@ -807,3 +807,76 @@ def test_coefficients_computed_on_the_device(zg, lanes):
     assert np.array_equal(y2, _oracle(expr, [x], params)[0])
     with pytest.raises(zg.ZgError):
         plan.set_param_device(0, torch.zeros(C - 1, device="cuda"))
+
+
+# ---- long delay lines (generated kernel): rings in HBM ------------------------------------------------------
+# Delay lines deeper than 16 floats are not register-resident: their state rows are used as a ring, far reads
+# become coalesced loads a chunk ahead of use, near reads come from a short register window (zg_ir.hpp).
+
+LONG = [
+    "~(_2 + 0.5f*_1[_100])",                                                   # feedback comb
+    "_1 + 0.5f*_1[_37] - 0.25f*_1[_1000]",                                     # sparse FIR on the input
+    "~(_2 + 0.5f*_1[_3] + 0.25f*_1[_500])",                                    # near and far reads of one line
+    "(0.5f*_1 + 0.5f*_1[_1]) |= ~(_2 + 0.7f*_1[_441]) |= (_1 - 0.7f*_1[_20])",  # damped echo, then a notch
+    "~(_2 + 0.4f*_1[_17]) |= ~(_2 - 0.3f*_1[_64]) |= (_1 , _1[_33])",            # two long lines, two outputs
+]
+
+
+@pytest.mark.parametrize("expr", LONG)
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+def test_long_delay_lines_exact_and_streaming(zg, expr, layout):
+    g = zg.compile(expr)
+    C, T = 70, 2600
+    x = [fo.noise(C, T, seed=120 + k) for k in range(g.n_in)]
+    ref = _oracle(expr, x)
+    ys, plan = _run(zg, expr, x, zg.MODE_EXACT, layout)
+    assert plan.info().jit == 1
+    for y, r in zip(ys, ref):
+        assert np.array_equal(y, r)
+    # ragged blocks, some shorter than the delays: the ring phase follows the stream position
+    ys, plan = _run(zg, expr, x, zg.MODE_EXACT, layout, blocks=[1, 7, 31, 32, 33, 100, 5, 1000, 1391])
+    for y, r in zip(ys, ref):
+        assert np.array_equal(y, r)
+    # the state crosses the ABI oldest value first, like the reference's arrays: a fresh plan continues from it
+    st = plan.get_state()
+    assert st.shape == (g.n_state, C)
+    x2 = [fo.noise(C, 700, seed=130 + k) for k in range(g.n_in)]
+    full = _oracle(expr, [np.concatenate([a, b], axis=1) for a, b in zip(x, x2)])
+    plan2 = g.plan(channels=C, mode=zg.MODE_EXACT, layout=zg.PLANAR if layout == "planar" else zg.INTERLEAVED)
+    plan2.set_state(st)
+    y2 = plan2.process([_to_dev(v.T if layout == "interleaved" else v) for v in x2])
+    for y, r in zip(y2, full):
+        y = y.cpu().numpy()
+        assert np.array_equal(y.T if layout == "interleaved" else y, r[:, T:])
+
+
+def test_long_delay_lines_state_is_in_reference_order(zg):
+    """a pure delay: after T ticks the line holds the last D inputs, oldest first (rotate_push_back)"""
+    D, C, T = 300, 40, 1000
+    expr = f"_1[_{D}]"
+    x = fo.noise(C, T, seed=140)
+    ys, plan = _run(zg, expr, [x], zg.MODE_EXACT, blocks=[123, 877])
+    want = np.concatenate([np.zeros((C, D), np.float32), x[:, :T - D]], axis=1)
+    assert np.array_equal(ys[0], want)
+    assert np.array_equal(plan.get_state(), x[:, T - D:].T)
+    plan.reset()
+    y = plan.process([_to_dev(x[:, :400])])[0].cpu().numpy()
+    assert np.array_equal(y, want[:, :400])
+
+
+def test_long_delay_lines_fast_mode_and_bf16(zg):
+    expr = LONG[3]
+    C, T = 64, 3000
+    x = [fo.noise(C, T, seed=150)]
+    ref = _oracle(expr, x)[0]
+    ys, _ = _run(zg, expr, x, zg.MODE_FAST)
+    assert _rel_err(ys[0], ref) <= TOL
+    yb, _ = _run_bf16(zg, expr, x, zg.MODE_EXACT, blocks=[1000, 2000])
+    assert np.array_equal(yb[0], fo.bf16_bits(_oracle(expr, [fo.bf16_round(x[0])])[0]))
+
+
+def test_long_delay_limits_are_reported(zg):
+    many = " + ".join(f"0.1f*_1[_{100 + 10 * k}]" for k in range(12))           # 12 far reads of one line: too many
+    with pytest.raises(zg.ZgError) as e:
+        zg.compile(many).plan(channels=8)
+    assert e.value.status == zg.ZG_ERR_UNSUPPORTED and "far reads" in str(e.value)

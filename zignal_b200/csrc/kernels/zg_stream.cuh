@@ -38,6 +38,8 @@ __host__ __device__ constexpr int box_samples(bool interleaved, int io) { return
 __host__ __device__ constexpr int box_bytes(bool interleaved, int io) { return interleaved ? 1024 * io : 4096; }
 constexpr int kMaxState = 64;       // state floats per channel a register-resident tick may keep
 constexpr int kMaxUniform = 64;     // uniform parameters passed by value
+constexpr int kMaxRingIn = 8;       // far reads of long delay lines per tick
+constexpr int kMaxRingOut = 4;      // long delay lines per graph
 
 struct StreamArgs {
     TensorMap in_map[kMaxWires];    // planar: 2-D {T, C}; interleaved: 2-D {C, T}; box 32 x 32
@@ -56,6 +58,12 @@ struct StreamArgs {
                                     // own slot order; generated ticks use the identity)
     float uparams[kMaxUniform];     // kUniform kernels: parameter values shared by all channels,
                                     // read straight from the constant bank (no register, no HBM)
+    // Long delay lines (generated ticks only): line rows [row0, row0 + depth) of `state` are a ring, the value
+    // pushed at absolute tick t sits in row t mod depth.  Ring input r (kernel input N_IN - N_RING_IN + r) reads
+    // row (t - delay) mod depth; ring output w (kernel output N_OUT - N_RING_OUT + w) is stored to row t mod depth.
+    int ring_in_row0[kMaxRingIn], ring_in_depth[kMaxRingIn], ring_in_delay[kMaxRingIn];
+    int ring_out_row0[kMaxRingOut], ring_out_depth[kMaxRingOut];
+    unsigned long long state_nowrite;   // bit j: state slot j is a window onto a ring -- loaded, never written back
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -200,6 +208,22 @@ struct extra_count { static constexpr int value = 0; };
 template <class T>
 struct extra_count<T, decltype((void)T::N_EXTRA)> { static constexpr int value = T::N_EXTRA; };
 
+// Long delay lines: the last Tick::N_RING_IN inputs / N_RING_OUT outputs of a tick are not sample wires but
+// reads / pushes of delay lines kept as rings in HBM (StreamArgs::ring_*).  Default: none.
+template <class T, class = void>
+struct ring_in_count { static constexpr int value = 0; };
+template <class T>
+struct ring_in_count<T, decltype((void)T::N_RING_IN)> { static constexpr int value = T::N_RING_IN; };
+template <class T, class = void>
+struct ring_out_count { static constexpr int value = 0; };
+template <class T>
+struct ring_out_count<T, decltype((void)T::N_RING_OUT)> { static constexpr int value = T::N_RING_OUT; };
+
+__device__ __forceinline__ int ring_mod(long long t, int depth) {     // t may be negative (before the stream began)
+    int r = (int)(t % depth);
+    return r < 0 ? r + depth : r;
+}
+
 // ---- the streaming loop ---------------------------------------------------------------------------
 //
 // Tick must provide
@@ -214,7 +238,11 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     constexpr int VPC = IO::kPerChunk;                         // ticks per 16-byte chunk
     constexpr int BT = box_samples(kInterleaved, kIo);        // samples per box
     constexpr int BB = box_bytes(kInterleaved, kIo);          // bytes per box
-    constexpr int NI = Tick::N_IN, NO = Tick::N_OUT, NS = Tick::N_STATE, NP = Tick::N_PARAM;
+    constexpr int NRI = ring_in_count<Tick>::value, NRO = ring_out_count<Tick>::value;
+    constexpr int NIT = Tick::N_IN, NOT = Tick::N_OUT;                       // all inputs / outputs of the tick
+    constexpr int NI = NIT - NRI, NO = NOT - NRO;                            // sample wires (TMA, shared memory)
+    constexpr int NS = Tick::N_STATE, NP = Tick::N_PARAM;
+    static_assert(NRI <= kMaxRingIn && NRO <= kMaxRingOut, "too many long delay lines / far reads");
     constexpr int NT = (NI > NO ? NI : NO) > 0 ? (NI > NO ? NI : NO) : 1;   // wires per stage
     constexpr unsigned kAllIn = NI > 0 ? ((1u << NI) - 1u) : 0u;
     constexpr unsigned kBufMask = kAllIn & ~Tick::SYNTH_MASK;
@@ -262,7 +290,7 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
         if constexpr (kUniform) Tick::init(s, prm_uni, ex);
         else Tick::init(s, prm_reg, ex);
     }
-    auto run_tick = [&](const Arr<NI>& x, Arr<NO>& y) {
+    auto run_tick = [&](const Arr<NIT>& x, Arr<NOT>& y) {
         if constexpr (NE > 0) {
             if constexpr (kUniform) Tick::tick(x, y, s, prm_uni, ex);
             else Tick::tick(x, y, s, prm_reg, ex);
@@ -322,6 +350,25 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     // (flags bit 1: refill only after the store of tile i has been issued, the first version.)
     const bool early_refill = (a.flags & 2) == 0;
 
+    // ---- long delay lines: ring rows of `state`, one coalesced 4-byte access per lane (128 bytes per warp) ----
+    int rin_idx[NRI > 0 ? NRI : 1];                    // next row to load, per ring input
+    int rout_idx[NRO > 0 ? NRO : 1];                   // next row to store, per ring output
+    auto ring_seek = [&](long long t_abs) {
+#pragma unroll
+        for (int r = 0; r < NRI; ++r) rin_idx[r] = ring_mod(t_abs - a.ring_in_delay[r], a.ring_in_depth[r]);
+#pragma unroll
+        for (int w = 0; w < NRO; ++w) rout_idx[w] = ring_mod(t_abs, a.ring_out_depth[w]);
+    };
+    auto ring_load = [&](int r) {
+        const float v = a.state[(long long)(a.ring_in_row0[r] + rin_idx[r]) * a.ch_stride + ch];
+        rin_idx[r] = rin_idx[r] + 1 == a.ring_in_depth[r] ? 0 : rin_idx[r] + 1;
+        return v;
+    };
+    auto ring_store = [&](int w, float v) {
+        a.state[(long long)(a.ring_out_row0[w] + rout_idx[w]) * a.ch_stride + ch] = v;
+        rout_idx[w] = rout_idx[w] + 1 == a.ring_out_depth[w] ? 0 : rout_idx[w] + 1;
+    };
+
     for (int i = 0; i < n_tiles; ++i) {
         const int slot = i % S;
         const int t0 = i * tile_t;
@@ -358,6 +405,14 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                         for (int k = 0; k < NI; ++k)
                             if (kBufMask & (1u << k))
                                 xn[k] = *reinterpret_cast<const uint4*>(base + k * wire_bytes + row + (sw << 4));
+                        // far reads of long delay lines: the rows of chunk j+1 are requested before the ticks of
+                        // chunk j (they were stored at least two chunks ago: delay >= 2 * VPC, zg_ir.hpp)
+                        float rn[NRI > 0 ? NRI : 1][VPC];
+                        ring_seek(t_abs0);
+#pragma unroll
+                        for (int r = 0; r < NRI; ++r)
+#pragma unroll
+                            for (int q = 0; q < VPC; ++q) rn[r][q] = ring_load(r);
                         constexpr int CU = chunk_unroll<Tick>::value;
                         static_assert(CU == 8 || CU == 4 || CU == 2 || CU == 1, "CHUNK_UNROLL must divide 8");
 #pragma unroll 1
@@ -366,8 +421,8 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                         for (int jj = 0; jj < CU; ++jj) {
                             const int j = h + jj;
                             const unsigned off = row + (((unsigned)j ^ sw) << 4);
-                            float xv[NI > 0 ? NI : 1][VPC];
-                            float yv[NO > 0 ? NO : 1][VPC];
+                            float xv[NIT > 0 ? NIT : 1][VPC];
+                            float yv[NOT > 0 ? NOT : 1][VPC];
 #pragma unroll
                             for (int k = 0; k < NI; ++k) {
                                 if (kBufMask & (1u << k)) {
@@ -381,34 +436,52 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                                 }
                             }
 #pragma unroll
-                            for (int q = 0; q < VPC; ++q) {
-                                Arr<NI> x;
-                                Arr<NO> y;
+                            for (int r = 0; r < NRI; ++r) {
 #pragma unroll
-                                for (int k = 0; k < NI; ++k) x[k] = xv[k][q];
+                                for (int q = 0; q < VPC; ++q) xv[NI + r][q] = rn[r][q];
+                                if (j < 7) {
+#pragma unroll
+                                    for (int q = 0; q < VPC; ++q) rn[r][q] = ring_load(r);
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < VPC; ++q) {
+                                Arr<NIT> x;
+                                Arr<NOT> y;
+#pragma unroll
+                                for (int k = 0; k < NIT; ++k) x[k] = xv[k][q];
                                 run_tick(x, y);
 #pragma unroll
-                                for (int o = 0; o < NO; ++o) yv[o][q] = y[o];
+                                for (int o = 0; o < NOT; ++o) yv[o][q] = y[o];
                             }
 #pragma unroll
                             for (int o = 0; o < NO; ++o)
                                 *reinterpret_cast<uint4*>(base + o * wire_bytes + off) = IO::pack(yv[o]);
+#pragma unroll
+                            for (int w = 0; w < NRO; ++w)
+#pragma unroll
+                                for (int q = 0; q < VPC; ++q) ring_store(w, yv[NO + w][q]);
                         }
                     } else {
                         // last, partial box of the block: TMA zero-filled the tail on load and clips it
                         // on store; only the state has to be protected
+                        ring_seek(t_abs0);
                         for (int t = 0; t < n_valid; ++t) {
                             const unsigned off = row + ((((unsigned)t / VPC) ^ sw) << 4) + ((unsigned)t % VPC) * kIo;
-                            Arr<NI> x;
-                            Arr<NO> y;
+                            Arr<NIT> x;
+                            Arr<NOT> y;
 #pragma unroll
                             for (int k = 0; k < NI; ++k) {
                                 if (kBufMask & (1u << k)) x[k] = IO::load(base + k * wire_bytes + off);
                                 else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
                             }
+#pragma unroll
+                            for (int r = 0; r < NRI; ++r) x[NI + r] = ring_load(r);
                             run_tick(x, y);
 #pragma unroll
                             for (int o = 0; o < NO; ++o) IO::store(base + o * wire_bytes + off, y[o]);
+#pragma unroll
+                            for (int w = 0; w < NRO; ++w) ring_store(w, y[NO + w]);
                         }
                     }
                 } else {
@@ -416,31 +489,61 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                     typename IO::Elem* box = reinterpret_cast<typename IO::Elem*>(base);
                     const unsigned wire_f = wire_bytes / kIo;
                     if (full_box) {
-#pragma unroll 8
-                        for (int t = 0; t < BT; ++t) {
-                            Arr<NI> x;
-                            Arr<NO> y;
+                        // groups of four frames; the ring rows of group g+1 are requested before the ticks of group g
+                        float rn[NRI > 0 ? NRI : 1][4];
+                        ring_seek(t_abs0);
 #pragma unroll
-                            for (int k = 0; k < NI; ++k) {
-                                if (kBufMask & (1u << k)) x[k] = IO::load(&box[k * wire_f + t * 32 + lane]);
-                                else x[k] = 0.f;
+                        for (int r = 0; r < NRI; ++r)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) rn[r][q] = ring_load(r);
+#pragma unroll 2
+                        for (int gq = 0; gq < BT / 4; ++gq) {
+                            float rc[NRI > 0 ? NRI : 1][4];
+#pragma unroll
+                            for (int r = 0; r < NRI; ++r) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) rc[r][q] = rn[r][q];
+                                if (gq < BT / 4 - 1) {
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) rn[r][q] = ring_load(r);
+                                }
                             }
-                            run_tick(x, y);
 #pragma unroll
-                            for (int o = 0; o < NO; ++o) IO::store(&box[o * wire_f + t * 32 + lane], y[o]);
+                            for (int q = 0; q < 4; ++q) {
+                                const int t = 4 * gq + q;
+                                Arr<NIT> x;
+                                Arr<NOT> y;
+#pragma unroll
+                                for (int k = 0; k < NI; ++k) {
+                                    if (kBufMask & (1u << k)) x[k] = IO::load(&box[k * wire_f + t * 32 + lane]);
+                                    else x[k] = 0.f;
+                                }
+#pragma unroll
+                                for (int r = 0; r < NRI; ++r) x[NI + r] = rc[r][q];
+                                run_tick(x, y);
+#pragma unroll
+                                for (int o = 0; o < NO; ++o) IO::store(&box[o * wire_f + t * 32 + lane], y[o]);
+#pragma unroll
+                                for (int w = 0; w < NRO; ++w) ring_store(w, y[NO + w]);
+                            }
                         }
                     } else {
+                        ring_seek(t_abs0);
                         for (int t = 0; t < n_valid; ++t) {
-                            Arr<NI> x;
-                            Arr<NO> y;
+                            Arr<NIT> x;
+                            Arr<NOT> y;
 #pragma unroll
                             for (int k = 0; k < NI; ++k) {
                                 if (kBufMask & (1u << k)) x[k] = IO::load(&box[k * wire_f + t * 32 + lane]);
                                 else x[k] = (((a.dirac_mask >> k) & 1u) && t_abs0 + t == 0) ? 1.f : 0.f;
                             }
+#pragma unroll
+                            for (int r = 0; r < NRI; ++r) x[NI + r] = ring_load(r);
                             run_tick(x, y);
 #pragma unroll
                             for (int o = 0; o < NO; ++o) IO::store(&box[o * wire_f + t * 32 + lane], y[o]);
+#pragma unroll
+                            for (int w = 0; w < NRO; ++w) ring_store(w, y[NO + w]);
                         }
                     }
                 }
@@ -475,7 +578,8 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     // ---- state back to HBM ----
     if (ch_ok) {
 #pragma unroll
-        for (int j = 0; j < NS; ++j) a.state[(long long)a.state_row[j] * a.ch_stride + ch] = s[j];
+        for (int j = 0; j < NS; ++j)
+            if (!((a.state_nowrite >> j) & 1ull)) a.state[(long long)a.state_row[j] * a.ch_stride + ch] = s[j];
     }
 }
 

@@ -34,7 +34,8 @@ void set_last_error(const std::string& msg);
 int fail(int status, const std::string& msg);
 
 // CUDA tick-functor source for one IR (zg_codegen.cpp)
-std::string generate_tick_source(const Ir& ir, bool exact, const std::string& struct_name);
+std::string generate_tick_source(const Ir& ir, bool exact, const std::string& struct_name, int n_ring_in = 0,
+                                 int n_ring_out = 0);
 
 // ---- prebuilt-kernel recognisers (zg_match.cpp) ----
 constexpr int kMaxBiquadSections = 8;

@@ -463,4 +463,73 @@ void host_block_f32(const Ir& ir, float* state, const float* params, const float
     }
 }
 
+// ---- long delay lines: kernel-side program ------------------------------------------------------------------------
+
+Ir split_long_lines(const Ir& ir, int reg_depth, int far, RingPlan& rp) {
+    Ir k = ir;
+    rp = RingPlan{};
+    const int L = (int)ir.lines.size();
+    std::vector<char> is_long(L, 0);
+    std::vector<int> near_depth(L, 0);         // deepest near read of a long line
+    for (int l = 0; l < L; ++l) is_long[l] = ir.lines[l].depth > reg_depth;
+    for (const IrNode& n : ir.nodes)
+        if (n.op == IrOp::DRead && is_long[n.a] && n.b < far) near_depth[n.a] = std::max(near_depth[n.a], n.b);
+    // far reads -> extra inputs (one per distinct (line, n))
+    std::vector<std::pair<int, int>> seen;
+    for (IrNode& n : k.nodes) {
+        if (n.op != IrOp::DRead || !is_long[n.a] || n.b < far) continue;
+        int idx = -1;
+        for (size_t i = 0; i < seen.size(); ++i)
+            if (seen[i].first == n.a && seen[i].second == n.b) idx = (int)i;
+        if (idx < 0) {
+            idx = (int)seen.size();
+            seen.push_back({n.a, n.b});
+            rp.taps.push_back({n.a, n.b});
+        }
+        n.op = IrOp::In;
+        n.a = ir.n_in + idx;
+        n.b = -1;
+    }
+    k.n_in = ir.n_in + (int)rp.taps.size();
+    k.in_dtypes.resize(k.n_in, Dtype::F32);
+    // pushed values of long lines -> extra outputs
+    for (int l = 0; l < L; ++l)
+        if (is_long[l]) {
+            rp.out_lines.push_back(l);
+            k.outs.push_back(ir.lines[l].src);
+        }
+    k.n_out = (int)k.outs.size();
+    // kernel lines: short lines as they are, long lines shrunk to their register window (possibly empty)
+    k.lines.clear();
+    std::vector<int> new_index(L, -1);
+    int off = 0;
+    for (int l = 0; l < L; ++l) {
+        const IrLine& o = ir.lines[l];
+        const int depth = is_long[l] ? near_depth[l] : o.depth;
+        if (depth == 0) continue;
+        IrLine nl;
+        nl.depth = depth;
+        nl.offset = off;
+        nl.src = o.src;
+        new_index[l] = (int)k.lines.size();
+        k.lines.push_back(nl);
+        for (int j = 0; j < depth; ++j) {
+            KernelSlot s;
+            if (is_long[l]) {                  // window slot j holds the value pushed depth - j ticks ago
+                s.row = o.offset;
+                s.ring_depth = o.depth;
+                s.ago = depth - j;
+            } else {
+                s.row = o.offset + j;
+            }
+            rp.slots.push_back(s);
+        }
+        off += depth;
+    }
+    k.n_state = off;
+    for (IrNode& n : k.nodes)
+        if (n.op == IrOp::DRead) n.a = new_index[n.a];
+    return k;
+}
+
 }  // namespace zg

@@ -48,6 +48,30 @@ struct LowerOptions {
 // `canonical` must come from canonical_with_front().  in_dtypes.size() must equal its input arity.
 Ir lower(const Expr& canonical, const std::vector<Dtype>& in_dtypes, const LowerOptions& opt = {});
 
+// ---- long delay lines on the device (zg_ir.cpp: split_long_lines) -----------------------------------------
+// A delay line deeper than `reg_depth` floats does not live in registers.  Its D floats of state stay where the
+// state layout puts them, [D rows][channels] in HBM, used as a ring: the value pushed at absolute tick t sits
+// in row t mod D.  The kernel-side tick program is the same program with
+//   * every far read  DRead(line, n >= far)   turned into an extra INPUT  (the skeleton loads ring row
+//     (t - n) mod D a chunk ahead of use: a coalesced 128-byte load per warp),
+//   * the line's pushed value                 turned into an extra OUTPUT (the skeleton stores it to row t mod D),
+//   * near reads      DRead(line, n <  far)   served by a short register window of the last `near` pushes
+//     (reloaded from the ring at block start; never written back: the ring already holds those values).
+struct RingTap { int line; int n; };           // extra kernel input k <-> original line, delay
+struct KernelSlot {                            // kernel register-state slot -> where it lives in d_state
+    int row = 0;                               // fixed row (short lines), or first row of the ring (windows)
+    int ring_depth = 0;                        // 0: fixed row; else the slot holds the value pushed `ago` ticks ago
+    int ago = 0;
+};
+struct RingPlan {
+    std::vector<RingTap> taps;                 // in kernel-input order, after the graph's own inputs
+    std::vector<int> out_lines;                // original line of extra kernel output k, after the graph's outputs
+    std::vector<KernelSlot> slots;             // one per kernel state slot (kir.n_state)
+    bool any() const { return !out_lines.empty(); }
+};
+// Returns the kernel-side program.  Lines with depth <= reg_depth are untouched (their slots map to fixed rows).
+Ir split_long_lines(const Ir& ir, int reg_depth, int far, RingPlan& rp);
+
 // Host scalar tick: this is stateful_lambda::operator() (flowz/flowz.hpp:1193-1201, 1225-1229)
 // for one voice.  `state` has ir.n_state floats, zero-initialised by the caller (:1191 value-init).
 // `params` has ir.n_params floats.  Inputs/outputs travel as doubles and are converted to/from

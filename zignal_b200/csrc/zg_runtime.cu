@@ -232,6 +232,8 @@ struct zg_plan {
     int kernel_n_state = 0, kernel_n_param = 0;   // as the kernel sees them
     std::vector<int> state_row;                   // kernel slot -> row of d_state
 
+    Ir kir;                                 // K2: the kernel-side tick program (long delay lines split off, zg_ir.hpp)
+    RingPlan ring;                          //     and where its extra inputs / outputs / window slots live
     bool is_fir = false;                    // K3: dense FIR (kernels/zg_fir.cuh)
     FirMatch fir;
     float* d_taps = nullptr;                // [n_taps]
@@ -287,11 +289,17 @@ namespace {
 
 // ---- NVRTC specialisation (K2) -----------------------------------------------------------------
 
-std::string jit_source(const Ir& ir, bool exact, bool interleaved, bool uniform, unsigned synth_mask, int io) {
+constexpr int kRegLineDepth = 16;           // delay lines up to this depth stay in registers whatever their reads
+
+// far reads are requested one chunk (of `ticks per 16 bytes`) ahead of use and must have been stored before that
+int ring_far(bool interleaved, int io) { return 2 * (interleaved ? 4 : 16 / io); }
+
+std::string jit_source(const Ir& ir, bool exact, bool interleaved, bool uniform, unsigned synth_mask, int io,
+                       int n_ring_in = 0, int n_ring_out = 0) {
     std::ostringstream src;
     src << "#define ZG_SYNTH_MASK " << synth_mask << "u\n";
     src << zg_stream_cuh_source << "\n";
-    src << generate_tick_source(ir, exact, "ZgTick") << "\n";
+    src << generate_tick_source(ir, exact, "ZgTick", n_ring_in, n_ring_out) << "\n";
     src << "extern \"C\" __global__ void __launch_bounds__(512, 1) zg_graph_kernel("
            "const __grid_constant__ zgk::StreamArgs a) {\n"
            "    zgk::stream_block<ZgTick, "
@@ -330,7 +338,9 @@ int jit_compile(zg_plan* p, bool uniform, Variant& v) {
     Driver& d = driver();
     if (!d.ok) return fail(ZG_ERR_CUDA, d.why);
     std::vector<char> cubin;
-    int st = jit_cubin(jit_source(p->ir, p->exact, p->interleaved, uniform, p->synth_mask, p->io), p->exact, cubin);
+    int st = jit_cubin(jit_source(p->kir, p->exact, p->interleaved, uniform, p->synth_mask, p->io, (int)p->ring.taps.size(),
+                                  (int)p->ring.out_lines.size()),
+                       p->exact, cubin);
     if (st != ZG_OK) return st;
     CUresult cr = d.moduleLoadData(&v.module, cubin.data());
     if (cr != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuModuleLoadData: " + cu_err(cr));
@@ -617,7 +627,31 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     a.channels = (int)c_count;
     a.n_samples = (int)T;
     a.dirac_mask = p->dirac_mask;
-    for (int j = 0; j < p->kernel_n_state; ++j) a.state_row[j] = p->state_row[j];
+    if (!p->is_biquad || p->opts.force_jit) {
+        // generated kernel: short lines at fixed rows; window slots of long lines at ring rows that move with the
+        // stream position (the value pushed `ago` ticks before this block starts), loaded but never written back
+        for (int j = 0; j < p->kernel_n_state; ++j) {
+            const KernelSlot& ks = p->ring.slots[j];
+            if (ks.ring_depth == 0) { a.state_row[j] = ks.row; continue; }
+            int64_t r = (p->stream_pos - ks.ago) % ks.ring_depth;
+            if (r < 0) r += ks.ring_depth;
+            a.state_row[j] = ks.row + (int)r;
+            a.state_nowrite |= 1ull << j;
+        }
+        for (size_t r = 0; r < p->ring.taps.size(); ++r) {
+            const IrLine& l = p->ir.lines[p->ring.taps[r].line];
+            a.ring_in_row0[r] = l.offset;
+            a.ring_in_depth[r] = l.depth;
+            a.ring_in_delay[r] = p->ring.taps[r].n;
+        }
+        for (size_t w = 0; w < p->ring.out_lines.size(); ++w) {
+            const IrLine& l = p->ir.lines[p->ring.out_lines[w]];
+            a.ring_out_row0[w] = l.offset;
+            a.ring_out_depth[w] = l.depth;
+        }
+    } else {
+        for (int j = 0; j < p->kernel_n_state; ++j) a.state_row[j] = p->state_row[j];
+    }
     if (p->uniform_now) std::memcpy(a.uparams, p->uparams, sizeof(float) * std::min(p->kernel_n_param, zgk::kMaxUniform));
 
     // wires per pipeline stage as the kernel lays them out: wire k of a stage belongs to input k / output k
@@ -732,6 +766,26 @@ int launch_fir(zg_plan* p, const void* const* in, void* const* out, int64_t T, i
     return ZG_OK;
 }
 
+// Long delay lines are rings in d_state (row t mod depth holds the value pushed at tick t); the ABI shows every
+// line oldest value first, like the reference's std::array after rotate_push_back (flowz.hpp:130-148).  Slot j of
+// a line of depth D holds the value pushed D - j ticks ago = ring row (stream_pos + j) mod D.
+void rotate_rings(const zg_plan* p, float* host /* [n_state][C] */, bool ring_to_abi) {
+    for (int l : p->ring.out_lines) {
+        const IrLine& line = p->ir.lines[l];
+        const int D = line.depth;
+        const int64_t phase = ((p->stream_pos % D) + D) % D;
+        std::vector<float> tmp((size_t)D * p->C);
+        float* rows = host + (size_t)line.offset * p->C;
+        for (int j = 0; j < D; ++j) {
+            const int ring_row = (int)((phase + j) % D);
+            const float* src = rows + (size_t)(ring_to_abi ? ring_row : j) * p->C;
+            float* dst = tmp.data() + (size_t)(ring_to_abi ? j : ring_row) * p->C;
+            std::memcpy(dst, src, p->C * sizeof(float));
+        }
+        std::memcpy(rows, tmp.data(), tmp.size() * sizeof(float));
+    }
+}
+
 int check_io(const zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out) {
     if (T < 0) return fail(ZG_ERR_ARG, "n_samples < 0");
     if (T > 0x7fffffffLL) return fail(ZG_ERR_ARG, "n_samples too large for one block");
@@ -763,14 +817,17 @@ int zg_graph_kernel_compile(const zg_graph* g, const zg_plan_opts* opts, int uni
     if (!g || !opts || !size) return fail(ZG_ERR_ARG, "NULL argument");
     const Ir& ir = g->ir_f32;
     if (!ir.all_f32()) return fail(ZG_ERR_UNSUPPORTED, "the device path evaluates fp32 graphs only");
-    if (ir.n_state > zgk::kMaxState) return fail(ZG_ERR_UNSUPPORTED, "too much delay state for the register-resident kernel");
+    if (opts->io_dtype != ZG_F32 && opts->io_dtype != ZG_BF16) return fail(ZG_ERR_ARG, "io_dtype must be ZG_F32 or ZG_BF16");
+    RingPlan ring;
+    const Ir kir = split_long_lines(ir, kRegLineDepth, ring_far(opts->layout == ZG_INTERLEAVED, opts->io_dtype == ZG_BF16 ? 2 : 4), ring);
+    if (kir.n_state > zgk::kMaxState || (int)ring.taps.size() > zgk::kMaxRingIn || (int)ring.out_lines.size() > zgk::kMaxRingOut)
+        return fail(ZG_ERR_UNSUPPORTED, "too much delay state for the generated kernel");
     unsigned synth = 0;
     for (int k = 0; k < ir.n_in; ++k)
         if (opts->input_kind[k] != ZG_IN_BUFFER) synth |= 1u << k;
     const bool exact = opts->mode == ZG_MODE_EXACT;
-    if (opts->io_dtype != ZG_F32 && opts->io_dtype != ZG_BF16) return fail(ZG_ERR_ARG, "io_dtype must be ZG_F32 or ZG_BF16");
-    std::string text = jit_source(ir, exact, opts->layout == ZG_INTERLEAVED, uniform_params != 0, synth,
-                                  opts->io_dtype == ZG_BF16 ? 2 : 4);
+    std::string text = jit_source(kir, exact, opts->layout == ZG_INTERLEAVED, uniform_params != 0, synth,
+                                  opts->io_dtype == ZG_BF16 ? 2 : 4, (int)ring.taps.size(), (int)ring.out_lines.size());
     std::vector<char> cubin;
     const char* data = text.data();
     size_t n = text.size();
@@ -817,11 +874,18 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     bool any_synth = false;
     for (int k = 0; k < ir.n_in; ++k) any_synth = any_synth || opts->input_kind[k] != ZG_IN_BUFFER;
     const bool is_fir = !opts->force_jit && !any_synth && opts->layout == ZG_PLANAR && !bf16 && match_fir(ir, fir);
-    if (!is_fir && ir.n_state > zgk::kMaxState)
-        return fail(ZG_ERR_UNSUPPORTED, "graph keeps " + std::to_string(ir.n_state) +
-                                            " floats of delay state per channel; the register-resident kernels take at most " +
-                                            std::to_string(zgk::kMaxState) +
-                                            " (longer delay lines: only the dense FIR form c0*_1 + c1*_1[_1] + ..., planar layout)");
+    // generated kernel: delay lines deeper than kRegLineDepth live in HBM as rings (zg_ir.hpp); what must fit in
+    // registers is the rest -- short lines and the near windows of the long ones
+    RingPlan ring;
+    const Ir kir = split_long_lines(ir, kRegLineDepth, ring_far(opts->layout == ZG_INTERLEAVED, bf16 ? 2 : 4), ring);
+    if (!is_fir && (kir.n_state > zgk::kMaxState || (int)ring.taps.size() > zgk::kMaxRingIn ||
+                    (int)ring.out_lines.size() > zgk::kMaxRingOut || ir.n_in + ring.taps.size() > 32))
+        return fail(ZG_ERR_UNSUPPORTED,
+                    "graph keeps " + std::to_string(kir.n_state) + " floats of register-resident delay state per channel (limit " +
+                        std::to_string(zgk::kMaxState) + "), " + std::to_string(ring.out_lines.size()) + " long delay lines (limit " +
+                        std::to_string(zgk::kMaxRingOut) + ") with " + std::to_string(ring.taps.size()) + " far reads (limit " +
+                        std::to_string(zgk::kMaxRingIn) +
+                        "); a dense FIR c0*_1 + c1*_1[_1] + ... on the input (planar fp32) has its own kernel");
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -897,10 +961,11 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
                           p->interleaved ? "interleaved" : "planar");
         p->kernel_name = nm;
     } else {
-        p->kernel_n_state = ir.n_state;
+        p->kir = kir;
+        p->ring = ring;
+        p->kernel_n_state = kir.n_state;
         p->kernel_n_param = ir.n_params;
-        p->state_row.resize(ir.n_state);
-        for (int j = 0; j < ir.n_state; ++j) p->state_row[j] = j;
+        p->state_row.assign(kir.n_state, 0);       // filled per launch (window slots move with the stream position)
         p->kernel_name = std::string("zg_graph_kernel<jit,") + (p->exact ? "exact," : "fma,") +
                          (p->interleaved ? "interleaved" : "planar") + (bf16 ? ",bf16>" : ">");
     }
@@ -1079,6 +1144,7 @@ int zg_state_get(zg_plan* p, float* host, size_t n_floats) {
     ZG_CUDA(cudaSetDevice(p->opts.device));
     ZG_CUDA(cudaDeviceSynchronize());
     ZG_CUDA(cudaMemcpy2D(host, p->C * 4, p->d_state, p->ch_stride * 4, p->C * 4, p->ir.n_state, cudaMemcpyDeviceToHost));
+    rotate_rings(p, host, true);
     return ZG_OK;
 }
 
@@ -1088,6 +1154,12 @@ int zg_state_set(zg_plan* p, const float* host, size_t n_floats) {
     if (n_floats == 0) return ZG_OK;
     ZG_CUDA(cudaSetDevice(p->opts.device));
     ZG_CUDA(cudaDeviceSynchronize());
+    if (p->ring.any()) {
+        std::vector<float> tmp(host, host + n_floats);
+        rotate_rings(p, tmp.data(), false);
+        ZG_CUDA(cudaMemcpy2D(p->d_state, p->ch_stride * 4, tmp.data(), p->C * 4, p->C * 4, p->ir.n_state, cudaMemcpyHostToDevice));
+        return ZG_OK;
+    }
     ZG_CUDA(cudaMemcpy2D(p->d_state, p->ch_stride * 4, host, p->C * 4, p->C * 4, p->ir.n_state, cudaMemcpyHostToDevice));
     return ZG_OK;
 }
