@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--sections", type=int, default=4)
     ap.add_argument("--pad", type=int, default=0, help="extra floats of row pitch (planar buffers)")
-    ap.add_argument("--graph", default="biquad", choices=["biquad", "osc", "poly", "copy"],
+    ap.add_argument("--graph", default="biquad", choices=["biquad", "osc", "poly", "copy", "comb"],
                     help="osc = configs[2] (dirac in, fp32 out), poly = configs[4] (dirac in, bf16 out), copy = y = 1.0f*x")
     ap.add_argument("--points", default="mode=exact,fast;boxes=1,2;wpc=0;stages=0;layout=planar;coef=uniform")
     a = ap.parse_args()
@@ -52,6 +52,8 @@ def main():
             out_dt, bytes_per_sample, has_in = torch.bfloat16, 2, False
         elif a.graph == "copy":
             g = zg.compile("0x1p+0f*_1")
+        elif a.graph == "comb":                        # feedback comb + feed-forward echo: two long delay lines (rings in HBM)
+            g = zg.compile("~(_2 + 0.5f*_1[_441]) |= (_1 + 0.25f*_1[_1000])")
         elif pt["coef"] == "uniform":
             g = zg.compile(fo.biquad_cascade(a.sections))
         else:

@@ -219,6 +219,12 @@ struct ring_out_count { static constexpr int value = 0; };
 template <class T>
 struct ring_out_count<T, decltype((void)T::N_RING_OUT)> { static constexpr int value = T::N_RING_OUT; };
 
+// chunks (planar) / groups of four frames (interleaved) a far read is requested ahead of its use: Tick::RING_PF
+template <class T, class = void>
+struct ring_prefetch { static constexpr int value = 1; };
+template <class T>
+struct ring_prefetch<T, decltype((void)T::RING_PF)> { static constexpr int value = T::RING_PF; };
+
 __device__ __forceinline__ int ring_mod(long long t, int depth) {     // t may be negative (before the stream began)
     int r = (int)(t % depth);
     return r < 0 ? r + depth : r;
@@ -243,6 +249,7 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     constexpr int NI = NIT - NRI, NO = NOT - NRO;                            // sample wires (TMA, shared memory)
     constexpr int NS = Tick::N_STATE, NP = Tick::N_PARAM;
     static_assert(NRI <= kMaxRingIn && NRO <= kMaxRingOut, "too many long delay lines / far reads");
+    constexpr int PF = ring_prefetch<Tick>::value;                           // >= 1
     constexpr int NT = (NI > NO ? NI : NO) > 0 ? (NI > NO ? NI : NO) : 1;   // wires per stage
     constexpr unsigned kAllIn = NI > 0 ? ((1u << NI) - 1u) : 0u;
     constexpr unsigned kBufMask = kAllIn & ~Tick::SYNTH_MASK;
@@ -407,12 +414,14 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                                 xn[k] = *reinterpret_cast<const uint4*>(base + k * wire_bytes + row + (sw << 4));
                         // far reads of long delay lines: the rows of chunk j+1 are requested before the ticks of
                         // chunk j (they were stored at least two chunks ago: delay >= 2 * VPC, zg_ir.hpp)
-                        float rn[NRI > 0 ? NRI : 1][VPC];
+                        float rn[PF][NRI > 0 ? NRI : 1][VPC];            // rows of chunks j .. j+PF-1, in flight
                         ring_seek(t_abs0);
 #pragma unroll
-                        for (int r = 0; r < NRI; ++r)
+                        for (int f = 0; f < PF; ++f)
 #pragma unroll
-                            for (int q = 0; q < VPC; ++q) rn[r][q] = ring_load(r);
+                            for (int r = 0; r < NRI; ++r)
+#pragma unroll
+                                for (int q = 0; q < VPC; ++q) rn[f][r][q] = ring_load(r);
                         constexpr int CU = chunk_unroll<Tick>::value;
                         static_assert(CU == 8 || CU == 4 || CU == 2 || CU == 1, "CHUNK_UNROLL must divide 8");
 #pragma unroll 1
@@ -438,10 +447,14 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
 #pragma unroll
                             for (int r = 0; r < NRI; ++r) {
 #pragma unroll
-                                for (int q = 0; q < VPC; ++q) xv[NI + r][q] = rn[r][q];
-                                if (j < 7) {
+                                for (int q = 0; q < VPC; ++q) xv[NI + r][q] = rn[0][r][q];
 #pragma unroll
-                                    for (int q = 0; q < VPC; ++q) rn[r][q] = ring_load(r);
+                                for (int f = 0; f + 1 < PF; ++f)
+#pragma unroll
+                                    for (int q = 0; q < VPC; ++q) rn[f][r][q] = rn[f + 1][r][q];
+                                if (j + PF < 8) {
+#pragma unroll
+                                    for (int q = 0; q < VPC; ++q) rn[PF - 1][r][q] = ring_load(r);
                                 }
                             }
 #pragma unroll
@@ -490,22 +503,28 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
                     const unsigned wire_f = wire_bytes / kIo;
                     if (full_box) {
                         // groups of four frames; the ring rows of group g+1 are requested before the ticks of group g
-                        float rn[NRI > 0 ? NRI : 1][4];
+                        float rn[PF][NRI > 0 ? NRI : 1][4];
                         ring_seek(t_abs0);
 #pragma unroll
-                        for (int r = 0; r < NRI; ++r)
+                        for (int f = 0; f < PF; ++f)
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) rn[r][q] = ring_load(r);
+                            for (int r = 0; r < NRI; ++r)
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) rn[f][r][q] = ring_load(r);
 #pragma unroll 2
                         for (int gq = 0; gq < BT / 4; ++gq) {
                             float rc[NRI > 0 ? NRI : 1][4];
 #pragma unroll
                             for (int r = 0; r < NRI; ++r) {
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) rc[r][q] = rn[r][q];
-                                if (gq < BT / 4 - 1) {
+                                for (int q = 0; q < 4; ++q) rc[r][q] = rn[0][r][q];
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) rn[r][q] = ring_load(r);
+                                for (int f = 0; f + 1 < PF; ++f)
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) rn[f][r][q] = rn[f + 1][r][q];
+                                if (gq + PF < BT / 4) {
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) rn[PF - 1][r][q] = ring_load(r);
                                 }
                             }
 #pragma unroll

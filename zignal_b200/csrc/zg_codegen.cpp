@@ -32,7 +32,7 @@ std::string literal(Dtype d, double v) {
 }  // namespace
 
 std::string generate_tick_source(const Ir& ir, bool exact, const std::string& struct_name, int n_ring_in,
-                                 int n_ring_out) {
+                                 int n_ring_out, int ring_pf) {
     std::ostringstream os;
     auto ref = [&](int id, Dtype to) {
         std::ostringstream r;
@@ -46,7 +46,8 @@ std::string generate_tick_source(const Ir& ir, bool exact, const std::string& st
     os << "    static constexpr unsigned SYNTH_MASK = ZG_SYNTH_MASK;\n";
     // the last n_ring_in inputs / n_ring_out outputs are far reads / pushes of long delay lines (zg_ir.hpp)
     if (n_ring_in || n_ring_out)
-        os << "    static constexpr int N_RING_IN = " << n_ring_in << ", N_RING_OUT = " << n_ring_out << ";\n";
+        os << "    static constexpr int N_RING_IN = " << n_ring_in << ", N_RING_OUT = " << n_ring_out
+           << ", RING_PF = " << ring_pf << ";\n";
     {
         // keep the unrolled loop body of the skeleton around 600 instructions (kernels/zg_stream.cuh)
         int arith = 0;

@@ -35,7 +35,7 @@ int fail(int status, const std::string& msg);
 
 // CUDA tick-functor source for one IR (zg_codegen.cpp)
 std::string generate_tick_source(const Ir& ir, bool exact, const std::string& struct_name, int n_ring_in = 0,
-                                 int n_ring_out = 0);
+                                 int n_ring_out = 0, int ring_pf = 1);
 
 // ---- prebuilt-kernel recognisers (zg_match.cpp) ----
 constexpr int kMaxBiquadSections = 8;

@@ -234,6 +234,7 @@ struct zg_plan {
 
     Ir kir;                                 // K2: the kernel-side tick program (long delay lines split off, zg_ir.hpp)
     RingPlan ring;                          //     and where its extra inputs / outputs / window slots live
+    int ring_pf = 1;                        //     chunks a far read is requested ahead of use
     bool is_fir = false;                    // K3: dense FIR (kernels/zg_fir.cuh)
     FirMatch fir;
     float* d_taps = nullptr;                // [n_taps]
@@ -291,15 +292,29 @@ namespace {
 
 constexpr int kRegLineDepth = 16;           // delay lines up to this depth stay in registers whatever their reads
 
-// far reads are requested one chunk (of `ticks per 16 bytes`) ahead of use and must have been stored before that
-int ring_far(bool interleaved, int io) { return 2 * (interleaved ? 4 : 16 / io); }
+// Far reads are requested `pf` chunks (of `ticks per 16 bytes`; groups of four frames when interleaved) ahead of
+// use and must have been stored before the request: a read is far from delay (pf + 1) * chunk on.
+int ring_chunk(bool interleaved, int io) { return interleaved ? 4 : 16 / io; }
+
+// The kernel-side program of a graph: two chunks of prefetch when the in-flight rows fit in <= 64 registers,
+// else one (more reads become far with the shorter distance; the caller checks the limits).
+Ir split_for_kernel(const Ir& ir, bool interleaved, int io, RingPlan& ring, int& pf) {
+    const int chunk = ring_chunk(interleaved, io);
+    pf = interleaved ? 1 : 2;              // (measured: the frame loop is not fully unrolled, a deeper queue costs moves)
+    Ir k = split_long_lines(ir, kRegLineDepth, (pf + 1) * chunk, ring);
+    if ((int)ring.taps.size() * chunk * pf > 64) {
+        pf = 1;
+        k = split_long_lines(ir, kRegLineDepth, (pf + 1) * chunk, ring);
+    }
+    return k;
+}
 
 std::string jit_source(const Ir& ir, bool exact, bool interleaved, bool uniform, unsigned synth_mask, int io,
-                       int n_ring_in = 0, int n_ring_out = 0) {
+                       int n_ring_in = 0, int n_ring_out = 0, int ring_pf = 1) {
     std::ostringstream src;
     src << "#define ZG_SYNTH_MASK " << synth_mask << "u\n";
     src << zg_stream_cuh_source << "\n";
-    src << generate_tick_source(ir, exact, "ZgTick", n_ring_in, n_ring_out) << "\n";
+    src << generate_tick_source(ir, exact, "ZgTick", n_ring_in, n_ring_out, ring_pf) << "\n";
     src << "extern \"C\" __global__ void __launch_bounds__(512, 1) zg_graph_kernel("
            "const __grid_constant__ zgk::StreamArgs a) {\n"
            "    zgk::stream_block<ZgTick, "
@@ -339,7 +354,7 @@ int jit_compile(zg_plan* p, bool uniform, Variant& v) {
     if (!d.ok) return fail(ZG_ERR_CUDA, d.why);
     std::vector<char> cubin;
     int st = jit_cubin(jit_source(p->kir, p->exact, p->interleaved, uniform, p->synth_mask, p->io, (int)p->ring.taps.size(),
-                                  (int)p->ring.out_lines.size()),
+                                  (int)p->ring.out_lines.size(), p->ring_pf),
                        p->exact, cubin);
     if (st != ZG_OK) return st;
     CUresult cr = d.moduleLoadData(&v.module, cubin.data());
@@ -534,7 +549,8 @@ Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, in
     // or on interleaved frames 14 x 2 is the faster one (profiles/r01_sweep_sym2.jsonl).
     const int ops = p->tick_ops - (variant_index(p) == 2 ? p->bq.sections : 0);
     const int bytes = p->io * std::max(1, p->n_buf_in + p->ir.n_out);
-    const bool long_runs = !p->interleaved && 4 * ops < 17 * bytes;
+    // (ring reads of long delay lines are plain loads, hidden by other warps only: no trade of warps for run length)
+    const bool long_runs = !p->interleaved && 4 * ops < 17 * bytes && !p->ring.any();
     if (long_runs && per_sm > 7) {
         wpc = std::min(wpc, 7);
         NB = 4;
@@ -819,7 +835,8 @@ int zg_graph_kernel_compile(const zg_graph* g, const zg_plan_opts* opts, int uni
     if (!ir.all_f32()) return fail(ZG_ERR_UNSUPPORTED, "the device path evaluates fp32 graphs only");
     if (opts->io_dtype != ZG_F32 && opts->io_dtype != ZG_BF16) return fail(ZG_ERR_ARG, "io_dtype must be ZG_F32 or ZG_BF16");
     RingPlan ring;
-    const Ir kir = split_long_lines(ir, kRegLineDepth, ring_far(opts->layout == ZG_INTERLEAVED, opts->io_dtype == ZG_BF16 ? 2 : 4), ring);
+    int ring_pf = 1;
+    const Ir kir = split_for_kernel(ir, opts->layout == ZG_INTERLEAVED, opts->io_dtype == ZG_BF16 ? 2 : 4, ring, ring_pf);
     if (kir.n_state > zgk::kMaxState || (int)ring.taps.size() > zgk::kMaxRingIn || (int)ring.out_lines.size() > zgk::kMaxRingOut)
         return fail(ZG_ERR_UNSUPPORTED, "too much delay state for the generated kernel");
     unsigned synth = 0;
@@ -827,7 +844,7 @@ int zg_graph_kernel_compile(const zg_graph* g, const zg_plan_opts* opts, int uni
         if (opts->input_kind[k] != ZG_IN_BUFFER) synth |= 1u << k;
     const bool exact = opts->mode == ZG_MODE_EXACT;
     std::string text = jit_source(kir, exact, opts->layout == ZG_INTERLEAVED, uniform_params != 0, synth,
-                                  opts->io_dtype == ZG_BF16 ? 2 : 4, (int)ring.taps.size(), (int)ring.out_lines.size());
+                                  opts->io_dtype == ZG_BF16 ? 2 : 4, (int)ring.taps.size(), (int)ring.out_lines.size(), ring_pf);
     std::vector<char> cubin;
     const char* data = text.data();
     size_t n = text.size();
@@ -877,7 +894,8 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     // generated kernel: delay lines deeper than kRegLineDepth live in HBM as rings (zg_ir.hpp); what must fit in
     // registers is the rest -- short lines and the near windows of the long ones
     RingPlan ring;
-    const Ir kir = split_long_lines(ir, kRegLineDepth, ring_far(opts->layout == ZG_INTERLEAVED, bf16 ? 2 : 4), ring);
+    int ring_pf = 1;
+    const Ir kir = split_for_kernel(ir, opts->layout == ZG_INTERLEAVED, bf16 ? 2 : 4, ring, ring_pf);
     if (!is_fir && (kir.n_state > zgk::kMaxState || (int)ring.taps.size() > zgk::kMaxRingIn ||
                     (int)ring.out_lines.size() > zgk::kMaxRingOut || ir.n_in + ring.taps.size() > 32))
         return fail(ZG_ERR_UNSUPPORTED,
@@ -963,6 +981,7 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     } else {
         p->kir = kir;
         p->ring = ring;
+        p->ring_pf = ring_pf;
         p->kernel_n_state = kir.n_state;
         p->kernel_n_param = ir.n_params;
         p->state_row.assign(kir.n_state, 0);       // filled per launch (window slots move with the stream position)
