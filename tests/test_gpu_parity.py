@@ -880,3 +880,20 @@ def test_long_delay_limits_are_reported(zg):
     with pytest.raises(zg.ZgError) as e:
         zg.compile(many).plan(channels=8)
     assert e.value.status == zg.ZG_ERR_UNSUPPORTED and "far reads" in str(e.value)
+
+
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+def test_long_delay_lines_through_process_host_chunks(zg, layout):
+    """zg_process_host streams a large block in chunks (channel ranges when planar, time ranges when interleaved):
+    the rings must follow -- same stream position for every channel chunk, advancing position for time chunks."""
+    expr = LONG[3]
+    C, T = 4096, 10240                                        # 80 MiB in + 80 MiB out per call: two chunks each
+    x = fo.noise(C, T, seed=160)
+    plan = zg.compile(expr).plan(channels=C, layout=zg.PLANAR if layout == "planar" else zg.INTERLEAVED)
+    xin = np.ascontiguousarray(x.T) if layout == "interleaved" else x
+    y = plan.process_host([xin[:T // 2] if layout == "interleaved" else np.ascontiguousarray(xin[:, :T // 2])])[0]
+    y2 = plan.process_host([xin[T // 2:] if layout == "interleaved" else np.ascontiguousarray(xin[:, T // 2:])])[0]
+    assert plan.info().host_chunks > 1
+    got = np.concatenate([y, y2], axis=0).T if layout == "interleaved" else np.concatenate([y, y2], axis=1)
+    idx = [0, 1, 1023, 1024, 2049, 4095]
+    assert np.array_equal(got[idx], _oracle(expr, [x[idx]])[0])

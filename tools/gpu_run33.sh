@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "long_delay" > gpurun_out/pytest_long.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_long.log
+timeout 300 python tools/sweep.py --workload ns --graph comb --iters 10 --points "mode=exact;layout=interleaved" 2>&1 | cut -c1-200
