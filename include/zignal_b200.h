@@ -126,7 +126,7 @@ typedef struct zg_plan_opts {
     int layout;           /* zg_layout                                                          */
     int io_dtype;         /* sample storage in HBM: ZG_F32, or ZG_BF16 (state, parameters and all
                              arithmetic stay fp32; outputs are rounded to nearest even; generated
-                             kernel only: no K1b / FIR)                                            */
+                             kernel only: no K1b / FIR kernel)                                     */
     int lanes_per_channel;/* 0 = auto; 1 = one lane per channel; S = S lanes per channel, lane k evaluating
                              section k of an S-section biquad cascade as a systolic pipeline (same
                              arithmetic, bit-identical in EXACT mode; planar layout, S = 2 or 4).  Auto

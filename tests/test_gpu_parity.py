@@ -406,12 +406,13 @@ def test_argument_errors(zg):
 
 @pytest.mark.parametrize("n_taps,C,T", [(256, 64, 1024), (256, 33, 700), (2, 32, 64), (17, 40, 100), (33, 5, 31),
                                         (100, 64, 4096), (255, 32, 513), (257, 32, 640), (512, 96, 2048)])
-def test_fir_exact_is_bit_identical(zg, n_taps, C, T):
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+def test_fir_exact_is_bit_identical(zg, n_taps, C, T, layout):
     h = fo.fir_taps(n_taps)
     expr = fo.fir_expr(h)
     x = fo.noise(C, T, seed=n_taps + C)
-    ys, plan = _run(zg, expr, [x], zg.MODE_EXACT)
-    assert plan.info().kernel.decode().startswith(f"zg_fir<{n_taps} taps,exact") and plan.info().jit == 0
+    ys, plan = _run(zg, expr, [x], zg.MODE_EXACT, layout)
+    assert plan.info().kernel.decode() == f"zg_fir<{n_taps} taps,exact,{layout}>" and plan.info().jit == 0
     assert np.array_equal(ys[0], fo.fir_direct(x, h))
     if C * T <= 64 * 1024:                                   # and the tick-by-tick oracle itself
         assert np.array_equal(ys[0], _oracle(expr, [x])[0])
@@ -426,7 +427,8 @@ def test_fir_fast_within_tolerance(zg):
     assert 0 < err <= TOL, err
 
 
-def test_fir_streaming_blocks_and_state(zg):
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+def test_fir_streaming_blocks_and_state(zg, layout):
     """Ragged block lengths (shorter than the delay line, not multiples of the 32-sample box) continue
     exactly like consecutive ticks; the delay line is visible through zg_state_get in the oracle's
     slot order (oldest first, rotate_push_back flowz.hpp:130-148)."""
@@ -434,19 +436,19 @@ def test_fir_streaming_blocks_and_state(zg):
     expr = fo.fir_expr(h)
     C, T = 40, 1500
     x = fo.noise(C, T, seed=9)
-    ys, plan = _run(zg, expr, [x], zg.MODE_EXACT, blocks=[7, 100, 33, 255, 256, 1, 848])
+    ys, plan = _run(zg, expr, [x], zg.MODE_EXACT, layout, blocks=[7, 100, 33, 255, 256, 1, 848])
     assert np.array_equal(ys[0], fo.fir_direct(x, h))
     st = plan.get_state()                                     # [255][C]
     assert np.array_equal(st, x[:, -255:].T)
     # set_state: a plan started from that delay line continues the stream
     x2 = fo.noise(C, 300, seed=10)
-    plan2 = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT)
+    inter = layout == "interleaved"
+    plan2 = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, layout=zg.INTERLEAVED if inter else zg.PLANAR)
     plan2.set_state(st)
-    y2 = plan2.process([_to_dev(x2)])[0].cpu().numpy()
-    assert np.array_equal(y2, fo.fir_direct(x2, h, history=x[:, -255:]))
+    run2 = lambda: (lambda y: y.T if inter else y)(plan2.process([_to_dev(x2.T if inter else x2)])[0].cpu().numpy())
+    assert np.array_equal(run2(), fo.fir_direct(x2, h, history=x[:, -255:]))
     plan2.reset()
-    y3 = plan2.process([_to_dev(x2)])[0].cpu().numpy()
-    assert np.array_equal(y3, fo.fir_direct(x2, h))
+    assert np.array_equal(run2(), fo.fir_direct(x2, h))
 
 
 def test_fir_time_segments_for_few_channels(zg):
@@ -495,9 +497,10 @@ def test_fir_process_host_and_long_delay_errors(zg):
     # a long delay line that is not a dense FIR runs the generated kernel (the line is a ring in HBM)
     ys, plan2 = _run(zg, "_1[_100] + 0.5f*_1", [x[:64, :600]], zg.MODE_EXACT)
     assert plan2.info().jit == 1 and np.array_equal(ys[0], _oracle("_1[_100] + 0.5f*_1", [x[:64, :600]])[0])
-    with pytest.raises(zg.ZgError) as e:
-        zg.compile(fo.fir_expr(fo.fir_taps(256))).plan(channels=8, layout=zg.INTERLEAVED)
-    assert e.value.status == zg.ZG_ERR_UNSUPPORTED
+    # interleaved frames through the host path: chunks are time ranges, the delay line ping-pongs per chunk
+    xi = np.ascontiguousarray(x.T)
+    yi = zg.compile(fo.fir_expr(h)).plan(channels=2048, layout=zg.INTERLEAVED).process_host([xi])[0]
+    assert np.array_equal(yi.T, fo.fir_direct(x, h))
 
 
 def test_full_size_config4_fir256_32768_channels(zg):
@@ -897,3 +900,19 @@ def test_long_delay_lines_through_process_host_chunks(zg, layout):
     got = np.concatenate([y, y2], axis=0).T if layout == "interleaved" else np.concatenate([y, y2], axis=1)
     idx = [0, 1, 1023, 1024, 2049, 4095]
     assert np.array_equal(got[idx], _oracle(expr, [x[idx]])[0])
+
+
+def test_long_delay_lines_set_state_at_any_stream_position(zg):
+    """zg_state_set on a plan whose rings are mid-phase (stream position not a multiple of the depths)"""
+    expr = LONG[2]
+    g = zg.compile(expr)
+    C = 33
+    xa, xb, xc = (fo.noise(C, n, seed=170 + i) for i, n in enumerate((777, 123, 400)))
+    a = g.plan(channels=C)
+    a.process([_to_dev(xa)])
+    b = g.plan(channels=C)
+    b.process([_to_dev(xb)])                                   # b is now at stream position 123, rings mid-phase
+    b.set_state(a.get_state())                                 # ... and takes over a's delay lines
+    y = b.process([_to_dev(xc)])[0].cpu().numpy()
+    ref = _oracle(expr, [np.concatenate([xa, xc], axis=1)])[0][:, 777:]
+    assert np.array_equal(y, ref)

@@ -25,13 +25,16 @@
 //     State is ping-ponged (read state_in, write state_out) because the segment that writes the new
 //     state may run before the segment that reads the old one.
 //   * outputs go to a per-warp double-buffered box and leave with a TMA store.
+//   * interleaved frames ([T][C] buffers): the same ring, but a box is 32 frames of 32 channels (no swizzle), a
+//     lane walks down its column with LDS.32 / STS.32 (all 32 lanes on one 128-byte row: conflict free) -- four
+//     times the shared-memory instructions of the planar form for the same arithmetic.
 #pragma once
 #include "zg_stream.cuh"
 
 namespace zgk {
 
 struct FirArgs {
-    TensorMap in_map;               // planar 2-D {T, C}, box 32 x 32, SWIZZLE_128B
+    TensorMap in_map;               // planar: 2-D {T, C}, box 32 x 32, SWIZZLE_128B; interleaved: 2-D {C, T}, no swizzle
     TensorMap out_map;
     const float* state_in;          // [n_taps-1][ch_stride]; slot j = x[t0 - (n_taps-1) + j]
     float* state_out;
@@ -50,8 +53,15 @@ struct FirCursor {                  // a 16-sample block of the ring: (slot, hal
     int slot, half;
 };
 
+template <bool kInterleaved>
 __device__ __forceinline__ void fir_load16(float (&x)[16], const unsigned char* ring, FirCursor c, unsigned row,
                                            unsigned sw) {
+    if (kInterleaved) {                                // frame f of the box at f * 128, this lane's channel at `row`
+        const unsigned char* base = ring + (size_t)c.slot * kTileBytes + (unsigned)c.half * 2048u + row;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = *reinterpret_cast<const float*>(base + i * 128);
+        return;
+    }
     const unsigned char* base = ring + (size_t)c.slot * kTileBytes + row;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -89,7 +99,7 @@ __device__ __forceinline__ void fir_body(float (&acc)[16], const float (&xn)[16]
     }
 }
 
-template <bool kExact>
+template <bool kExact, bool kInterleaved = false>
 __device__ __forceinline__ void fir_block(const FirArgs& a) {
     extern __shared__ __align__(1024) unsigned char smem[];
 
@@ -126,7 +136,8 @@ __device__ __forceinline__ void fir_block(const FirArgs& a) {
         mbar_expect_tx(&bars[s & 1], (unsigned)nb * kTileBytes);
         for (int i = 0; i < nb; ++i) {
             const int lb = b0 + i - b_begin + H;
-            tma_load_2d(ring + (size_t)(lb % NR) * kTileBytes, &a.in_map, (b0 + i) * kTileT, c0, &bars[s & 1]);
+            const int tx = kInterleaved ? c0 : (b0 + i) * kTileT, ty = kInterleaved ? (b0 + i) * kTileT : c0;
+            tma_load_2d(ring + (size_t)(lb % NR) * kTileBytes, &a.in_map, tx, ty, &bars[s & 1]);
         }
     };
 
@@ -139,12 +150,19 @@ __device__ __forceinline__ void fir_block(const FirArgs& a) {
         prefetch_tmap(&a.out_map);
         if (seg > 0) {                                              // history = the input before the segment
             mbar_expect_tx(&bars[2], (unsigned)H * kTileBytes);
-            for (int i = 0; i < H; ++i)
-                tma_load_2d(ring + (size_t)i * kTileBytes, &a.in_map, (b_begin - H + i) * kTileT, c0, &bars[2]);
+            for (int i = 0; i < H; ++i) {
+                const int t = (b_begin - H + i) * kTileT;
+                tma_load_2d(ring + (size_t)i * kTileBytes, &a.in_map, kInterleaved ? c0 : t, kInterleaved ? t : c0, &bars[2]);
+            }
         }
         issue_step(0);
     }
     for (int i = tid; i < n_taps_pad; i += blockDim.x) taps_s[i] = i < N ? a.taps[i] : 0.f;
+    // byte offset of sample `s` (0..31) of this lane's channel inside a box
+    auto elem = [&](unsigned s) {
+        return kInterleaved ? s * 128u + (unsigned)lane * 4u
+                            : (unsigned)lane * 128u + (((s >> 2) ^ ((unsigned)lane & 7u)) << 4) + (s & 3u) * 4u;
+    };
     if (seg == 0) {
         // history = the delay line of the previous block: slot j = x[-(N-1) + j]  ->  local sample
         // 32H - (N-1) + j; older positions are never read by the arithmetic, zero them
@@ -153,8 +171,7 @@ __device__ __forceinline__ void fir_block(const FirArgs& a) {
         for (int ls = warp; ls < 32 * H; ls += W) {
             const int j = ls - first;
             const float v = (j >= 0 && ch_ok) ? a.state_in[(long long)j * a.ch_stride + ch] : 0.f;
-            const unsigned off = (unsigned)(ls >> 5) * kTileBytes + (unsigned)lane * 128u +
-                                 (((((unsigned)ls & 31u) >> 2) ^ ((unsigned)lane & 7u)) << 4) + ((unsigned)ls & 3u) * 4u;
+            const unsigned off = (unsigned)(ls >> 5) * kTileBytes + elem((unsigned)ls & 31u);
             *reinterpret_cast<float*>(ring + off) = v;
         }
         fence_proxy_async();                                        // these slots are overwritten by TMA later
@@ -162,7 +179,7 @@ __device__ __forceinline__ void fir_block(const FirArgs& a) {
     __syncthreads();
     if (seg > 0) mbar_wait(&bars[2], 0);
 
-    const unsigned row = (unsigned)lane * 128u;
+    const unsigned row = kInterleaved ? (unsigned)lane * 4u : (unsigned)lane * 128u;
     const unsigned sw = (unsigned)lane & 7u;
     const int n_full = N >> 4;
     const int rem = N & 15;
@@ -192,37 +209,42 @@ __device__ __forceinline__ void fir_block(const FirArgs& a) {
                     --back;
                 };
                 float xa[16], xb[16];
-                fir_load16(xa, ring, cur, row, sw);
+                fir_load16<kInterleaved>(xa, ring, cur, row, sw);
                 prev();
-                fir_load16(xb, ring, cur, row, sw);
+                fir_load16<kInterleaved>(xb, ring, cur, row, sw);
                 int j = 0;
                 for (; j + 2 <= n_full; j += 2) {
                     fir_body<kExact, false>(acc, xa, xb, taps_s + 16 * j, 16);
                     prev();
-                    if (back >= 0) fir_load16(xa, ring, cur, row, sw);
+                    if (back >= 0) fir_load16<kInterleaved>(xa, ring, cur, row, sw);
                     fir_body<kExact, false>(acc, xb, xa, taps_s + 16 * (j + 1), 16);
                     prev();
-                    if (back >= 0) fir_load16(xb, ring, cur, row, sw);
+                    if (back >= 0) fir_load16<kInterleaved>(xb, ring, cur, row, sw);
                 }
                 if (j < n_full) {
                     fir_body<kExact, false>(acc, xa, xb, taps_s + 16 * j, 16);
                     if (rem) {
                         prev();
-                        if (back >= 0) fir_load16(xa, ring, cur, row, sw);
+                        if (back >= 0) fir_load16<kInterleaved>(xa, ring, cur, row, sw);
                         fir_body<kExact, true>(acc, xb, xa, taps_s + 16 * (j + 1), rem);
                     }
                 } else if (rem) {
                     fir_body<kExact, true>(acc, xa, xb, taps_s + 16 * j, rem);
                 }
+                if (kInterleaved) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    *reinterpret_cast<float4*>(ob + row + ((((unsigned)(h * 4 + i)) ^ sw) << 4)) =
-                        make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                    for (int r = 0; r < 16; ++r) *reinterpret_cast<float*>(ob + (unsigned)(16 * h + r) * 128u + row) = acc[r];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<float4*>(ob + row + ((((unsigned)(h * 4 + i)) ^ sw) << 4)) =
+                            make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                }
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                tma_store_2d(&a.out_map, b * kTileT, c0, ob);
+                tma_store_2d(&a.out_map, kInterleaved ? c0 : b * kTileT, kInterleaved ? b * kTileT : c0, ob);
                 tma_commit();
             }
         }
@@ -234,8 +256,7 @@ __device__ __forceinline__ void fir_block(const FirArgs& a) {
         for (int j = warp; j < N - 1; j += W) {
             const long long t = (long long)a.n_samples - (N - 1) + j;            // block time, may be < 0
             const int ls = (int)(t - 32ll * (b_begin - H));
-            const unsigned off = (unsigned)((ls >> 5) % NR) * kTileBytes + row + (((((unsigned)ls & 31u) >> 2) ^ sw) << 4) +
-                                 ((unsigned)ls & 3u) * 4u;
+            const unsigned off = (unsigned)((ls >> 5) % NR) * kTileBytes + elem((unsigned)ls & 31u);
             const float v = *reinterpret_cast<const float*>(ring + off);
             if (ch_ok) a.state_out[(long long)j * a.ch_stride + ch] = v;
         }

@@ -154,9 +154,14 @@ __global__ void __launch_bounds__(512, 1) zg_biquad_lanes_kernel(const __grid_co
     zgk::biquad_lanes_block<S, kExact, kUniform>(a);
 }
 
-template <bool kExact>
+template <bool kExact, bool kInterleaved>
 __global__ void __launch_bounds__(512, 1) zg_fir_kernel(const __grid_constant__ zgk::FirArgs a) {
-    zgk::fir_block<kExact>(a);
+    zgk::fir_block<kExact, kInterleaved>(a);
+}
+
+const void* fir_kernel_for(bool exact, bool interleaved) {
+    if (exact) return interleaved ? (const void*)zg_fir_kernel<true, true> : (const void*)zg_fir_kernel<true, false>;
+    return interleaved ? (const void*)zg_fir_kernel<false, true> : (const void*)zg_fir_kernel<false, false>;
 }
 
 using KernelPtr = void (*)(zgk::StreamArgs);
@@ -384,7 +389,7 @@ int get_variant(zg_plan* p, bool uniform, Variant*& out) {
     if (v.ready) return ZG_OK;
     if (p->is_fir) {
         cudaFuncAttributes fa;
-        ZG_CUDA(cudaFuncGetAttributes(&fa, p->exact ? (const void*)zg_fir_kernel<true> : (const void*)zg_fir_kernel<false>));
+        ZG_CUDA(cudaFuncGetAttributes(&fa, fir_kernel_for(p->exact, p->interleaved)));
         v.regs = fa.numRegs;
         v.ready = true;
         return ZG_OK;
@@ -761,7 +766,7 @@ int launch_fir(zg_plan* p, const void* const* in, void* const* out, int64_t T, i
     a.seg_boxes = (int)seg_boxes;
     a.n_segs = (int)n_segs;
     const int smem = fixed + (NR - H + 2 * W) * zgk::kTileBytes;
-    const void* fn = p->exact ? (const void*)zg_fir_kernel<true> : (const void*)zg_fir_kernel<false>;
+    const void* fn = fir_kernel_for(p->exact, p->interleaved);
     Variant& v = p->variant[1];
     if (smem > v.max_smem_set) {
         ZG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -890,7 +895,7 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     FirMatch fir;
     bool any_synth = false;
     for (int k = 0; k < ir.n_in; ++k) any_synth = any_synth || opts->input_kind[k] != ZG_IN_BUFFER;
-    const bool is_fir = !opts->force_jit && !any_synth && opts->layout == ZG_PLANAR && !bf16 && match_fir(ir, fir);
+    const bool is_fir = !opts->force_jit && !any_synth && !bf16 && match_fir(ir, fir);
     // generated kernel: delay lines deeper than kRegLineDepth live in HBM as rings (zg_ir.hpp); what must fit in
     // registers is the rest -- short lines and the near windows of the long ones
     RingPlan ring;
@@ -960,7 +965,8 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     if (p->is_fir) {
         p->kernel_n_state = ir.n_state;
         p->kernel_n_param = 0;
-        p->kernel_name = "zg_fir<" + std::to_string(fir.taps.size()) + (p->exact ? " taps,exact,planar>" : " taps,fma,planar>");
+        p->kernel_name = "zg_fir<" + std::to_string(fir.taps.size()) + (p->exact ? " taps,exact," : " taps,fma,") +
+                         (p->interleaved ? "interleaved>" : "planar>");
     } else if (p->is_biquad && !opts->force_jit) {
         const int S = p->bq.sections;
         p->kernel_n_state = 2 * (S + 1);
