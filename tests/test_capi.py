@@ -83,3 +83,32 @@ def test_bf16_storage_kernels_compile_for_sm100a(zg):
     with pytest.raises(zg.ZgError) as e:
         g.kernel(io_dtype=zg.I32)
     assert e.value.status == zg.ZG_ERR_ARG
+
+
+@pytest.mark.parametrize("expr,n_ring_in,n_ring_out", [
+    ("~(_2 + 0.5f*_1[_100])", 1, 1),                                        # feedback comb
+    ("_1 + 0.5f*_1[_37] - 0.25f*_1[_1000]", 2, 1),                          # two far reads of one long line
+    ("~(_2 + 0.5f*_1[_3] + 0.25f*_1[_500])", 1, 1),                         # the near read stays in a register window
+    ("~(_2 + 0.4f*_1[_17]) |= ~(_2 - 0.3f*_1[_64]) |= (_1 , _1[_33])", 3, 2),
+    ("~(_2 + 0.5f*_1[_16])", 0, 0),                                         # 16 floats: still register-resident
+])
+def test_long_delay_lines_become_ring_wires_of_the_generated_kernel(zg, expr, n_ring_in, n_ring_out):
+    """Host-side split of long delay lines (zg_ir.cpp: split_long_lines): far reads become extra kernel inputs,
+    pushes extra outputs; the kernel builds for sm_100a in every layout / storage (NVRTC, no device needed)."""
+    g = zg.compile(expr)
+    src = g.kernel().decode()
+    tick = src[src.index("struct ZgTick"):]
+    if n_ring_out:
+        assert f"N_RING_IN = {n_ring_in}, N_RING_OUT = {n_ring_out}" in tick
+        assert f"N_IN = {g.n_in + n_ring_in}, N_OUT = {g.n_out + n_ring_out}" in tick
+    else:
+        assert "N_RING_IN" not in tick
+    for kw in (dict(), dict(layout=zg.INTERLEAVED), dict(io_dtype=zg.BF16), dict(mode=zg.MODE_FAST)):
+        assert g.kernel(cubin=True, **kw)[:4] == b"\x7fELF"
+
+
+def test_too_many_far_reads_is_unsupported_not_wrong(zg):
+    many = " + ".join(f"0.1f*_1[_{100 + 10 * k}]" for k in range(12))
+    with pytest.raises(zg.ZgError) as e:
+        zg.compile(many).kernel()
+    assert e.value.status == zg.ZG_ERR_UNSUPPORTED
