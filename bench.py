@@ -267,6 +267,8 @@ def other_configs(zg, wl, torch, dev, local, world, rank, args, barrier, dist):
                    "steps": steps, "bytes_per_sample": bytes_per_sample,
                    "roofline_frac": bytes_per_sample * C * T / (ms * 1e-3) / 1e9 / peak, "kernel": info.kernel.decode(),
                    "jit": info.jit, "regs": info.regs_per_thread, "mode": args.mode}
+            if name == "c5":
+                ent["bound"] = "FP32 issue (23 arithmetic instructions per 2-byte sample), not HBM"
             if instr_per_sample:
                 sm = torch.cuda.get_device_properties(dev).multi_processor_count
                 mhz = ClockSampler(local).max_mhz or 1965
@@ -425,6 +427,10 @@ def run_ours(args):
                         "roofline_frac": BYTES_PER_SAMPLE * Co * To / (ms_o * 1e-3) / 1e9 / _peak_hbm()[0],
                         "kernel": io.kernel.decode(), "lanes_per_channel": io.lanes_per_channel,
                         "traffic": _traffic(other)}}
+        if other == "c2" and args.mode == "exact":
+            also[other]["bound"] = ("recurrence latency, not HBM: 4096 channels x 4 sections = one warp per scheduler, "
+                                    "y = (v + a1*y1) + a2*y2 is three dependent 5-cycle instructions per sample, so "
+                                    "0.50 ms / 0.67 of the HBM roofline is the ceiling of EXACT arithmetic (DESIGN.md K1b)")
         del plan_o, xo, yo
         torch.cuda.empty_cache()
         also.update(other_configs(zg, wl, torch, dev, local, world, rank, args, barrier, dist))
