@@ -327,8 +327,39 @@ std::string jit_source(const Ir& ir, bool exact, bool interleaved, bool uniform,
     return src.str();
 }
 
-// source -> sm_100a cubin.  Needs libnvrtc only (no device, no driver).
+// source -> sm_100a cubin.  Needs libnvrtc only (no device, no driver).  Compiling takes ~0.5-1 s, so the cubins
+// of the last few dozen distinct kernels are kept for the life of the process (key: the source text, which
+// contains every specialisation: graph, layout, storage, parameter passing; plus the contraction flag) --
+// a second plan of the same graph, e.g. one per rank-local stream or per test, costs a module load only.
+struct CubinCache {
+    std::mutex mu;
+    std::vector<std::pair<std::string, std::vector<char>>> entries;     // most recent last
+    static constexpr size_t kMax = 48;
+};
+CubinCache& cubin_cache() {
+    static CubinCache c;
+    return c;
+}
+
+int jit_cubin_uncached(const std::string& text, bool exact, std::vector<char>& cubin);
+
 int jit_cubin(const std::string& text, bool exact, std::vector<char>& cubin) {
+    const std::string key = (exact ? "E" : "F") + text;
+    CubinCache& c = cubin_cache();
+    {
+        std::lock_guard<std::mutex> lock(c.mu);
+        for (auto& e : c.entries)
+            if (e.first == key) { cubin = e.second; return ZG_OK; }
+    }
+    int st = jit_cubin_uncached(text, exact, cubin);
+    if (st != ZG_OK) return st;
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (c.entries.size() >= CubinCache::kMax) c.entries.erase(c.entries.begin());
+    c.entries.emplace_back(key, cubin);
+    return ZG_OK;
+}
+
+int jit_cubin_uncached(const std::string& text, bool exact, std::vector<char>& cubin) {
     Nvrtc& n = nvrtc();
     if (!n.ok) return fail(ZG_ERR_CUDA, n.why);
     void* prog = nullptr;
