@@ -916,3 +916,34 @@ def test_long_delay_lines_set_state_at_any_stream_position(zg):
     y = b.process([_to_dev(xc)])[0].cpu().numpy()
     ref = _oracle(expr, [np.concatenate([xa, xc], axis=1)])[0][:, 777:]
     assert np.array_equal(y, ref)
+
+
+def test_small_blocks_replayed_from_a_cuda_graph(zg):
+    """Launch-bound use (real-time style 64-sample blocks): zg_process is capturable -- tensor maps travel in the
+    kernel parameters, nothing in the call synchronises once the plan is warm -- so a run of block calls can be
+    replayed as one CUDA graph.  State lives in device memory, so every replay continues the stream."""
+    torch = _torch()
+    C, T, NBLK = 4096, 64, 16
+    expr = fo.biquad_cascade(4)
+    plan = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, lanes_per_channel=1)
+    x = fo.noise(C, 2 * NBLK * T, seed=181)
+    xin = torch.empty((C, NBLK * T), device="cuda")
+    yout = torch.empty_like(xin)
+    plan.process([xin[:, :T]], [yout[:, :T]])                 # warm: kernel attributes set, parameters uploaded
+    plan.reset()
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for b in range(NBLK):
+                plan.process([xin[:, b * T:(b + 1) * T]], [yout[:, b * T:(b + 1) * T]])
+    plan.reset()                                               # capture ran nothing; start the stream from zero
+    outs = []
+    for rep in range(2):
+        xin.copy_(torch.from_numpy(x[:, rep * NBLK * T:(rep + 1) * NBLK * T]))
+        graph.replay()
+        torch.cuda.synchronize()
+        outs.append(yout.cpu().numpy().copy())
+    idx = [0, 17, 4095]
+    ref = _oracle(expr, [x[idx]])[0]
+    assert np.array_equal(np.concatenate(outs, axis=1)[idx], ref)
