@@ -154,9 +154,11 @@ typedef struct zg_plan_info {
     int smem_bytes;
     int launches;         /* kernels launched by this plan so far                               */
     int threads_per_cta;  /* geometry of the last launch                                        */
-    int stages;           /* TMA pipeline depth per warp of the last launch                     */
+    int stages;           /* TMA pipeline depth per warp of the last launch (FIR kernel: boxes in
+                             the CTA's input ring)                                              */
     int uniform_params;   /* 1 = all parameters are scalars and travel in the constant bank     */
-    int boxes;            /* 4 KB boxes (32 channels x 32 samples) per wire per pipeline stage  */
+    int boxes;            /* 4 KB boxes (32 channels x 32 samples) per wire per pipeline stage
+                             (FIR kernel: boxes per time segment)                               */
 } zg_plan_info;
 int zg_plan_get_info(const zg_plan* p, zg_plan_info* info);
 
