@@ -64,6 +64,13 @@ struct StreamArgs {
     int ring_in_row0[kMaxRingIn], ring_in_depth[kMaxRingIn], ring_in_delay[kMaxRingIn];
     int ring_out_row0[kMaxRingOut], ring_out_depth[kMaxRingOut];
     unsigned long long state_nowrite;   // bit j: state slot j is a window onto a ring -- loaded, never written back
+    // L2 prefetch of the input rows ahead of the TMA loads (flags bit 4, planar only): every lane asks for
+    // `pf_window` contiguous bytes of its own channel row `pf_dist` tiles before the tile that starts the window is
+    // computed, so DRAM sees long runs per row although the shared-memory boxes stay 128 bytes wide.
+    const unsigned char* in_base[kMaxWires];
+    long long in_pitch_bytes;
+    int pf_window;                      // bytes, a multiple of the tile's bytes per row
+    int pf_dist;                        // tiles
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -123,6 +130,9 @@ __device__ __forceinline__ void tma_store_2d_hint(const TensorMap* map, int x, i
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(map),
                  "r"(x), "r"(y), "r"(smem_u32(src)), "l"(policy)
                  : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned bytes) {     // bytes % 16 == 0, gptr 16-byte aligned
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -382,6 +392,16 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
         const int nb = boxes_in_tile(t0);
         unsigned char* stage = my + (size_t)slot * stage_bytes;
 
+        if (!kInterleaved && kNumBuf > 0 && (a.flags & 16) && ch_ok) {
+            const long long off = (long long)(i + a.pf_dist) * tile_t * kIo;          // byte offset inside the row
+            const long long row_bytes = ((long long)a.n_samples * kIo) & ~15ll;
+            if (off % a.pf_window == 0 && off < row_bytes) {
+                const unsigned sz = (unsigned)(row_bytes - off < a.pf_window ? row_bytes - off : a.pf_window);
+#pragma unroll
+                for (int k = 0; k < NI; ++k)
+                    if (kBufMask & (1u << k)) l2_prefetch_bulk(a.in_base[k] + (long long)ch * a.in_pitch_bytes + off, sz);
+            }
+        }
         if (kNumBuf > 0) mbar_wait(&bars[slot], (unsigned)((i / S) & 1));
 
         if (ch_ok) {

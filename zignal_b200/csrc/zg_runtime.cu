@@ -727,6 +727,16 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     if (int t = tune_env("ZG_TUNE_LATE_REFILL")) late = t == 1;
     if (late) a.flags |= 2;
     if (int h = tune_env("ZG_TUNE_L2HINT")) a.flags |= (h & 3) << 2;       // 1 = loads, 2 = stores, 3 = both: evict-first
+    // L2 prefetch of the input rows in long runs ahead of the 128-byte-wide TMA boxes (experiment, off by default):
+    // ZG_TUNE_PF = window in bytes per channel row, ZG_TUNE_PFD = tiles ahead (default 2)
+    if (int w = tune_env("ZG_TUNE_PF"); w > 0 && !p->interleaved && p->lanes == 1) {
+        const int tile_bytes = g.boxes * 128;
+        a.pf_window = std::max(tile_bytes, w / tile_bytes * tile_bytes);
+        a.pf_dist = tune_env("ZG_TUNE_PFD") > 0 ? tune_env("ZG_TUNE_PFD") : 2;
+        a.in_pitch_bytes = ld_in * p->io;
+        for (int k = 0; k < p->ir.n_in; ++k) a.in_base[k] = static_cast<const unsigned char*>(in[k]);
+        a.flags |= 16;
+    }
 
     if (g.smem > v->max_smem_set) {
         if (v->prebuilt) {
