@@ -31,6 +31,7 @@
 
 #include <array>
 #include <cstdint>
+#include <complex>
 #include <cstdio>
 #include <functional>
 #include <memory>
@@ -113,6 +114,10 @@ struct placeholder_expr : expr_tag {
     }
 };
 
+template <class T> struct is_complex : std::false_type {};
+template <> struct is_complex<std::complex<float>> : std::true_type {};
+template <> struct is_complex<std::complex<double>> : std::true_type {};
+
 template <class T>
 struct literal_expr : expr_tag {
     static constexpr int in = 0, out = 1;
@@ -120,7 +125,11 @@ struct literal_expr : expr_tag {
     T value;
     void write(writer& w) const {
         char buf[64];
-        if constexpr (std::is_integral<T>::value) std::snprintf(buf, sizeof buf, "%d", (int)value);
+        if constexpr (is_complex<T>::value) {          // typed by ResultType, not evaluated (flowz.hpp:1245)
+            std::snprintf(buf, sizeof buf, "%s{%a,%a}", sizeof(T) == 8 ? "cplx" : "cplxd", (double)value.real(), (double)value.imag());
+            w.os << buf;
+            return;
+        } else if constexpr (std::is_integral<T>::value) std::snprintf(buf, sizeof buf, "%d", (int)value);
         else if constexpr (std::is_same<T, float>::value) std::snprintf(buf, sizeof buf, "%af", (double)value);
         else std::snprintf(buf, sizeof buf, "%a", (double)value);
         if (buf[0] == '-') w.os << "(" << buf << ")"; else w.os << buf;
@@ -189,6 +198,11 @@ struct as_expr_impl<T, std::enable_if_t<std::is_arithmetic<std::decay_t<T>>::val
     static type make(const T& t) { return {{}, (V)t}; }
 };
 template <class T>
+struct as_expr_impl<T, std::enable_if_t<is_complex<std::decay_t<T>>::value>> {
+    using type = literal_expr<std::decay_t<T>>;
+    static type make(const T& t) { return {{}, t}; }
+};
+template <class T>
 struct as_expr_impl<std::reference_wrapper<T>, void> {
     static_assert(std::is_same<std::remove_const_t<T>, float>::value, "std::ref parameters must be float");
     using type = ref_expr;
@@ -198,7 +212,7 @@ template <class T> using as_expr_t = typename as_expr_impl<std::decay_t<T>>::typ
 template <class T> as_expr_t<T> as_expr(const T& t) { return as_expr_impl<std::decay_t<T>>::make(t); }
 
 template <class T> constexpr bool is_operand_v =
-    is_expr_v<T> || std::is_arithmetic<std::decay_t<T>>::value;
+    is_expr_v<T> || std::is_arithmetic<std::decay_t<T>>::value || is_complex<std::decay_t<T>>::value;
 template <class T> struct is_refw : std::false_type {};
 template <class T> struct is_refw<std::reference_wrapper<T>> : std::true_type {};
 template <class A, class B> constexpr bool arith_ok_v =
@@ -319,6 +333,44 @@ using flowz::input_arity;
 using flowz::output_arity;
 using flowz::max_input_delays;
 using flowz::min_input_delays;
+// ResultType (flowz.hpp:515-644).  The reference returns a *value of the result type*, to be inspected with
+// decltype; here the types are run-time data: r(expr, std::tuple<float>{}).is<std::tuple<float, double>>().
+struct result_type_info {
+    std::vector<int> types;                              // zg_dtype per output wire (ZG_TYPE_OPEN = leftover absorber)
+    bool is_tuple = false;                               // false: the reference yields a bare scalar (test/tests.cpp:198)
+    template <class T> bool is() const { return match(static_cast<T*>(nullptr)); }
+
+private:
+    template <class T> static constexpr int code() {
+        return std::is_same<T, int>::value ? ZG_I32 : std::is_same<T, float>::value ? ZG_F32
+             : std::is_same<T, double>::value ? ZG_F64 : std::is_same<T, std::complex<float>>::value ? ZG_C64
+             : std::is_same<T, std::complex<double>>::value ? ZG_C128 : -2;
+    }
+    template <class T> bool match(T*) const { return !is_tuple && types.size() == 1 && types[0] == code<T>(); }
+    template <class... Ts> bool match(std::tuple<Ts...>*) const {
+        const int want[] = {code<Ts>()..., 0};
+        if (!is_tuple || types.size() != sizeof...(Ts)) return false;
+        for (size_t i = 0; i < sizeof...(Ts); ++i) if (types[i] != want[i]) return false;
+        return true;
+    }
+};
+struct ResultType {
+    template <class E, class... Ts> result_type_info operator()(const E& e, const std::tuple<Ts...>&) const {
+        const int in[] = {result_type_code<Ts>()..., 0};
+        int out[64], n = 0, tup = 0;
+        detail::check(zg_expr_result_types(detail::to_text(e).c_str(), in, (int)sizeof...(Ts), out, 64, &n, &tup));
+        result_type_info r;
+        r.types.assign(out, out + (n < 64 ? n : 64));
+        r.is_tuple = tup != 0;
+        return r;
+    }
+
+private:
+    template <class T> static constexpr int result_type_code() {
+        return std::is_same<T, int>::value ? ZG_I32 : std::is_same<T, float>::value ? ZG_F32
+             : std::is_same<T, double>::value ? ZG_F64 : std::is_same<T, std::complex<float>>::value ? ZG_C64 : ZG_C128;
+    }
+};
 struct make_canonical {                                  // flowz.hpp:794-805
     template <class E> dyn_expr operator()(const E& e) const {
         std::string s = detail::to_text(e);

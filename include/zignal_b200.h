@@ -21,6 +21,7 @@
  *     ~a              feedback                                  flowz.hpp:93
  *     + - * / unary - leaf arithmetic (C++ built-in semantics)  flowz.hpp:769-772
  *     0.5f 0.5 2      float / double / int literal terminals    flowz.hpp:68-72
+ *     cplx{1,0}       std::complex<float> terminal (cplxd: double); type analysis only   test/tests.cpp:188,205
  *     $k              run-time parameter k (std::ref terminal)  flowz/README.md:42-63
  */
 #ifndef ZIGNAL_B200_H
@@ -43,7 +44,12 @@ typedef enum zg_status {
     ZG_ERR_INTERNAL = -6
 } zg_status;
 
-typedef enum zg_dtype { ZG_I32 = 0, ZG_F32 = 1, ZG_F64 = 2, ZG_BF16 = 3 /* sample storage only */ } zg_dtype;
+typedef enum zg_dtype {
+    ZG_I32 = 0, ZG_F32 = 1, ZG_F64 = 2,
+    ZG_BF16 = 3,            /* sample storage only */
+    ZG_C64 = 4, ZG_C128 = 5,/* std::complex<float> / <double>: type analysis only (zg_expr_result_types) */
+    ZG_TYPE_OPEN = -1       /* zg_expr_result_types: the reference's `absorber`, a type the feedback cycle leaves open */
+} zg_dtype;
 
 typedef struct zg_graph zg_graph; /* immutable, shareable between threads        */
 typedef struct zg_voice zg_voice; /* one voice on the host: state_ of stateful_lambda */
@@ -59,6 +65,15 @@ const char* zg_version(void);
 int zg_expr_arity(const char* expr, int* n_in, int* n_out);
 int zg_expr_delays(const char* expr, int which, int* delays, int capacity, int* count);
 int zg_expr_canonical(const char* expr, char* buf, size_t capacity);
+/* ResultType                            flowz.hpp:515-644  (pinned by test/tests.cpp:182-232)
+ * C++ type (zg_dtype) of every output wire when input wire k has type in_dtypes[k-1].  Fed-back wires start as
+ * `absorber` and take the type of whatever they are combined with (:523-548); a wire no operand ever types is
+ * reported as ZG_TYPE_OPEN (the reference's leftover absorber, :575-578).  *is_tuple = 0 where the reference
+ * yields a bare scalar (terminal, delayed placeholder, plain arithmetic) and 1 where it yields a std::tuple.
+ * cplx{re,im} / cplxd{re,im} spell std::complex<float> / <double> terminals; such graphs can be analysed,
+ * not compiled (the reference's compile() keeps float state only, :1245).                        */
+int zg_expr_result_types(const char* expr, const int* in_dtypes, int n_in, int* out_dtypes, int capacity,
+                         int* count, int* is_tuple);
 
 /* ---- compile()  flowz.hpp:1233-1249 -----------------------------------------------------------
  * front panel (:273-277) + canonical form (:794-935) + state layout (:685-725) + lowering to the

@@ -56,6 +56,7 @@ import numpy as np
 # --------------------------------------------------------------------------------------------------
 
 I32, F32, F64 = 0, 1, 2
+C64, C128 = 4, 5                 # std::complex<float> / <double>: result_type() only, never evaluated
 _NP = {I32: np.int32, F32: np.float32, F64: np.float64}
 _CT = {I32: "int", F32: "float", F64: "double"}
 
@@ -104,6 +105,7 @@ _TOKEN = re.compile(r"""\s*(?:
             |(?:\d+\.\d*|\.\d+|\d+)(?:[eE][+-]?\d+)?f?)
     | (?P<ph>_\d+)
     | (?P<par>\$\d+)
+    | (?P<cplx>cplxd?\{[^}]*\})
     | (?P<name>bfb|front)
     | (?P<op>\|=|>>|[-+*/~|,()\[\]])
     )""", re.X)
@@ -215,6 +217,8 @@ class _Parser:
         if kind == "ph": return ph(int(val[1:]))
         if kind == "par": return Node("param", k=int(val[1:]))
         if kind == "num": return _literal(val)
+        if kind == "cplx":                          # cplx{re,im}: typed, not evaluated
+            return Node("const", dtype=C128 if val.startswith("cplxd") else C64, value=0.0)
         if kind == "name" and val == "bfb":
             self.expect("("); l = self.assign(); self.expect(","); r = self.assign(); self.expect(")")
             return bfb(l, r)
@@ -296,6 +300,90 @@ def input_delays(e: Node, minimum: bool) -> List[int]:
 
 def max_input_delays(e): return input_delays(e, False)
 def min_input_delays(e): return input_delays(e, True)
+
+
+# --------------------------------------------------------------------------------------------------
+# ResultType (:515-644), pinned by test/tests.cpp:182-232
+#
+# Kept in the reference's two-pass shape: pass 1 walks the flowz expression and, wherever a fed-back wire is
+# involved, builds a *type expression* with ABSORBER leaves instead of a type; pass 2 (_resolve) applies the
+# absorb_left / absorb_right rules (:536-548) and C++'s usual arithmetic conversions to what pass 1 left over.
+# --------------------------------------------------------------------------------------------------
+
+ABSORBER = -1
+
+
+def _cpp_binary(a: int, b: int) -> int:
+    """decltype(a op b) for + - * / on {int, float, double, complex<float>, complex<double>}."""
+    cplx = {C64: F32, C128: F64}
+    if a in cplx or b in cplx:
+        if a in cplx and b in cplx:
+            ok = a == b
+        elif a in cplx:
+            ok = b == cplx[a]
+        else:
+            ok = a == cplx[b]
+        if not ok:
+            raise TypeError("no operator for these operand types")        # a compile error in the reference
+        return a if a in cplx else b
+    return max(a, b)
+
+
+def _resolve(t):
+    """Pass 2: t is a type (int), or ('u', t) / ('b', l, r) left over by pass 1."""
+    if isinstance(t, int):
+        return t
+    if t[0] == "u":
+        return _resolve(t[1])                       # "unary-op absorber -> absorber" (:533)
+    l, r = t[1], t[2]
+    if l == ABSORBER:                               # absorb_left  :539-542  (structural: the operand IS the absorber)
+        return _resolve(r)
+    if r == ABSORBER:                               # absorb_right :544-545
+        return _resolve(l)
+    lt, rt_ = _resolve(l), _resolve(r)
+    if lt == ABSORBER: return rt_                   # an operand that *resolved* to the absorber: the reference would
+    if rt_ == ABSORBER: return lt                   # need another pass; same answer wherever it has one
+    return _cpp_binary(lt, rt_)
+
+
+def _rt1(e: "Node", state: list):
+    """Pass 1.  Returns (list of type expressions, is_tuple)."""
+    o = e.op
+    if o in ("ph", "delay"):                        # get_fn :550-557, :582-589
+        if e.k > len(state):
+            raise TypeError(f"_{e.k} reads past the typed wires")
+        return [state[e.k - 1]], False
+    if o == "const": return [e.dtype], False        # :590-593
+    if o == "param": return [F32], False
+    if o in ("fb", "bfb"):                          # :594-615
+        body = e.ch[0] if o == "fb" else e.ch[1]
+        n_abs = output_arity(e.ch[0])
+        types, _ = _rt1(body, [ABSORBER] * n_abs + list(state))
+        return [_resolve(t) for t in types], True   # the second ResultType(...) call + make_flat_tuple
+    if o == "seq":                                  # :616-624
+        l, _ = _rt1(e.ch[0], state)
+        n = input_arity(e.ch[1])
+        r, _ = _rt1(e.ch[1], _take(l, n))
+        return r + _drop(l, n), True
+    if o == "par":                                  # :625-630
+        n = input_arity(e.ch[0])
+        return _rt1(e.ch[0], _take(state, n))[0] + _rt1(e.ch[1], _drop(state, n))[0], True
+    if o == "chan":                                 # :631-636
+        return _rt1(e.ch[0], state)[0] + _rt1(e.ch[1], state)[0], True
+    kids = []
+    for c in e.ch:                                  # proto::_default :637-641
+        t, tup = _rt1(c, state)
+        if tup:
+            raise TypeError("arithmetic on a tuple")
+        kids.append(t[0])
+    return [("u", kids[0]) if len(kids) == 1 else ("b", kids[0], kids[1])], False
+
+
+def result_type(expr, in_types: Sequence[int]):
+    """(types of the output wires, is_tuple) -- ResultType{}(expr, tuple<in_types...>)."""
+    e = parse(expr) if isinstance(expr, str) else expr
+    types, tup = _rt1(e, list(in_types))
+    return [_resolve(t) for t in types], tup
 
 
 # --------------------------------------------------------------------------------------------------

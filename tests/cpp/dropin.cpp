@@ -6,15 +6,16 @@
 #include <flowz/flowz.hpp>
 
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstring>
 #include <functional>
 #include <vector>
 
 static int failures = 0;
-#define CHECK(cond)                                                          \
+#define CHECK(...)                                                           \
     do {                                                                     \
-        if (!(cond)) { std::printf("FAILED %s:%d  %s\n", __FILE__, __LINE__, #cond); ++failures; } \
+        if (!(__VA_ARGS__)) { std::printf("FAILED %s:%d  %s\n", __FILE__, __LINE__, #__VA_ARGS__); ++failures; } \
     } while (0)
 
 static float noise(unsigned& s) {                       // deterministic input in [-1, 1)
@@ -64,6 +65,36 @@ int main(int argc, char** argv) {
     CHECK(std::get<0>(amp(2.0f)) == 6.0f);
     auto fork = one_pole;                                 // continues from the same state, independently
     CHECK(std::get<0>(fork(0.25f)) == std::get<0>(one_pole(0.25f)));
+
+    // ---- ResultType (flowz.hpp:515-644), the reference's test_result_type_transform (test/tests.cpp:182-232) in the
+    //      reference's spelling; `expect_type(T{}, expr)` becomes r(expr, x).is<T>() because types are run-time data ----
+    {
+        using namespace flowz::transforms;
+        using std::tuple;
+        using cplx = std::complex<float>;
+        ResultType r;
+        tuple<float> xin;
+        CHECK(r(_1, xin).is<float>());
+        CHECK(r(_1 * 1.0, xin).is<double>());
+        CHECK(r(_1 |= _1, xin).is<tuple<float>>());
+        CHECK(r(_1 * 1.0 |= _1, xin).is<tuple<double>>());
+        CHECK(r(_1 |= 1.0 * _1, xin).is<tuple<double>>());
+        CHECK(r(_1 |= cplx{1, 0} * _1, xin).is<tuple<cplx>>());
+        CHECK(r(2 * _1 |= _1 * cplx{1, 0} |= _1, xin).is<tuple<cplx>>());
+        CHECK(r((_1, _1), xin).is<tuple<float, float>>());
+        CHECK(r((_1, _1 * 1.0), xin).is<tuple<float, double>>());
+        CHECK(r((_1 * 1.0, _1), xin).is<tuple<double, float>>());
+        CHECK(r((_1 * 1.0, _1) |= (_2, _1), xin).is<tuple<float, double>>());
+        CHECK(r((_1, 1.0 * _1) |= (_1 | _1), xin).is<tuple<float, double>>());
+        CHECK(r(_1[_1], xin).is<float>());
+        CHECK(r((_1[_1], 1.0 * _1) |= _2[_1], xin).is<tuple<double>>());
+        CHECK(r(~(_1[_1] + _2), xin).is<tuple<float>>());
+        CHECK(r(~(1.0 * _1[_1] + _2), xin).is<tuple<double>>());
+        CHECK(r(~(_1[_1] + 1.0), xin).is<tuple<double>>());
+        make_canonical c;
+        CHECK(r(c(~(_1[_1] + 1.0 * _2)), xin).is<tuple<double>>());
+        CHECK(!r(~(_1[_1] + _2), xin).is<tuple<double>>());
+    }
 
     if (gpu) {
         // the same graphs for 96 voices at once; every voice gets the same input, so every row must equal

@@ -62,6 +62,38 @@ TICKS = [
     ("~(_1[_1] + _2)", [((1,), (1,)), ((2,), (3,)), ((3,), (6,)), ((4,), (10,))], 25),
 ]
 
+# G15: ResultType                                             test/tests.cpp:182-232
+#   (expression, expected types of the output wires, is a std::tuple, line); the input is tuple<float> throughout
+#   (:192).  Types: "i" int, "f" float, "d" double, "c" std::complex<float>.  cplx{1,0} as in :188.  Lines 225-228
+#   apply make_canonical first ("c(...)"): canonical=True.
+RESULT_TYPES = [
+    ("_1", "f", False, False, 198),
+    ("_1 * 1.0", "d", False, False, 199),
+    ("_1 |= _1", "f", True, False, 201),
+    ("_1 * 1.0 |= _1", "d", True, False, 202),
+    ("_1 |= 1.0 * _1", "d", True, False, 203),
+    ("_1 |= cplx{1,0} * _1", "c", True, False, 205),
+    ("2*_1 |= _1*cplx{1,0} |= _1", "c", True, False, 206),
+    ("(_1,_1)", "ff", True, False, 208),
+    ("(_1,_1*1.0)", "fd", True, False, 209),
+    ("(_1*1.0,_1)", "df", True, False, 210),
+    ("(1.0*_1,1.0*_1)", "dd", True, False, 211),
+    ("(_1*1.0,_1) |= (_2,_1)", "fd", True, False, 212),
+    ("(_1,1.0*_1) |= (_1|_1)", "fd", True, False, 213),
+    ("_1[_1]", "f", False, False, 215),
+    ("_1 |= _1[_1]", "f", True, False, 216),
+    ("(_1[_1],1.0*_1) |= _2[_1]", "d", True, False, 217),
+    ("~( _1[_1] + _2 )", "f", True, False, 219),
+    ("~( 1.0*_1[_1] + _2 )", "d", True, False, 220),
+    ("~( _1[_1] + 1.0*_2 )", "d", True, False, 221),
+    ("~( _1[_1] + 1.0 )", "d", True, False, 222),
+    ("~( _1[_1] + _2 )", "f", True, True, 226),
+    ("~( 1.0*_1[_1] + _2 )", "d", True, True, 227),
+    ("~( _1[_1] + 1.0*_2 )", "d", True, True, 228),
+    ("~( _1[_1] + 1.0 )", "d", True, True, 229),
+]
+TYPE_CODE = {"i": 0, "f": 1, "d": 2, "c": 4}
+
 # G14: the reference's benchmark graphs (test/benchmark.cpp:14-129), coefficients :18-23.
 BENCH_COEF = dict(b0=0.2, b1=-0.3, b2=1.1, a1=-0.2, a2=0.8)
 

@@ -41,6 +41,36 @@ def test_known_answer_ticks(zg, expr, steps, line):
         assert all(isinstance(g, int) for g in got) or "[" in expr   # ints stay ints unless they went through a float line
 
 
+@pytest.mark.parametrize("expr,types,is_tuple,canonical,line", rv.RESULT_TYPES, ids=[f"tests.cpp:{c[4]}" for c in rv.RESULT_TYPES])
+def test_result_type(zg, expr, types, is_tuple, canonical, line):
+    # ResultType, flowz.hpp:515-644; input tuple<float> as in test/tests.cpp:192
+    text = zg.canonical(expr) if canonical else expr
+    assert zg.result_types(text, [zg.F32]) == ([rv.TYPE_CODE[c] for c in types], is_tuple)
+
+
+def test_result_type_agrees_with_the_oracle_beyond_the_reference_vectors(zg):
+    # the product resolves absorbers in one pass, the oracle keeps the reference's two passes (:594-609)
+    import itertools
+    exprs = ["~(_1[_1] + _2 + _3)", "~(_1[_1]*2 + _2) |= _1*_1", "(_1 | _1*1.0) |= (_2,_1,_1+_2)", "~(_1[_1])",
+             "~(-_1[_1] + _2)", "~( (_1[_1] + _2)*0.5f |= _1 )", "_1*$0 |= ~(_2 + $1*_1[_1])", "~~( _1[_1] + _2[_1] )",
+             "(_1, _2) |= ~(_1[_1] + _2 + _3)", "_1/2 |= _1*_1[_1]", "~(_1[_1] + _2*cplx{0,1})", "_1 | ~(_1[_2]*_2)"]
+    for expr in exprs:
+        n_in = zg.arity(expr)[0]
+        for sig in itertools.product([zg.I32, zg.F32, zg.F64], repeat=n_in):
+            try:
+                want = fo.result_type(expr, list(sig))
+            except TypeError:
+                with pytest.raises(zg.ZgError):
+                    zg.result_types(expr, list(sig))
+                continue
+            assert zg.result_types(expr, list(sig)) == want, (expr, sig)
+    assert zg.result_types("~(_1[_1])", [zg.F32]) == ([zg.TYPE_OPEN], True)      # the reference's leftover absorber (:575-578)
+    with pytest.raises(zg.ZgError):                                              # complex<float> * double: no such operator
+        zg.result_types("_1*cplx{1,0}", [zg.F64])
+    with pytest.raises(zg.ZgError):                                              # typed, but not evaluated
+        zg.compile("_1*cplx{1,0}")
+
+
 def test_series_and_delay_spellings_of_the_prototypes(zg):
     # north star: `>>` and `_1[-n]` (experimental_steps/wires_mono_only.cpp:37, delay_expression.cpp:99)
     assert zg.canonical("_1 >> _1[-1]") == zg.canonical("_1 |= _1[_1]")

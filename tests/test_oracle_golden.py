@@ -38,6 +38,14 @@ def test_known_answer_ticks(expr, steps, line):
         assert tuple(int(v[0]) for _, v in res) == outs
 
 
+@pytest.mark.parametrize("expr,types,is_tuple,canonical,line", rv.RESULT_TYPES, ids=[f"tests.cpp:{c[4]}" for c in rv.RESULT_TYPES])
+def test_result_type(expr, types, is_tuple, canonical, line):
+    e = fo.parse(expr)
+    if canonical:
+        e = fo.make_canonical(e)
+    assert fo.result_type(e, [fo.F32]) == ([rv.TYPE_CODE[c] for c in types], is_tuple)
+
+
 def test_state_starts_at_zero_and_is_float():
     # value-initialised std::array<float,N> (flowz.hpp:1191, 1245): first output of a delay is 0,
     # and an int pushed into a line comes back as float

@@ -27,6 +27,7 @@ PLANAR, INTERLEAVED = 0, 1
 IN_BUFFER, IN_DIRAC, IN_ZERO = 0, 1, 2
 MAX_WIRES = 8
 I32, F32, F64, BF16 = 0, 1, 2, 3            # zg_dtype (BF16: sample storage only)
+C64, C128, TYPE_OPEN = 4, 5, -1             # complex<float> / <double> and the open `absorber` type: result_types() only
 
 
 class ZgError(RuntimeError):
@@ -65,6 +66,7 @@ def _load() -> C.CDLL:
         "zg_expr_arity": (ci, [cp, P(ci), P(ci)]),
         "zg_expr_delays": (ci, [cp, ci, P(ci), ci, P(ci)]),
         "zg_expr_canonical": (ci, [cp, C.c_char_p, sz]),
+        "zg_expr_result_types": (ci, [cp, P(ci), ci, P(ci), ci, P(ci), P(ci)]),
         "zg_graph_compile": (ci, [cp, P(vp)]),
         "zg_graph_destroy": (None, [vp]),
         "zg_graph_get_info": (ci, [vp, P(GraphInfo)]),
@@ -97,7 +99,7 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
-EXPORTED = ["zg_last_error", "zg_version", "zg_expr_arity", "zg_expr_delays", "zg_expr_canonical",
+EXPORTED = ["zg_last_error", "zg_version", "zg_expr_arity", "zg_expr_delays", "zg_expr_canonical", "zg_expr_result_types",
             "zg_graph_compile", "zg_graph_destroy", "zg_graph_get_info", "zg_graph_canonical", "zg_graph_dump", "zg_graph_kernel_class",
             "zg_voice_create", "zg_voice_clone", "zg_voice_destroy", "zg_voice_tick", "zg_voice_set_param",
             "zg_voice_state", "zg_plan_opts_default", "zg_graph_kernel_compile", "zg_plan_create",
@@ -133,6 +135,15 @@ def canonical(expr: str) -> str:
     buf = C.create_string_buffer(len(expr) * 16 + 4096)
     _check(lib.zg_expr_canonical(expr.encode(), buf, len(buf)))
     return buf.value.decode()
+
+
+def result_types(expr: str, in_dtypes):
+    """ResultType (flowz.hpp:515-644): (types of the output wires, is_tuple) for the given input wire types."""
+    ins = (C.c_int * max(len(in_dtypes), 1))(*in_dtypes)
+    out = (C.c_int * 64)()
+    n, tup = C.c_int(), C.c_int()
+    _check(lib.zg_expr_result_types(expr.encode(), ins, len(in_dtypes), out, 64, C.byref(n), C.byref(tup)))
+    return list(out[:n.value]), bool(tup.value)
 
 
 # ---- compile() ------------------------------------------------------------------------------------------

@@ -79,6 +79,24 @@ int zg_expr_canonical(const char* expr, char* buf, size_t capacity) {
     });
 }
 
+int zg_expr_result_types(const char* expr, const int* in_dtypes, int n_in, int* out_dtypes, int capacity, int* count,
+                         int* is_tuple) {
+    if (!expr || !count || (n_in > 0 && !in_dtypes)) return fail(ZG_ERR_ARG, "NULL argument");
+    for (int i = 0; i < n_in; ++i) {
+        const int t = in_dtypes[i];
+        if (!(t == ZG_I32 || t == ZG_F32 || t == ZG_F64 || t == ZG_C64 || t == ZG_C128 || t == ZG_TYPE_OPEN))
+            return fail(ZG_ERR_ARG, "in_dtypes: not a wire type");
+    }
+    return guarded([&] {
+        ExprP e = parse(expr);
+        const ResultTypes r = result_types(*e, std::vector<int>(in_dtypes, in_dtypes + std::max(n_in, 0)));
+        *count = (int)r.types.size();
+        for (int i = 0; i < *count && i < capacity; ++i) out_dtypes[i] = r.types[i];
+        if (is_tuple) *is_tuple = r.is_tuple ? 1 : 0;
+        return (int)ZG_OK;
+    });
+}
+
 int zg_graph_compile(const char* expr, zg_graph** out) {
     if (!expr || !out) return fail(ZG_ERR_ARG, "NULL argument");
     *out = nullptr;

@@ -26,12 +26,14 @@ ExprP delay(int k, int n) {
     if (n < 1) throw Error("delay must be >= 1 (write _k for the undelayed wire)");
     Expr e; e.op = Op::Delay; e.k = k; e.n = n; return mk(e);
 }
-ExprP constant(Dtype dt, double v) {
+ExprP constant(Dtype dt, double v, double imag) {
     Expr e; e.op = Op::Const; e.dtype = dt;
     switch (dt) {
         case Dtype::I32: e.value = (double)(int32_t)v; break;
         case Dtype::F32: e.value = (double)(float)v; break;
         case Dtype::F64: e.value = v; break;
+        case Dtype::C64: e.value = (double)(float)v; e.imag = (double)(float)imag; break;
+        case Dtype::C128: e.value = v; e.imag = imag; break;
     }
     return mk(e);
 }
@@ -63,6 +65,10 @@ static void print_const(std::ostringstream& os, const Expr& e) {
         case Dtype::I32: std::snprintf(buf, sizeof buf, "%d", (int)e.value); break;
         case Dtype::F32: std::snprintf(buf, sizeof buf, "%af", e.value); break;   // hex float: exact
         case Dtype::F64: std::snprintf(buf, sizeof buf, "%a", e.value); break;
+        case Dtype::C64: case Dtype::C128:
+            std::snprintf(buf, sizeof buf, "%s{%a,%a}", e.dtype == Dtype::C64 ? "cplx" : "cplxd", e.value, e.imag);
+            os << buf;
+            return;
     }
     // a negative literal is printed as a parenthesised literal so that it is re-read as a Const,
     // not as Neg(Const)
@@ -97,7 +103,8 @@ std::string to_string(const Expr& e) {
 
 bool same_structure(const Expr& a, const Expr& b) {
     if (a.op != b.op || a.k != b.k || a.n != b.n || a.ch.size() != b.ch.size()) return false;
-    if (a.op == Op::Const && (a.dtype != b.dtype || std::memcmp(&a.value, &b.value, sizeof(double)) != 0))
+    if (a.op == Op::Const && (a.dtype != b.dtype || std::memcmp(&a.value, &b.value, sizeof(double)) != 0 ||
+                              std::memcmp(&a.imag, &b.imag, sizeof(double)) != 0))
         return false;
     for (size_t i = 0; i < a.ch.size(); ++i)
         if (!same_structure(*a.ch[i], *b.ch[i])) return false;
@@ -271,6 +278,22 @@ struct Parser {
             ExprP l = assign(); expect(","); ExprP r = assign(); expect(")");
             return binary(Op::Bfb, l, r);
         }
+        if (s.compare(p, 5, "cplx{") == 0 || s.compare(p, 6, "cplxd{") == 0) {      // std::complex<float> / <double>
+            const bool dbl = s[p + 4] == 'd';
+            p += dbl ? 6 : 5;
+            auto part = [&] {
+                ws();
+                const bool neg = p < s.size() && s[p] == '-';
+                if (neg) ++p;
+                ExprP n = number();
+                return neg ? -n->value : n->value;
+            };
+            const double re = part();
+            double im = 0;
+            if (eat(",")) im = part();
+            expect("}");
+            return constant(dbl ? Dtype::C128 : Dtype::C64, re, im);
+        }
         if (s.compare(p, 6, "front(") == 0) {
             p += 6; int n = integer(); expect(")");
             return make_front(n);
@@ -335,6 +358,112 @@ int n_params(const Expr& e) {
 // ------------------------------------------------------------------------------------------------
 // per-wire delays  (flowz/flowz.hpp:286-506)
 // ------------------------------------------------------------------------------------------------
+
+// ------------------------------------------------------------------------------------------------
+// ResultType  (flowz/flowz.hpp:515-644)
+//
+// The reference computes, at C++ compile time, the type of every output wire from the types of the input wires.
+// Inside a feedback the fed-back wires have no type yet, so it evaluates the body with a placeholder type
+// `absorber` on those wires and lets every binary operation with an absorber operand take the type of the other
+// operand (:536-548, applied in a second pass over the expression the first pass built, :572-589).  Here types are
+// run-time values, so one pass with the rule  absorber op T = T op absorber = T  gives the same answer;
+// absorber op absorber stays absorber (the reference's "leftover", TODO at :575-578: ~(_1[_1]) has no type).
+// Unary minus keeps the type ("unary-op absorber -> absorber", :533).  Leaf arithmetic on actual types follows the
+// usual arithmetic conversions of C++ (proto::_default, :640-642); std::complex<T> combines with T and with
+// itself only, as operator* etc. of <complex> do.
+// ------------------------------------------------------------------------------------------------
+
+namespace {
+
+const char* type_name(int t) {
+    switch (t) {
+        case (int)Dtype::I32: return "int";
+        case (int)Dtype::F32: return "float";
+        case (int)Dtype::F64: return "double";
+        case (int)Dtype::C64: return "std::complex<float>";
+        case (int)Dtype::C128: return "std::complex<double>";
+        default: return "absorber";
+    }
+}
+
+int arith_type(int a, int b) {
+    if (a == kAbsorber) return b;                                  // absorb_left  :539-542
+    if (b == kAbsorber) return a;                                  // absorb_right :544-545
+    auto cplx = [](int t) { return t == (int)Dtype::C64 || t == (int)Dtype::C128; };
+    auto base = [](int t) { return t == (int)Dtype::C64 ? (int)Dtype::F32 : (int)Dtype::F64; };
+    if (cplx(a) || cplx(b)) {
+        const bool ok = cplx(a) && cplx(b) ? a == b : cplx(a) ? b == base(a) : a == base(b);
+        if (!ok)
+            throw Error(std::string("no arithmetic operator for ") + type_name(a) + " and " + type_name(b) +
+                        " (std::complex<T> combines with T and std::complex<T> only)");
+        return cplx(a) ? a : b;
+    }
+    return std::max(a, b);                                         // int < float < double
+}
+
+std::vector<int> take_types(const std::vector<int>& v, int n) {   // tuple_take, tuple_tools.hpp:92-103
+    return n >= (int)v.size() ? v : std::vector<int>(v.begin(), v.begin() + std::max(n, 0));
+}
+std::vector<int> drop_types(const std::vector<int>& v, int n) {   // tuple_drop, tuple_tools.hpp:138-150
+    return n >= (int)v.size() ? std::vector<int>{} : std::vector<int>(v.begin() + std::max(n, 0), v.end());
+}
+
+ResultTypes rt(const Expr& e, const std::vector<int>& st) {
+    auto wire = [&](int k) {                                       // get_fn :550-557
+        if (k > (int)st.size())
+            throw Error("ResultType: _" + std::to_string(k) + " reads past the " + std::to_string(st.size()) +
+                        " typed wires available at this point");
+        return ResultTypes{{st[k - 1]}, false};
+    };
+    auto with_absorbers = [&](int n) {                             // repeat_fn + tuple_cat_fn :600, :607
+        std::vector<int> s2((size_t)n, kAbsorber);
+        s2.insert(s2.end(), st.begin(), st.end());
+        return s2;
+    };
+    auto tuple = [](ResultTypes r) { r.is_tuple = true; return r; };   // make_flat_tuple :559-566
+    switch (e.op) {
+        case Op::Delay:                                            // :582-585
+        case Op::Placeholder: return wire(e.k);                    // :586-589
+        case Op::Const: return {{(int)e.dtype}, false};            // :590-593
+        case Op::Param: return {{(int)Dtype::F32}, false};         // std::ref(float): converts to float in arithmetic
+        case Op::Bfb: return tuple(rt(*e.ch[1], with_absorbers(output_arity(*e.ch[0]))));   // :594-609
+        case Op::Fb: return tuple(rt(*e.ch[0], with_absorbers(output_arity(*e.ch[0]))));    // :610-615
+        case Op::Seq: {                                            // :616-624
+            const std::vector<int> l = rt(*e.ch[0], st).types;
+            const int n = input_arity(*e.ch[1]);
+            ResultTypes r = tuple(rt(*e.ch[1], take_types(l, n)));
+            const std::vector<int> around = drop_types(l, n);
+            r.types.insert(r.types.end(), around.begin(), around.end());
+            return r;
+        }
+        case Op::Par: {                                            // :625-630
+            const int n = input_arity(*e.ch[0]);
+            ResultTypes r = tuple(rt(*e.ch[0], take_types(st, n)));
+            const std::vector<int> b = rt(*e.ch[1], drop_types(st, n)).types;
+            r.types.insert(r.types.end(), b.begin(), b.end());
+            return r;
+        }
+        case Op::Chan: {                                           // :631-636
+            ResultTypes r = tuple(rt(*e.ch[0], st));
+            const std::vector<int> b = rt(*e.ch[1], st).types;
+            r.types.insert(r.types.end(), b.begin(), b.end());
+            return r;
+        }
+        default: {                                                 // leaf arithmetic, proto::_default :637-641
+            int t = kAbsorber;
+            for (size_t i = 0; i < e.ch.size(); ++i) {
+                const ResultTypes c = rt(*e.ch[i], st);
+                if (c.is_tuple) throw Error("ResultType: arithmetic on a tuple of wires (operands must be single wires)");
+                t = i == 0 ? c.types[0] : arith_type(t, c.types[0]);
+            }
+            return {{t}, false};
+        }
+    }
+}
+
+}  // namespace
+
+ResultTypes result_types(const Expr& e, const std::vector<int>& in) { return rt(e, in); }
 
 namespace {
 

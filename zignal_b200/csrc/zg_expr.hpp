@@ -23,7 +23,10 @@ struct Error : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
-enum class Dtype : uint8_t { I32 = 0, F32 = 1, F64 = 2 };
+// C64 / C128 (std::complex<float> / <double>) exist for the type analysis only (result_types): a graph with a
+// complex terminal is analysed like any other but cannot be lowered to a tick program.
+enum class Dtype : uint8_t { I32 = 0, F32 = 1, F64 = 2, C64 = 4, C128 = 5 };
+constexpr int kAbsorber = -1;   // result_types: a wire whose type the feedback cycle leaves open (flowz.hpp:542)
 
 enum class Op : uint8_t {
     Placeholder,  // _k                       (k >= 1)
@@ -47,12 +50,13 @@ struct Expr {
     int n = 0;            // delay
     Dtype dtype = Dtype::F32;  // Const only
     double value = 0;     // Const only (already rounded to dtype)
+    double imag = 0;      // Const of a complex dtype only
     std::vector<ExprP> ch;
 };
 
 ExprP placeholder(int k);
 ExprP delay(int k, int n);
-ExprP constant(Dtype dt, double v);
+ExprP constant(Dtype dt, double v, double imag = 0);
 ExprP param(int idx);
 ExprP unary(Op op, ExprP a);
 ExprP binary(Op op, ExprP a, ExprP b);
@@ -63,7 +67,8 @@ bool is_arith(const Expr& e);
 // ---- text form -------------------------------------------------------------------------------
 // parse():  C++ operator precedence (postfix [] > unary - ~ > * / > + - > >> > | > |= (right
 // assoc) > ,).  Literals: 2 (int), 0.5 (double), 0.5f (float), hex floats, $k (parameter k),
-// bfb(L, R) builds the private binary feedback node, front(n) builds make_front<n>().
+// bfb(L, R) builds the private binary feedback node, front(n) builds make_front<n>(), cplx{re,im} /
+// cplxd{re,im} are std::complex<float> / <double> terminals (type analysis only).
 ExprP parse(const std::string& text);
 std::string to_string(const Expr& e);       // fully parenthesised, round-trips through parse()
 bool same_structure(const Expr& a, const Expr& b);
@@ -74,6 +79,15 @@ int output_arity(const Expr& e);
 std::vector<int> max_input_delays(const Expr& e);
 std::vector<int> min_input_delays(const Expr& e);   // -1 = wire unused
 int n_params(const Expr& e);                        // 1 + highest $k used, 0 if none
+
+// ResultType (flowz.hpp:515-644): the C++ type of every output wire of `e` when input wire k has type in[k-1]
+// ((int)Dtype, or kAbsorber).  is_tuple = false when the reference yields a bare scalar (a terminal, a delayed
+// placeholder or plain arithmetic: test/tests.cpp:198-199, 215) instead of a std::tuple.
+struct ResultTypes {
+    std::vector<int> types;
+    bool is_tuple = false;
+};
+ResultTypes result_types(const Expr& e, const std::vector<int>& in);
 
 // ---- canonicalisation ------------------------------------------------------------------------
 ExprP make_front(int n);

@@ -140,7 +140,11 @@ struct Lowering {
                 IrNode n{IrOp::DRead, Dtype::F32, line, e.n, 0};
                 return {b.add(n)};
             }
-            case Op::Const: return {b.add(IrNode{IrOp::Const, e.dtype, -1, -1, e.value})};
+            case Op::Const:
+                if (e.dtype == Dtype::C64 || e.dtype == Dtype::C128)
+                    throw Error("complex terminals are typed (zg_expr_result_types) but not evaluated: the reference's "
+                                "compile() keeps float state only (flowz.hpp:1245)");
+                return {b.add(IrNode{IrOp::Const, e.dtype, -1, -1, e.value})};
             case Op::Param: return {b.add(IrNode{IrOp::Param, Dtype::F32, e.k, -1, 0})};
             case Op::Neg: {
                 int a = scalar(e, *e.ch[0], input, in_state);
@@ -373,6 +377,7 @@ inline Cell arith(Dtype t, Cell a, Dtype ta, Cell b, Dtype tb, F32 f32, F64 f64,
         case Dtype::I32: r.i = i32(a.i, b.i); break;
         case Dtype::F32: r.f = f32(as_f32(a, ta), as_f32(b, tb)); break;
         case Dtype::F64: r.d = f64(as_f64(a, ta), as_f64(b, tb)); break;
+        default: break;                                  // complex: never lowered (Builder::eval rejects it)
     }
     return r;
 }
@@ -439,6 +444,7 @@ void host_tick(const Ir& ir, float* state, const float* params, const double* in
             case Dtype::I32: v[i].i = (int32_t)in[i]; break;
             case Dtype::F32: v[i].f = (float)in[i]; break;
             case Dtype::F64: v[i].d = in[i]; break;
+            default: break;
         }
     }
     run_tick(ir, state, params, v.data());
@@ -455,6 +461,7 @@ void host_block_f32(const Ir& ir, float* state, const float* params, const float
                 case Dtype::I32: v[i].i = (int32_t)x; break;
                 case Dtype::F32: v[i].f = x; break;
                 case Dtype::F64: v[i].d = x; break;
+                default: break;
             }
         }
         run_tick(ir, state, params, v.data());
