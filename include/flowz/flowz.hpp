@@ -145,8 +145,26 @@ struct ref_expr : expr_tag {                       // std::ref(x): non-owning, r
 
 // ---- operator nodes ---------------------------------------------------------------------------
 
+template <class Tag, class A, class B> struct binary_expr;
+
+// expr[_n] for a one-output expression: "(_1+_2)[_1] is equivalent to _1+_2 |= _1[_1]" (reference TODO.md:51-52)
+template <class Self>
+struct delayable {
+    template <int N>
+    auto operator[](placeholder_expr<N>) const { return delayed_by(N); }
+    auto operator[](int n) const {
+        if (n == 0) throw error("a delay of 0 is the wire itself");
+        return delayed_by(n < 0 ? -n : n);
+    }
+private:
+    auto delayed_by(int n) const {
+        static_assert(Self::out == 1, "expr[_n] needs an expression with one output");
+        return binary_expr<tag::sequence, Self, delayed_expr<1>>{{}, {}, static_cast<const Self&>(*this), delayed_expr<1>{{}, n}};
+    }
+};
+
 template <class Tag, class A>
-struct unary_expr : expr_tag {
+struct unary_expr : expr_tag, delayable<unary_expr<Tag, A>> {
     A a;
     static constexpr int in = std::is_same<Tag, tag::feedback>::value ? cmax(0, A::in - A::out) : A::in;
     static constexpr int out = std::is_same<Tag, tag::feedback>::value ? A::out : 1;
@@ -159,7 +177,7 @@ struct unary_expr : expr_tag {
 };
 
 template <class Tag, class A, class B>
-struct binary_expr : expr_tag {
+struct binary_expr : expr_tag, delayable<binary_expr<Tag, A, B>> {
     A a;
     B b;
     static constexpr bool has_double = A::has_double || B::has_double;
@@ -221,7 +239,7 @@ template <class A, class B> constexpr bool arith_ok_v =
 
 template <class Tag, class A, class B>
 binary_expr<Tag, as_expr_t<A>, as_expr_t<B>> make_binary(const A& a, const B& b) {
-    return {{}, as_expr(a), as_expr(b)};
+    return {{}, {}, as_expr(a), as_expr(b)};
 }
 
 template <class E>
@@ -259,9 +277,9 @@ template <class A, class B, class = std::enable_if_t<is_expr_v<A> && is_expr_v<B
 auto operator,(const A& a, const B& b) { return make_binary<tag::channel>(a, b); }
 
 template <class A, class = std::enable_if_t<is_expr_v<A>>>
-unary_expr<tag::negate, A> operator-(const A& a) { return {{}, a}; }
+unary_expr<tag::negate, A> operator-(const A& a) { return {{}, {}, a}; }
 template <class A, class = std::enable_if_t<is_expr_v<A>>>
-unary_expr<tag::feedback, A> operator~(const A& a) { return {{}, a}; }
+unary_expr<tag::feedback, A> operator~(const A& a) { return {{}, {}, a}; }
 
 }  // namespace detail
 

@@ -15,6 +15,7 @@
  * Expressions travel as text in flowz syntax with C++ operator precedence:
  *     _k              input wire k (1-based)                    flowz.hpp:75-82, 1252-1257
  *     _k[_n]  _k[-n]  wire k delayed by n samples               flowz.hpp:84-85 / prototypes
+ *     _k<-n>  e[_n]   planned spellings: same; (e |= _1[_n])    TODO.md:8-9, 51-52
  *     a |= b, a >> b  series                                    flowz.hpp:92 / wires_mono_only.cpp:37
  *     a | b           parallel (splits the inputs)              flowz.hpp:91
  *     (a , b)         fan-out ("channel")                       flowz.hpp:90

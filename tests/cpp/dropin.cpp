@@ -66,6 +66,15 @@ int main(int argc, char** argv) {
     auto fork = one_pole;                                 // continues from the same state, independently
     CHECK(std::get<0>(fork(0.25f)) == std::get<0>(one_pole(0.25f)));
 
+    // ---- expr[_n], a spelling the reference plans (TODO.md:51-52): (_1+_2)[_1] == _1+_2 |= _1[_1] ----
+    {
+        auto a = compile((_1 + _2)[_1]);
+        auto b = compile(_1 + _2 |= _1[_1]);
+        for (int t = 0; t < 8; ++t) CHECK(a(float(t), 2.f) == b(float(t), 2.f));
+        CHECK(same_expr((_1 + _2)[_1], _1 + _2 |= _1[_1]));
+        CHECK(same_expr((0.5f * _1)[-3], 0.5f * _1 |= _1[_3]));
+    }
+
     // ---- ResultType (flowz.hpp:515-644), the reference's test_result_type_transform (test/tests.cpp:182-232) in the
     //      reference's spelling; `expect_type(T{}, expr)` becomes r(expr, x).is<T>() because types are run-time data ----
     {

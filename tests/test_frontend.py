@@ -71,6 +71,19 @@ def test_result_type_agrees_with_the_oracle_beyond_the_reference_vectors(zg):
         zg.compile("_1*cplx{1,0}")
 
 
+def test_spellings_the_reference_plans(zg):
+    # TODO.md:8-9  `_1<-2>` = input one delayed by 2;  TODO.md:51-52  `(_1+_2)[_1]` is equivalent to `_1+_2 |= _1[_1]`
+    assert zg.canonical("_1<-2> + _2") == zg.canonical("_1[_2] + _2")
+    assert zg.canonical("(_1+_2)[_1]") == zg.canonical("_1+_2 |= _1[_1]")
+    assert zg.canonical("(_1 , 2*_1)[_3]") == zg.canonical("(_1 , 2*_1) |= (_1[_3] | _1[_3])")
+    assert zg.canonical("_1[_1][_2]") == zg.canonical("_1[_1] |= _1[_2]")
+    a, b = zg.compile("~((_1 + _2)[_1])").voice(), fo.Oracle("~(_1 + _2 |= _1[_1])")
+    for t in range(6):
+        assert a(float(t + 1)) == tuple(float(v[0]) for _, v in b.tick(float(t + 1)))
+    with pytest.raises(zg.ZgError):
+        zg.canonical("_1<2>")
+
+
 def test_series_and_delay_spellings_of_the_prototypes(zg):
     # north star: `>>` and `_1[-n]` (experimental_steps/wires_mono_only.cpp:37, delay_expression.cpp:99)
     assert zg.canonical("_1 >> _1[-1]") == zg.canonical("_1 |= _1[_1]")

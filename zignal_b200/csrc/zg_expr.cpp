@@ -209,18 +209,34 @@ struct Parser {
     ExprP postfix() { return postfix_on(primary()); }
     ExprP postfix_on(ExprP e) {
         ws();
-        while (p < s.size() && s[p] == '[') {
-            ++p;
-            if (e->op != Op::Placeholder) fail("only placeholders can be delayed: write _k[_n]");
+        for (;;) {
             int n;
-            if (eat("_")) n = integer();
-            else if (eat("-")) n = integer();
-            else n = integer();
-            expect("]");
-            e = delay(e->k, n);
+            if (p < s.size() && s[p] == '[') {          // _k[_n]  _k[-n]  _k[n]
+                ++p;
+                if (eat("_")) n = integer();
+                else if (eat("-")) n = integer();
+                else n = integer();
+                expect("]");
+            } else if (p + 1 < s.size() && s[p] == '<' && e->op == Op::Placeholder) {   // _k<-n>  (TODO.md:8-9)
+                ++p;
+                expect("-");
+                n = integer();
+                expect(">");
+            } else break;
+            if (e->op == Op::Placeholder) e = delay(e->k, n);
+            else e = delay_expr(e, n);
             ws();
         }
         return e;
+    }
+    // expr[_n]: "(_1+_2)[_1] is equivalent to _1+_2 |= _1[_1]" (TODO.md:51-52); with m outputs every wire is delayed:
+    // expr |= (_1[_n] | ... | _1[_n])
+    ExprP delay_expr(const ExprP& e, int n) {
+        const int m = output_arity(*e);
+        if (m < 1) fail("cannot delay an expression without outputs");
+        ExprP d = delay(1, n);
+        for (int i = 1; i < m; ++i) d = binary(Op::Par, d, delay(1, n));
+        return binary(Op::Seq, e, d);
     }
     ExprP number() {
         ws();

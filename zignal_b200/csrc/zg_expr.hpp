@@ -68,7 +68,8 @@ bool is_arith(const Expr& e);
 // parse():  C++ operator precedence (postfix [] > unary - ~ > * / > + - > >> > | > |= (right
 // assoc) > ,).  Literals: 2 (int), 0.5 (double), 0.5f (float), hex floats, $k (parameter k),
 // bfb(L, R) builds the private binary feedback node, front(n) builds make_front<n>(), cplx{re,im} /
-// cplxd{re,im} are std::complex<float> / <double> terminals (type analysis only).
+// cplxd{re,im} are std::complex<float> / <double> terminals (type analysis only).  Two spellings the reference only
+// plans (TODO.md:8-9, 51-52) are accepted: _k<-n> == _k[_n], and expr[_n] == expr |= _1[_n] (every output delayed).
 ExprP parse(const std::string& text);
 std::string to_string(const Expr& e);       // fully parenthesised, round-trips through parse()
 bool same_structure(const Expr& a, const Expr& b);
