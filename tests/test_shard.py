@@ -62,3 +62,56 @@ def test_scatter_gather_world_size_2_gloo(C, T):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _peer_worker(rank, world, port, C, T, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import zignal_b200 as zg
+    from zignal_b200 import workloads
+    from zignal_b200.shard import channel_range, process_on_root_block, share_from_root
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)     # both ranks drive cuda:0; gloo carries the handles
+    try:
+        torch.cuda.set_device(0)
+        expr = workloads.biquad_cascade(2)
+        x = y = None
+        if rank == 0:
+            gen = torch.Generator(device="cuda").manual_seed(11)
+            x = torch.rand((C, T), generator=gen, device="cuda") * 2 - 1
+            y = torch.zeros_like(x)
+        xa, ya = share_from_root(x, 0), share_from_root(y, 0)
+        b, e = channel_range(C, world, rank)
+        plan = zg.compile(expr).plan(channels=e - b, device=0)
+        process_on_root_block(plan, xa, ya)                          # reads / writes the root's allocation directly
+        ok = True
+        if rank == 0:
+            import flowz_oracle as fo
+            want = fo.COracle(expr, C).process([x.cpu().numpy()])[0]
+            ok = bool((y.cpu().numpy().view(np.uint32) == want.view(np.uint32)).all())
+        dist.barrier()
+        xa.close(); ya.close()
+        dist.barrier()
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_edge_step_through_peer_mappings_two_processes():
+    """share_from_root / process_on_root_block (the edge step fused into the kernels): two processes, the
+    block lives in rank 0's allocation, rank 1 reaches it through a CUDA IPC mapping and its kernel's TMA maps point
+    into it.  On a one-GPU box both ranks drive cuda:0 (same code path, no NVLink); bit-identical to the oracle."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, 200, 1000, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
