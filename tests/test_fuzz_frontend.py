@@ -1,0 +1,93 @@
+"""Random flowz expressions: the product's front end and host voice against the oracle (CPU only).
+
+Every expression is generated from the grammar (flowz.hpp:68-102); for each one the two sides must agree on whether it
+is a valid graph at all, on arity, per-wire max/min delays, the canonical form, the ResultType of the bare expression,
+and on six ticks of one voice with small-integer inputs (exact in int, float and double alike).  The seeds are fixed:
+the test is deterministic."""
+import random
+
+import pytest
+
+import flowz_oracle as fo
+
+CONSTS = ["2", "3", "0.5f", "0.25f", "1.5", "-1", "0x1p-1f", "-0.75f"]
+
+
+def _gen(rng, depth, wires, scalar=False):
+    """A random expression over placeholders _1.._wires; scalar=True: leaf arithmetic only (what an operand of + - *
+    must be; a combinator there is ill-formed in the reference, and one in ten operands is generated that way)."""
+    if depth <= 0 or rng.random() < 0.2:
+        k = rng.randint(1, wires)
+        r = rng.random()
+        if r < 0.45:
+            return f"_{k}"
+        if r < 0.8:
+            return f"_{k}[_{rng.randint(1, 3)}]"
+        return rng.choice(CONSTS)
+    r = rng.random() * (0.45 if scalar else 1.0)
+    sub_scalar = r < 0.45 and rng.random() < 0.9
+    a, b = _gen(rng, depth - 1, wires, sub_scalar), _gen(rng, depth - 1, wires, sub_scalar)
+    if r < 0.40:
+        return f"({a} {rng.choice('+-*')} {b})"
+    if r < 0.45:
+        return f"(-{a})"
+    if r < 0.62:
+        return f"({a} |= {b})"
+    if r < 0.72:
+        return f"({a} | {b})"
+    if r < 0.84:
+        return f"({a} , {b})"
+    return f"(~{a})"
+
+
+def _product(zg, expr):
+    try:
+        g = zg.compile(expr)
+    except zg.ZgError as e:
+        return None, str(e)
+    return g, None
+
+
+def _oracle(expr):
+    try:
+        o = fo.Oracle(expr)
+        n_in = fo.input_arity(fo.parse(expr))
+        fo.Oracle(expr).tick(*([0.0] * n_in))   # ill-formed operands only surface when the walk reaches them
+        return o, None
+    except Exception as e:                      # the restatement signals invalid graphs with plain exceptions
+        return None, str(e)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_graphs_product_equals_oracle(zg, seed):
+    rng = random.Random(1000 + seed)
+    checked = rejected = 0
+    for _ in range(60):
+        expr = _gen(rng, rng.randint(1, 4), rng.randint(1, 3))
+        g, perr = _product(zg, expr)
+        o, oerr = _oracle(expr)
+        assert (g is None) == (o is None), f"{expr}\n product: {perr}\n oracle: {oerr}"
+        if g is None:
+            rejected += 1
+            continue
+        e = fo.parse(expr)
+        n_in, n_out = fo.input_arity(e), fo.output_arity(e)
+        assert zg.arity(expr) == (n_in, n_out), expr
+        assert zg.delays(expr) == fo.max_input_delays(e), expr
+        assert zg.delays(expr, minimum=True) == fo.min_input_delays(e), expr
+        assert zg.canonical(expr) == zg.canonical(str(fo.make_canonical(e))), expr
+        try:
+            want_t = fo.result_type(e, [fo.F32] * n_in)
+        except TypeError:
+            with pytest.raises(zg.ZgError):
+                zg.result_types(expr, [zg.F32] * n_in)
+        else:
+            assert zg.result_types(expr, [zg.F32] * n_in) == want_t, expr
+        v = g.voice()
+        for t in range(6):
+            xs = [float(rng.randint(-3, 3)) for _ in range(n_in)]
+            want = tuple(float(val[0]) for _, val in o.tick(*xs))
+            got = tuple(float(y) for y in v(*xs))
+            assert got == want, f"{expr} tick {t}: {got} != {want}"
+        checked += 1
+    assert checked >= 10, (checked, rejected)
