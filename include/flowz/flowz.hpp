@@ -447,6 +447,11 @@ public:
         zg_graph* g = nullptr;
         detail::check(zg_graph_compile(text.c_str(), &g));
         graph_.reset(g, zg_graph_destroy);
+        zg_graph_info gi;
+        detail::check(zg_graph_get_info(g, &gi));
+        if ((size_t)gi.n_out != n_out)      // the reference's tick would return a tuple of another size than output_arity says
+            throw error("this graph returns " + std::to_string(gi.n_out) + " values per tick but its output_arity is " +
+                        std::to_string(n_out) + " (sequence passes surplus inputs through, flowz.hpp:996-999)");
         zg_voice* v = nullptr;
         detail::check(zg_voice_create(g, &v));
         voice_.reset(v);

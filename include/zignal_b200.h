@@ -84,7 +84,8 @@ void zg_graph_destroy(zg_graph* g);
 
 typedef struct zg_graph_info {
     int n_in;      /* input_arity of the user expression                                       */
-    int n_out;     /* output_arity                                                             */
+    int n_out;     /* values one tick returns: output_arity, except where the reference's sequence passes surplus
+                      inputs through uncounted (flowz.hpp:996-999 vs :238-247; `_1 |= (_1[_3] | _2[_1])`: 3, not 2) */
     int n_params;  /* number of $k parameters                                                  */
     int n_state;   /* floats of delay-line state per channel after line sharing                */
     int n_lines;   /* delay lines                                                              */

@@ -696,6 +696,10 @@ def emit_c(expr: str) -> Tuple[str, int, int, int]:
     b = _CBackend()
     inp = [(F32, f"x{i}") for i in range(n_in)]
     res = _flatten([_Walker(b).eval(canonical, inp, ([], tree))])
+    if any(v is BOTTOM for v in res):
+        raise ValueError("an output is a fed-back wire nothing ever assigns (bottom_type, :1004)")
+    n_out = len(res)        # the tick decides: `sequence` passes surplus inputs through (:996-999), output_arity
+                            # (:238-247) does not count them -- `_1 |= (_1[_3] | _2[_1])` returns three values
     b.end_tick()
     body = "\n            ".join(b.lines)
     loads = "\n            ".join(f"const float x{i} = in[{i}][c * ld_in + t];" for i in range(n_in))

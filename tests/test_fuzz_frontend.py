@@ -13,7 +13,7 @@ import flowz_oracle as fo
 CONSTS = ["2", "3", "0.5f", "0.25f", "1.5", "-1", "0x1p-1f", "-0.75f"]
 
 
-def _gen(rng, depth, wires, scalar=False):
+def _gen(rng, depth, wires, scalar=False, consts=CONSTS):
     """A random expression over placeholders _1.._wires; scalar=True: leaf arithmetic only (what an operand of + - *
     must be; a combinator there is ill-formed in the reference, and one in ten operands is generated that way)."""
     if depth <= 0 or rng.random() < 0.2:
@@ -23,10 +23,10 @@ def _gen(rng, depth, wires, scalar=False):
             return f"_{k}"
         if r < 0.8:
             return f"_{k}[_{rng.randint(1, 3)}]"
-        return rng.choice(CONSTS)
+        return rng.choice(consts)
     r = rng.random() * (0.45 if scalar else 1.0)
     sub_scalar = r < 0.45 and rng.random() < 0.9
-    a, b = _gen(rng, depth - 1, wires, sub_scalar), _gen(rng, depth - 1, wires, sub_scalar)
+    a, b = _gen(rng, depth - 1, wires, sub_scalar, consts), _gen(rng, depth - 1, wires, sub_scalar, consts)
     if r < 0.40:
         return f"({a} {rng.choice('+-*')} {b})"
     if r < 0.45:
@@ -44,7 +44,7 @@ def _product(zg, expr):
     try:
         g = zg.compile(expr)
     except zg.ZgError as e:
-        return None, str(e)
+        return None, ("limit" if e.status == zg.ZG_ERR_UNSUPPORTED else str(e))
     return g, None
 
 
@@ -52,20 +52,24 @@ def _oracle(expr):
     try:
         o = fo.Oracle(expr)
         n_in = fo.input_arity(fo.parse(expr))
-        fo.Oracle(expr).tick(*([0.0] * n_in))   # ill-formed operands only surface when the walk reaches them
+        res = fo.Oracle(expr).tick(*([0.0] * n_in))   # ill-formed operands only surface when the walk reaches them
+        if any(r is fo.BOTTOM for r in res):          # the reference would hand back a bottom_type (flowz.hpp:1004)
+            return None, "an output is a fed-back wire nothing ever assigns"
         return o, None
     except Exception as e:                      # the restatement signals invalid graphs with plain exceptions
         return None, str(e)
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(16))
 def test_random_graphs_product_equals_oracle(zg, seed):
     rng = random.Random(1000 + seed)
     checked = rejected = 0
     for _ in range(60):
-        expr = _gen(rng, rng.randint(1, 4), rng.randint(1, 3))
+        expr = _gen(rng, rng.randint(1, 5), rng.randint(1, 4))
         g, perr = _product(zg, expr)
         o, oerr = _oracle(expr)
+        if perr == "limit":                          # more than ZG_MAX_WIRES wires: a limit of the product, not of flowz
+            continue
         assert (g is None) == (o is None), f"{expr}\n product: {perr}\n oracle: {oerr}"
         if g is None:
             rejected += 1
@@ -73,6 +77,8 @@ def test_random_graphs_product_equals_oracle(zg, seed):
         e = fo.parse(expr)
         n_in, n_out = fo.input_arity(e), fo.output_arity(e)
         assert zg.arity(expr) == (n_in, n_out), expr
+        n_tick = len(fo.Oracle(expr).tick(*([0.0] * n_in)))         # what one tick returns (flowz.hpp:996-999 can exceed
+        assert g.n_out == n_tick, (expr, g.n_out, n_tick)           # output_arity: surplus inputs pass through a sequence)
         assert zg.delays(expr) == fo.max_input_delays(e), expr
         assert zg.delays(expr, minimum=True) == fo.min_input_delays(e), expr
         assert zg.canonical(expr) == zg.canonical(str(fo.make_canonical(e))), expr

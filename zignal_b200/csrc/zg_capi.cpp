@@ -110,7 +110,11 @@ int zg_graph_compile(const char* expr, zg_graph** out) {
             return fail(ZG_ERR_UNSUPPORTED, "more than ZG_MAX_WIRES inputs or outputs");
         g->canonical = canonical_with_front(g->user);
         g->ir_f32 = lower(*g->canonical, std::vector<Dtype>(g->n_in, Dtype::F32));
-        if (g->ir_f32.n_out != g->n_out) return fail(ZG_ERR_INTERNAL, "output arity mismatch after lowering");
+        // The tick decides how many values come back, as in the reference, whose `sequence` appends the inputs
+        // beyond in(L) + out(L) to its result (flowz.hpp:996-999) although output_arity (:238-247) does not count them:
+        // `_1 |= (_1[_3] | _2[_1])` has output_arity 2 and returns a 3-tuple.  zg_expr_arity keeps the static answer.
+        g->n_out = g->ir_f32.n_out;
+        if (g->n_out > ZG_MAX_WIRES) return fail(ZG_ERR_UNSUPPORTED, "more than ZG_MAX_WIRES inputs or outputs");
         g->canonical_str = to_string(*g->canonical);
         g->dump_str = g->ir_f32.dump();
         *out = g.release();
