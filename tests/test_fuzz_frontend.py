@@ -90,10 +90,13 @@ def test_random_graphs_product_equals_oracle(zg, seed):
         else:
             assert zg.result_types(expr, [zg.F32] * n_in) == want_t, expr
         v = g.voice()
+        dt = rng.choice([fo.I32, fo.F32, fo.F64])             # the C++ type of the arguments: int stays int (:769-772)
         for t in range(6):
             xs = [float(rng.randint(-3, 3)) for _ in range(n_in)]
-            want = tuple(float(val[0]) for _, val in o.tick(*xs))
-            got = tuple(float(y) for y in v(*xs))
+            res = o.tick(*xs, dtype=dt)
+            want = tuple(float(val[0]) for _, val in res)
+            got = tuple(float(y) for y in v.tick(*xs, dtypes=[dt] * n_in))
             assert got == want, f"{expr} tick {t}: {got} != {want}"
+            assert v.out_dtypes == tuple(d for d, _ in res), f"{expr}: result types {v.out_dtypes} != {[d for d, _ in res]}"
         checked += 1
     assert checked >= 10, (checked, rejected)

@@ -234,6 +234,7 @@ class Voice:
         outs = (C.c_double * n_out)()
         odt = (C.c_int * n_out)()
         _check(lib.zg_voice_tick(self._h, ins, dts, outs, odt))
+        self.out_dtypes = tuple(odt)         # the C++ type of every returned value (zg_dtype), as the reference's tuple has it
         return tuple(int(v) if t == I32 else float(v) for v, t in zip(outs, odt))
 
     __call__ = tick
