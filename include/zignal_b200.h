@@ -159,6 +159,9 @@ void zg_plan_opts_default(zg_plan_opts* o);
  * device -- so it doubles as an offline build check.  buf may be NULL to query *size.           */
 int zg_graph_kernel_compile(const zg_graph* g, const zg_plan_opts* opts, int uniform_params, int want_cubin,
                             char* buf, size_t capacity, size_t* size);
+/* Environment: ZG_KERNEL_CACHE_DIR=<dir> keeps the NVRTC-built cubins of generated kernels across processes
+ * (keyed by the specialised source, the contraction mode and the NVRTC version); without it they are cached for
+ * the life of the process only.                                                                   */
 int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out);
 void zg_plan_destroy(zg_plan* p);
 

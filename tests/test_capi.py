@@ -112,3 +112,37 @@ def test_too_many_far_reads_is_unsupported_not_wrong(zg):
     with pytest.raises(zg.ZgError) as e:
         zg.compile(many).kernel()
     assert e.value.status == zg.ZG_ERR_UNSUPPORTED
+
+
+def test_kernel_cache_on_disk(tmp_path):
+    """ZG_KERNEL_CACHE_DIR keeps NVRTC cubins across processes; damaged or foreign files are ignored and replaced."""
+    import struct
+    import subprocess
+    import sys
+    prog = ("import sys, hashlib; sys.path.insert(0, %r); import zignal_b200 as zg; "
+            "c = zg.compile('~(_2 + 0.5f*_1[_1]) |= _1 - 0.25f*_1[_3]').kernel(cubin=True); "
+            "print(len(c), hashlib.sha1(c).hexdigest())" % ROOT)
+    env = dict(os.environ, ZG_KERNEL_CACHE_DIR=str(tmp_path))
+
+    def run():
+        out = subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        return out.stdout.split()
+
+    first = run()
+    files = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
+    assert len(files) == 1 and not [f for f in os.listdir(tmp_path) if ".tmp" in f]
+    path = os.path.join(tmp_path, files[0])
+    blob = open(path, "rb").read()
+    magic, key_len, check, n = struct.unpack("<4Q", blob[:32])
+    assert n == int(first[0]) == len(blob) - 32 and blob[32:36] == b"\x7fELF"
+    # a well-formed entry is what the next process returns: swap the payload for a marker of the same size
+    marker = b"M" * n
+    open(path, "wb").write(blob[:32] + marker)
+    import hashlib
+    assert run() == [str(n), hashlib.sha1(marker).hexdigest()]
+    # a truncated file and one whose key check differs are ignored, recompiled and rewritten
+    open(path, "wb").write(blob[:100])
+    assert run() == first and open(path, "rb").read() == blob
+    open(path, "wb").write(struct.pack("<4Q", magic, key_len, check ^ 1, n) + marker)
+    assert run() == first and open(path, "rb").read() == blob

@@ -13,6 +13,7 @@
 #include <cuda.h>            // driver API *types* only; entry points come from cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -96,6 +97,7 @@ struct Nvrtc {
     int (*getProgramLogSize)(void*, size_t*) = nullptr;
     int (*getProgramLog)(void*, char*) = nullptr;
     const char* (*getErrorString)(int) = nullptr;
+    int (*version)(int*, int*) = nullptr;
     bool ok = false;
     std::string why;
 };
@@ -121,6 +123,7 @@ Nvrtc& nvrtc() {
         r.getProgramLogSize = (decltype(r.getProgramLogSize))sym("nvrtcGetProgramLogSize");
         r.getProgramLog = (decltype(r.getProgramLog))sym("nvrtcGetProgramLog");
         r.getErrorString = (decltype(r.getErrorString))sym("nvrtcGetErrorString");
+        r.version = (decltype(r.version))sym("nvrtcVersion");
         r.ok = r.createProgram && r.destroyProgram && r.compileProgram && r.getCUBINSize && r.getCUBIN &&
                r.getProgramLogSize && r.getProgramLog && r.getErrorString;
         if (!r.ok) r.why = "libnvrtc is missing expected symbols";
@@ -343,6 +346,51 @@ CubinCache& cubin_cache() {
 
 int jit_cubin_uncached(const std::string& text, bool exact, std::vector<char>& cubin);
 
+// Optional second level on disk: ZG_KERNEL_CACHE_DIR=<dir> keeps the cubins across processes (a service that
+// restarts with the same graphs pays the NVRTC compile once).  File name = two independent 64-bit FNV-1a hashes of
+// the key (contraction flag + NVRTC version + specialised source); the file repeats the key length and a third
+// hash, so a truncated or foreign file is ignored, never loaded.  Written to a temporary name and renamed.
+uint64_t fnv1a(const std::string& s, uint64_t h) {
+    for (unsigned char c : s) { h ^= c; h *= 0x100000001b3ull; }
+    return h;
+}
+struct DiskKey {
+    std::string path;
+    uint64_t len, check;
+};
+bool disk_key(const std::string& key, DiskKey& k) {
+    const char* dir = std::getenv("ZG_KERNEL_CACHE_DIR");
+    if (!dir || !*dir) return false;
+    char name[64];
+    std::snprintf(name, sizeof name, "/zg_%016llx%016llx.cubin", (unsigned long long)fnv1a(key, 0xcbf29ce484222325ull),
+                  (unsigned long long)fnv1a(key, 0x84222325cbf29ce4ull));
+    k.path = std::string(dir) + name;
+    k.len = key.size();
+    k.check = fnv1a(key, 0x9e3779b97f4a7c15ull);
+    return true;
+}
+bool disk_load(const DiskKey& k, std::vector<char>& cubin) {
+    FILE* f = std::fopen(k.path.c_str(), "rb");
+    if (!f) return false;
+    uint64_t head[4] = {0, 0, 0, 0};                          // magic, key length, check hash, cubin bytes
+    bool ok = std::fread(head, sizeof head, 1, f) == 1 && head[0] == 0x31434755425a47ull /* file magic */ &&
+              head[1] == k.len && head[2] == k.check && head[3] > 0 && head[3] < (64u << 20);
+    if (ok) {
+        cubin.resize(head[3]);
+        ok = std::fread(cubin.data(), 1, cubin.size(), f) == cubin.size() && std::fgetc(f) == EOF;
+    }
+    std::fclose(f);
+    return ok;
+}
+void disk_store(const DiskKey& k, const std::vector<char>& cubin) {
+    const std::string tmp = k.path + ".tmp" + std::to_string((long)getpid());
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return;                                           // an unwritable cache directory is not an error
+    const uint64_t head[4] = {0x31434755425a47ull, k.len, k.check, cubin.size()};
+    const bool ok = std::fwrite(head, sizeof head, 1, f) == 1 && std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    if (std::fclose(f) != 0 || !ok || std::rename(tmp.c_str(), k.path.c_str()) != 0) std::remove(tmp.c_str());
+}
+
 int jit_cubin(const std::string& text, bool exact, std::vector<char>& cubin) {
     const std::string key = (exact ? "E" : "F") + text;
     CubinCache& c = cubin_cache();
@@ -351,8 +399,15 @@ int jit_cubin(const std::string& text, bool exact, std::vector<char>& cubin) {
         for (auto& e : c.entries)
             if (e.first == key) { cubin = e.second; return ZG_OK; }
     }
-    int st = jit_cubin_uncached(text, exact, cubin);
-    if (st != ZG_OK) return st;
+    DiskKey dk;
+    int major = 0, minor = 0;
+    if (nvrtc().ok && nvrtc().version) nvrtc().version(&major, &minor);
+    const bool on_disk = disk_key("nvrtc" + std::to_string(major) + "." + std::to_string(minor) + key, dk);
+    if (!(on_disk && disk_load(dk, cubin))) {
+        int st = jit_cubin_uncached(text, exact, cubin);
+        if (st != ZG_OK) return st;
+        if (on_disk) disk_store(dk, cubin);
+    }
     std::lock_guard<std::mutex> lock(c.mu);
     if (c.entries.size() >= CubinCache::kMax) c.entries.erase(c.entries.begin());
     c.entries.emplace_back(key, cubin);
