@@ -186,7 +186,10 @@ int zg_plan_get_info(const zg_plan* p, zg_plan_info* info);
  * (io_dtype) in the plan's layout; ld is the leading dimension in elements (planar: >= n_samples,
  * interleaved: >= channels; a multiple of 16 bytes).  Buffers must be 16-byte aligned.  Asynchronous on
  * `stream` (a cudaStream_t, may be NULL).  Consecutive calls continue the stream exactly like
- * consecutive ticks: state is read at block start and written back at block end.               */
+ * consecutive ticks: state is read at block start and written back at block end.
+ * In place: out[j] may be the same buffer as in[i] (same pointer and ld; any pairing, e.g. two wires swapped) --
+ * the block is then overwritten with the result, like `x[t] = f(x[t])` around the reference's tick.  Buffers that
+ * overlap in any other way are ZG_ERR_ARG; the FIR kernel does not run in place (ZG_ERR_UNSUPPORTED).          */
 int zg_process(zg_plan* p, const void* const* in, void* const* out, int64_t n_samples,
                int64_t ld_in, int64_t ld_out, void* stream);
 /* Same, with HOST pointers: copies in, runs, copies out, synchronises (what a CPU-side caller of

@@ -947,3 +947,63 @@ def test_small_blocks_replayed_from_a_cuda_graph(zg):
     idx = [0, 17, 4095]
     ref = _oracle(expr, [x[idx]])[0]
     assert np.array_equal(np.concatenate(outs, axis=1)[idx], ref)
+
+
+@pytest.mark.parametrize("layout", ["planar", "interleaved"])
+def test_in_place_blocks(zg, layout):
+    """out[j] may be the same buffer as in[i] (zignal_b200.h): `x[t] = f(x[t])` around the reference's tick.  K1, K1b,
+    a generated two-wire graph with the wires swapped, bf16 storage; partial overlaps and the FIR kernel refuse."""
+    torch = _torch()
+    inter = layout == "interleaved"
+    C, T = 200, 1000
+    lay = zg.INTERLEAVED if inter else zg.PLANAR
+
+    def dev(a):
+        return _to_dev(a.T if inter else a)
+
+    def host(t):
+        a = t.cpu().numpy()
+        return a.T if inter else a
+
+    x = fo.noise(C, T, seed=21)
+    expr = fo.biquad_cascade(4)
+    want = fo.COracle(expr, C).process([x])[0]
+    for lanes in ([1] if inter else [1, 4]):                         # K1, K1b (planar only)
+        plan = zg.compile(expr).plan(channels=C, layout=lay, lanes_per_channel=lanes)
+        buf = dev(x)
+        for t0, n in ((0, 600), (600, T - 600)):                     # two blocks, each overwritten in place
+            blk = buf[t0:t0 + n] if inter else buf[:, t0:t0 + n]
+            out = plan.process([blk], [blk], n_samples=n)[0]
+            assert out.data_ptr() == blk.data_ptr()
+        torch.cuda.synchronize()
+        assert np.array_equal(host(buf), want), f"lanes={lanes}"
+
+    # generated kernel, two wires, swapped: out[0] overwrites in[1] and out[1] overwrites in[0]
+    g2 = "(_1 + _2 , _1 - _2[_1]) |= (~(_2 + 0.5f*_1[_1]) | (_1 - 0.25f*_1[_2]))"
+    x2 = [fo.noise(C, T, seed=22), fo.noise(C, T, seed=23)]
+    w2 = fo.COracle(g2, C).process(x2)
+    a, b = dev(x2[0]), dev(x2[1])
+    zg.compile(g2).plan(channels=C, layout=lay).process([a, b], [b, a])
+    torch.cuda.synchronize()
+    assert np.array_equal(host(b), w2[0]) and np.array_equal(host(a), w2[1])
+
+    # bf16 storage in place
+    xb = fo.bf16_round(x)
+    wb = fo.COracle(expr, C).process([xb])[0]
+    bb = zg.to_block(xb.T if inter else xb, dtype=torch.bfloat16)
+    zg.compile(expr).plan(channels=C, layout=lay, io_dtype=zg.BF16).process([bb], [bb])
+    torch.cuda.synchronize()
+    assert np.array_equal(host(bb.view(torch.int16)).view(np.uint16), fo.bf16_bits(wb))
+
+    # anything else that overlaps is refused before a kernel is launched
+    plan = zg.compile(expr).plan(channels=C, layout=lay)
+    big = _to_dev(np.zeros((C + 8, T + 8) if not inter else (T + 8, C + 8), np.float32))
+    src, dst = (big[:C, :T], big[4:C + 4, :T]) if not inter else (big[:T, :C], big[4:T + 4, :C])
+    with pytest.raises(zg.ZgError) as e:
+        plan.process([src], [dst])
+    assert e.value.status == zg.ZG_ERR_ARG
+    fir = zg.compile(fo.fir_expr(fo.fir_taps(32))).plan(channels=C, layout=lay)
+    buf = dev(x)
+    with pytest.raises(zg.ZgError) as e:
+        fir.process([buf], [buf])
+    assert e.value.status == zg.ZG_ERR_UNSUPPORTED

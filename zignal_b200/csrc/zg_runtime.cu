@@ -918,6 +918,25 @@ int check_io(const zg_plan* p, const void* const* in, void* const* out, int64_t 
     }
     for (int o = 0; o < p->ir.n_out; ++o)
         if (!out[o] || ((uintptr_t)out[o] & 15)) return fail(ZG_ERR_ARG, "output buffer NULL or not 16-byte aligned");
+    // In place: an output may BE an input (same pointer, same pitch) -- every tile of every input is in shared memory
+    // before any output of that tile is stored, and a tile is stored exactly where it was loaded.  Any other overlap
+    // is refused, and so is aliasing for the FIR kernel (later time segments read their history from the input).
+    const int64_t rows = p->interleaved ? T : p->C, cols = p->interleaved ? p->C : T;
+    auto extent = [&](int64_t ld) { return rows > 0 ? ((rows - 1) * ld + cols) * (int64_t)p->io : 0; };
+    auto overlap = [](const void* a, int64_t na, const void* b, int64_t nb) {
+        const uintptr_t x = (uintptr_t)a, y = (uintptr_t)b;
+        return x < y + (uintptr_t)nb && y < x + (uintptr_t)na;
+    };
+    for (int o = 0; o < p->ir.n_out; ++o) {
+        for (int q = 0; q < o; ++q)
+            if (overlap(out[o], extent(ld_out), out[q], extent(ld_out))) return fail(ZG_ERR_ARG, "output buffers overlap");
+        for (int k = 0; k < p->ir.n_in; ++k) {
+            if ((p->synth_mask & (1u << k)) || !overlap(out[o], extent(ld_out), in[k], extent(ld_in))) continue;
+            if (out[o] != in[k] || ld_in != ld_out)
+                return fail(ZG_ERR_ARG, "an output overlaps an input without being the same buffer (same pointer and pitch)");
+            if (p->is_fir) return fail(ZG_ERR_UNSUPPORTED, "the FIR kernel does not run in place (its history is read from the input block)");
+        }
+    }
     return ZG_OK;
 }
 
