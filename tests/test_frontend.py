@@ -84,6 +84,21 @@ def test_spellings_the_reference_plans(zg):
         zg.canonical("_1<2>")
 
 
+def test_expression_depth_is_bounded_not_the_stack(zg):
+    # every analysis recurses over the tree: trees up to 512 levels are accepted (a 256-tap FIR sum is 257 high), deeper
+    # text is an error, never a stack overflow; whatever is accepted prints to text that parses back to the same tree
+    for e in ["(" * 500 + "_1" + ")" * 500, "-" * 500 + "_1", "_1" + " + 0.5f*_1[_1]" * 500, "_1" + " |= _1" * 500]:
+        c = zg.canonical(e)
+        assert zg.canonical(c) == c
+        assert zg.arity(c) == zg.arity(e) == (1, 1)
+        zg.compile(e).voice()(1.0)
+    for e in ["(" * 5000 + "_1" + ")" * 5000, "-" * 5000 + "_1", "~" * 5000 + "_1", "_1" + " + _1" * 5000, "_1" + " |= _1" * 5000,
+              "_1" + "[_1]" * 3000]:
+        with pytest.raises(zg.ZgError) as err:
+            zg.arity(e)
+        assert err.value.status in (zg.ZG_ERR_PARSE, zg.ZG_ERR_GRAPH) and len(str(err.value)) < 400
+
+
 def test_series_and_delay_spellings_of_the_prototypes(zg):
     # north star: `>>` and `_1[-n]` (experimental_steps/wires_mono_only.cpp:37, delay_expression.cpp:99)
     assert zg.canonical("_1 >> _1[-1]") == zg.canonical("_1 |= _1[_1]")

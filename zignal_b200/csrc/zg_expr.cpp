@@ -41,11 +41,16 @@ ExprP param(int idx) {
     if (idx < 0) throw Error("parameter index must be >= 0");
     Expr e; e.op = Op::Param; e.k = idx; return mk(e);
 }
+static void set_depth(Expr& e) {
+    for (auto& c : e.ch) e.depth = std::max(e.depth, c->depth + 1);
+    if (e.depth > kMaxDepth)
+        throw Error("expression is nested more than " + std::to_string(kMaxDepth) + " levels deep");
+}
 ExprP unary(Op op, ExprP a) {
-    Expr e; e.op = op; e.ch = {std::move(a)}; return mk(e);
+    Expr e; e.op = op; e.ch = {std::move(a)}; set_depth(e); return mk(e);
 }
 ExprP binary(Op op, ExprP a, ExprP b) {
-    Expr e; e.op = op; e.ch = {std::move(a), std::move(b)}; return mk(e);
+    Expr e; e.op = op; e.ch = {std::move(a), std::move(b)}; set_depth(e); return mk(e);
 }
 
 bool is_terminal(const Expr& e) {
@@ -123,7 +128,10 @@ struct Parser {
     explicit Parser(const std::string& text) : s(text) {}
 
     [[noreturn]] void fail(const std::string& msg) const {
-        throw Error("flowz parse error at column " + std::to_string(p + 1) + ": " + msg + "  in \"" + s + "\"");
+        // (the text is echoed around the column only: expressions can be tens of kilobytes long)
+        const size_t b = p > 60 ? p - 60 : 0, n = std::min<size_t>(s.size() - b, 120);
+        throw Error("flowz parse error at column " + std::to_string(p + 1) + ": " + msg + "  in \"" + (b ? "..." : "") +
+                    s.substr(b, n) + (b + n < s.size() ? "..." : "") + "\"");
     }
     void ws() { while (p < s.size() && std::isspace((unsigned char)s[p])) ++p; }
     bool eat(const char* tok) {
@@ -146,14 +154,29 @@ struct Parser {
         return std::atoi(s.substr(b, p - b).c_str());
     }
 
+    int nest = 0;                     // open parentheses / prefix operators: the parser recurses once per level
+    struct Nest {
+        Parser& ps;
+        explicit Nest(Parser& q) : ps(q) {
+            // a tree level prints as at most one parenthesis and one prefix operator (to_string): twice the tree limit
+            // keeps every printed tree readable again
+            if (++ps.nest > 2 * kMaxDepth + 8) ps.fail("nested more than " + std::to_string(2 * kMaxDepth + 8) + " levels deep");
+        }
+        ~Nest() { --ps.nest; }
+    };
+
     ExprP comma() {
+        Nest guard(*this);
         ExprP l = assign();
         while (peek(",")) { eat(","); l = binary(Op::Chan, l, assign()); }
         return l;
     }
     ExprP assign() {          // |= is right associative
         ExprP l = bitor_();
-        if (eat("|=")) return binary(Op::Seq, l, assign());
+        if (eat("|=")) {
+            Nest guard(*this);
+            return binary(Op::Seq, l, assign());
+        }
         return l;
     }
     ExprP bitor_() {
@@ -190,6 +213,8 @@ struct Parser {
         return l;
     }
     ExprP unary_() {
+        if (!peek("~") && !peek("+") && !peek("-")) return postfix();
+        Nest guard(*this);                                  // one level per prefix operator
         if (eat("~")) return unary(Op::Fb, unary_());
         if (eat("+")) return unary_();
         if (peek("-")) {

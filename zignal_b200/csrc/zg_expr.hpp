@@ -26,6 +26,10 @@ struct Error : std::runtime_error {
 // C64 / C128 (std::complex<float> / <double>) exist for the type analysis only (result_types): a graph with a
 // complex terminal is analysed like any other but cannot be lowered to a tick program.
 enum class Dtype : uint8_t { I32 = 0, F32 = 1, F64 = 2, C64 = 4, C128 = 5 };
+// Every analysis walks the tree recursively: the height is bounded so that no expression text can exhaust the stack
+// (a 256-tap FIR written as one sum is 256 levels high; the deepest accepted text needs about 1.5 MB of stack, threads get
+// 8 MB by default).
+constexpr int kMaxDepth = 512;
 constexpr int kAbsorber = -1;   // result_types: a wire whose type the feedback cycle leaves open (flowz.hpp:542)
 
 enum class Op : uint8_t {
@@ -51,6 +55,7 @@ struct Expr {
     Dtype dtype = Dtype::F32;  // Const only
     double value = 0;     // Const only (already rounded to dtype)
     double imag = 0;      // Const of a complex dtype only
+    int depth = 1;        // height of the tree below (and including) this node; bounded by kMaxDepth
     std::vector<ExprP> ch;
 };
 
