@@ -27,3 +27,9 @@ PY
 # sanitizer frames are several times larger than the product's: give the deepest accepted expressions room
 ulimit -s 1000000 2>/dev/null || ulimit -s unlimited 2>/dev/null || true
 ASAN_OPTIONS=detect_leaks=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 "$OUT/harness" < "$OUT/exprs.txt"
+
+# the same sources under ThreadSanitizer: one graph shared by 8 threads (host_abi_threads.cpp)
+g++ -std=c++17 -O1 -g -fsanitize=thread -ffp-contract=off -I"$ROOT/include" -I"$R" \
+    "$ROOT/tools/sanitize/host_abi_threads.cpp" "$R/zg_expr.cpp" "$R/zg_ir.cpp" "$R/zg_capi.cpp" "$R/zg_codegen.cpp" "$R/zg_match.cpp" \
+    -o "$OUT/tsan_harness" -lpthread
+"$OUT/tsan_harness"
