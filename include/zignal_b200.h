@@ -24,7 +24,7 @@
  *     0.5f 0.5 2      float / double / int literal terminals    flowz.hpp:68-72
  *     cplx{1,0}       std::complex<float> terminal (cplxd: double); type analysis only   test/tests.cpp:188,205
  *     $k              run-time parameter k (std::ref terminal)  flowz/README.md:42-63
- * Expression trees may be up to 512 levels high (a 256-tap FIR written as one sum is 257); deeper text is refused
+ * Expression trees may be up to 1536 levels high (a 512-tap FIR written as one sum is 513); deeper text is refused
  * (ZG_ERR_PARSE / ZG_ERR_GRAPH) instead of exhausting the stack of the recursive analyses.
  */
 #ifndef ZIGNAL_B200_H

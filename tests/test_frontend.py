@@ -85,9 +85,9 @@ def test_spellings_the_reference_plans(zg):
 
 
 def test_expression_depth_is_bounded_not_the_stack(zg):
-    # every analysis recurses over the tree: trees up to 512 levels are accepted (a 256-tap FIR sum is 257 high), deeper
+    # every analysis recurses over the tree: trees up to 1536 levels are accepted (a 512-tap FIR sum is 513 high), deeper
     # text is an error, never a stack overflow; whatever is accepted prints to text that parses back to the same tree
-    for e in ["(" * 500 + "_1" + ")" * 500, "-" * 500 + "_1", "_1" + " + 0.5f*_1[_1]" * 500, "_1" + " |= _1" * 500]:
+    for e in ["(" * 1500 + "_1" + ")" * 1500, "-" * 1500 + "_1", "_1" + " + 0.5f*_1[_1]" * 1500, "_1" + " |= _1" * 1500]:
         c = zg.canonical(e)
         assert zg.canonical(c) == c
         assert zg.arity(c) == zg.arity(e) == (1, 1)

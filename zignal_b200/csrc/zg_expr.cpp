@@ -154,19 +154,21 @@ struct Parser {
         return std::atoi(s.substr(b, p - b).c_str());
     }
 
-    int nest = 0;                     // open parentheses / prefix operators: the parser recurses once per level
+    // The parser recurses once per open parenthesis / right-nested `|=` (a chain of nine frames) and once per prefix
+    // operator (one frame).  A tree level prints as at most one parenthesis and one prefix operator (to_string), so with
+    // each kind bounded by the tree limit every printed tree can be read again.
+    int nest[3] = {0, 0, 0};          // parentheses, prefix operators, right-nested |=
     struct Nest {
         Parser& ps;
-        explicit Nest(Parser& q) : ps(q) {
-            // a tree level prints as at most one parenthesis and one prefix operator (to_string): twice the tree limit
-            // keeps every printed tree readable again
-            if (++ps.nest > 2 * kMaxDepth + 8) ps.fail("nested more than " + std::to_string(2 * kMaxDepth + 8) + " levels deep");
+        int kind;
+        Nest(Parser& q, int k) : ps(q), kind(k) {
+            if (++ps.nest[kind] > kMaxDepth + 8) ps.fail("nested more than " + std::to_string(kMaxDepth + 8) + " levels deep");
         }
-        ~Nest() { --ps.nest; }
+        ~Nest() { --ps.nest[kind]; }
     };
 
     ExprP comma() {
-        Nest guard(*this);
+        Nest guard(*this, 0);
         ExprP l = assign();
         while (peek(",")) { eat(","); l = binary(Op::Chan, l, assign()); }
         return l;
@@ -174,7 +176,7 @@ struct Parser {
     ExprP assign() {          // |= is right associative
         ExprP l = bitor_();
         if (eat("|=")) {
-            Nest guard(*this);
+            Nest guard(*this, 2);
             return binary(Op::Seq, l, assign());
         }
         return l;
@@ -214,7 +216,7 @@ struct Parser {
     }
     ExprP unary_() {
         if (!peek("~") && !peek("+") && !peek("-")) return postfix();
-        Nest guard(*this);                                  // one level per prefix operator
+        Nest guard(*this, 1);                               // one level per prefix operator
         if (eat("~")) return unary(Op::Fb, unary_());
         if (eat("+")) return unary_();
         if (peek("-")) {

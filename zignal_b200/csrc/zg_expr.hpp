@@ -27,9 +27,9 @@ struct Error : std::runtime_error {
 // complex terminal is analysed like any other but cannot be lowered to a tick program.
 enum class Dtype : uint8_t { I32 = 0, F32 = 1, F64 = 2, C64 = 4, C128 = 5 };
 // Every analysis walks the tree recursively: the height is bounded so that no expression text can exhaust the stack
-// (a 256-tap FIR written as one sum is 256 levels high; the deepest accepted text needs about 1.5 MB of stack, threads get
-// 8 MB by default).
-constexpr int kMaxDepth = 512;
+// (a 256-tap FIR written as one sum is 256 levels high; a 512-tap one 513; the deepest accepted text needs about 3 MB of
+// stack, threads get 8 MB by default).
+constexpr int kMaxDepth = 1536;
 constexpr int kAbsorber = -1;   // result_types: a wire whose type the feedback cycle leaves open (flowz.hpp:542)
 
 enum class Op : uint8_t {
