@@ -210,6 +210,14 @@ int zg_param_set(zg_plan* p, int index, const float* host_values, int64_t n);
  * Synchronises the device (the values are copied before the call returns).                               */
 int zg_param_set_device(zg_plan* p, int index, const float* device_values, int64_t n);
 
+/* ---- channel sharding across the GPUs of a box --------------------------------------------------
+ * Voices are independent (each is its own stateful_lambda, flowz.hpp:1181-1230), so rank r of world_size owns the
+ * contiguous channel range [*begin, *end) with its own plan; sizes differ by at most one, the first ranks are the
+ * larger ones.  The library itself is single-device: the exchange at the edges (one scatter of the input block, one
+ * gather of the output block, or none when the kernels work on the root's blocks through peer mappings) belongs to
+ * the caller's process group -- zignal_b200/shard.py does it over torch.distributed.                             */
+int zg_shard_range(int64_t channels, int world_size, int rank, int64_t* begin, int64_t* end);
+
 #ifdef __cplusplus
 }
 #endif

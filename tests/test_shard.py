@@ -23,6 +23,18 @@ def test_channel_ranges_partition_exactly():
         channel_range(8, 2, 2)
 
 
+def test_c_abi_shard_range_is_the_same_partition(zg):
+    import ctypes
+    from zignal_b200.shard import channel_range
+    b, e = ctypes.c_int64(), ctypes.c_int64()
+    for C in (0, 1, 7, 64, 65536, 1048576 + 3):
+        for G in (1, 2, 3, 8):
+            for r in range(G):
+                assert zg.lib.zg_shard_range(C, G, r, ctypes.byref(b), ctypes.byref(e)) == 0
+                assert (b.value, e.value) == channel_range(C, G, r)
+    assert zg.lib.zg_shard_range(8, 2, 2, ctypes.byref(b), ctypes.byref(e)) == zg.ZG_ERR_ARG
+
+
 def _worker(rank, world, port, C, T, q):
     import torch
     import torch.distributed as dist

@@ -91,6 +91,7 @@ def _load() -> C.CDLL:
         "zg_state_set": (ci, [vp, P(C.c_float), sz]),
         "zg_param_set": (ci, [vp, ci, P(C.c_float), i64]),
         "zg_param_set_device": (ci, [vp, ci, vp, i64]),
+        "zg_shard_range": (ci, [i64, ci, ci, P(i64), P(i64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here = header and library disagree
@@ -104,7 +105,7 @@ EXPORTED = ["zg_last_error", "zg_version", "zg_expr_arity", "zg_expr_delays", "z
             "zg_voice_create", "zg_voice_clone", "zg_voice_destroy", "zg_voice_tick", "zg_voice_set_param",
             "zg_voice_state", "zg_plan_opts_default", "zg_graph_kernel_compile", "zg_plan_create",
             "zg_plan_destroy", "zg_plan_get_info", "zg_process", "zg_process_host", "zg_state_reset",
-            "zg_state_get", "zg_state_set", "zg_param_set", "zg_param_set_device"]
+            "zg_state_get", "zg_state_set", "zg_param_set", "zg_param_set_device", "zg_shard_range"]
 
 
 def _check(status: int) -> None:

@@ -1,4 +1,5 @@
 // zignal-b200 :: host half of the C ABI (analysis, compile, host voice).  Device half: zg_runtime.cu
+#include <algorithm>
 #include <cstring>
 
 #include "zg_internal.hpp"
@@ -95,6 +96,15 @@ int zg_expr_result_types(const char* expr, const int* in_dtypes, int n_in, int* 
         if (is_tuple) *is_tuple = r.is_tuple ? 1 : 0;
         return (int)ZG_OK;
     });
+}
+
+int zg_shard_range(int64_t channels, int world_size, int rank, int64_t* begin, int64_t* end) {
+    if (!begin || !end) return fail(ZG_ERR_ARG, "NULL argument");
+    if (channels < 0 || world_size < 1 || rank < 0 || rank >= world_size) return fail(ZG_ERR_ARG, "rank out of range");
+    const int64_t base = channels / world_size, extra = channels % world_size;
+    *begin = rank * base + std::min<int64_t>(rank, extra);
+    *end = *begin + base + (rank < extra ? 1 : 0);
+    return ZG_OK;
 }
 
 int zg_graph_compile(const char* expr, zg_graph** out) {
