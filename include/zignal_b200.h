@@ -80,7 +80,11 @@ int zg_expr_result_types(const char* expr, const int* in_dtypes, int n_in, int* 
 
 /* ---- compile()  flowz.hpp:1233-1249 -----------------------------------------------------------
  * front panel (:273-277) + canonical form (:794-935) + state layout (:685-725) + lowering to the
- * flat tick program that both the host tick and the CUDA kernels execute.                      */
+ * flat tick program that both the host tick and the CUDA kernels execute.
+ * Graphs the reference compiles are walked exactly as it walks them.  Graphs it cannot compile because of a
+ * feedback (nested loops, parallel combiners inside a loop: TODO.md:11-29) compile here as long as every loop
+ * contains a delay: `~x` ties the first inputs of x to x's own outputs.  A loop without a delay, and a delayed
+ * read the reference's state sizing does not cover (undefined behaviour there), are ZG_ERR_GRAPH.          */
 int zg_graph_compile(const char* expr, zg_graph** out);
 void zg_graph_destroy(zg_graph* g);
 

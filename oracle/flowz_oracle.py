@@ -566,6 +566,13 @@ class _Walker:
 def _promote(a, b): return max(a, b)
 
 
+# binary_feedback hands its future part ALL external inputs (:1043-1047, the drop<min(0, ...)> with its TODO), while
+# the delay analysis that sizes the state (:443-506) gives the future part the wires after the promise part's.  Where the
+# two disagree a delayed read indexes before the start of its std::array (s[size - n] with n > size, :950-958):
+# undefined behaviour in the reference, an error here and in the product.
+_OUT_OF_LINE = "delayed read reaches past the delay line the reference allocates (out-of-bounds in the reference)"
+
+
 class _NumpyBackend:
     """Values are (dtype, ndarray[C]).  Pushes are deferred to the end of the tick, which is
     equivalent because every line is read before its owner pushes it."""
@@ -578,6 +585,8 @@ class _NumpyBackend:
 
     def read(self, line, n):                                    # s[s.size() - n]
         depth, off = line
+        if n > depth:
+            raise ValueError(_OUT_OF_LINE)
         return (F32, self.state[off + depth - n].copy())
     def const(self, dtype, value):
         return (dtype, np.full(self.channels, value, _NP[dtype]))
@@ -660,6 +669,8 @@ class _CBackend:
         return (dtype, name)
     def read(self, line, n):
         depth, off = line
+        if n > depth:
+            raise ValueError(_OUT_OF_LINE)
         return self._new(F32, f"s[{off + depth - n}]")
     def const(self, dtype, value):
         if dtype == I32: return self._new(I32, str(int(value)))

@@ -84,6 +84,42 @@ def test_spellings_the_reference_plans(zg):
         zg.canonical("_1<2>")
 
 
+def test_feedbacks_the_reference_cannot_compile(zg):
+    """Nested feedback (TODO.md:11-27; the disabled expectation test/tests.cpp:59) and parallel combiners inside a loop
+    (TODO.md:29): the reference cannot split these, or its split touches the current value of a fed-back wire.  compile()
+    takes such graphs at their word -- `~x` ties the first inputs of x to x's outputs -- and refuses only loops without
+    a delay.  Expected sequences derived by hand; tests/netlist_flowz.py agrees."""
+    import netlist_flowz as nl
+    # s[t] = y + y + 1 with y = s[t-1]:  y = 0, 1, 3, 7, 15, 31
+    g = zg.compile("~~( _1 + _2 + 1 |= _1[_1] )")
+    v = g.voice()
+    assert [v()[0] for _ in range(6)] == [0.0, 1.0, 3.0, 7.0, 15.0, 31.0]
+    assert (g.n_in, g.n_out, g.n_state) == (0, 1, 1)
+    with pytest.raises(zg.ZgError):                                  # the reference-shaped analysis still says no
+        zg.canonical("~~( _1 + _2 |= _1[_1] )")
+    # the TODO's picture: f = 0.5*, inner loop integrates: y[t] = s[t-1], s[t] = y + (0.5 y + u)  ->  impulse response 1.5^t
+    v = zg.compile("~( (0.5f*_1 + _2) |= ~(_1 + _2 |= _1[_1]) )").voice()
+    assert [v(u)[0] for u in (1.0, 0.0, 0.0, 0.0, 0.0)] == [0.0, 1.0, 1.5, 2.25, 3.375]
+    # parallel combiner inside the loop
+    e = "~((_1[_2] |= _2) | (_1 - _2))"
+    g, net = zg.compile(e), nl.Netlist(e)
+    assert (g.n_in, g.n_out) == (2, 2)
+    v = g.voice()
+    for t in range(8):
+        assert v(float(t + 1), 2.0) == tuple(float(x) for _, x in net.tick(float(t + 1), 2.0))
+    # a graph the reference does compile keeps the reference's walk, state layout included
+    assert zg.compile("~(_2 + 0.5f*_1[_1])").canonical == zg.canonical("_1 |= ~(_2 + 0.5f*_1[_1])")
+    # loops without a delay stay errors, with a message that says so
+    for bad in ["~(_1 + _2)", "~(_1)", "~(2*_1)", "~~(_1 + _2 |= _1)"]:
+        with pytest.raises(zg.ZgError, match="without a delay"):
+            zg.compile(bad)
+    # undefined behaviour in the reference is an error, not a silent read of a neighbouring line (flowz.hpp:950-958, 1043-1047)
+    with pytest.raises(zg.ZgError, match="out-of-bounds in the reference"):
+        zg.compile("~(((_3 * _1) + (_2 - _3[_1])) |= ((1.5 - _2) * (_3[_2] + _3)))")
+    with pytest.raises(ValueError, match="out-of-bounds in the reference"):
+        fo.Oracle("~(((_3 * _1) + (_2 - _3[_1])) |= ((1.5 - _2) * (_3[_2] + _3)))").tick(1.0, 2.0, 3.0, 4.0)
+
+
 def test_expression_depth_is_bounded_not_the_stack(zg):
     # every analysis recurses over the tree: trees up to 1536 levels are accepted (a 512-tap FIR sum is 513 high), deeper
     # text is an error, never a stack overflow; whatever is accepted prints to text that parses back to the same tree

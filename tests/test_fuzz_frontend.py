@@ -2,13 +2,17 @@
 
 Every expression is generated from the grammar (flowz.hpp:68-102); for each one the two sides must agree on whether it
 is a valid graph at all, on arity, per-wire max/min delays, the canonical form, the ResultType of the bare expression,
-and on six ticks of one voice with small-integer inputs (exact in int, float and double alike).  The seeds are fixed:
-the test is deterministic."""
+and on six ticks of one voice with small-integer inputs (exact in int, float and double alike).  A third evaluator of different
+construction (tests/netlist_flowz.py: a netlist of the uncanonicalised expression, evaluated by need) ticks along; it
+alone checks the graphs the product accepts beyond the reference -- feedbacks that cannot be split into a promise and
+a future part but still have a delay in every loop (nested feedback, TODO.md:11-27).  The seeds are fixed: the test is
+deterministic."""
 import random
 
 import pytest
 
 import flowz_oracle as fo
+import netlist_flowz as nl
 
 CONSTS = ["2", "3", "0.5f", "0.25f", "1.5", "-1", "0x1p-1f", "-0.75f"]
 
@@ -63,12 +67,27 @@ def _oracle(expr):
 @pytest.mark.parametrize("seed", range(16))
 def test_random_graphs_product_equals_oracle(zg, seed):
     rng = random.Random(1000 + seed)
-    checked = rejected = 0
+    checked = rejected = extended = 0
     for _ in range(60):
         expr = _gen(rng, rng.randint(1, 5), rng.randint(1, 4))
         g, perr = _product(zg, expr)
         o, oerr = _oracle(expr)
         if perr == "limit":                          # more than ZG_MAX_WIRES wires: a limit of the product, not of flowz
+            continue
+        if g is not None and o is None:
+            # beyond the reference: a feedback that cannot be split, or whose split would make the reference touch the
+            # current value of a fed-back wire (its bottom_type) -- the product resolves fed-back wires as forward
+            # references and accepts whatever has a delay in every loop; the netlist evaluator is the only other opinion
+            assert any(m in oerr for m in ("cannot be split", "fed-back wire", "not a single value")), f"{expr}: {oerr}"
+            net = nl.Netlist(expr)
+            dt = rng.choice([fo.I32, fo.F32, fo.F64])
+            v = g.voice()
+            for t in range(6):
+                xs = [float(rng.randint(-3, 3)) for _ in range(g.n_in)]
+                res = net.tick(*xs, dtype=dt)
+                assert tuple(float(y) for y in v.tick(*xs, dtypes=[dt] * g.n_in)) == tuple(float(x) for _, x in res), expr
+                assert v.out_dtypes == tuple(d for d, _ in res), expr
+            extended += 1
             continue
         assert (g is None) == (o is None), f"{expr}\n product: {perr}\n oracle: {oerr}"
         if g is None:
@@ -90,10 +109,14 @@ def test_random_graphs_product_equals_oracle(zg, seed):
         else:
             assert zg.result_types(expr, [zg.F32] * n_in) == want_t, expr
         v = g.voice()
+        net = nl.Netlist(expr)
         dt = rng.choice([fo.I32, fo.F32, fo.F64])             # the C++ type of the arguments: int stays int (:769-772)
         for t in range(6):
             xs = [float(rng.randint(-3, 3)) for _ in range(n_in)]
             res = o.tick(*xs, dtype=dt)
+            if "~" not in expr:      # (inside a feedback the reference's split can route external inputs differently from
+                #  the plain reading of the expression -- its "thinning" bug, TODO.md:11 -- and product and oracle follow it)
+                assert [(d, float(x)) for d, x in net.tick(*xs, dtype=dt)] == [(d, float(x[0])) for d, x in res], expr
             want = tuple(float(val[0]) for _, val in res)
             got = tuple(float(y) for y in v.tick(*xs, dtypes=[dt] * n_in))
             assert got == want, f"{expr} tick {t}: {got} != {want}"

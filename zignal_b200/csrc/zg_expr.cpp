@@ -625,9 +625,18 @@ Split u2b(const ExprP& e) {                                   // :811-846
     return out;
 }
 
+// compile() only (canonical_with_front): for a graph the reference cannot compile because of a feedback -- nested
+// feedback whose inner loop takes the outer fed-back wire in its promise part, parallel combiners inside a loop,
+// TODO.md:11-29 and the disabled test/tests.cpp:59 -- every `~x` stays a unary feedback over the canonical x (mode 2;
+// mode 1 keeps only those that do not split).  The lowering resolves the fed-back wires of such a node as forward
+// references and refuses only genuine zero-delay loops (zg_ir.cpp).  make_canonical() itself stays strict.
+thread_local int g_keep_feedback = 0;
+
 ExprP split_future_subexpr(const ExprP& x) {                  // :862-884
+    if (g_keep_feedback == 2) return unary(Op::Fb, make_canonical(x));
     ExprP chain = binary(Op::Seq, make_front(output_arity(*x)), x);
     Split s = u2b(make_canonical(chain));
+    if (s.size() != 2 && g_keep_feedback == 1) return unary(Op::Fb, make_canonical(x));
     if (s.size() != 2)
         throw Error("feedback ~(" + to_string(*x) +
                     ") cannot be split into a promise and a future part: every path from the "
@@ -645,7 +654,12 @@ ExprP make_canonical(ExprP e) {                               // :794-805
     return mk(n);
 }
 
-ExprP canonical_with_front(ExprP e) {                         // compile(), :1233-1249
+ExprP canonical_with_front(ExprP e, int keep_feedback) {      // compile(), :1233-1249
+    struct Mode {
+        int old = g_keep_feedback;
+        explicit Mode(int m) { g_keep_feedback = m; }
+        ~Mode() { g_keep_feedback = old; }
+    } mode(keep_feedback);
     if (input_arity(*e) == 0) return make_canonical(e);       // extension, see header
     return make_canonical(add_front_panel(e));
 }

@@ -101,6 +101,9 @@ ExprP add_front_panel(ExprP e);
 ExprP make_canonical(ExprP e);                      // replaces every ~x by bfb(promise, future)
 // compile(): front panel + canonical form.  arity 0 is accepted as an extension (the reference has
 // no make_front<0>, TODO.md:65): the expression is canonicalised without a front panel.
-ExprP canonical_with_front(ExprP e);
+// keep_feedback: 0 = every ~x must split into binary_feedback(promise, future) as in the reference (else Error);
+// 1 = a ~x that cannot be split stays a unary feedback over its canonical body; 2 = every ~x stays whole.  Kept
+// feedbacks are lowered with forward references (zg_ir.cpp) -- beyond the reference, which cannot compile them.
+ExprP canonical_with_front(ExprP e, int keep_feedback = 0);
 
 }  // namespace zg

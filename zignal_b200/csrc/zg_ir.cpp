@@ -79,6 +79,19 @@ struct Builder {
         lines.push_back(l);
         return (int)lines.size() - 1;
     }
+
+    // The current value of a fed-back wire (the reference's bottom_type, flowz.hpp:1004) as a forward reference:
+    // a Fwd node stands for it until binary_feedback has evaluated its promise part and binds it to the node that
+    // is fed back.  Its dtype is a guess (lower() iterates until the guesses match what was bound).
+    std::vector<int> fwd_nodes;                  // in creation order
+    std::vector<int> fwd_target;                 // same order; -1 = not bound yet
+    int add_fwd(Dtype guess) {
+        nodes.push_back(IrNode{IrOp::Fwd, guess, (int)fwd_nodes.size(), -1, 0});
+        fwd_nodes.push_back((int)nodes.size() - 1);
+        fwd_target.push_back(-1);
+        return (int)nodes.size() - 1;
+    }
+    void bind(int fwd_node, int target) { fwd_target[nodes[fwd_node].a] = target; }
 };
 
 using Vals = std::vector<int>;
@@ -103,6 +116,7 @@ std::vector<T> cat(std::vector<T> a, const std::vector<T>& b) {
 struct Lowering {
     Builder& b;
     const std::vector<Dtype>& in_dtypes;
+    const std::vector<Dtype>& fwd_guess;         // dtype of the k-th forward reference (F32 beyond its end)
 
     Lines make_node_state(const Expr& left, const Expr& right) {
         // StateCtor( tuple_take_( output_arity(_left), max_input_delays(_right) ) )  (:699, :707)
@@ -136,7 +150,13 @@ struct Lowering {
                     throw Error("_" + std::to_string(e.k) + "[_" + std::to_string(e.n) +
                                 "]: this wire has no delay line here (no_state, flowz.hpp:1059/1148)");
                 int line = in_state[e.k - 1];
-                if (e.n > b.lines[line].depth) throw Error("delay exceeds line depth (internal)");
+                if (e.n > b.lines[line].depth)
+                    // binary_feedback hands its future part ALL external inputs (:1043-1047, drop<min(0, ...)> and its
+                    // TODO) while the delay analysis that sizes the state (:443-506) gives it the wires after the
+                    // promise part's; where they disagree the reference indexes before the start of a std::array
+                    throw Error("_" + std::to_string(e.k) + "[_" + std::to_string(e.n) + "] reaches past the delay line the " +
+                                "reference allocates for this wire (" + std::to_string(b.lines[line].depth) +
+                                " deep): out-of-bounds in the reference (flowz.hpp:950-958, 1043-1047)");
                 IrNode n{IrOp::DRead, Dtype::F32, line, e.n, 0};
                 return {b.add(n)};
             }
@@ -198,8 +218,28 @@ struct Lowering {
                 push_all(node_state, promise_result, "binary_feedback");
                 return result;                                                     // :1069
             }
-            case Op::Fb:
-                throw Error("unary feedback survived canonicalisation (internal)");
+            case Op::Fb: {
+                // A feedback kept whole (zg_expr.cpp: the reference cannot split it, or its split would touch the
+                // current value of a fed-back wire): the first out(x) inputs of x are x's own outputs.  They enter as
+                // forward references, bound once x has been walked; delayed reads of them come from lines this node
+                // owns, as in binary_feedback.  Only a loop without a delay is an error (resolve_forward_references).
+                const Expr& X = *e.ch[0];
+                const int n = output_arity(X);
+                std::vector<int> depths = take(max_input_delays(X), n);
+                Lines node_state;
+                for (int d : depths) node_state.push_back(d > 0 ? b.new_line(d) : kNoLine);
+                node_state.resize(n, kNoLine);
+                Vals fed(n);
+                for (int i = 0; i < n; ++i) {
+                    const size_t k = b.fwd_nodes.size();
+                    fed[i] = b.add_fwd(k < fwd_guess.size() ? fwd_guess[k] : Dtype::F32);
+                }
+                Vals result = eval(X, cat(fed, input), cat(node_state, in_state));
+                if ((int)result.size() < n) throw Error("feedback: the expression returns fewer wires than it feeds back");
+                push_all(node_state, result, "feedback");
+                for (int i = 0; i < n; ++i) b.bind(fed[i], result[i]);
+                return result;
+            }
         }
         throw Error("unknown expression node");
     }
@@ -226,6 +266,95 @@ struct Lowering {
     }
 };
 
+// Forward references (Builder::add_fwd) -> the nodes they were bound to; then a topological order, because a node that
+// used a fed-back wire directly was created before the node that feeds it.  A cycle here is a loop without a delay --
+// delayed reads (DRead) depend on nothing within a tick.  Programs without feedback are left untouched, programs whose
+// feedbacks were split canonically keep their order (their forward references are never read).
+// Returns false when a dtype guess was wrong (fwd_guess is updated; the caller lowers again).
+bool resolve_forward_references(Builder& b, Vals& outs, std::vector<Dtype>& fwd_guess) {
+    const size_t nf = b.fwd_nodes.size();
+    if (nf == 0) return true;
+    auto resolve = [&](int id) {
+        size_t hops = 0;
+        while (id >= 0 && b.nodes[id].op == IrOp::Fwd) {
+            id = b.fwd_target[b.nodes[id].a];
+            if (id < 0) throw Error("a fed-back wire was never given a value (internal)");
+            if (++hops > nf) throw Error("feedback loop without a delay: a fed-back wire is fed by itself");
+        }
+        return id;
+    };
+    bool settled = true;
+    fwd_guess.resize(std::max(fwd_guess.size(), nf), Dtype::F32);
+    for (size_t k = 0; k < nf; ++k) {
+        const Dtype actual = b.nodes[resolve(b.fwd_nodes[k])].dtype;
+        if (b.nodes[b.fwd_nodes[k]].dtype != actual) { fwd_guess[k] = actual; settled = false; }
+    }
+    if (!settled) return false;
+
+    auto binary = [](IrOp op) { return op == IrOp::Add || op == IrOp::Sub || op == IrOp::Mul || op == IrOp::Div; };
+    bool used = false;                                       // is any forward reference actually read?
+    for (IrNode& n : b.nodes) {
+        if (n.op == IrOp::Neg || binary(n.op)) {
+            const int a = resolve(n.a);
+            used = used || a != n.a;
+            n.a = a;
+        }
+        if (binary(n.op)) {
+            const int c = resolve(n.b);
+            used = used || c != n.b;
+            n.b = c;
+        }
+    }
+    for (int& o : outs) { const int r = resolve(o); used = used || r != o; o = r; }
+    for (IrLine& l : b.lines) if (l.src >= 0) { const int r = resolve(l.src); used = used || r != l.src; l.src = r; }
+    if (!used) return true;
+
+    // depth-first post-order over the nodes in index order: the identity wherever the order already was topological
+    const int n = (int)b.nodes.size();
+    std::vector<int> order, where(n, -1);
+    std::vector<char> mark(n, 0);                            // 1 = on the stack, 2 = emitted
+    order.reserve(n);
+    std::vector<std::pair<int, int>> stack;
+    for (int root = 0; root < n; ++root) {
+        if (mark[root]) continue;
+        stack.push_back({root, 0});
+        mark[root] = 1;
+        while (!stack.empty()) {
+            auto& [id, next] = stack.back();
+            const IrNode& nd = b.nodes[id];
+            const int deps[2] = {(nd.op == IrOp::Neg || binary(nd.op)) ? nd.a : -1, binary(nd.op) ? nd.b : -1};
+            if (next < 2) {
+                const int d = deps[next++];
+                if (d < 0 || mark[d] == 2) continue;
+                if (mark[d] == 1)
+                    throw Error("feedback loop without a delay: a fed-back wire is used undelayed by the expression that "
+                                "produces it (put a _k[_n] somewhere in the loop)");
+                mark[d] = 1;
+                stack.push_back({d, 0});
+            } else {
+                mark[id] = 2;
+                where[id] = (int)order.size();
+                order.push_back(id);
+                stack.pop_back();
+            }
+        }
+    }
+    std::vector<IrNode> sorted;
+    sorted.reserve(n);
+    for (int id : order) {
+        IrNode nd = b.nodes[id];
+        if (nd.op == IrOp::Neg || binary(nd.op)) nd.a = where[nd.a];
+        if (binary(nd.op)) nd.b = where[nd.b];
+        sorted.push_back(nd);
+    }
+    b.nodes.swap(sorted);
+    for (int& o : outs) o = where[o];
+    for (IrLine& l : b.lines) if (l.src >= 0) l.src = where[l.src];
+    for (int& f : b.fwd_nodes) f = where[f];
+    b.memo.clear();                                          // (node ids changed; the rebuild below re-runs CSE)
+    return true;
+}
+
 }  // namespace
 
 bool Ir::all_f32() const {
@@ -235,7 +364,7 @@ bool Ir::all_f32() const {
 }
 
 std::string Ir::dump() const {
-    static const char* opn[] = {"in", "const", "param", "dread", "neg", "add", "sub", "mul", "div"};
+    static const char* opn[] = {"in", "const", "param", "dread", "neg", "add", "sub", "mul", "div", "fwd"};
     static const char* dtn[] = {"i32", "f32", "f64"};
     std::ostringstream os;
     os << "graph n_in=" << n_in << " n_out=" << n_out << " n_params=" << n_params
@@ -268,13 +397,20 @@ Ir lower(const Expr& canonical, const std::vector<Dtype>& in_dtypes, const Lower
         throw Error("lower(): expected " + std::to_string(n_in) + " input dtypes");
 
     Builder b;
-    b.cse = opt.cse;
-    Vals input;
-    for (int i = 0; i < n_in; ++i) input.push_back(b.add(IrNode{IrOp::In, in_dtypes[i], i, -1, 0}));
-    Lowering lw{b, in_dtypes};
-    Vals outs = lw.eval(canonical, input, Lines{});          // in_state = std::tuple<>{} (:1196)
-    for (int o : outs)
-        if (o == kBottom) throw Error("graph output is an unresolved fed-back wire");
+    Vals outs;
+    std::vector<Dtype> fwd_guess;                            // dtypes of the forward references, by creation order
+    for (int pass = 0;; ++pass) {
+        b = Builder();
+        b.cse = opt.cse;
+        Vals input;
+        for (int i = 0; i < n_in; ++i) input.push_back(b.add(IrNode{IrOp::In, in_dtypes[i], i, -1, 0}));
+        Lowering lw{b, in_dtypes, fwd_guess};
+        outs = lw.eval(canonical, input, Lines{});           // in_state = std::tuple<>{} (:1196)
+        for (int o : outs)
+            if (o == kBottom) throw Error("graph output is an unresolved fed-back wire");
+        if (resolve_forward_references(b, outs, fwd_guess)) break;
+        if (pass >= 4) throw Error("the types of the fed-back wires do not settle (internal)");
+    }
 
     // ---- line merging: lines fed by the same node hold the same history --------------------
     std::vector<int> line_map(b.lines.size());
@@ -424,6 +560,7 @@ inline void run_tick(const Ir& ir, float* state, const float* params, Cell* v) {
                              [](float a, float b) { return a / b; }, [](double a, double b) { return a / b; },
                              [](int32_t a, int32_t b) { return b == 0 ? 0 : a / b; });
                 break;
+            case IrOp::Fwd: break;                       // never survives lower()
         }
     }
     // rotate_push_back (:130-148) for every line, after everything has been read

@@ -13,7 +13,8 @@
 
 namespace zg {
 
-enum class IrOp : uint8_t { In, Const, Param, DRead, Neg, Add, Sub, Mul, Div };
+enum class IrOp : uint8_t { In, Const, Param, DRead, Neg, Add, Sub, Mul, Div,
+                            Fwd /* lower() only: current value of a fed-back wire, bound when the loop closes */ };
 
 struct IrNode {
     IrOp op;
