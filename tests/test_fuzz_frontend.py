@@ -100,7 +100,9 @@ def test_random_graphs_product_equals_oracle(zg, seed):
         assert g.n_out == n_tick, (expr, g.n_out, n_tick)           # output_arity: surplus inputs pass through a sequence)
         assert zg.delays(expr) == fo.max_input_delays(e), expr
         assert zg.delays(expr, minimum=True) == fo.min_input_delays(e), expr
-        assert zg.canonical(expr) == zg.canonical(str(fo.make_canonical(e))), expr
+        c = zg.canonical(expr)
+        assert c == zg.canonical(str(fo.make_canonical(e))), expr
+        assert zg.canonical(c) == c, expr                                     # printed trees read back as themselves
         try:
             want_t = fo.result_type(e, [fo.F32] * n_in)
         except TypeError:
