@@ -633,10 +633,12 @@ class Oracle:
         self.walker = _Walker(self.backend)
 
     def tick(self, *xs, dtype=F32):
-        """xs: n_in scalars or arrays[C].  Returns list of (dtype, array[C])."""
+        """xs: n_in scalars or arrays[C]; dtype: the C++ type of the arguments (one for all, or one per argument).
+        Returns list of (dtype, array[C])."""
         if len(xs) != self.n_in:
             raise ValueError("wrong number of inputs")
-        inp = [(dtype, np.broadcast_to(np.asarray(x, _NP[dtype]), (self.channels,)).copy()) for x in xs]
+        dts = [dtype] * len(xs) if isinstance(dtype, int) else list(dtype)
+        inp = [(d, np.broadcast_to(np.asarray(x, _NP[d]), (self.channels,)).copy()) for x, d in zip(xs, dts)]
         res = _flatten([self.walker.eval(self.canonical, inp, ([], self.state_tree))])   # :1193-1201
         self.backend.end_tick()
         return res

@@ -138,7 +138,8 @@ class Netlist:
 
     def tick(self, *xs, dtype=fo.F32):
         self.memo = {}
-        self.cur = [(dtype, _NP[dtype](x)) for x in xs]
+        dts = [dtype] * len(xs) if isinstance(dtype, int) else list(dtype)
+        self.cur = [(d, _NP[d](x)) for x, d in zip(xs, dts)]
         outs = [self._value(w) for w in self.outputs]
         pushed = [np.float32(self._value(w)[1]) for w in self.delay_sources]   # every line is read before it is pushed
         for w, v in zip(self.delay_sources, pushed):

@@ -80,12 +80,12 @@ def test_random_graphs_product_equals_oracle(zg, seed):
             # references and accepts whatever has a delay in every loop; the netlist evaluator is the only other opinion
             assert any(m in oerr for m in ("cannot be split", "fed-back wire", "not a single value")), f"{expr}: {oerr}"
             net = nl.Netlist(expr)
-            dt = rng.choice([fo.I32, fo.F32, fo.F64])
+            dt = [rng.choice([fo.I32, fo.F32, fo.F64]) for _ in range(g.n_in)]
             v = g.voice()
             for t in range(6):
                 xs = [float(rng.randint(-3, 3)) for _ in range(g.n_in)]
                 res = net.tick(*xs, dtype=dt)
-                assert tuple(float(y) for y in v.tick(*xs, dtypes=[dt] * g.n_in)) == tuple(float(x) for _, x in res), expr
+                assert tuple(float(y) for y in v.tick(*xs, dtypes=dt)) == tuple(float(x) for _, x in res), expr
                 assert v.out_dtypes == tuple(d for d, _ in res), expr
             extended += 1
             continue
@@ -112,7 +112,7 @@ def test_random_graphs_product_equals_oracle(zg, seed):
             assert zg.result_types(expr, [zg.F32] * n_in) == want_t, expr
         v = g.voice()
         net = nl.Netlist(expr)
-        dt = rng.choice([fo.I32, fo.F32, fo.F64])             # the C++ type of the arguments: int stays int (:769-772)
+        dt = [rng.choice([fo.I32, fo.F32, fo.F64]) for _ in range(n_in)]   # the C++ type of each argument: int stays int (:769-772)
         for t in range(6):
             xs = [float(rng.randint(-3, 3)) for _ in range(n_in)]
             res = o.tick(*xs, dtype=dt)
@@ -120,7 +120,7 @@ def test_random_graphs_product_equals_oracle(zg, seed):
                 #  the plain reading of the expression -- its "thinning" bug, TODO.md:11 -- and product and oracle follow it)
                 assert [(d, float(x)) for d, x in net.tick(*xs, dtype=dt)] == [(d, float(x[0])) for d, x in res], expr
             want = tuple(float(val[0]) for _, val in res)
-            got = tuple(float(y) for y in v.tick(*xs, dtypes=[dt] * n_in))
+            got = tuple(float(y) for y in v.tick(*xs, dtypes=dt))
             assert got == want, f"{expr} tick {t}: {got} != {want}"
             assert v.out_dtypes == tuple(d for d, _ in res), f"{expr}: result types {v.out_dtypes} != {[d for d, _ in res]}"
         checked += 1
