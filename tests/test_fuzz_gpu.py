@@ -19,7 +19,7 @@ GRAPHS_PER_SEED = 6
 
 def _valid_f32_graph(zg, rng, want_feedback):
     for _ in range(5000):
-        expr = _gen(rng, rng.randint(3, 5), rng.randint(1, 3), consts=["0.5f", "0.25f", "-0.75f", "0x1p-1f", "1.5f", "-1.0f"])
+        expr = _gen(rng, rng.randint(3, 5), rng.randint(1, 3), consts=["0.5f", "0.25f", "-0.75f", "0x1p-1f", "1.5f", "-1.0f"], ops="+-*")
         if ("~" in expr) != want_feedback or (not want_feedback and "|" not in expr and "," not in expr):
             continue                                 # half the graphs recurse, the others at least route wires
         try:
