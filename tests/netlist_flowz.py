@@ -39,7 +39,7 @@ class Netlist:
         self.params = list(params)
         self.inputs = [Wire("in", k=k) for k in range(self.n_in)]
         self.delay_sources = []
-        self.outputs = self._walk(self.tree, list(self.inputs))
+        self.outputs = self._walk(self.tree, list(self.inputs), list(self.inputs))
         self.memo = {}
 
     # ---- netlist construction: routing only, nothing is evaluated --------------------------------------------
@@ -48,48 +48,57 @@ class Netlist:
             self.delay_sources.append(src)
         return Wire("delay", src=src, n=n)
 
-    def _scalar(self, e, ins):
-        out = self._walk(e, ins)
+    def _scalar(self, e, ins, dins):
+        out = self._walk(e, ins, dins)
         if len(out) != 1:
             raise ValueError("arithmetic on a multi-wire sub-expression")
         return out[0]
 
-    def _walk(self, e, ins):
+    def _walk(self, e, ins, dins):
+        """ins: the wires whose CURRENT values the placeholders of e see; dins: the wires whose HISTORY `_k[_n]` reads.
+        The two lists name the same wires except where the reference lets them drift apart: a sequence hands its right
+        side the left side's actual results plus the remaining inputs (flowz.hpp:984), but the delay lines of
+        output_arity(left) results plus the remaining inputs' lines (:985) -- they differ when the left side passes
+        surplus inputs through (:996-999)."""
         o = e.op
         if o == "ph":
             return [ins[e.k - 1]]
         if o == "delay":
-            return [self._delay(ins[e.k - 1], e.n)]
+            if e.k > len(dins) or dins[e.k - 1] is None:
+                raise ValueError("no delay line for this wire")
+            return [self._delay(dins[e.k - 1], e.n)]
         if o == "const":
             return [Wire("const", dtype=e.dtype, value=e.value)]
         if o == "param":
             return [Wire("param", k=e.k)]
         if o == "neg":
-            return [Wire("neg", a=self._scalar(e.ch[0], ins))]
+            return [Wire("neg", a=self._scalar(e.ch[0], ins, dins))]
         if o in ("add", "sub", "mul", "div"):
-            return [Wire("op", op=o, a=self._scalar(e.ch[0], ins), b=self._scalar(e.ch[1], ins))]
+            return [Wire("op", op=o, a=self._scalar(e.ch[0], ins, dins), b=self._scalar(e.ch[1], ins, dins))]
         l, r = e.ch[0], (e.ch[1] if len(e.ch) > 1 else None)
         if o == "chan":
-            return self._walk(l, ins) + self._walk(r, ins)
+            return self._walk(l, ins, dins) + self._walk(r, ins, dins)
         if o == "par":
             n = fo.input_arity(l)
-            return self._walk(l, ins[:n]) + self._walk(r, ins[n:])
+            return self._walk(l, ins[:n], dins[:n]) + self._walk(r, ins[n:], dins[n:])
         if o == "seq":
             n_l, n_r = fo.input_arity(l), fo.input_arity(r)
-            lo = self._walk(l, ins[:n_l])
-            ro = self._walk(r, lo + ins[n_l:])
+            lo = self._walk(l, ins[:n_l], dins[:n_l])
+            node = (lo + [None] * fo.output_arity(l))[:fo.output_arity(l)]
+            ro = self._walk(r, lo + ins[n_l:], node + dins[n_l:])
             return ro + lo[n_r:] + ins[n_l + len(lo):]
         if o == "fb":
             cells = [Wire("cell", target=None) for _ in range(fo.output_arity(l))]
-            outs = self._walk(l, cells + ins)
+            outs = self._walk(l, cells + ins, cells + dins)
             for c, w in zip(cells, outs):
                 c.target = w
             return outs
         if o == "bfb":
             n_l, out_l, out_r = fo.input_arity(l), fo.output_arity(l), fo.output_arity(r)
             cells = [Wire("cell", target=None) for _ in range(out_l)]
-            res = self._walk(r, cells + ins)
-            fed = self._walk(l, res + ins[:max(n_l - out_r, 0)])
+            res = self._walk(r, cells + ins, cells + dins)
+            k = max(n_l - out_r, 0)
+            fed = self._walk(l, res + ins[:k], [None] * out_l + dins[:k])
             for c, w in zip(cells, fed):
                 c.target = w
             return res
