@@ -62,6 +62,7 @@ def _graphs(zg):
     rng = random.Random(4242)
     consts = ["0.5f", "0.25f", "-0.75f", "0x1p-1f", "1.5f", "-1.0f"]
     out = ["~(_2 + 0.9f*_1[_1])", fo.osc_lp_expr(), fo.poly_voice_expr(), fo.biquad_cascade(3),
+           fo.biquad_cascade_params(2), "$0*_1 + $1*_1[_2] |= ~(_2 + $2*_1[_1])",
            "~~( _1 + _2 + 1.0f |= _1[_1] )", "~( (0.5f*_1 + _2) |= ~(_1 + _2 |= _1[_1]) )", "~((_1[_2] |= _2) | (_1 - _2))"]
     while len(out) < 60:
         e = _gen(rng, rng.randint(2, 5), rng.randint(1, 3), consts=consts)
@@ -94,15 +95,15 @@ def test_generated_tick_functors_on_the_host(zg, tmp_path):
         x = [np.ascontiguousarray(fo.noise(1, T, seed=50 + 7 * i + k)[0]) for k in range(g.n_in)]
         y = [np.zeros(T, np.float32) for _ in range(g.n_out)]
         state = np.zeros(max(g.n_state, 1), np.float32)
-        params = np.zeros(1, np.float32)
+        params = (np.random.default_rng(i).uniform(-0.6, 0.6, max(g.n_params, 1))).astype(np.float32)   # std::ref terminals
         for t0, n in ((0, 41), (41, T - 41)):                        # two blocks: the state array carries over
             ins = (P * max(g.n_in, 1))(*[a[t0:].ctypes.data_as(P) for a in x])
             outs = (P * g.n_out)(*[a[t0:].ctypes.data_as(P) for a in y])
             lib.zg_host_run(i, ins, outs, ctypes.c_long(n), state.ctypes.data_as(P), params.ctypes.data_as(P))
         try:
-            want = [w[0] for w in fo.COracle(e, 1).process([a[None, :] for a in x])]
+            want = [w[0] for w in fo.COracle(e, 1, params=params).process([a[None, :] for a in x])]
         except ValueError:                                           # beyond the reference: the netlist is the checker
-            net = nl.Netlist(e)
+            net = nl.Netlist(e, params=params)
             ticks = [net.tick(*[float(a[t]) for a in x]) for t in range(T)]
             want = [np.array([tk[o][1] for tk in ticks], np.float32) for o in range(g.n_out)]
             extended += 1
