@@ -120,6 +120,22 @@ def test_feedbacks_the_reference_cannot_compile(zg):
         fo.Oracle("~(((_3 * _1) + (_2 - _3[_1])) |= ((1.5 - _2) * (_3[_2] + _3)))").tick(1.0, 2.0, 3.0, 4.0)
 
 
+def test_callable_arity_is_the_user_expressions(zg):
+    # compile() takes arity_t from the expression as written (flowz.hpp:1238); the canonical tree may count more inputs
+    # (the split can move a sub-expression with unused inputs into the promise part) without anything reading them.
+    # Found by fuzzing: the product used to insist on the canonical tree's count.
+    for e in ["~((_1 |= _3) , (_2 / _2[_2]))", "~((_1 |= _2) * (((_1[_3] * _2) - (_2[_2] * _2)) * 2))",
+              "~((_1 | _2) |= (((_1[_1] |= $0) |= (_2 |= _1[_2])) |= _1))"]:
+        g, o = zg.compile(e), fo.Oracle(e, params=[0.5])
+        assert g.n_in == zg.arity(e)[0] == fo.input_arity(fo.parse(e))
+        v = g.voice()
+        if g.n_params:
+            v.set_param(0, 0.5)
+        for t in range(6):
+            xs = [float(t + 1 + k) for k in range(g.n_in)]
+            assert v(*xs) == tuple(float(x[0]) for _, x in o.tick(*xs))
+
+
 def test_expression_depth_is_bounded_not_the_stack(zg):
     # every analysis recurses over the tree: trees up to 1536 levels are accepted (a 512-tap FIR sum is 513 high), deeper
     # text is an error, never a stack overflow; whatever is accepted prints to text that parses back to the same tree

@@ -46,7 +46,7 @@ struct LowerOptions {
     bool cse = true;               // common sub-expression elimination (bit-exact, same ops)
 };
 
-// `canonical` must come from canonical_with_front().  in_dtypes.size() must equal its input arity.
+// `canonical` must come from canonical_with_front(); in_dtypes holds one dtype per input of the USER expression.
 Ir lower(const Expr& canonical, const std::vector<Dtype>& in_dtypes, const LowerOptions& opt = {});
 
 // ---- long delay lines on the device (zg_ir.cpp: split_long_lines) -----------------------------------------
