@@ -23,6 +23,10 @@ the biquad graphs the reference's tests hold no numbers; the oracle is instead c
 against the reference's own hand-written biquad lambdas (test/benchmark.cpp:35-126), compiled from
 the reference sources where they lie into oracle/_ref (oracle/Makefile).
 
+Where the reference's behaviour is undefined (a delayed read its state sizing does not cover, :950-958 with :1043-1047) the
+oracle raises instead of reading a neighbouring slot; graphs the reference cannot compile (unsplittable feedbacks) raise too:
+for those the product is checked against tests/netlist_flowz.py.
+
 Reference map (file:line are /root/reference/flowz/flowz.hpp unless noted):
   grammar                        :68-102
   input_arity / output_arity     :162-246
@@ -37,6 +41,7 @@ Reference map (file:line are /root/reference/flowz/flowz.hpp unless noted):
   parallel                       :1076-1101
   rotate_push_back               :130-148
   compile / stateful_lambda      :1181-1249
+  ResultType                     :515-644  (result_type(), pinned by test/tests.cpp:182-232)
   tuple_take / tuple_drop        flowz/tuple_tools.hpp:78-160
 """
 from __future__ import annotations

@@ -8,6 +8,9 @@
 // with *symbolic* wire values, following the routing rules of the reference evaluators
 // (sequence :960-1001, binary_feedback :1031-1074, parallel :1076-1101, channel :765-768,
 // place_the_holder/place_delay :941-958) and records the result as straight-line SSA.
+// A unary feedback that canonical_with_front() kept whole (a graph the reference cannot compile) is walked with forward
+// references for its fed-back wires; they are bound when the loop closes and the SSA is re-sorted topologically, so the
+// result is the same kind of program -- or an Error if a loop has no delay in it.
 #pragma once
 #include "zg_expr.hpp"
 
