@@ -75,6 +75,17 @@ int main(int argc, char** argv) {
         CHECK(same_expr((0.5f * _1)[-3], 0.5f * _1 |= _1[_3]));
     }
 
+    // ---- nested feedback, which the reference cannot split (TODO.md:11-27, disabled test/tests.cpp:59):
+    //      s[t] = y + y + 1 with y = s[t-1]  ->  y = 0, 1, 3, 7, 15 ----
+    {
+        auto nested = compile(~~(_1 + _2 + 1 |= _1[_1]));
+        const float want[5] = {0.f, 1.f, 3.f, 7.f, 15.f};
+        for (int t = 0; t < 5; ++t) CHECK(std::get<0>(nested()) == want[t]);
+        bool threw = false;
+        try { (void)compile(~(_1 + _2)); } catch (const std::exception& e) { threw = std::strstr(e.what(), "without a delay") != nullptr; }
+        CHECK(threw);
+    }
+
     // ---- ResultType (flowz.hpp:515-644), the reference's test_result_type_transform (test/tests.cpp:182-232) in the
     //      reference's spelling; `expect_type(T{}, expr)` becomes r(expr, x).is<T>() because types are run-time data ----
     {
