@@ -109,6 +109,13 @@ const char* zg_graph_dump(const zg_graph* g);
  *   "host-only"       int / double terminals: zg_voice_tick only
  * Pure host analysis (no device).                                                              */
 int zg_graph_kernel_class(const zg_graph* g, char* buf, size_t capacity);
+/* Is one tick a linear map of (inputs, delay-line state) -> (outputs, new state)?  Literals and $k parameters count as
+ * coefficients.  ZG_LINEAR: superposition holds (every biquad / FIR / comb / oscillator graph of the reference's
+ * benchmarks); ZG_AFFINE: linear plus constant terms (`_1 + 1`); ZG_NONLINEAR: a product or quotient of two signals.
+ * Pure host analysis on the tick program -- what a time-parallel (scan) evaluation of few long channels would have
+ * to ask first (the state-space idea is sketched in experimental_steps/tuprix.cpp:239-254). */
+typedef enum zg_linearity { ZG_NONLINEAR = 0, ZG_AFFINE = 1, ZG_LINEAR = 2 } zg_linearity;
+int zg_graph_linearity(const zg_graph* g, int* kind);
 
 /* ---- host voice: stateful_lambda (flowz.hpp:1181-1230) ----------------------------------------
  * zg_voice_tick is operator()(args...) for exactly n_in arguments; in_dtypes[i] says what C++

@@ -65,3 +65,50 @@ def test_package_workloads_equal_the_oracles_copies(zg):
         assert wl.fir_expr(wl.fir_taps(n)) == fo.fir_expr(fo.fir_taps(n))
     for f in (440.0, 3520.0, 440.0 * 1.37):
         assert wl.rbj_lowpass(f) == tuple(float(v) for v in fo.rbj_lowpass(f))
+
+
+def test_linearity_of_the_tick_program(zg):
+    import flowz_oracle as fo
+    L, A, N = zg.LINEAR, zg.AFFINE, zg.NONLINEAR
+    cases = [(fo.biquad_cascade(4), L), (fo.biquad_cascade_params(2), L), (fo.osc_lp_expr(), L), (fo.poly_voice_expr(), L),
+             (fo.fir_expr(fo.fir_taps(16)), L), ("~(_2 + 0.5f*_1[_441]) |= (_1 + 0.25f*_1[_1000])", L), ("_1/2", L),
+             ("~(_2 + $0*_1[_1])", L), ("_1 + 1", A), ("0*_1 + 3", A), ("~(_2 + 0.5f*_1[_1] + 0.125f)", A),
+             ("_1*_1", N), ("_1*_1[_1]", N), ("_1/_2", N), ("~(_2 + _1[_1]*_1[_2])", N)]
+    for expr, want in cases:
+        assert zg.compile(expr).linearity() == want, expr
+
+
+def test_linear_graphs_obey_superposition(zg):
+    """Property behind the label: for every random graph reported LINEAR, tick(a + b) == tick(a) + tick(b) with the
+    state carried along, exactly (small integers and dyadic constants: no rounding anywhere); AFFINE graphs obey it
+    after subtracting the zero-input response; and some NONLINEAR graph must break it."""
+    import random
+    from test_fuzz_frontend import _gen
+    rng = random.Random(77)
+    consts = ["2", "3", "0.5f", "0.25f", "-1", "0x1p-1f", "-0.75f"]
+    seen = {zg.LINEAR: 0, zg.AFFINE: 0, zg.NONLINEAR: 0}
+    broke = 0
+    for _ in range(400):
+        e = _gen(rng, rng.randint(1, 4), rng.randint(1, 3), consts=consts, ops="+-*")
+        try:
+            g = zg.compile(e)
+        except zg.ZgError:
+            continue
+        if g.n_in == 0:
+            continue
+        kind = g.linearity()
+        seen[kind] += 1
+        va, vb, vs, v0 = g.voice(), g.voice(), g.voice(), g.voice()
+        ok = True
+        for t in range(5):
+            a = [float(rng.randint(-3, 3)) for _ in range(g.n_in)]
+            b = [float(rng.randint(-3, 3)) for _ in range(g.n_in)]
+            ya, yb, ys, y0 = va(*a), vb(*b), vs(*[p + q for p, q in zip(a, b)]), v0(*([0.0] * g.n_in))
+            ok = ok and all(s - z == (p - z) + (q - z) for s, p, q, z in zip(ys, ya, yb, y0))
+            if kind == zg.LINEAR:
+                assert all(z == 0 for z in y0), e
+        if kind != zg.NONLINEAR:
+            assert ok, e
+        else:
+            broke += not ok
+    assert min(seen.values()) >= 10 and broke >= 5, (seen, broke)

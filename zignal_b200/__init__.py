@@ -27,6 +27,7 @@ PLANAR, INTERLEAVED = 0, 1
 IN_BUFFER, IN_DIRAC, IN_ZERO = 0, 1, 2
 MAX_WIRES = 8
 I32, F32, F64, BF16 = 0, 1, 2, 3            # zg_dtype (BF16: sample storage only)
+NONLINEAR, AFFINE, LINEAR = 0, 1, 2          # zg_linearity
 C64, C128, TYPE_OPEN = 4, 5, -1             # complex<float> / <double> and the open `absorber` type: result_types() only
 
 
@@ -73,6 +74,7 @@ def _load() -> C.CDLL:
         "zg_graph_canonical": (cp, [vp]),
         "zg_graph_dump": (cp, [vp]),
         "zg_graph_kernel_class": (ci, [vp, C.c_char_p, sz]),
+        "zg_graph_linearity": (ci, [vp, P(ci)]),
         "zg_voice_create": (ci, [vp, P(vp)]),
         "zg_voice_clone": (ci, [vp, P(vp)]),
         "zg_voice_destroy": (None, [vp]),
@@ -101,7 +103,7 @@ def _load() -> C.CDLL:
 
 lib = _load()
 EXPORTED = ["zg_last_error", "zg_version", "zg_expr_arity", "zg_expr_delays", "zg_expr_canonical", "zg_expr_result_types",
-            "zg_graph_compile", "zg_graph_destroy", "zg_graph_get_info", "zg_graph_canonical", "zg_graph_dump", "zg_graph_kernel_class",
+            "zg_graph_compile", "zg_graph_destroy", "zg_graph_get_info", "zg_graph_canonical", "zg_graph_dump", "zg_graph_kernel_class", "zg_graph_linearity",
             "zg_voice_create", "zg_voice_clone", "zg_voice_destroy", "zg_voice_tick", "zg_voice_set_param",
             "zg_voice_state", "zg_plan_opts_default", "zg_graph_kernel_compile", "zg_plan_create",
             "zg_plan_destroy", "zg_plan_get_info", "zg_process", "zg_process_host", "zg_state_reset",
@@ -179,6 +181,12 @@ class Graph:
         buf = C.create_string_buffer(64)
         _check(lib.zg_graph_kernel_class(self._h, buf, len(buf)))
         return buf.value.decode()
+
+    def linearity(self) -> int:
+        """NONLINEAR (0) | AFFINE (1) | LINEAR (2): is one tick a linear map of inputs and state (zg_graph_linearity)."""
+        k = C.c_int()
+        _check(lib.zg_graph_linearity(self._h, C.byref(k)))
+        return k.value
 
     def voice(self) -> "Voice":
         return Voice(self)

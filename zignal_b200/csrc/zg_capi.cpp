@@ -169,6 +169,45 @@ int zg_graph_get_info(const zg_graph* g, zg_graph_info* info) {
 const char* zg_graph_canonical(const zg_graph* g) { return g ? g->canonical_str.c_str() : ""; }
 const char* zg_graph_dump(const zg_graph* g) { return g ? g->dump_str.c_str() : ""; }
 
+// Linearity of the tick program in its signals (inputs and delay-line reads); literals and $k parameters are
+// coefficients.  Every node is CONST (no signal in it), LIN (homogeneous), AFF (linear plus a constant) or NONLIN
+// (a product or quotient of two signals); the graph is as good as the worst value it returns or pushes into a line.
+int zg_graph_linearity(const zg_graph* g, int* kind) {
+    if (!g || !kind) return fail(ZG_ERR_ARG, "NULL argument");
+    enum { CONST = 0, LIN = 1, AFF = 2, NONLIN = 3 };
+    const Ir& ir = g->ir_f32;
+    std::vector<int> cls(ir.nodes.size(), CONST);
+    for (size_t i = 0; i < ir.nodes.size(); ++i) {
+        const IrNode& n = ir.nodes[i];
+        switch (n.op) {
+            case IrOp::In: case IrOp::DRead: cls[i] = LIN; break;
+            case IrOp::Const: case IrOp::Param: cls[i] = CONST; break;
+            case IrOp::Neg: cls[i] = cls[n.a]; break;
+            case IrOp::Add: case IrOp::Sub: {
+                const int a = cls[n.a], b = cls[n.b];
+                cls[i] = (a == NONLIN || b == NONLIN) ? NONLIN : a == b && a != AFF ? a : (a == CONST && b == CONST) ? CONST : AFF;
+                break;
+            }
+            case IrOp::Mul: {
+                const int a = cls[n.a], b = cls[n.b];
+                cls[i] = a == CONST ? b : b == CONST ? a : NONLIN;
+                break;
+            }
+            case IrOp::Div: cls[i] = cls[n.b] == CONST ? cls[n.a] : NONLIN; break;
+            default: cls[i] = NONLIN; break;
+        }
+    }
+    int worst = LIN;
+    auto see = [&](int id) {
+        const int c = cls[id] == CONST ? (ir.nodes[id].op == IrOp::Const && ir.nodes[id].value == 0 ? LIN : AFF) : cls[id];
+        worst = std::max(worst, c);
+    };
+    for (int o : ir.outs) see(o);
+    for (const IrLine& l : ir.lines) see(l.src);
+    *kind = worst == NONLIN ? ZG_NONLINEAR : worst == AFF ? ZG_AFFINE : ZG_LINEAR;
+    return ZG_OK;
+}
+
 int zg_graph_kernel_class(const zg_graph* g, char* buf, size_t capacity) {
     if (!g || !buf || capacity == 0) return fail(ZG_ERR_ARG, "NULL argument");
     std::string s;
