@@ -24,6 +24,8 @@ int main() {
         zg_graph_info gi;
         zg_graph_get_info(g, &gi);
         zg_graph_kernel_class(g, buf, sizeof buf);
+        int lin = 0;
+        zg_graph_linearity(g, &lin);
         (void)zg_graph_dump(g);
         zg_voice* v = nullptr;
         if (zg_voice_create(g, &v) == ZG_OK) {
