@@ -112,3 +112,33 @@ def test_linear_graphs_obey_superposition(zg):
         else:
             broke += not ok
     assert min(seen.values()) >= 10 and broke >= 5, (seen, broke)
+
+
+def test_state_space_of_linear_graphs(zg):
+    """state' = A state + B x, y = C state + D x read off the tick program reproduces the ticks (float64 recursion against
+    the fp32 host voice: agreement to what fp32 rounding noise allows on these recursions -- the oscillator is marginally
+    stable, the 440 Hz section has a noise gain of ~40), and the poles of the benchmark biquad are where the RBJ design puts them."""
+    import flowz_oracle as fo
+    rng = np.random.default_rng(5)
+    for expr, params in [(fo.biquad_cascade(4), ()), (fo.osc_lp_expr(), ()), ("~(_2 + $0*_1[_1]) |= _1 - 0.5f*_1[_3]", (0.75,)),
+                         ("(_1 + _2 , _1 - _2[_1]) |= (~(_2 + 0.5f*_1[_1]) | (_1 - 0.25f*_1[_2]))", ())]:
+        g = zg.compile(expr)
+        A, B, Cm, D = g.state_space(params)
+        assert A.shape == (g.n_state, g.n_state) and D.shape == (g.n_out, g.n_in)
+        v = g.voice()
+        for k, p in enumerate(params):
+            v.set_param(k, p)
+        x, peak = np.zeros(g.n_state), 0.0
+        for t in range(200):
+            u = rng.uniform(-1, 1, g.n_in).astype(np.float32)
+            y = np.array(v.tick(*[float(a) for a in u], dtypes=[zg.F32] * g.n_in))
+            want = Cm @ x + D @ u
+            peak = max(peak, float(np.abs(want).max()))
+            assert np.allclose(y, want, rtol=0, atol=2e-3 * max(peak, 1.0)), (expr, t, y, want)
+            x = A @ x + B @ u
+    # 4 x RBJ low-pass: every section contributes a conjugate pole pair inside the unit circle (plus the zeros of the shift rows)
+    A = zg.compile(fo.biquad_cascade(4)).state_space()[0]
+    poles = np.linalg.eigvals(A)
+    assert np.abs(poles).max() < 1.0 and (np.abs(poles) > 0.5).sum() == 8
+    with pytest.raises(ValueError):
+        zg.compile("_1*_1").state_space()

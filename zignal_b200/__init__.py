@@ -188,6 +188,33 @@ class Graph:
         _check(lib.zg_graph_linearity(self._h, C.byref(k)))
         return k.value
 
+    def state_space(self, params: Sequence[float] = ()):
+        """(A, B, C, D) of a LINEAR graph, float64 [n_state, n_state], [n_state, n_in], [n_out, n_state], [n_out, n_in]:
+        state' = A state + B x, y = C state + D x, with the state in zg_state_get order.  Read off the host tick by
+        probing it with unit vectors (exact: every entry is one coefficient path of the tick program).  What a
+        time-parallel evaluation of few, long channels would scan over."""
+        import numpy as np
+        if self.linearity() != LINEAR:
+            raise ValueError("state_space() needs a LINEAR graph (zg_graph_linearity)")
+        ns, ni, no = self.n_state, self.n_in, self.n_out
+        A, B = np.zeros((ns, ns)), np.zeros((ns, ni))
+        Cm, D = np.zeros((no, ns)), np.zeros((no, ni))
+        v = Voice(self)
+        for k, p in enumerate(params):
+            v.set_param(k, float(p))
+        p_state, n = C.POINTER(C.c_float)(), C.c_int()
+        _check(lib.zg_voice_state(v._h, C.byref(p_state), C.byref(n)))
+        for j in range(ns + ni):
+            for i in range(ns):
+                p_state[i] = 1.0 if i == j else 0.0
+            y = v.tick(*[1.0 if ns + i == j else 0.0 for i in range(ni)], dtypes=[F32] * ni)
+            col = [p_state[i] for i in range(ns)]
+            if j < ns:
+                A[:, j], Cm[:, j] = col, y
+            else:
+                B[:, j - ns], D[:, j - ns] = col, y
+        return A, B, Cm, D
+
     def voice(self) -> "Voice":
         return Voice(self)
 
