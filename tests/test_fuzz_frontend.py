@@ -14,7 +14,8 @@ import pytest
 import flowz_oracle as fo
 import netlist_flowz as nl
 
-CONSTS = ["2", "3", "0.5f", "0.25f", "1.5", "-1", "0x1p-1f", "-0.75f"]
+CONSTS = ["2", "3", "0.5f", "0.25f", "1.5", "-1", "0x1p-1f", "-0.75f", "$0", "$1"]
+PARAMS = [0.5, -0.25]                       # values of the std::ref terminals $0, $1
 
 
 def _gen(rng, depth, wires, scalar=False, consts=CONSTS, ops="+-*+-*/"):
@@ -58,11 +59,18 @@ def _product(zg, expr):
     return g, None
 
 
+def _voice(g):
+    v = g.voice()
+    for k in range(g.n_params):
+        v.set_param(k, PARAMS[k])
+    return v
+
+
 def _oracle(expr):
     try:
-        o = fo.Oracle(expr)
+        o = fo.Oracle(expr, params=PARAMS)
         n_in = fo.input_arity(fo.parse(expr))
-        res = fo.Oracle(expr).tick(*([0.0] * n_in))   # ill-formed operands only surface when the walk reaches them
+        res = fo.Oracle(expr, params=PARAMS).tick(*([0.0] * n_in))   # ill-formed operands only surface when the walk reaches them
         if any(r is fo.BOTTOM for r in res):          # the reference would hand back a bottom_type (flowz.hpp:1004)
             return None, "an output is a fed-back wire nothing ever assigns"
         return o, None
@@ -85,9 +93,9 @@ def test_random_graphs_product_equals_oracle(zg, seed):
             # current value of a fed-back wire (its bottom_type) -- the product resolves fed-back wires as forward
             # references and accepts whatever has a delay in every loop; the netlist evaluator is the only other opinion
             assert any(m in oerr for m in ("cannot be split", "fed-back wire", "not a single value")), f"{expr}: {oerr}"
-            net = nl.Netlist(expr)
+            net = nl.Netlist(expr, params=PARAMS)
             dt = [rng.choice([fo.I32, fo.F32, fo.F64]) for _ in range(g.n_in)]
-            v = g.voice()
+            v = _voice(g)
             for t in range(6):
                 xs = [float(rng.randint(-3, 3)) for _ in range(g.n_in)]
                 res = net.tick(*xs, dtype=dt)
@@ -102,7 +110,7 @@ def test_random_graphs_product_equals_oracle(zg, seed):
         e = fo.parse(expr)
         n_in, n_out = fo.input_arity(e), fo.output_arity(e)
         assert zg.arity(expr) == (n_in, n_out), expr
-        n_tick = len(fo.Oracle(expr).tick(*([0.0] * n_in)))         # what one tick returns (flowz.hpp:996-999 can exceed
+        n_tick = len(fo.Oracle(expr, params=PARAMS).tick(*([0.0] * n_in)))         # what one tick returns (flowz.hpp:996-999 can exceed
         assert g.n_out == n_tick, (expr, g.n_out, n_tick)           # output_arity: surplus inputs pass through a sequence)
         assert zg.delays(expr) == fo.max_input_delays(e), expr
         assert zg.delays(expr, minimum=True) == fo.min_input_delays(e), expr
@@ -116,8 +124,8 @@ def test_random_graphs_product_equals_oracle(zg, seed):
                 zg.result_types(expr, [zg.F32] * n_in)
         else:
             assert zg.result_types(expr, [zg.F32] * n_in) == want_t, expr
-        v = g.voice()
-        net = nl.Netlist(expr) if "~" not in expr else None
+        v = _voice(g)
+        net = nl.Netlist(expr, params=PARAMS) if "~" not in expr else None
         dt = [rng.choice([fo.I32, fo.F32, fo.F64]) for _ in range(n_in)]   # the C++ type of each argument: int stays int (:769-772)
         for t in range(6):
             xs = [float(rng.randint(-3, 3)) for _ in range(n_in)]
