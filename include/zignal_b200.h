@@ -116,6 +116,14 @@ int zg_graph_kernel_class(const zg_graph* g, char* buf, size_t capacity);
  * to ask first (the state-space idea is sketched in experimental_steps/tuprix.cpp:239-254). */
 typedef enum zg_linearity { ZG_NONLINEAR = 0, ZG_AFFINE = 1, ZG_LINEAR = 2 } zg_linearity;
 int zg_graph_linearity(const zg_graph* g, int* kind);
+/* The state matrix A of a LINEAR / AFFINE tick, state' = A state + B x + c, for one set of $k values: row-major
+ * [n_state][n_state] doubles in zg_state_get order, read off the tick program by unit-vector probes (every entry is
+ * one coefficient path of the tick).  n_params must be the graph's parameter count.  Host analysis.              */
+int zg_graph_state_matrix(const zg_graph* g, const float* params, int n_params, double* A, size_t capacity);
+/* How fast the tick forgets its state: *K = the smallest multiple of `step` (<= k_max) with |A^K|_inf <= tol, 0 if
+ * there is none (poles on or outside the unit circle).  ZG_TP_WARMUP below uses step = 4 boxes, k_max = 8192,
+ * tol = 2^-30 and the worst channel.                                                                              */
+int zg_graph_settling_time(const zg_graph* g, const float* params, int n_params, int step, int k_max, double tol, int* K);
 
 /* ---- host voice: stateful_lambda (flowz.hpp:1181-1230) ----------------------------------------
  * zg_voice_tick is operator()(args...) for exactly n_in arguments; in_dtypes[i] says what C++
@@ -147,6 +155,24 @@ typedef enum zg_input_kind {
     ZG_IN_ZERO = 2    /* all zeros; synthesised in the kernel                                   */
 } zg_input_kind;
 
+/* Few, long channels (BASELINE configs[1]: 4096 channels x 65 536 samples = 128 warps for 148 SMs): a LINEAR or
+ * AFFINE tick (zg_graph_linearity) is cut in time as well, one warp per (32 channels, time segment), in ZG_MODE_FAST --
+ * a time-parallel evaluation re-associates the arithmetic, so ZG_MODE_EXACT always stays serial per channel
+ * (flowz.hpp:1031-1074 evaluates the recurrence sample after sample; state-space reading: experimental_steps/
+ * tuprix.cpp:239-254).  Two forms:
+ *   ZG_TP_WARMUP    one launch.  Segment g starts K samples early from zero state and discards those outputs; K is
+ *                   derived from the parameter values (float64, every channel): the smallest multiple of 4 boxes with
+ *                   |A^K|_inf <= 2^-30, A = the tick's state matrix -- what is left of the true state after K ticks is
+ *                   below fp32 resolution.  8 + 4K/L bytes per sample.  Not in place; ZG_ERR_UNSUPPORTED if some
+ *                   channel does not forget within 8192 samples (poles on the unit circle: oscillators).
+ *   ZG_TP_TWO_PASS  any linear tick: pass 1 runs every segment from zero state and keeps its final state, a small
+ *                   kernel applies x <- A^L x + z along the boundaries, pass 2 runs every segment from its true
+ *                   state.  12 bytes per sample (the input is read twice).
+ *   ZG_TP_AUTO      warm-up form when there are too few channels to fill the GPU with one lane each, the block is long
+ *                   enough (segments >= 8 K) and K exists; else, for graphs without a section-parallel kernel, the
+ *                   two-pass form; else serial.          ZG_TP_OFF: never cut time.                              */
+typedef enum zg_time_parallel { ZG_TP_AUTO = 0, ZG_TP_OFF = 1, ZG_TP_WARMUP = 2, ZG_TP_TWO_PASS = 3 } zg_time_parallel;
+
 #define ZG_MAX_WIRES 8
 
 typedef struct zg_plan_opts {
@@ -163,7 +189,8 @@ typedef struct zg_plan_opts {
                              picks S when there are too few channels to fill the GPU with one lane each */
     int input_kind[ZG_MAX_WIRES];
     int force_jit;        /* 1 = never use the prebuilt biquad kernels (tests)                  */
-    int reserved[7];
+    int time_parallel;    /* zg_time_parallel (ZG_MODE_FAST only; ignored -- serial -- in ZG_MODE_EXACT when AUTO) */
+    int reserved[6];
 } zg_plan_opts;
 
 void zg_plan_opts_default(zg_plan_opts* o);
@@ -192,6 +219,10 @@ typedef struct zg_plan_info {
     int uniform_params;   /* 1 = all parameters are scalars and travel in the constant bank     */
     int boxes;            /* 4 KB boxes (32 channels x 32 samples) per wire per pipeline stage
                              (FIR kernel: boxes per time segment)                               */
+    int time_segments;    /* segments the last launch cut the block into (1 = serial in time)    */
+    int segment_samples;  /* L: samples per segment                                              */
+    int warmup_samples;   /* K of the warm-up form (0: serial or two-pass)                       */
+    int linearity;        /* zg_linearity of the tick                                            */
 } zg_plan_info;
 int zg_plan_get_info(const zg_plan* p, zg_plan_info* info);
 

@@ -8,7 +8,7 @@ OUT=${TMPDIR:-/tmp}/zg_sanitize
 mkdir -p "$OUT"
 R=$ROOT/zignal_b200/csrc
 g++ -std=c++17 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -ffp-contract=off -I"$ROOT/include" -I"$R" \
-    "$ROOT/tools/sanitize/host_abi_driver.cpp" "$R/zg_expr.cpp" "$R/zg_ir.cpp" "$R/zg_capi.cpp" "$R/zg_codegen.cpp" "$R/zg_match.cpp" \
+    "$ROOT/tools/sanitize/host_abi_driver.cpp" "$R/zg_expr.cpp" "$R/zg_ir.cpp" "$R/zg_capi.cpp" "$R/zg_codegen.cpp" "$R/zg_match.cpp" "$R/zg_scan.cpp" \
     -o "$OUT/harness"
 PYTHONPATH="$ROOT/tests:$ROOT/oracle:$ROOT/tests/golden:$ROOT" python - > "$OUT/exprs.txt" <<'PY'
 import random
@@ -30,6 +30,6 @@ ASAN_OPTIONS=detect_leaks=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 "$O
 
 # the same sources under ThreadSanitizer: one graph shared by 8 threads (host_abi_threads.cpp)
 g++ -std=c++17 -O1 -g -fsanitize=thread -ffp-contract=off -I"$ROOT/include" -I"$R" \
-    "$ROOT/tools/sanitize/host_abi_threads.cpp" "$R/zg_expr.cpp" "$R/zg_ir.cpp" "$R/zg_capi.cpp" "$R/zg_codegen.cpp" "$R/zg_match.cpp" \
+    "$ROOT/tools/sanitize/host_abi_threads.cpp" "$R/zg_expr.cpp" "$R/zg_ir.cpp" "$R/zg_capi.cpp" "$R/zg_codegen.cpp" "$R/zg_match.cpp" "$R/zg_scan.cpp" \
     -o "$OUT/tsan_harness" -lpthread
 "$OUT/tsan_harness"

@@ -25,6 +25,7 @@ I32, F32, F64 = 0, 1, 2
 MODE_EXACT, MODE_FAST = 0, 1
 PLANAR, INTERLEAVED = 0, 1
 IN_BUFFER, IN_DIRAC, IN_ZERO = 0, 1, 2
+TP_AUTO, TP_OFF, TP_WARMUP, TP_TWO_PASS = 0, 1, 2, 3     # zg_time_parallel
 MAX_WIRES = 8
 I32, F32, F64, BF16 = 0, 1, 2, 3            # zg_dtype (BF16: sample storage only)
 NONLINEAR, AFFINE, LINEAR = 0, 1, 2          # zg_linearity
@@ -44,14 +45,15 @@ class GraphInfo(C.Structure):
 class PlanOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("channels", C.c_int64), ("mode", C.c_int), ("layout", C.c_int),
                 ("io_dtype", C.c_int), ("lanes_per_channel", C.c_int), ("input_kind", C.c_int * MAX_WIRES),
-                ("force_jit", C.c_int), ("reserved", C.c_int * 7)]
+                ("force_jit", C.c_int), ("time_parallel", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class PlanInfo(C.Structure):
     _fields_ = [("kernel", C.c_char * 96), ("jit", C.c_int), ("lanes_per_channel", C.c_int),
                 ("host_chunks", C.c_int), ("regs_per_thread", C.c_int), ("smem_bytes", C.c_int),
                 ("launches", C.c_int), ("threads_per_cta", C.c_int), ("stages", C.c_int),
-                ("uniform_params", C.c_int), ("boxes", C.c_int)]
+                ("uniform_params", C.c_int), ("boxes", C.c_int), ("time_segments", C.c_int),
+                ("segment_samples", C.c_int), ("warmup_samples", C.c_int), ("linearity", C.c_int)]
 
 
 def _load() -> C.CDLL:
@@ -75,6 +77,8 @@ def _load() -> C.CDLL:
         "zg_graph_dump": (cp, [vp]),
         "zg_graph_kernel_class": (ci, [vp, C.c_char_p, sz]),
         "zg_graph_linearity": (ci, [vp, P(ci)]),
+        "zg_graph_state_matrix": (ci, [vp, P(C.c_float), ci, P(C.c_double), sz]),
+        "zg_graph_settling_time": (ci, [vp, P(C.c_float), ci, ci, ci, C.c_double, P(ci)]),
         "zg_voice_create": (ci, [vp, P(vp)]),
         "zg_voice_clone": (ci, [vp, P(vp)]),
         "zg_voice_destroy": (None, [vp]),
@@ -104,6 +108,7 @@ def _load() -> C.CDLL:
 lib = _load()
 EXPORTED = ["zg_last_error", "zg_version", "zg_expr_arity", "zg_expr_delays", "zg_expr_canonical", "zg_expr_result_types",
             "zg_graph_compile", "zg_graph_destroy", "zg_graph_get_info", "zg_graph_canonical", "zg_graph_dump", "zg_graph_kernel_class", "zg_graph_linearity",
+            "zg_graph_state_matrix", "zg_graph_settling_time",
             "zg_voice_create", "zg_voice_clone", "zg_voice_destroy", "zg_voice_tick", "zg_voice_set_param",
             "zg_voice_state", "zg_plan_opts_default", "zg_graph_kernel_compile", "zg_plan_create",
             "zg_plan_destroy", "zg_plan_get_info", "zg_process", "zg_process_host", "zg_state_reset",
@@ -215,6 +220,24 @@ class Graph:
                 B[:, j - ns], D[:, j - ns] = col, y
         return A, B, Cm, D
 
+    def state_matrix(self, params: Sequence[float] = ()):
+        """A of state' = A state + B x + c, float64 [n_state, n_state] (zg_graph_state_matrix): what the time-segmented
+        launches of few, long channels are planned with.  Same matrix as state_space()[0]; affine ticks allowed."""
+        import numpy as np
+        n = self.n_state
+        a = np.zeros((n, n), np.float64)
+        prm = (C.c_float * max(len(params), 1))(*[float(p) for p in params])
+        _check(lib.zg_graph_state_matrix(self._h, prm, len(params), a.ctypes.data_as(C.POINTER(C.c_double)), max(a.size, 1)))
+        return a
+
+    def settling_time(self, params: Sequence[float] = (), step: int = 128, k_max: int = 8192, tol: float = 2.0 ** -30) -> int:
+        """Smallest K = m * step <= k_max with |A^K|_inf <= tol, 0 if the tick does not forget its state that fast
+        (zg_graph_settling_time): the warm-up length of ZG_TP_WARMUP."""
+        k = C.c_int()
+        prm = (C.c_float * max(len(params), 1))(*[float(p) for p in params])
+        _check(lib.zg_graph_settling_time(self._h, prm, len(params), step, k_max, tol, C.byref(k)))
+        return k.value
+
     def voice(self) -> "Voice":
         return Voice(self)
 
@@ -285,11 +308,11 @@ class Voice:
 
 def _opts(channels: int, device: int = 0, mode: int = MODE_EXACT, layout: int = PLANAR,
           input_kind: Optional[Sequence[int]] = None, lanes_per_channel: int = 0, force_jit: bool = False,
-          io_dtype: int = 1) -> PlanOpts:
+          io_dtype: int = 1, time_parallel: int = 0) -> PlanOpts:
     o = PlanOpts()
     lib.zg_plan_opts_default(C.byref(o))
     o.device, o.channels, o.mode, o.layout, o.io_dtype = device, channels, mode, layout, io_dtype
-    o.lanes_per_channel, o.force_jit = lanes_per_channel, int(force_jit)
+    o.lanes_per_channel, o.force_jit, o.time_parallel = lanes_per_channel, int(force_jit), time_parallel
     for i, k in enumerate(input_kind or []):
         o.input_kind[i] = k
     return o
@@ -372,6 +395,9 @@ class Plan:
             if t.dtype != dt or not t.is_cuda or t.stride(1) != 1 or tuple(t.shape) != shape:
                 raise TypeError(f"buffers must be {dt} CUDA tensors of shape {shape} with unit inner stride")
         ld_in = ref.stride(0) if ref is not None else (shape[1] + 7) // 8 * 8
+        # zg_process takes one pitch for all inputs and one for all outputs
+        if any(t is not None and t.stride(0) != ld_in for t in ins) or any(t.stride(0) != outputs[0].stride(0) for t in outputs):
+            raise TypeError("all input buffers must share one row pitch, and all output buffers one row pitch")
         in_ptrs = [t.data_ptr() if t is not None else None for t in ins]
         out_ptrs = [t.data_ptr() for t in outputs]
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -395,6 +421,14 @@ class Plan:
                 outputs = [torch.empty(shape, dtype=torch.bfloat16) for _ in range(self.graph.n_out)]
         elif outputs is None:
             outputs = [np.empty(shape, np.float32) for _ in range(self.graph.n_out)]
+
+        for t in [t for t in ins if t is not None] + list(outputs):
+            is_torch = hasattr(t, "data_ptr")
+            ok = tuple(t.shape) == shape and (t.is_contiguous() if is_torch else t.flags["C_CONTIGUOUS"])
+            if not bf16:
+                ok = ok and str(t.dtype).endswith("float32")
+            if not ok:
+                raise TypeError(f"host buffers must be contiguous {'bfloat16' if bf16 else 'float32'} arrays of shape {shape}")
 
         def ptr(a):
             return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data

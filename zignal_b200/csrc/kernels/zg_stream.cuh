@@ -53,6 +53,8 @@ struct StreamArgs {
     int boxes;                      // NB: boxes (of 32 samples) per pipeline stage
     int stages;                     // S >= 2
     int flags;                      // bit 0: in_map[1] / out_map[1] hold the 3-D whole-tile maps (K1b)
+                                    // bit 1: late refill; bits 2-3: L2 hints; bit 4: L2 prefetch (see below)
+                                    // bit 5 / bit 6: first / second pass of a two-pass time-segmented launch
     unsigned dirac_mask;            // synthesised input k is a dirac (else zeros)
     int state_row[kMaxState];       // row of state slot j inside `state` (prebuilt ticks use their
                                     // own slot order; generated ticks use the identity)
@@ -71,6 +73,19 @@ struct StreamArgs {
     long long in_pitch_bytes;
     int pf_window;                      // bytes, a multiple of the tile's bytes per row
     int pf_dist;                        // tiles
+    // Time segments (linear ticks, FAST mode; zg_runtime.cu: scan_*): with n_segs > 1 a warp is (channel group,
+    // segment) instead of a channel group, and runs samples [seg * seg_len, (seg + 1) * seg_len) of its 32 channels.
+    //   warm-up form (no flag): segment g > 0 starts from ZERO state `seg_warm` samples early and discards the
+    //     outputs of those samples -- the host has checked that the graph forgets its state within seg_warm ticks
+    //     (|A^seg_warm| below fp32 resolution), so the state at the segment's first sample is the serial one;
+    //   two-pass form, any linear tick: pass 1 (flag bit 5) runs every segment but the last from zero state
+    //     (segment 0 from the true state), stores no samples and leaves its final state in seg_state[g]; a small
+    //     kernel turns those into the true boundary states (x <- A^seg_len x + z, zg_scan_fixup_kernel); pass 2
+    //     (flag bit 6) starts segment g > 0 from seg_state[g - 1].
+    // seg_len and seg_warm are multiples of the tile length; the last segment takes the ragged end of the block.
+    int n_segs, seg_len, seg_warm;
+    float* seg_state;                   // [n_segs][seg_state_stride]; rows laid out like `state`
+    long long seg_state_stride;         // floats per segment
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -274,9 +289,17 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     const int NB = a.boxes;
     const int tile_t = NB * BT;
     const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
-    const long long c0ll = gw * 32;
-    if (c0ll >= a.channels) return;                    // warp-uniform
-    const int c0 = (int)c0ll;
+    // warp -> (segment, channel group): the warps of a CTA are neighbouring channel groups at the same place in time
+    const int n_groups = (a.channels + 31) >> 5;
+    const int n_segs = a.n_segs > 1 ? a.n_segs : 1;
+    const int seg = (int)(gw / n_groups);
+    if (seg >= n_segs) return;                         // warp-uniform
+    const bool pass1 = (a.flags & 32) != 0, pass2 = (a.flags & 64) != 0;
+    if (pass1 && seg + 1 == n_segs) return;            // the block's final state comes out of pass 2
+    const int t_seg = n_segs > 1 ? seg * a.seg_len : 0;                        // first sample this warp answers for
+    const int t_lo = seg > 0 && !pass1 && !pass2 ? t_seg - a.seg_warm : t_seg; // first sample it evaluates
+    const int t_hi = seg + 1 < n_segs ? t_seg + a.seg_len : a.n_samples;       // end of its samples
+    const int c0 = (int)(gw - (long long)seg * n_groups) * 32;
     const int ch = c0 + lane;
     const bool ch_ok = ch < a.channels;
 
@@ -293,8 +316,11 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     static_assert(NS <= kMaxState, "too much state for a register-resident tick");
     static_assert(!kUniform || NP <= kMaxUniform, "too many uniform parameters");
     Arr<NS> s;
+    // segment 0 continues the stream from `state`; a later segment starts from zero (warm-up form, pass 1) or from the
+    // boundary state the fix-up kernel left for it (pass 2)
+    const float* st_in = seg == 0 ? a.state : pass2 ? a.seg_state + (long long)(seg - 1) * a.seg_state_stride : nullptr;
 #pragma unroll
-    for (int j = 0; j < NS; ++j) s[j] = ch_ok ? a.state[(long long)a.state_row[j] * a.ch_stride + ch] : 0.f;
+    for (int j = 0; j < NS; ++j) s[j] = ch_ok && st_in ? st_in[(long long)a.state_row[j] * a.ch_stride + ch] : 0.f;
     Arr<kUniform ? 0 : NP> prm_reg;
     if (!kUniform) {
 #pragma unroll
@@ -330,19 +356,19 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     }
     __syncwarp();
 
-    const int n_tiles = (a.n_samples + tile_t - 1) / tile_t;
+    const int n_tiles = (t_hi - t_lo + tile_t - 1) / tile_t;
     // flags bit 2 / bit 3: L2 evict-first hint on the sample loads / stores
     const bool hint_loads = (a.flags & 4) != 0, hint_stores = (a.flags & 8) != 0;
     const unsigned long long policy = (a.flags & 12) ? l2_policy_evict_first() : 0ull;
 
     auto boxes_in_tile = [&](int t0) {                 // boxes of tile at t0 that hold samples
-        const int left = (a.n_samples - t0 + BT - 1) / BT;
+        const int left = (t_hi - t0 + BT - 1) / BT;
         return left < NB ? left : NB;
     };
     auto issue_load = [&](int i) {                     // lane 0 only
         if (kNumBuf == 0) return;
         const int slot = i % S;
-        const int t0 = i * tile_t;
+        const int t0 = t_lo + i * tile_t;
         const int nb = boxes_in_tile(t0);
         mbar_expect_tx(&bars[slot], (unsigned)(nb * kNumBuf * BB));
 #pragma unroll
@@ -388,12 +414,12 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
 
     for (int i = 0; i < n_tiles; ++i) {
         const int slot = i % S;
-        const int t0 = i * tile_t;
+        const int t0 = t_lo + i * tile_t;
         const int nb = boxes_in_tile(t0);
         unsigned char* stage = my + (size_t)slot * stage_bytes;
 
         if (!kInterleaved && kNumBuf > 0 && (a.flags & 16) && ch_ok) {
-            const long long off = (long long)(i + a.pf_dist) * tile_t * kIo;          // byte offset inside the row
+            const long long off = ((long long)t0 + (long long)a.pf_dist * tile_t) * kIo;  // byte offset inside the row
             const long long row_bytes = ((long long)a.n_samples * kIo) & ~15ll;
             if (off % a.pf_window == 0 && off < row_bytes) {
                 const unsigned sz = (unsigned)(row_bytes - off < a.pf_window ? row_bytes - off : a.pf_window);
@@ -408,7 +434,7 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
 #pragma unroll 1
             for (int b = 0; b < nb; ++b) {
                 const int tb0 = t0 + b * BT;
-                const int n_valid = a.n_samples - tb0 < BT ? a.n_samples - tb0 : BT;
+                const int n_valid = t_hi - tb0 < BT ? t_hi - tb0 : BT;
                 unsigned char* base = stage + b * BB;              // wire k of this box: base + k * wire_bytes
                 if (early_refill && lane == 0 && b == 1 && i + S - 1 < n_tiles) {
                     tma_wait_read<0>();                            // the store of tile i-1 (the only one pending)
@@ -592,9 +618,12 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
         fence_proxy_async();                           // generic-proxy writes -> visible to TMA
         __syncwarp();
         if (lane == 0) {
+            // warm-up tiles and the whole of pass 1 produce state, not samples: nothing is stored (the commit
+            // group stays, empty, so that the refill logic below counts the same groups)
+            const bool discard = pass1 || t0 < t_seg;
 #pragma unroll
             for (int o = 0; o < NO; ++o) {
-                for (int b = 0; b < nb; ++b) {
+                for (int b = 0; b < (discard ? 0 : nb); ++b) {
                     const unsigned char* src = stage + (size_t)o * wire_bytes + b * BB;
                     const int cx = kInterleaved ? c0 : t0 + b * BT, cy = kInterleaved ? t0 + b * BT : c0;
                     if (hint_stores) tma_store_2d_hint(&a.out_map[o], cx, cy, src, policy);
@@ -614,11 +643,12 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
 
     if (lane == 0) tma_wait_all<0>();                  // smem must outlive the last stores
 
-    // ---- state back to HBM ----
-    if (ch_ok) {
+    // ---- state back to HBM: the last segment ends the block; pass 1 leaves every segment's final state for the fix-up ----
+    float* st_out = pass1 ? a.seg_state + (long long)seg * a.seg_state_stride : seg + 1 == n_segs ? a.state : nullptr;
+    if (ch_ok && st_out) {
 #pragma unroll
         for (int j = 0; j < NS; ++j)
-            if (!((a.state_nowrite >> j) & 1ull)) a.state[(long long)a.state_row[j] * a.ch_stride + ch] = s[j];
+            if (!((a.state_nowrite >> j) & 1ull)) st_out[(long long)a.state_row[j] * a.ch_stride + ch] = s[j];
     }
 }
 

@@ -174,38 +174,37 @@ const char* zg_graph_dump(const zg_graph* g) { return g ? g->dump_str.c_str() : 
 // (a product or quotient of two signals); the graph is as good as the worst value it returns or pushes into a line.
 int zg_graph_linearity(const zg_graph* g, int* kind) {
     if (!g || !kind) return fail(ZG_ERR_ARG, "NULL argument");
-    enum { CONST = 0, LIN = 1, AFF = 2, NONLIN = 3 };
-    const Ir& ir = g->ir_f32;
-    std::vector<int> cls(ir.nodes.size(), CONST);
-    for (size_t i = 0; i < ir.nodes.size(); ++i) {
-        const IrNode& n = ir.nodes[i];
-        switch (n.op) {
-            case IrOp::In: case IrOp::DRead: cls[i] = LIN; break;
-            case IrOp::Const: case IrOp::Param: cls[i] = CONST; break;
-            case IrOp::Neg: cls[i] = cls[n.a]; break;
-            case IrOp::Add: case IrOp::Sub: {
-                const int a = cls[n.a], b = cls[n.b];
-                cls[i] = (a == NONLIN || b == NONLIN) ? NONLIN : a == b && a != AFF ? a : (a == CONST && b == CONST) ? CONST : AFF;
-                break;
-            }
-            case IrOp::Mul: {
-                const int a = cls[n.a], b = cls[n.b];
-                cls[i] = a == CONST ? b : b == CONST ? a : NONLIN;
-                break;
-            }
-            case IrOp::Div: cls[i] = cls[n.b] == CONST ? cls[n.a] : NONLIN; break;
-            default: cls[i] = NONLIN; break;
-        }
-    }
-    int worst = LIN;
-    auto see = [&](int id) {
-        const int c = cls[id] == CONST ? (ir.nodes[id].op == IrOp::Const && ir.nodes[id].value == 0 ? LIN : AFF) : cls[id];
-        worst = std::max(worst, c);
-    };
-    for (int o : ir.outs) see(o);
-    for (const IrLine& l : ir.lines) see(l.src);
-    *kind = worst == NONLIN ? ZG_NONLINEAR : worst == AFF ? ZG_AFFINE : ZG_LINEAR;
+    *kind = ir_linearity(g->ir_f32);
     return ZG_OK;
+}
+
+int zg_graph_state_matrix(const zg_graph* g, const float* params, int n_params, double* A, size_t capacity) {
+    if (!g || !A) return fail(ZG_ERR_ARG, "NULL argument");
+    const Ir& ir = g->ir_f32;
+    if (!ir.all_f32()) return fail(ZG_ERR_UNSUPPORTED, "state matrix of fp32 graphs only");
+    if (ir_linearity(ir) == ZG_NONLINEAR) return fail(ZG_ERR_UNSUPPORTED, "the tick is not linear in its state (zg_graph_linearity)");
+    if (n_params != ir.n_params || (n_params > 0 && !params)) return fail(ZG_ERR_ARG, "expected one value per $k parameter");
+    if (capacity < (size_t)ir.n_state * ir.n_state) return fail(ZG_ERR_ARG, "buffer too small for n_state * n_state doubles");
+    return guarded([&] {
+        std::vector<double> M;
+        if (!tick_matrix(ir, params, M)) return fail(ZG_ERR_ARG, "the parameter values give a non-finite state matrix");
+        std::copy(M.begin(), M.end(), A);
+        return (int)ZG_OK;
+    });
+}
+
+int zg_graph_settling_time(const zg_graph* g, const float* params, int n_params, int step, int k_max, double tol, int* K) {
+    if (!g || !K) return fail(ZG_ERR_ARG, "NULL argument");
+    if (step < 1 || k_max < step || !(tol > 0)) return fail(ZG_ERR_ARG, "need step >= 1, k_max >= step, tol > 0");
+    const Ir& ir = g->ir_f32;
+    std::vector<double> A((size_t)ir.n_state * ir.n_state + 1);
+    int st = zg_graph_state_matrix(g, params, n_params, A.data(), A.size());
+    if (st != ZG_OK) return st;
+    A.resize((size_t)ir.n_state * ir.n_state);
+    return guarded([&] {
+        *K = decay_length(A, ir.n_state, step, k_max, tol);
+        return (int)ZG_OK;
+    });
 }
 
 int zg_graph_kernel_class(const zg_graph* g, char* buf, size_t capacity) {
@@ -224,18 +223,24 @@ int zg_graph_kernel_class(const zg_graph* g, char* buf, size_t capacity) {
 
 int zg_voice_create(const zg_graph* g, zg_voice** out) {
     if (!g || !out) return fail(ZG_ERR_ARG, "NULL argument");
-    auto v = new zg_voice();
-    v->g = g;
-    v->state.assign(g->ir_f32.n_state, 0.f);
-    v->params.assign(g->ir_f32.n_params, 0.f);
-    *out = v;
-    return ZG_OK;
+    *out = nullptr;
+    return guarded([&] {
+        auto v = std::make_unique<zg_voice>();
+        v->g = g;
+        v->state.assign(g->ir_f32.n_state, 0.f);
+        v->params.assign(g->ir_f32.n_params, 0.f);
+        *out = v.release();
+        return (int)ZG_OK;
+    });
 }
 
 int zg_voice_clone(const zg_voice* v, zg_voice** out) {
     if (!v || !out) return fail(ZG_ERR_ARG, "NULL argument");
-    *out = new zg_voice(*v);
-    return ZG_OK;
+    *out = nullptr;
+    return guarded([&] {
+        *out = new zg_voice(*v);
+        return (int)ZG_OK;
+    });
 }
 
 void zg_voice_destroy(zg_voice* v) { delete v; }

@@ -75,7 +75,7 @@ std::string generate_tick_source(const Ir& ir, bool exact, const std::string& st
                 std::string a = ref(n.a, n.dtype), b = ref(n.b, n.dtype);
                 const char* sym = n.op == IrOp::Add ? "+" : n.op == IrOp::Sub ? "-" : n.op == IrOp::Mul ? "*" : "/";
                 if (n.dtype == Dtype::I32) {
-                    if (n.op == IrOp::Div) os << "(" << b << " == 0 ? 0 : " << a << " / " << b << ")";
+                    if (n.op == IrOp::Div) os << "(" << b << " == 0 ? 0 : " << b << " == -1 ? (int)(0u - (unsigned)" << a << ") : " << a << " / " << b << ")";
                     else os << a << " " << sym << " " << b;
                 } else if (exact) {
                     // separately rounded, never contracted into FMA

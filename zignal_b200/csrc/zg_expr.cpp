@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cerrno>
 #include <cstring>
 #include <sstream>
 
@@ -146,12 +147,20 @@ struct Parser {
     }
     void expect(const char* tok) { if (!eat(tok)) fail(std::string("expected '") + tok + "'"); }
 
+    // wire / delay / parameter indices: bounded, so that no text can make the analyses or a voice's state
+    // allocation overflow (a delay line of 2^20 samples is 4 MB of state per voice)
+    static constexpr long kMaxIndex = 1l << 20;
     int integer() {
         ws();
         size_t b = p;
-        while (p < s.size() && std::isdigit((unsigned char)s[p])) ++p;
+        long v = 0;
+        while (p < s.size() && std::isdigit((unsigned char)s[p])) {
+            v = v * 10 + (s[p] - '0');
+            if (v > kMaxIndex) fail("index larger than " + std::to_string(kMaxIndex));
+            ++p;
+        }
         if (b == p) fail("expected integer");
-        return std::atoi(s.substr(b, p - b).c_str());
+        return (int)v;
     }
 
     // The parser recurses once per open parenthesis / right-nested `|=` (a chain of nine frames) and once per prefix
@@ -282,7 +291,9 @@ struct Parser {
             if (q < s.size() && (s[q] == 'e' || s[q] == 'E')) floating = true;
         }
         if (!floating && !(q < s.size() && (s[q] == 'f' || s[q] == 'F') && !hex)) {
-            long v = std::strtol(b, &end, 0);
+            errno = 0;
+            long long v = std::strtoll(b, &end, 0);
+            if (errno == ERANGE || v > 2147483647ll || v < -2147483648ll) fail("integer literal does not fit a C++ int");
             p += (size_t)(end - b);
             return constant(Dtype::I32, (double)v);
         }

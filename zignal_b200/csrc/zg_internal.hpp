@@ -37,6 +37,15 @@ int fail(int status, const std::string& msg);
 std::string generate_tick_source(const Ir& ir, bool exact, const std::string& struct_name, int n_ring_in = 0,
                                  int n_ring_out = 0, int ring_pf = 1);
 
+// ---- linear ticks (zg_scan.cpp): what the time-segmented launches of few, long channels need ----
+int ir_linearity(const Ir& ir);                                   // zg_linearity of one tick
+// A of  state' = A state + B x + c  (row-major [n_state][n_state], float64) for one set of parameter values;
+// false when an entry is not finite
+bool tick_matrix(const Ir& ir, const float* params, std::vector<double>& A);
+void mat_pow(const std::vector<double>& A, int n, long e, std::vector<double>& out);
+// smallest K = m * step <= k_max with |A^K|_inf <= tol, 0 if there is none (a tick that does not forget its state)
+int decay_length(const std::vector<double>& A, int n, int step, int k_max, double tol);
+
 // ---- prebuilt-kernel recognisers (zg_match.cpp) ----
 constexpr int kMaxBiquadSections = 8;
 struct BiquadCoef {

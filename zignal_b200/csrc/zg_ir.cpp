@@ -486,13 +486,14 @@ Ir lower(const Expr& canonical, const std::vector<Dtype>& in_dtypes, const Lower
     ir.nodes = std::move(c.nodes);
     for (int o : outs) ir.outs.push_back(remap[o]);
     ir.n_out = (int)ir.outs.size();
-    int off = 0;
+    int64_t off = 0;
     for (auto& l : lines) {
         l.src = remap[l.src];
-        l.offset = off;
+        l.offset = (int)off;
         off += l.depth;
+        if (off > (int64_t(1) << 26)) throw Error("graph keeps more than 2^26 floats of delay-line state per voice");
     }
-    ir.n_state = off;
+    ir.n_state = (int)off;
     ir.lines = std::move(lines);
     return ir;
 }
@@ -502,6 +503,12 @@ Ir lower(const Expr& canonical, const std::vector<Dtype>& in_dtypes, const Lower
 // ------------------------------------------------------------------------------------------------
 
 namespace {
+
+// double -> C++ int at the ABI: out-of-range and NaN values (undefined behaviour as a plain cast) saturate / become 0
+inline int32_t to_i32(double v) {
+    if (!(v == v)) return 0;
+    return v >= 2147483647.0 ? INT32_MAX : v <= -2147483648.0 ? INT32_MIN : (int32_t)v;
+}
 
 union Cell { int32_t i; float f; double d; };
 
@@ -527,7 +534,7 @@ inline void run_tick(const Ir& ir, float* state, const float* params, Cell* v) {
         switch (nd.op) {
             case IrOp::In: break;  // pre-filled
             case IrOp::Const:
-                if (nd.dtype == Dtype::I32) v[i].i = (int32_t)nd.value;
+                if (nd.dtype == Dtype::I32) v[i].i = to_i32(nd.value);
                 else if (nd.dtype == Dtype::F32) v[i].f = (float)nd.value;
                 else v[i].d = nd.value;
                 break;
@@ -560,7 +567,7 @@ inline void run_tick(const Ir& ir, float* state, const float* params, Cell* v) {
             case IrOp::Div:
                 v[i] = arith(nd.dtype, v[nd.a], ir.nodes[nd.a].dtype, v[nd.b], ir.nodes[nd.b].dtype,
                              [](float a, float b) { return a / b; }, [](double a, double b) { return a / b; },
-                             [](int32_t a, int32_t b) { return b == 0 ? 0 : a / b; });
+                             [](int32_t a, int32_t b) { return b == 0 ? 0 : b == -1 ? (int32_t)(0u - (uint32_t)a) : a / b; });
                 break;
             case IrOp::Fwd: break;                       // never survives lower()
         }
@@ -580,7 +587,7 @@ void host_tick(const Ir& ir, float* state, const float* params, const double* in
     std::vector<Cell> v(ir.nodes.size());
     for (int i = 0; i < ir.n_in; ++i) {
         switch (ir.in_dtypes[i]) {
-            case Dtype::I32: v[i].i = (int32_t)in[i]; break;
+            case Dtype::I32: v[i].i = to_i32(in[i]); break;
             case Dtype::F32: v[i].f = (float)in[i]; break;
             case Dtype::F64: v[i].d = in[i]; break;
             default: break;
@@ -597,7 +604,7 @@ void host_block_f32(const Ir& ir, float* state, const float* params, const float
         for (int i = 0; i < ir.n_in; ++i) {
             float x = in[i][t * in_stride];
             switch (ir.in_dtypes[i]) {
-                case Dtype::I32: v[i].i = (int32_t)x; break;
+                case Dtype::I32: v[i].i = to_i32(x); break;
                 case Dtype::F32: v[i].f = x; break;
                 case Dtype::F64: v[i].d = x; break;
                 default: break;

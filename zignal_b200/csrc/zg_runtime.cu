@@ -162,6 +162,52 @@ __global__ void __launch_bounds__(512, 1) zg_fir_kernel(const __grid_constant__ 
     zgk::fir_block<kExact, kInterleaved>(a);
 }
 
+// Boundary fix-up of the two-pass time-segmented form (kernels/zg_stream.cuh, StreamArgs::n_segs): pass 1 left in
+// seg[g] the state segment g ends with when it starts from zero (g = 0: from the true state, so seg[0] is already
+// the state segment 1 starts from).  One thread per channel walks the boundaries in order,
+//      x_{g+1} = A^L x_g + z_g          (the tick is linear: flowz/flowz.hpp:1031-1074 evaluated L times),
+// and overwrites seg[g] with the true state at the start of segment g + 1.  A^L is computed on the host in float64
+// from the tick program (zg_scan.cpp) and shared by all channels, or one matrix per channel ([n*n][ch_stride]).
+__global__ void zg_scan_fixup_kernel(float* seg, long long seg_stride, long long ch_stride, int channels, int n,
+                                     int n_bounds, const float* __restrict__ AL, int per_channel) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels) return;
+    float x[zgk::kMaxState], y[zgk::kMaxState];
+    for (int i = 0; i < n; ++i) x[i] = seg[(long long)i * ch_stride + c];
+    for (int g = 1; g < n_bounds; ++g) {
+        float* z = seg + (long long)g * seg_stride;
+        for (int i = 0; i < n; ++i) {
+            float acc = z[(long long)i * ch_stride + c];
+            for (int j = 0; j < n; ++j) {
+                const float a = per_channel ? AL[(long long)(i * n + j) * ch_stride + c] : AL[i * n + j];
+                acc = fmaf(a, x[j], acc);
+            }
+            y[i] = acc;
+        }
+        for (int i = 0; i < n; ++i) {
+            x[i] = y[i];
+            z[(long long)i * ch_stride + c] = y[i];
+        }
+    }
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel FUNCTION (per device), which every plan of the
+// process shares: remember the largest value set so far per (function, device) and only ever raise it.
+int raise_max_smem(const void* fn, int device, int smem) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> set_so_far;
+    std::lock_guard<std::mutex> lock(mu);
+    int& cur = set_so_far[{fn, device}];
+    if (smem <= cur) return ZG_OK;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(ZG_ERR_CUDA, std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(e));
+    }
+    cur = smem;
+    return ZG_OK;
+}
+
 const void* fir_kernel_for(bool exact, bool interleaved) {
     if (exact) return interleaved ? (const void*)zg_fir_kernel<true, true> : (const void*)zg_fir_kernel<true, false>;
     return interleaved ? (const void*)zg_fir_kernel<false, true> : (const void*)zg_fir_kernel<false, false>;
@@ -250,7 +296,23 @@ struct zg_plan {
     int fir_regs = 0;
     int last_grid = 0;
 
-    Variant variant[3];                     // [0] per-channel parameters, [1] uniform, [2] uniform + symmetric biquads
+    Variant variant[5];                     // [0] per-channel parameters, [1] uniform, [2] uniform + symmetric biquads;
+                                            // [3], [4]: the lane-per-channel kernel of a K1b plan (time-segmented launches)
+    int lanes_now = 1;                      // lanes per channel of the launch being prepared
+
+    // Time segments for few, long channels (FAST mode, linear ticks; kernels/zg_stream.cuh StreamArgs::n_segs)
+    int linearity = ZG_NONLINEAR;
+    bool scan_ok = false;                   // graph and options allow a time-segmented launch
+    bool scan_dirty = true;                 // parameters changed since the analysis below
+    int scan_warm = 0;                      // ticks after which every channel has forgotten its state (|A^K| <= 2^-30);
+                                            // 0: some channel never does
+    float* d_seg_state = nullptr;           // [segments][n_state][ch_stride]: boundary states of the two-pass form
+    size_t seg_state_floats = 0;
+    float* d_AL = nullptr;                  // A^L: [n*n] shared, or [n*n][ch_stride] per channel
+    size_t AL_floats = 0;
+    int AL_len = 0;                         // the L it was computed for (0: stale)
+    bool AL_per_channel = false;
+    int last_segs = 1, last_seg_mode = 0, last_seg_len = 0, last_seg_warm = 0;
     bool sym_now = false;                   // K1: every section has b0 == b2 (bit for bit), coefficients uniform
     std::string kernel_name;
 
@@ -287,6 +349,8 @@ struct zg_plan {
         if (d_params) cudaFree(d_params);
         if (d_user_params) cudaFree(d_user_params);
         if (d_stage) cudaFree(d_stage);
+        if (d_seg_state) cudaFree(d_seg_state);
+        if (d_AL) cudaFree(d_AL);
         if (own_stream) cudaStreamDestroy(own_stream);
         if (h2d_stream) cudaStreamDestroy(h2d_stream);
         if (d2h_stream) cudaStreamDestroy(d2h_stream);
@@ -463,9 +527,10 @@ int tune_env(const char* name) {
 }
 
 int variant_index(const zg_plan* p) {
-    const bool sym = p->uniform_now && p->sym_now && p->is_biquad && !p->opts.force_jit && p->lanes == 1 && p->exact &&
+    const bool sym = p->uniform_now && p->sym_now && p->is_biquad && !p->opts.force_jit && p->lanes_now == 1 && p->exact &&
                      !tune_env("ZG_TUNE_NO_SYM");
-    return p->uniform_now ? (sym ? 2 : 1) : 0;
+    const int lane_per_channel_of_k1b = p->lanes > 1 && p->lanes_now == 1 ? 3 : 0;     // never EXACT, hence never sym
+    return (p->uniform_now ? (sym ? 2 : 1) : 0) + lane_per_channel_of_k1b;
 }
 
 int get_variant(zg_plan* p, bool uniform, Variant*& out) {
@@ -481,8 +546,8 @@ int get_variant(zg_plan* p, bool uniform, Variant*& out) {
         return ZG_OK;
     }
     if (p->is_biquad && !p->opts.force_jit) {
-        v.prebuilt = p->lanes > 1 ? biquad_lanes_kernel_for(p->bq.sections, p->exact, uniform)
-                                  : biquad_kernel_for(p->bq.sections, p->exact, p->interleaved, uniform, vi == 2);
+        v.prebuilt = p->lanes_now > 1 ? biquad_lanes_kernel_for(p->bq.sections, p->exact, uniform)
+                                      : biquad_kernel_for(p->bq.sections, p->exact, p->interleaved, uniform, vi == 2);
         if (!v.prebuilt) return fail(ZG_ERR_INTERNAL, "no prebuilt biquad kernel for this section count");
         cudaFuncAttributes fa;
         ZG_CUDA(cudaFuncGetAttributes(&fa, (const void*)v.prebuilt));
@@ -498,6 +563,8 @@ int get_variant(zg_plan* p, bool uniform, Variant*& out) {
 // value of kernel parameter slot j for channel c (c = -1: the scalar)
 int sync_params(zg_plan* p) {
     if (!p->params_dirty) return ZG_OK;
+    p->scan_dirty = true;                   // the tick's A matrix is made of these values
+    p->AL_len = 0;
     if (p->is_fir) {
         // taps are shared by all channels: literals, or scalar $k parameters
         std::vector<float> taps(p->fir.taps.size());
@@ -621,7 +688,7 @@ struct Geometry {
     int wpc, grid, stages, boxes, smem;
 };
 
-Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, int64_t T) {
+Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, int64_t T, bool segmented = false) {
     Geometry g{};
     const int BT = zgk::box_samples(p->interleaved, p->io), BB = zgk::box_bytes(p->interleaved, p->io);
     const int64_t per_sm = (n_warps + p->sm_count - 1) / p->sm_count;
@@ -642,13 +709,14 @@ Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, in
     const int bytes = p->io * std::max(1, p->n_buf_in + p->ir.n_out);
     // (ring reads of long delay lines are plain loads, hidden by other warps only: no trade of warps for run length)
     const bool long_runs = !p->interleaved && 4 * ops < 17 * bytes && !p->ring.any();
-    if (long_runs && per_sm > 7) {
+    if (long_runs && per_sm >= 7) {
         wpc = std::min(wpc, 7);
         NB = 4;
     }
     if (int w = tune_env("ZG_TUNE_WPC")) wpc = std::min(std::max(w, 1), 16);
     const int budget = p->max_smem_optin - 1024 /*alignment slack*/ - 16 * 8 * 8 /*barriers*/;
     if (int b = tune_env("ZG_TUNE_BOXES")) NB = std::min(std::max(b, 1), 8);
+    if (segmented) NB = NB >= 4 ? 4 : NB >= 2 ? 2 : 1;       // segment boundaries are multiples of 4 boxes
     NB = (int)std::min<int64_t>(NB, std::max<int64_t>(1, (T + BT - 1) / BT));
     auto stages_for = [&](int w, int nb) { return budget / (w * NT * nb * BB); };
     while (NB > 1 && stages_for(wpc, NB) < 2) --NB;
@@ -700,6 +768,158 @@ Geometry choose_geometry_lanes(const zg_plan* p, int64_t n_warps, int regs, int6
     return g;
 }
 
+// ---- time segments (few, long channels; FAST mode; linear ticks) -------------------------------------------------
+//
+// A lane-per-channel launch of C channels is C/32 warps however long the block is: BASELINE configs[1] (4096 channels
+// x 65 536 samples) is 128 warps on 148 SMs.  A linear tick can be cut in time instead:
+//   warm-up form  one launch, 8 + 4*K/L bytes per sample: segment g starts K samples early from zero state and
+//                 discards those outputs.  Valid when every channel's |A^K|_inf <= 2^-30 (K = scan_warm, from the
+//                 parameter values, float64): what is left of the true state after K ticks is below fp32 resolution.
+//   two-pass form any linear / affine tick (poles on or outside the unit circle included), 12 bytes per sample:
+//                 pass 1 from zero state -> boundary fix-up with A^L -> pass 2 from the true states.
+// Both re-associate the arithmetic in time, so they are FAST-mode only; EXACT stays serial per channel.
+struct Segments {
+    int mode = 0;       // 0 none, 1 warm-up, 2 two-pass
+    int n = 1, len = 0, warm = 0;
+};
+
+// per-channel parameter values on the host: row k has 1 (scalar) or C values
+int host_params(zg_plan* p, std::vector<std::vector<float>>& rows) {
+    rows = p->h_params;
+    for (size_t k = 0; k < rows.size(); ++k) {
+        if (!p->param_on_device[k]) continue;
+        rows[k].resize(p->C);
+        ZG_CUDA(cudaMemcpy(rows[k].data(), p->d_user_params + k * (size_t)p->ch_stride, p->C * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return ZG_OK;
+}
+
+constexpr double kScanTol = 9.3132257461547852e-10;     // 2^-30
+constexpr int kScanMaxWarm = 8192;
+constexpr int64_t kScanMaxChannels = 65536;             // beyond this a launch has enough warps without segments
+
+template <class F>   // f(channel or -1, params of that channel) for the distinct parameter sets of the plan
+int for_each_param_set(zg_plan* p, F&& f) {
+    std::vector<std::vector<float>> rows;
+    int st = host_params(p, rows);
+    if (st != ZG_OK) return st;
+    bool per_channel = false;
+    for (auto& r : rows) per_channel = per_channel || r.size() != 1;
+    std::vector<float> prm(rows.size());
+    if (!per_channel) {
+        for (size_t k = 0; k < rows.size(); ++k) prm[k] = rows[k][0];
+        f(-1, prm.data());
+        return ZG_OK;
+    }
+    for (int64_t c = 0; c < p->C; ++c) {
+        for (size_t k = 0; k < rows.size(); ++k) prm[k] = rows[k].size() == 1 ? rows[k][0] : rows[k][c];
+        if (!f((int)c, prm.data())) break;
+    }
+    return ZG_OK;
+}
+
+int scan_analyse(zg_plan* p) {
+    p->scan_dirty = false;
+    p->scan_warm = 0;
+    if (!p->scan_ok || p->C > kScanMaxChannels) return ZG_OK;
+    const int unit = 4 * zgk::box_samples(p->interleaved, p->io);
+    int worst = unit;
+    bool all = true;
+    std::vector<double> A;
+    int st = for_each_param_set(p, [&](int, const float* prm) {
+        const int K = tick_matrix(p->ir, prm, A) ? decay_length(A, p->ir.n_state, unit, kScanMaxWarm, kScanTol) : 0;
+        if (K == 0) all = false;
+        worst = std::max(worst, K);
+        return all;
+    });
+    if (st != ZG_OK) return st;
+    p->scan_warm = all ? worst : 0;
+    return ZG_OK;
+}
+
+// A^L on the device for the fix-up kernel
+int scan_prepare_AL(zg_plan* p, int L) {
+    if (p->AL_len == L) return ZG_OK;
+    const int n = p->ir.n_state;
+    bool per_channel = false;
+    for (size_t k = 0; k < p->h_params.size(); ++k) per_channel = per_channel || p->h_params[k].size() != 1 || p->param_on_device[k];
+    const size_t need = (size_t)n * n * (per_channel ? (size_t)p->ch_stride : 1);
+    std::vector<float> host(std::max<size_t>(need, 1), 0.f);
+    std::vector<double> A, AL;
+    bool finite = true;
+    int st = for_each_param_set(p, [&](int c, const float* prm) {
+        if (!tick_matrix(p->ir, prm, A)) { finite = false; return false; }
+        mat_pow(A, n, L, AL);
+        for (int e = 0; e < n * n; ++e) {
+            if (!std::isfinite(AL[e]) || std::fabs(AL[e]) > 3e38) { finite = false; return false; }
+            if (c < 0) host[e] = (float)AL[e];
+            else host[(size_t)e * p->ch_stride + c] = (float)AL[e];
+        }
+        return true;
+    });
+    if (st != ZG_OK) return st;
+    if (!finite) return fail(ZG_ERR_UNSUPPORTED, "the tick's state matrix overflows fp32 over one time segment (unstable graph): "
+                                                  "use time_parallel = ZG_TP_OFF");
+    if (need > p->AL_floats) {
+        if (p->d_AL) cudaFree(p->d_AL);
+        p->d_AL = nullptr;
+        p->AL_floats = 0;
+        ZG_CUDA(cudaMalloc(&p->d_AL, std::max<size_t>(need, 1) * sizeof(float)));
+        p->AL_floats = need;
+    }
+    if (need) ZG_CUDA(cudaMemcpy(p->d_AL, host.data(), need * sizeof(float), cudaMemcpyHostToDevice));
+    p->AL_len = L;
+    p->AL_per_channel = per_channel;
+    return ZG_OK;
+}
+
+bool tick_is_light(const zg_plan* p) {       // the HBM-bound side of choose_geometry's trade (7 warps x 4 boxes)
+    const int bytes = p->io * std::max(1, p->n_buf_in + p->ir.n_out);
+    return !p->interleaved && 4 * p->tick_ops < 17 * bytes;
+}
+
+int choose_segments(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t c_count, Segments& sg) {
+    sg = Segments{};
+    const int tp = tune_env("ZG_TUNE_TP") ? tune_env("ZG_TUNE_TP") - 1 : p->opts.time_parallel;
+    if (tp == ZG_TP_OFF || !p->scan_ok) return ZG_OK;
+    const int unit = 4 * zgk::box_samples(p->interleaved, p->io);
+    const int64_t groups = (c_count + 31) / 32;
+    const int64_t target = (int64_t)(tick_is_light(p) ? 7 : 14) * p->sm_count;
+    int64_t G = target / groups;
+    if (int g = tune_env("ZG_TUNE_SEGS")) G = g;
+    else if (tp == ZG_TP_AUTO && groups * 2 > target) return ZG_OK;         // enough channels for one lane each
+    G = std::max<int64_t>(G, 2);
+    if (p->scan_dirty) {
+        int st = scan_analyse(p);
+        if (st != ZG_OK) return st;
+    }
+    bool in_place = false;
+    for (int o = 0; o < p->ir.n_out; ++o)
+        for (int k = 0; k < p->ir.n_in; ++k)
+            in_place = in_place || (!(p->synth_mask & (1u << k)) && out[o] == in[k]);
+    int K = p->scan_warm;
+    if (int w = tune_env("ZG_TUNE_WARM")) K = (w + unit - 1) / unit * unit;
+    // the warm-up of a segment re-reads the end of the previous one, which an in-place block has overwritten by then
+    const bool warm_form = K > 0 && !in_place && tp != ZG_TP_TWO_PASS;
+    if (tp == ZG_TP_WARMUP && !warm_form)
+        return fail(in_place ? ZG_ERR_ARG : ZG_ERR_UNSUPPORTED,
+                    in_place ? "the warm-up form of time_parallel does not run in place (segments re-read their predecessor's samples)"
+                             : "time_parallel = ZG_TP_WARMUP: with these parameter values some channel does not forget its state "
+                               "within " + std::to_string(kScanMaxWarm) + " samples (use ZG_TP_TWO_PASS)");
+    // K1b (sections across lanes) is as fast as the two-pass form, which moves 12 instead of 8 bytes per sample
+    if (!warm_form && tp == ZG_TP_AUTO && p->lanes > 1) return ZG_OK;
+    int64_t L = ((T + G - 1) / G + unit - 1) / unit * unit;
+    if (warm_form) L = std::max<int64_t>(L, tp == ZG_TP_AUTO ? 8 * (int64_t)K : 2 * (int64_t)K);   // auto: <= 12.5 % more samples evaluated
+    else L = std::max<int64_t>(L, 2 * unit);
+    G = (T + L - 1) / L;
+    if (G < 2) return ZG_OK;                                               // the block is too short to cut
+    sg.mode = warm_form ? 1 : 2;
+    sg.n = (int)G;
+    sg.len = (int)L;
+    sg.warm = warm_form ? K : 0;
+    return ZG_OK;
+}
+
 // One kernel launch over channels [c_begin, c_begin + c_count) of the plan; in/out point at the first
 // of those channels.  `advance` = this launch ends the block (the stream position moves on by T).
 int launch_fir(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out,
@@ -712,6 +932,10 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     int st = sync_params(p);
     if (st != ZG_OK) return st;
     if (p->is_fir) return launch_fir(p, in, out, T, ld_in, ld_out, stream, c_begin, c_count, advance);
+    Segments sg;
+    st = choose_segments(p, in, out, T, c_count, sg);
+    if (st != ZG_OK) return st;
+    p->lanes_now = sg.mode ? 1 : p->lanes;
     Variant* v = nullptr;
     st = get_variant(p, p->uniform_now, v);
     if (st != ZG_OK) return st;
@@ -720,11 +944,11 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     std::memset(&a, 0, sizeof a);
     for (int k = 0; k < p->ir.n_in; ++k) {
         if (p->synth_mask & (1u << k)) continue;
-        st = encode_map(p, &a.in_map[k], in[k], c_count, T, ld_in, 32 / p->lanes);
+        st = encode_map(p, &a.in_map[k], in[k], c_count, T, ld_in, 32 / p->lanes_now);
         if (st != ZG_OK) return st;
     }
     for (int o = 0; o < p->ir.n_out; ++o) {
-        st = encode_map(p, &a.out_map[o], out[o], c_count, T, ld_out, 32 / p->lanes);
+        st = encode_map(p, &a.out_map[o], out[o], c_count, T, ld_out, 32 / p->lanes_now);
         if (st != ZG_OK) return st;
     }
     a.state = p->d_state + c_begin;
@@ -764,12 +988,35 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     // wires per pipeline stage as the kernel lays them out: wire k of a stage belongs to input k / output k
     // (kernels/zg_stream.cuh: NT = max(N_IN, N_OUT)), whether or not input k is synthesised
     const int NT = std::max(1, std::max(p->ir.n_in, p->ir.n_out));
-    const int cpw = 32 / p->lanes;                     // channels per warp
-    const int64_t n_warps = (c_count + cpw - 1) / cpw;
-    Geometry g = p->lanes > 1 ? choose_geometry_lanes(p, n_warps, v->regs, T) : choose_geometry(p, n_warps, NT, v->regs, T);
+    const int cpw = 32 / p->lanes_now;                 // channels per warp
+    const int64_t n_warps = (c_count + cpw - 1) / cpw * sg.n;               // (channel group, time segment)
+    if (n_warps > 0x7fffffffLL / 32) return fail(ZG_ERR_ARG, "block too large for one launch");
+    Geometry g = p->lanes_now > 1 ? choose_geometry_lanes(p, n_warps, v->regs, T)
+                                  : choose_geometry(p, n_warps, NT, v->regs, sg.mode ? sg.len + sg.warm : T, sg.mode != 0);
     a.stages = g.stages;
     a.boxes = g.boxes;
-    if (p->lanes > 1 && !tune_env("ZG_TUNE_NO3D")) {
+    if (sg.mode) {
+        a.n_segs = sg.n;
+        a.seg_len = sg.len;
+        a.seg_warm = sg.warm;
+    }
+    const int n_rows = std::max(p->ir.n_state, 1);
+    if (sg.mode == 2) {
+        const size_t need = (size_t)(sg.n - 1) * n_rows * p->ch_stride;
+        if (need > p->seg_state_floats) {
+            if (p->d_seg_state) cudaFree(p->d_seg_state);
+            p->d_seg_state = nullptr;
+            p->seg_state_floats = 0;
+            ZG_CUDA(cudaMalloc(&p->d_seg_state, need * sizeof(float)));
+            ZG_CUDA(cudaMemset(p->d_seg_state, 0, need * sizeof(float)));      // rows no kernel slot maps to stay zero
+            p->seg_state_floats = need;
+        }
+        st = scan_prepare_AL(p, sg.len);
+        if (st != ZG_OK) return st;
+        a.seg_state = p->d_seg_state + c_begin;
+        a.seg_state_stride = (long long)n_rows * p->ch_stride;
+    }
+    if (p->lanes_now > 1 && !tune_env("ZG_TUNE_NO3D")) {
         const bool ok = encode_map_tile3d(&a.in_map[1], in[0], c_count, T, ld_in, cpw, g.boxes) &&
                         encode_map_tile3d(&a.out_map[1], out[0], c_count, T, ld_out, cpw, g.boxes);
         a.flags = ok ? 1 : 0;
@@ -784,7 +1031,7 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     if (int h = tune_env("ZG_TUNE_L2HINT")) a.flags |= (h & 3) << 2;       // 1 = loads, 2 = stores, 3 = both: evict-first
     // L2 prefetch of the input rows in long runs ahead of the 128-byte-wide TMA boxes (experiment, off by default):
     // ZG_TUNE_PF = window in bytes per channel row, ZG_TUNE_PFD = tiles ahead (default 2)
-    if (int w = tune_env("ZG_TUNE_PF"); w > 0 && !p->interleaved && p->lanes == 1) {
+    if (int w = tune_env("ZG_TUNE_PF"); w > 0 && !p->interleaved && p->lanes_now == 1) {
         const int tile_bytes = g.boxes * 128;
         a.pf_window = std::max(tile_bytes, w / tile_bytes * tile_bytes);
         a.pf_dist = tune_env("ZG_TUNE_PFD") > 0 ? tune_env("ZG_TUNE_PFD") : 2;
@@ -793,25 +1040,49 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
         a.flags |= 16;
     }
 
-    if (g.smem > v->max_smem_set) {
-        if (v->prebuilt) {
-            ZG_CUDA(cudaFuncSetAttribute((const void*)v->prebuilt, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
-        } else {
-            CUresult cr = d.funcSetAttribute(v->function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, g.smem);
-            if (cr != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuFuncSetAttribute(max dynamic smem): " + cu_err(cr));
-        }
+    if (v->prebuilt) {
+        st = raise_max_smem((const void*)v->prebuilt, p->opts.device, g.smem);
+        if (st != ZG_OK) return st;
+    } else if (g.smem > v->max_smem_set) {                  // a generated kernel is this plan's own module
+        CUresult cr = d.funcSetAttribute(v->function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, g.smem);
+        if (cr != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuFuncSetAttribute(max dynamic smem): " + cu_err(cr));
         v->max_smem_set = g.smem;
     }
-    if (v->prebuilt) {
-        void* args[] = {&a};
-        ZG_CUDA(cudaLaunchKernel((const void*)v->prebuilt, dim3(g.grid), dim3(g.wpc * 32), args, g.smem, stream));
+    auto launch_once = [&](int pass_flag) -> int {
+        zgk::StreamArgs b = a;
+        b.flags |= pass_flag;
+        void* args[] = {&b};
+        if (v->prebuilt) {
+            ZG_CUDA(cudaLaunchKernel((const void*)v->prebuilt, dim3(g.grid), dim3(g.wpc * 32), args, g.smem, stream));
+        } else {
+            CUresult cr = d.launchKernel(v->function, g.grid, 1, 1, g.wpc * 32, 1, 1, g.smem, (CUstream)stream, args, nullptr);
+            if (cr != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuLaunchKernel: " + cu_err(cr));
+        }
+        p->launches += 1;
+        return ZG_OK;
+    };
+    if (sg.mode == 2) {
+        // pass 1: final states from zero; fix-up: true boundary states; pass 2: the samples
+        st = launch_once(32);
+        if (st != ZG_OK) return st;
+        if (sg.n > 2) {
+            const int threads = 128;
+            zg_scan_fixup_kernel<<<(unsigned)((c_count + threads - 1) / threads), threads, 0, stream>>>(
+                a.seg_state, a.seg_state_stride, p->ch_stride, (int)c_count, p->ir.n_state, sg.n - 1,
+                p->AL_per_channel ? p->d_AL + c_begin : p->d_AL, p->AL_per_channel ? 1 : 0);
+            ZG_CUDA(cudaGetLastError());
+            p->launches += 1;
+        }
+        st = launch_once(64);
     } else {
-        void* args[] = {&a};
-        CUresult cr = d.launchKernel(v->function, g.grid, 1, 1, g.wpc * 32, 1, 1, g.smem, (CUstream)stream, args, nullptr);
-        if (cr != CUDA_SUCCESS) return fail(ZG_ERR_CUDA, "cuLaunchKernel: " + cu_err(cr));
+        st = launch_once(0);
     }
+    if (st != ZG_OK) return st;
+    p->last_segs = sg.n;
+    p->last_seg_mode = sg.mode;
+    p->last_seg_len = sg.len;
+    p->last_seg_warm = sg.warm;
     if (advance) p->stream_pos += T;
-    p->launches += 1;
     p->last_smem = g.smem;
     p->last_threads = g.wpc * 32;
     p->last_stages = g.stages;
@@ -863,11 +1134,8 @@ int launch_fir(zg_plan* p, const void* const* in, void* const* out, int64_t T, i
     a.n_segs = (int)n_segs;
     const int smem = fixed + (NR - H + 2 * W) * zgk::kTileBytes;
     const void* fn = fir_kernel_for(p->exact, p->interleaved);
-    Variant& v = p->variant[1];
-    if (smem > v.max_smem_set) {
-        ZG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        v.max_smem_set = smem;
-    }
+    st = raise_max_smem(fn, p->opts.device, smem);
+    if (st != ZG_OK) return st;
     void* args[] = {&a};
     ZG_CUDA(cudaLaunchKernel(fn, dim3((unsigned)(groups * n_segs)), dim3(W * 32), args, smem, stream));
     if (advance) {
@@ -1001,6 +1269,7 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     const bool bf16 = opts->io_dtype == ZG_BF16;
     if (opts->mode != ZG_MODE_EXACT && opts->mode != ZG_MODE_FAST) return fail(ZG_ERR_ARG, "bad mode");
     if (opts->layout != ZG_PLANAR && opts->layout != ZG_INTERLEAVED) return fail(ZG_ERR_ARG, "bad layout");
+    if (opts->time_parallel < ZG_TP_AUTO || opts->time_parallel > ZG_TP_TWO_PASS) return fail(ZG_ERR_ARG, "bad time_parallel");
     const Ir& ir = g->ir_f32;
     if (!ir.all_f32())
         return fail(ZG_ERR_UNSUPPORTED,
@@ -1077,6 +1346,15 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
         const bool too_few = (p->C + 31) / 32 < (int64_t)p->sm_count * 5 / 2;
         if (want_lanes > 1 || (want_lanes == 0 && too_few)) p->lanes = p->bq.sections;
     }
+    p->lanes_now = p->lanes;
+    // time segments: FAST mode (they re-associate the arithmetic in time), linear or affine tick, all delay lines in
+    // registers, one lane per channel not ruled out by an explicit lanes_per_channel
+    p->linearity = ir_linearity(ir);
+    p->scan_ok = !is_fir && !p->exact && p->linearity != ZG_NONLINEAR && !ring.any() && want_lanes <= 1 && ir.n_state <= zgk::kMaxState;
+    if (opts->time_parallel >= ZG_TP_WARMUP && !p->scan_ok)
+        return fail(ZG_ERR_UNSUPPORTED,
+                    "time_parallel needs ZG_MODE_FAST, a linear or affine tick (zg_graph_linearity), delay lines of at most " +
+                        std::to_string(kRegLineDepth) + " samples, lanes_per_channel <= 1 and a graph that is not a dense FIR");
     if (p->is_fir) {
         p->kernel_n_state = ir.n_state;
         p->kernel_n_param = 0;
@@ -1147,11 +1425,19 @@ void zg_plan_destroy(zg_plan* p) { delete p; }
 int zg_plan_get_info(const zg_plan* p, zg_plan_info* info) {
     if (!p || !info) return fail(ZG_ERR_ARG, "NULL argument");
     std::memset(info, 0, sizeof *info);
-    std::snprintf(info->kernel, sizeof info->kernel, "%s%s", p->kernel_name.c_str(),
-                  variant_index(p) == 2 ? "+b0=b2" : "");      // the product-reusing tick (kernels/zg_biquad.cuh)
+    std::string name = p->kernel_name;
+    if (p->lanes > 1 && p->lanes_now == 1)                      // a K1b plan whose last launch was cut in time instead
+        name = "zg_biquad_df1<" + std::to_string(p->bq.sections) + (p->exact ? ",exact,planar>" : ",fma,planar>");
+    std::snprintf(info->kernel, sizeof info->kernel, "%s%s%s", name.c_str(),
+                  variant_index(p) == 2 ? "+b0=b2" : "",       // the product-reusing tick (kernels/zg_biquad.cuh)
+                  p->last_seg_mode == 1 ? "+segments:warm-up" : p->last_seg_mode == 2 ? "+segments:two-pass" : "");
     const Variant& v = p->variant[variant_index(p)];
     info->jit = (v.prebuilt || p->is_fir) ? 0 : 1;
-    info->lanes_per_channel = p->lanes;
+    info->lanes_per_channel = p->lanes_now;
+    info->time_segments = p->last_segs;
+    info->segment_samples = p->last_seg_len;
+    info->warmup_samples = p->last_seg_warm;
+    info->linearity = p->linearity;
     info->host_chunks = p->last_host_chunks;
     info->regs_per_thread = v.regs;
     info->smem_bytes = p->last_smem;
