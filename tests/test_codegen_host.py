@@ -34,6 +34,10 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 struct Params { const float* p; float operator[](int i) const { return p[i]; } };
+// ticks that carry delayed products declare N_EXTRA registers, rebuilt from the state at block start (init)
+template <class T, class = void> struct extra_count { static constexpr int value = 0; };
+template <class T> struct extra_count<T, decltype((void)T::N_EXTRA)> { static constexpr int value = T::N_EXTRA; };
+int g_extra_seen = 0;
 template <class Tick>
 static void run_tick(const float* const* in, float* const* out, long n, float* state, const float* params) {
     zgk::Arr<Tick::N_IN> x;
@@ -41,13 +45,18 @@ static void run_tick(const float* const* in, float* const* out, long n, float* s
     zgk::Arr<Tick::N_STATE> s;
     for (int j = 0; j < Tick::N_STATE; ++j) s[j] = state[j];
     const Params p{params};
+    constexpr int NE = extra_count<Tick>::value;
+    zgk::Arr<NE> e;
+    if constexpr (NE > 0) { Tick::init(s, p, e); g_extra_seen += 1; }
     for (long t = 0; t < n; ++t) {
         for (int k = 0; k < Tick::N_IN; ++k) x[k] = in[k][t];
-        Tick::tick(x, y, s, p);
+        if constexpr (NE > 0) Tick::tick(x, y, s, p, e);
+        else Tick::tick(x, y, s, p);
         for (int o = 0; o < Tick::N_OUT; ++o) out[o][t] = y[o];
     }
     for (int j = 0; j < Tick::N_STATE; ++j) state[j] = s[j];
 }
+extern "C" int zg_host_extra_seen() { return g_extra_seen; }
 """
 
 
@@ -63,6 +72,7 @@ def _graphs(zg):
     consts = ["0.5f", "0.25f", "-0.75f", "0x1p-1f", "1.5f", "-1.0f"]
     out = ["~(_2 + 0.9f*_1[_1])", fo.osc_lp_expr(), fo.poly_voice_expr(), fo.biquad_cascade(3),
            fo.biquad_cascade_params(2), "$0*_1 + $1*_1[_2] |= ~(_2 + $2*_1[_1])",
+           "0.5f*_1 + 0.25f*_1[_1] + 0.5f*_1[_2] + 0.25f*_1[_3]", "$0*_1 + $1*_1[_1] + $0*_1[_2] |= ~(_2 + $1*_1[_1])",
            "~~( _1 + _2 + 1.0f |= _1[_1] )", "~( (0.5f*_1 + _2) |= ~(_1 + _2 |= _1[_1]) )", "~((_1[_2] |= _2) | (_1 - _2))"]
     while len(out) < 60:
         e = _gen(rng, rng.randint(2, 5), rng.randint(1, 3), consts=consts)
@@ -112,3 +122,4 @@ def test_generated_tick_functors_on_the_host(zg, tmp_path):
             same = (y[o].view(np.uint32) == want[o].view(np.uint32)) | (np.isnan(y[o]) & np.isnan(want[o]))
             assert same.all(), f"{e}: output {o} differs at {np.argwhere(~same)[:3].ravel().tolist()}"
     assert extended >= 3
+    assert lib.zg_host_extra_seen() >= 2 * 4          # the delayed-product reuse was exercised (four graphs, two blocks each)

@@ -226,10 +226,14 @@ KernelPtr biquad_lanes_kernel_for(int sections, bool exact, bool uniform) {
 
 template <int S>
 KernelPtr biquad_kernel(bool exact, bool interleaved, bool uniform, bool sym) {
-    // b0 == b2 in every section, EXACT, shared coefficients: the product-reusing tick (kernels/zg_biquad.cuh)
-    if (sym && exact && uniform)
-        return interleaved ? (KernelPtr)zg_stream_kernel<zgk::BiquadDf1Cascade<S, true, true>, true, true>
-                           : (KernelPtr)zg_stream_kernel<zgk::BiquadDf1Cascade<S, true, true>, false, true>;
+    // b0 == b2 in every section (of every channel), EXACT: the product-reusing tick (kernels/zg_biquad.cuh)
+    if (sym && exact) {
+        if (uniform)
+            return interleaved ? (KernelPtr)zg_stream_kernel<zgk::BiquadDf1Cascade<S, true, true>, true, true>
+                               : (KernelPtr)zg_stream_kernel<zgk::BiquadDf1Cascade<S, true, true>, false, true>;
+        return interleaved ? (KernelPtr)zg_stream_kernel<zgk::BiquadDf1Cascade<S, true, true>, true, false>
+                           : (KernelPtr)zg_stream_kernel<zgk::BiquadDf1Cascade<S, true, true>, false, false>;
+    }
 #define ZG_PICK(E, I, U) \
     if (exact == E && interleaved == I && uniform == U) \
         return (KernelPtr)zg_stream_kernel<zgk::BiquadDf1Cascade<S, E>, I, U>;
@@ -296,8 +300,8 @@ struct zg_plan {
     int fir_regs = 0;
     int last_grid = 0;
 
-    Variant variant[5];                     // [0] per-channel parameters, [1] uniform, [2] uniform + symmetric biquads;
-                                            // [3], [4]: the lane-per-channel kernel of a K1b plan (time-segmented launches)
+    Variant variant[6];                     // [0] per-channel parameters, [1] uniform, [2], [3] the same with symmetric biquads;
+                                            // [4], [5]: the lane-per-channel kernel of a K1b plan (time-segmented launches)
     int lanes_now = 1;                      // lanes per channel of the launch being prepared
 
     // Time segments for few, long channels (FAST mode, linear ticks; kernels/zg_stream.cuh StreamArgs::n_segs)
@@ -313,7 +317,7 @@ struct zg_plan {
     int AL_len = 0;                         // the L it was computed for (0: stale)
     bool AL_per_channel = false;
     int last_segs = 1, last_seg_mode = 0, last_seg_len = 0, last_seg_warm = 0;
-    bool sym_now = false;                   // K1: every section has b0 == b2 (bit for bit), coefficients uniform
+    bool sym_now = false;                   // K1: every section of every channel has b0 == b2 (bit for bit)
     std::string kernel_name;
 
     float* d_state = nullptr;               // [n_state][ch_stride]
@@ -526,11 +530,12 @@ int tune_env(const char* name) {
     return v && *v ? std::atoi(v) : 0;
 }
 
+bool variant_is_sym(const zg_plan* p) {
+    return p->sym_now && p->is_biquad && !p->opts.force_jit && p->lanes_now == 1 && p->exact && !tune_env("ZG_TUNE_NO_SYM");
+}
 int variant_index(const zg_plan* p) {
-    const bool sym = p->uniform_now && p->sym_now && p->is_biquad && !p->opts.force_jit && p->lanes_now == 1 && p->exact &&
-                     !tune_env("ZG_TUNE_NO_SYM");
-    const int lane_per_channel_of_k1b = p->lanes > 1 && p->lanes_now == 1 ? 3 : 0;     // never EXACT, hence never sym
-    return (p->uniform_now ? (sym ? 2 : 1) : 0) + lane_per_channel_of_k1b;
+    const int lane_per_channel_of_k1b = p->lanes > 1 && p->lanes_now == 1 ? 4 : 0;     // never EXACT, hence never sym
+    return (p->uniform_now ? 1 : 0) + (variant_is_sym(p) ? 2 : 0) + lane_per_channel_of_k1b;
 }
 
 int get_variant(zg_plan* p, bool uniform, Variant*& out) {
@@ -547,7 +552,7 @@ int get_variant(zg_plan* p, bool uniform, Variant*& out) {
     }
     if (p->is_biquad && !p->opts.force_jit) {
         v.prebuilt = p->lanes_now > 1 ? biquad_lanes_kernel_for(p->bq.sections, p->exact, uniform)
-                                      : biquad_kernel_for(p->bq.sections, p->exact, p->interleaved, uniform, vi == 2);
+                                      : biquad_kernel_for(p->bq.sections, p->exact, p->interleaved, uniform, variant_is_sym(p));
         if (!v.prebuilt) return fail(ZG_ERR_INTERNAL, "no prebuilt biquad kernel for this section count");
         cudaFuncAttributes fa;
         ZG_CUDA(cudaFuncGetAttributes(&fa, (const void*)v.prebuilt));
@@ -610,6 +615,23 @@ int sync_params(zg_plan* p) {
             p->sym_now = sym;
         }
     } else if (NP > 0) {
+        if (p->is_biquad && !p->opts.force_jit) {
+            // per-channel coefficients: b0 and b2 of a section are the same literal, or two parameters holding the
+            // same values for every channel (every RBJ low-pass / high-pass / notch section, whatever f and Q)
+            bool sym = true;
+            for (int k = 0; k < p->bq.sections && sym; ++k) {
+                const BiquadCoef& b0 = p->bq.coef[k][0];
+                const BiquadCoef& b2 = p->bq.coef[k][2];
+                if (b0.is_param != b2.is_param) sym = false;
+                else if (!b0.is_param) sym = std::memcmp(&b0.value, &b2.value, sizeof(float)) == 0;
+                else {
+                    const std::vector<float>&u = p->h_params[b0.param], &w = p->h_params[b2.param];
+                    sym = !p->param_on_device[b0.param] && !p->param_on_device[b2.param] && u.size() == w.size() &&
+                          std::memcmp(u.data(), w.data(), u.size() * sizeof(float)) == 0;
+                }
+            }
+            p->sym_now = sym;
+        }
         std::vector<float> host((size_t)NP * p->ch_stride, 0.f);
         for (int j = 0; j < NP; ++j) {
             int prm; float lit;
@@ -705,7 +727,7 @@ Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, in
     // Planar blocks keep gaining from that trade up to ~4.25 instructions per byte -- the product-reusing EXACT
     // 4-section tick (32 instructions / 8 B): 0.791 ms against 0.805-0.845 with 14 x 2; at 8 sections (8 per byte)
     // or on interleaved frames 14 x 2 is the faster one (profiles/r01_sweep_sym2.jsonl).
-    const int ops = p->tick_ops - (variant_index(p) == 2 ? p->bq.sections : 0);
+    const int ops = p->tick_ops - (variant_is_sym(p) ? p->bq.sections : 0);
     const int bytes = p->io * std::max(1, p->n_buf_in + p->ir.n_out);
     // (ring reads of long delay lines are plain loads, hidden by other warps only: no trade of warps for run length)
     const bool long_runs = !p->interleaved && 4 * ops < 17 * bytes && !p->ring.any();
@@ -1429,7 +1451,7 @@ int zg_plan_get_info(const zg_plan* p, zg_plan_info* info) {
     if (p->lanes > 1 && p->lanes_now == 1)                      // a K1b plan whose last launch was cut in time instead
         name = "zg_biquad_df1<" + std::to_string(p->bq.sections) + (p->exact ? ",exact,planar>" : ",fma,planar>");
     std::snprintf(info->kernel, sizeof info->kernel, "%s%s%s", name.c_str(),
-                  variant_index(p) == 2 ? "+b0=b2" : "",       // the product-reusing tick (kernels/zg_biquad.cuh)
+                  variant_is_sym(p) ? "+b0=b2" : "",           // the product-reusing tick (kernels/zg_biquad.cuh)
                   p->last_seg_mode == 1 ? "+segments:warm-up" : p->last_seg_mode == 2 ? "+segments:two-pass" : "");
     const Variant& v = p->variant[variant_index(p)];
     info->jit = (v.prebuilt || p->is_fir) ? 0 : 1;
