@@ -18,7 +18,11 @@ Channels are independent, so N GPUs = N x the channels (weak scaling), no data-p
             CPU leg is also the only place the arm touches oracle/ (a spot check of the timed kernel's output
             against the oracle rides along as cpu_baseline.parity_spot_check); graphs and coefficients of
             the GPU legs come from zignal_b200/workloads.py
-  also      the other biquad shape (c2 when the headline is ns and vice versa), device-resident, same rules
+  also      the other biquad shape (c2 when the headline is ns and vice versa), device-resident, same rules;
+            c2_scan = configs[1] in FAST mode, cut in time (zg_plan_opts.time_parallel, DESIGN.md 3 K5);
+            ns_per_channel = the north-star shape with the per-channel coefficients SURVEY.md 8(d) prescribes
+  edge      (N > 1) a 65 536 x 8192 block resident on rank 0 -> N shard plans -> back on rank 0, three ways:
+            NCCL scatter + compute + gather, kernels working on the root's block over NVLink peer memory, compute only
 Default mode is EXACT: bit-identical to the reference's x86 build, checked on sampled channels.
 """
 from __future__ import annotations
@@ -58,6 +62,10 @@ def _peak_hbm():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of "
+                  "the same kernel and shape (profiles/traffic.json), not from this run")
 
 
 def _traffic(workload):
@@ -282,6 +290,92 @@ def other_configs(zg, wl, torch, dev, local, world, rank, args, barrier, dist):
     return out
 
 
+# ---- the edge step: the only exchange the path has, when a block lives on one GPU ---------------
+
+def edge_step(zg, wl, torch, dist, dev, local, world, rank, args):
+    """A planar 65 536 x 8192 fp32 block resident on rank 0 is evaluated by `world` shard plans and ends up on rank 0
+    again, three ways, each timed on the device (CUDA events per rank, max over ranks) after a warm-up round:
+      nccl          one grouped NCCL send/recv scatter, the shard kernels, one grouped gather (shard.scatter_channels /
+                    gather_channels) -- the literal reading of `a single NCCL scatter/gather at the edges`;
+      peer_fused    no collective: every rank's TMA tensor maps point at the root's HBM (CUDA IPC peer mappings,
+                    shard.share_from_root), its kernel pulls its rows over NVLink / NVSwitch and stores the results back,
+                    tile by tile, overlapped with the arithmetic (shard.process_on_root_block);
+      compute_only  every rank on a local copy of its shard: what the exchange costs on top.
+    The root's NVLink port (900 GB/s per direction) carries (world - 1) / world of the block out and the same back."""
+    from zignal_b200.shard import (channel_range, gather_channels, process_on_root_block, scatter_channels,
+                                   share_from_root)
+    C, T = WORKLOADS["ns"]
+    mode = zg.MODE_EXACT if args.mode == "exact" else zg.MODE_FAST
+    g = zg.compile(wl.biquad_cascade(SECTIONS))
+    b, e = channel_range(C, world, rank)
+    x_root = y_root = None
+    if rank == 0:
+        gen = torch.Generator(device=dev).manual_seed(99)
+        x_root = torch.rand((C, T), generator=gen, device=dev) * 2 - 1
+        y_root = torch.empty_like(x_root)
+    xa, ya = share_from_root(x_root, 0), share_from_root(y_root, 0)
+    plan = g.plan(channels=e - b, device=local, mode=mode)
+    own = scatter_channels(x_root, C, T, root=0, device=dev)           # also the compute-only input
+    y_own = torch.empty_like(own)
+    out_nccl = torch.empty_like(x_root) if rank == 0 else None
+    steps = 5
+
+    def timed(fn):
+        fn()                                                           # warm-up (NCCL channels, peer mappings, L2 state)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def run_nccl():
+        o = scatter_channels(x_root, C, T, root=0, device=dev)
+        plan.process([o], [y_own])
+        gather_channels(y_own, C, T, root=0, out=out_nccl)
+
+    def run_peer():
+        stream = torch.cuda.current_stream().cuda_stream
+        plan.process_ptrs([xa.rows(b)], [ya.rows(b)], T, xa.ld, ya.ld, stream)
+
+    def run_local():
+        plan.process([own], [y_own])
+
+    ms_nccl = timed(run_nccl)
+    ms_peer = timed(run_peer)
+    ms_local = timed(run_local)
+    # every rank's kernel must have finished before the root reads its block
+    plan.reset(); process_on_root_block(plan, xa, ya)
+    plan.reset(); run_nccl(); torch.cuda.synchronize(); dist.barrier()
+    res = None
+    if rank == 0:
+        ref = g.plan(channels=C, device=local, mode=mode).process([x_root])[0]
+        torch.cuda.synchronize()
+        port_bytes = 4.0 * C * T * (world - 1) / world                # per direction
+        res = {"block": f"{C} channels x {T} samples fp32 planar, resident on rank 0 (2 GiB in, 2 GiB out)",
+               "steps": steps, "timing": "CUDA events per rank, max over ranks",
+               "nccl_scatter_compute_gather_ms": ms_nccl, "peer_fused_ms": ms_peer, "compute_only_ms": ms_local,
+               "bit_identical": {"peer_fused": bool(torch.equal(y_root, ref)), "nccl": bool(torch.equal(out_nccl, ref))},
+               "root_port_gbs_per_direction": {"peer_fused": port_bytes / (ms_peer * 1e-3) / 1e9,
+                                               "nccl": port_bytes / (ms_nccl * 1e-3) / 1e9},
+               "root_port_frac_of_900": {"peer_fused": port_bytes / (ms_peer * 1e-3) / 1e9 / 900.0,
+                                         "nccl": port_bytes / (ms_nccl * 1e-3) / 1e9 / 900.0},
+               "msamples_per_s": {"peer_fused": C * T / (ms_peer * 1e-3) / 1e6, "nccl": C * T / (ms_nccl * 1e-3) / 1e6,
+                                  "compute_only": C * T / (ms_local * 1e-3) / 1e6},
+               "limiter": "the root's NVLink port: (N-1)/N of the block leaves and returns through it; both directions "
+                          "run at once in the fused form (loads and stores of the same kernels), one after the other "
+                          "(scatter, then gather) through NCCL"}
+        del ref
+    dist.barrier()
+    xa.close(); ya.close()
+    dist.barrier()
+    return res
+
+
 def _bind_to_gpu_numa_node(index):
     """Pin this rank to the CPUs NVML reports as local to its GPU, before any pinned host buffer is allocated:
     with one rank per GPU on a two-socket box, host staging memory that sits on the other socket turns the e2e
@@ -327,10 +421,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_rate(workload):
+    def device_rate(workload, coef=None, mode_name=None):
         """K launches of one zg_process() each between CUDA events; returns the plan, buffers and timing."""
         C, T = WORKLOADS[workload]
-        if args.coef == "uniform":
+        coef = coef or args.coef
+        mode_name = mode_name or args.mode
+        if coef == "uniform":
             graph = zg.compile(wl.biquad_cascade(SECTIONS))
             params = []
         else:
@@ -340,7 +436,7 @@ def run_ours(args):
             for k in range(SECTIONS):
                 per = np.array([wl.rbj_lowpass(440.0 * 2 ** k * (1.0 + ci / (C * world))) for ci in c], np.float32)
                 params += [per[:, j].copy() for j in range(5)]
-        mode = zg.MODE_EXACT if args.mode == "exact" else zg.MODE_FAST
+        mode = zg.MODE_EXACT if mode_name == "exact" else zg.MODE_FAST
         plan = graph.plan(channels=C, device=local, mode=mode,
                           layout=zg.INTERLEAVED if args.layout == "interleaved" else zg.PLANAR)
         for i, p in enumerate(params):
@@ -395,7 +491,32 @@ def run_ours(args):
             dt = float(t.item())
         e2e = {"value": world * C * T * e2e_steps / dt / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": int(C * T * 4), "d2h_bytes_per_step": int(C * T * 4), "steps": e2e_steps,
-               "ms_per_step": dt / e2e_steps * 1e3, "api": "zg_process_host (pinned host buffers)"}
+               "ms_per_step": dt / e2e_steps * 1e3, "api": "zg_process_host (pinned host buffers)",
+               "host_chunks": plan.info().host_chunks,
+               "gbs_per_rank_both_directions": 2 * C * T * 4 * e2e_steps / dt / 1e9}
+        # what the host link gives this rank with all ranks copying at once and no kernel in the way: one direction
+        # alone, then both together -- tells PCIe (per-GPU link) from host DRAM / root-complex saturation
+        copies = {}
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        for name, do_h2d, do_d2h in (("h2d", True, False), ("d2h", False, True), ("both", True, True)):
+            barrier()
+            t0 = time.perf_counter()
+            if do_h2d:
+                with torch.cuda.stream(s1):
+                    x.copy_(hx, non_blocking=True)
+            if do_d2h:
+                with torch.cuda.stream(s2):
+                    hy.copy_(y, non_blocking=True)
+            torch.cuda.synchronize()
+            dtc = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([dtc], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dtc = float(t.item())
+            copies[name + "_gbs_per_rank"] = (int(do_h2d) + int(do_d2h)) * C * T * 4 / dtc / 1e9
+        e2e["copy_only"] = copies
+        e2e["limiter"] = ("host link: a step moves 2 x %.2f GB per rank; the kernel is %.1f %% of the step" %
+                          (C * T * 4 / 1e9, 100 * ms_per_step / (dt / e2e_steps * 1e3)))
         del hx, hy
 
     # ---- CPU leg, part 1 (rank 0, N = 1 only; the one place this arm may execute oracle/): a spot check of the
@@ -433,7 +554,61 @@ def run_ours(args):
                                     "0.50 ms / 0.67 of the HBM roofline is the ceiling of EXACT arithmetic (DESIGN.md K1b)")
         del plan_o, xo, yo
         torch.cuda.empty_cache()
+        peak_hbm = _peak_hbm()[0]
+        try:
+            # BASELINE configs[1] in FAST mode: too few channels for a lane each -> cut in time (warm-up form)
+            Cs, Ts = WORKLOADS["c2"]
+            plan_s, xs, ys, _, ms_s, launches_s, _ = device_rate("c2", coef="uniform", mode_name="fast")
+            i_s = plan_s.info()
+            K, L = i_s.warmup_samples, max(i_s.segment_samples, 1)
+            ent = {"workload": workload_string("c2", args.layout) + ", FAST (FMA) mode, time-parallel",
+                   "value": world * Cs * Ts / (ms_s * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_s,
+                   "roofline_frac": BYTES_PER_SAMPLE * Cs * Ts / (ms_s * 1e-3) / 1e9 / peak_hbm,
+                   "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE,
+                   "moved_bytes_per_sample": (8 + 4.0 * K / L) if i_s.time_segments > 1 and K else (12 if i_s.time_segments > 1 else 8),
+                   "kernel": i_s.kernel.decode(), "time_segments": i_s.time_segments, "segment_samples": i_s.segment_samples,
+                   "warmup_samples": K, "launches_per_step": launches_s // max(args.steps, 1),
+                   "numerics": "FAST: FMA contraction + segments that start from a warmed-up state; held to the FAST bar of "
+                               "tests/test_time_parallel.py (<= 3e-5 block-relative on this cascade, no further from float64 "
+                               "than the reference)"}
+            if rank == 0 and world == 1 and not args.no_cpu and args.layout == "planar":
+                import flowz_oracle as fo                     # CPU leg: the checker, on four channels
+                plan_s.reset()
+                plan_s.process([xs], [ys])
+                torch.cuda.synchronize()
+                idx = [0, 1, Cs // 2, Cs - 1]
+                xi = xs[idx].cpu().numpy()
+                ref = fo.COracle(fo.biquad_cascade(SECTIONS), len(idx)).process([xi])[0]
+                got = ys[idx].cpu().numpy().astype(np.float64)
+                ent["parity_spot_check"] = {"max_block_rel_err_vs_oracle": float((np.abs(got - ref).max(axis=1) / np.abs(ref).max(axis=1)).max()),
+                                            "channels_checked": idx}
+            also["c2_scan"] = ent
+            del plan_s, xs, ys
+        except Exception as e:
+            also["c2_scan"] = {"error": str(e)[:300]}
+        torch.cuda.empty_cache()
+        try:
+            # the coefficients SURVEY.md 8(d) prescribes: every channel its own RBJ sections, f * (1 + c / C)
+            Cn, Tn = WORKLOADS["ns"]
+            plan_p, xp, yp, _, ms_p, _, _ = device_rate("ns", coef="per-channel", mode_name=args.mode)
+            i_p = plan_p.info()
+            also["ns_per_channel"] = {"workload": workload_string("ns", args.layout) + ", per-channel coefficients f*(1+c/C)",
+                                      "value": world * Cn * Tn / (ms_p * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_p,
+                                      "roofline_frac": BYTES_PER_SAMPLE * Cn * Tn / (ms_p * 1e-3) / 1e9 / peak_hbm,
+                                      "kernel": i_p.kernel.decode(), "uniform_params": i_p.uniform_params, "mode": args.mode}
+            del plan_p, xp, yp
+        except Exception as e:
+            also["ns_per_channel"] = {"error": str(e)[:300]}
+        torch.cuda.empty_cache()
         also.update(other_configs(zg, wl, torch, dev, local, world, rank, args, barrier, dist))
+
+    edge = None
+    if world > 1 and not args.no_edge:
+        try:
+            edge = edge_step(zg, wl, torch, dist, dev, local, world, rank, args)
+        except Exception as e:
+            edge = {"error": str(e)[:300]}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_src = _peak_hbm()
@@ -449,7 +624,7 @@ def run_ours(args):
                        "threads_per_cta": info.threads_per_cta,
                        "stages": info.stages, "boxes": info.boxes, "smem_bytes": info.smem_bytes, "regs": info.regs_per_thread},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": _traffic(args.workload), "peak_source": peak_src,
+                         "traffic": _traffic(args.workload), "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * C * T},
             "clocks": clk.summary(),
             "gpu_launches": launches,
@@ -458,6 +633,8 @@ def run_ours(args):
             line["e2e"] = e2e
         if also is not None:
             line["also"] = also
+        if edge is not None:
+            line["edge"] = edge
         if world == 1 and not args.no_cpu:                  # CPU leg, part 2: the reference's loop on the host cores
             line["cpu_baseline"], _ = cpu_reference_rate()
             if parity is not None:
@@ -482,6 +659,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the second workload")
+    ap.add_argument("--no-edge", action="store_true", help="N > 1: skip the edge step (block resident on rank 0)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

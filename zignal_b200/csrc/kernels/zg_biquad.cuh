@@ -30,6 +30,9 @@ struct BiquadDf1Cascade {
     static constexpr int N_PARAM = 5 * SECTIONS;
     static constexpr int N_EXTRA = kSym ? 2 * SECTIONS : 0;   // registers that are not delay-line state
     static constexpr unsigned SYNTH_MASK = 0;
+#ifdef ZG_K1_CHUNK_UNROLL
+    static constexpr int CHUNK_UNROLL = ZG_K1_CHUNK_UNROLL;
+#endif
 
     // e[2k] = b0*x[t-2], e[2k+1] = b0*x[t-1] of section k, rebuilt from the delay lines at block start
     template <class P>

@@ -263,7 +263,9 @@ __device__ __forceinline__ int ring_mod(long long t, int depth) {     // t may b
 //   template <class P>                            // P = Arr<N_PARAM> or UniformParams
 //   static __device__ void tick(const Arr<N_IN>& x, Arr<N_OUT>& y, Arr<N_STATE>& s, const P& p);
 
-template <class Tick, bool kInterleaved, bool kUniform, int kIo = 4>
+// kSeg: the kernel understands time segments (StreamArgs::n_segs).  Only FAST-mode kernels are built with it -- a cut
+// in time re-associates the arithmetic, EXACT launches never ask for one, and their code stays free of the bookkeeping.
+template <class Tick, bool kInterleaved, bool kUniform, int kIo = 4, bool kSeg = false>
 __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     typedef Io<kIo> IO;
     constexpr int VPC = IO::kPerChunk;                         // ticks per 16-byte chunk
@@ -290,16 +292,32 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     const int tile_t = NB * BT;
     const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
     // warp -> (segment, channel group): the warps of a CTA are neighbouring channel groups at the same place in time
-    const int n_groups = (a.channels + 31) >> 5;
-    const int n_segs = a.n_segs > 1 ? a.n_segs : 1;
-    const int seg = (int)(gw / n_groups);
-    if (seg >= n_segs) return;                         // warp-uniform
-    const bool pass1 = (a.flags & 32) != 0, pass2 = (a.flags & 64) != 0;
-    if (pass1 && seg + 1 == n_segs) return;            // the block's final state comes out of pass 2
-    const int t_seg = n_segs > 1 ? seg * a.seg_len : 0;                        // first sample this warp answers for
-    const int t_lo = seg > 0 && !pass1 && !pass2 ? t_seg - a.seg_warm : t_seg; // first sample it evaluates
-    const int t_hi = seg + 1 < n_segs ? t_seg + a.seg_len : a.n_samples;       // end of its samples
-    const int c0 = (int)(gw - (long long)seg * n_groups) * 32;
+    // (every use below goes through T_LO / T_HI / T_SEG so that a kernel built without kSeg reads a.n_samples and
+    //  literal zeros exactly as it did before segments existed: ptxas allocates the hot loop differently otherwise,
+    //  and the EXACT 4-section tick lost 9 % to that)
+    int seg_v = 0, n_segs_v = 1, c0_v = 0, t_seg_v = 0, t_lo_v = 0, t_hi_v = 0;
+    bool pass1_v = false, pass2_v = false;
+    if constexpr (kSeg) {
+        const int n_groups = (a.channels + 31) >> 5;
+        n_segs_v = a.n_segs > 1 ? a.n_segs : 1;
+        seg_v = (int)(gw / n_groups);
+        if (seg_v >= n_segs_v) return;                 // warp-uniform
+        pass1_v = (a.flags & 32) != 0;
+        pass2_v = (a.flags & 64) != 0;
+        if (pass1_v && seg_v + 1 == n_segs_v) return;  // the block's final state comes out of pass 2
+        t_seg_v = n_segs_v > 1 ? seg_v * a.seg_len : 0;                             // first sample this warp answers for
+        t_lo_v = seg_v > 0 && !pass1_v && !pass2_v ? t_seg_v - a.seg_warm : t_seg_v; // first sample it evaluates
+        t_hi_v = seg_v + 1 < n_segs_v ? t_seg_v + a.seg_len : a.n_samples;          // end of its samples
+        c0_v = (int)(gw - (long long)seg_v * n_groups) * 32;
+    }
+    const long long c0ll = gw * 32;
+    if (!kSeg && c0ll >= a.channels) return;           // warp-uniform
+    const int c0 = kSeg ? c0_v : (int)c0ll;
+    const int seg = seg_v, n_segs = n_segs_v;
+    const bool pass1 = pass1_v, pass2 = pass2_v;
+#define T_LO (kSeg ? t_lo_v : 0)
+#define T_HI (kSeg ? t_hi_v : a.n_samples)
+#define T_SEG (kSeg ? t_seg_v : 0)
     const int ch = c0 + lane;
     const bool ch_ok = ch < a.channels;
 
@@ -318,9 +336,14 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     Arr<NS> s;
     // segment 0 continues the stream from `state`; a later segment starts from zero (warm-up form, pass 1) or from the
     // boundary state the fix-up kernel left for it (pass 2)
-    const float* st_in = seg == 0 ? a.state : pass2 ? a.seg_state + (long long)(seg - 1) * a.seg_state_stride : nullptr;
+    if constexpr (kSeg) {
+        const float* st_in = seg == 0 ? a.state : pass2 ? a.seg_state + (long long)(seg - 1) * a.seg_state_stride : nullptr;
 #pragma unroll
-    for (int j = 0; j < NS; ++j) s[j] = ch_ok && st_in ? st_in[(long long)a.state_row[j] * a.ch_stride + ch] : 0.f;
+        for (int j = 0; j < NS; ++j) s[j] = ch_ok && st_in ? st_in[(long long)a.state_row[j] * a.ch_stride + ch] : 0.f;
+    } else {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) s[j] = ch_ok ? a.state[(long long)a.state_row[j] * a.ch_stride + ch] : 0.f;
+    }
     Arr<kUniform ? 0 : NP> prm_reg;
     if (!kUniform) {
 #pragma unroll
@@ -356,19 +379,19 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     }
     __syncwarp();
 
-    const int n_tiles = (t_hi - t_lo + tile_t - 1) / tile_t;
+    const int n_tiles = (T_HI - T_LO + tile_t - 1) / tile_t;
     // flags bit 2 / bit 3: L2 evict-first hint on the sample loads / stores
     const bool hint_loads = (a.flags & 4) != 0, hint_stores = (a.flags & 8) != 0;
     const unsigned long long policy = (a.flags & 12) ? l2_policy_evict_first() : 0ull;
 
     auto boxes_in_tile = [&](int t0) {                 // boxes of tile at t0 that hold samples
-        const int left = (t_hi - t0 + BT - 1) / BT;
+        const int left = (T_HI - t0 + BT - 1) / BT;
         return left < NB ? left : NB;
     };
     auto issue_load = [&](int i) {                     // lane 0 only
         if (kNumBuf == 0) return;
         const int slot = i % S;
-        const int t0 = t_lo + i * tile_t;
+        const int t0 = T_LO + i * tile_t;
         const int nb = boxes_in_tile(t0);
         mbar_expect_tx(&bars[slot], (unsigned)(nb * kNumBuf * BB));
 #pragma unroll
@@ -414,12 +437,13 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
 
     for (int i = 0; i < n_tiles; ++i) {
         const int slot = i % S;
-        const int t0 = t_lo + i * tile_t;
+        const int t0 = T_LO + i * tile_t;
         const int nb = boxes_in_tile(t0);
         unsigned char* stage = my + (size_t)slot * stage_bytes;
 
         if (!kInterleaved && kNumBuf > 0 && (a.flags & 16) && ch_ok) {
-            const long long off = ((long long)t0 + (long long)a.pf_dist * tile_t) * kIo;  // byte offset inside the row
+            const long long off = kSeg ? ((long long)t0 + (long long)a.pf_dist * tile_t) * kIo
+                                       : (long long)(i + a.pf_dist) * tile_t * kIo;          // byte offset inside the row
             const long long row_bytes = ((long long)a.n_samples * kIo) & ~15ll;
             if (off % a.pf_window == 0 && off < row_bytes) {
                 const unsigned sz = (unsigned)(row_bytes - off < a.pf_window ? row_bytes - off : a.pf_window);
@@ -434,7 +458,7 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
 #pragma unroll 1
             for (int b = 0; b < nb; ++b) {
                 const int tb0 = t0 + b * BT;
-                const int n_valid = t_hi - tb0 < BT ? t_hi - tb0 : BT;
+                const int n_valid = T_HI - tb0 < BT ? T_HI - tb0 : BT;
                 unsigned char* base = stage + b * BB;              // wire k of this box: base + k * wire_bytes
                 if (early_refill && lane == 0 && b == 1 && i + S - 1 < n_tiles) {
                     tma_wait_read<0>();                            // the store of tile i-1 (the only one pending)
@@ -620,7 +644,7 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
         if (lane == 0) {
             // warm-up tiles and the whole of pass 1 produce state, not samples: nothing is stored (the commit
             // group stays, empty, so that the refill logic below counts the same groups)
-            const bool discard = pass1 || t0 < t_seg;
+            const bool discard = kSeg && (pass1 || t0 < T_SEG);
 #pragma unroll
             for (int o = 0; o < NO; ++o) {
                 for (int b = 0; b < (discard ? 0 : nb); ++b) {
@@ -644,12 +668,17 @@ __device__ __forceinline__ void stream_block(const StreamArgs& a) {
     if (lane == 0) tma_wait_all<0>();                  // smem must outlive the last stores
 
     // ---- state back to HBM: the last segment ends the block; pass 1 leaves every segment's final state for the fix-up ----
-    float* st_out = pass1 ? a.seg_state + (long long)seg * a.seg_state_stride : seg + 1 == n_segs ? a.state : nullptr;
-    if (ch_ok && st_out) {
+    float* st_out = a.state;
+    if constexpr (kSeg) st_out = pass1 ? a.seg_state + (long long)seg * a.seg_state_stride : seg + 1 == n_segs ? a.state : nullptr;
+    if (ch_ok && (!kSeg || st_out)) {
 #pragma unroll
         for (int j = 0; j < NS; ++j)
             if (!((a.state_nowrite >> j) & 1ull)) st_out[(long long)a.state_row[j] * a.ch_stride + ch] = s[j];
     }
 }
+
+#undef T_LO
+#undef T_HI
+#undef T_SEG
 
 }  // namespace zgk

@@ -147,9 +147,9 @@ int cuda_fail(cudaError_t e, const char* what) {
 // prebuilt kernels (K1)
 // ------------------------------------------------------------------------------------------------
 
-template <class Tick, bool kInterleaved, bool kUniform>
+template <class Tick, bool kInterleaved, bool kUniform, bool kSeg = false>
 __global__ void __launch_bounds__(512, 1) zg_stream_kernel(const __grid_constant__ zgk::StreamArgs a) {
-    zgk::stream_block<Tick, kInterleaved, kUniform>(a);
+    zgk::stream_block<Tick, kInterleaved, kUniform, 4, kSeg>(a);
 }
 
 template <int S, bool kExact, bool kUniform>
@@ -225,7 +225,15 @@ KernelPtr biquad_lanes_kernel_for(int sections, bool exact, bool uniform) {
 }
 
 template <int S>
-KernelPtr biquad_kernel(bool exact, bool interleaved, bool uniform, bool sym) {
+KernelPtr biquad_kernel(bool exact, bool interleaved, bool uniform, bool sym, bool seg) {
+    // FAST kernels exist with and without time segments (kernels/zg_stream.cuh kSeg): the bookkeeping costs the
+    // unsegmented launch 3.5 % on the north-star shape, so it only runs when a launch is actually cut in time
+    if (seg && !exact) {
+#define ZG_PICK(I, U) \
+    if (interleaved == I && uniform == U) return (KernelPtr)zg_stream_kernel<zgk::BiquadDf1Cascade<S, false>, I, U, true>;
+        ZG_PICK(false, false) ZG_PICK(false, true) ZG_PICK(true, false) ZG_PICK(true, true)
+#undef ZG_PICK
+    }
     // b0 == b2 in every section (of every channel), EXACT: the product-reusing tick (kernels/zg_biquad.cuh)
     if (sym && exact) {
         if (uniform)
@@ -243,16 +251,16 @@ KernelPtr biquad_kernel(bool exact, bool interleaved, bool uniform, bool sym) {
     return nullptr;
 }
 
-KernelPtr biquad_kernel_for(int sections, bool exact, bool interleaved, bool uniform, bool sym) {
+KernelPtr biquad_kernel_for(int sections, bool exact, bool interleaved, bool uniform, bool sym, bool seg) {
     switch (sections) {
-        case 1: return biquad_kernel<1>(exact, interleaved, uniform, sym);
-        case 2: return biquad_kernel<2>(exact, interleaved, uniform, sym);
-        case 3: return biquad_kernel<3>(exact, interleaved, uniform, sym);
-        case 4: return biquad_kernel<4>(exact, interleaved, uniform, sym);
-        case 5: return biquad_kernel<5>(exact, interleaved, uniform, sym);
-        case 6: return biquad_kernel<6>(exact, interleaved, uniform, sym);
-        case 7: return biquad_kernel<7>(exact, interleaved, uniform, sym);
-        case 8: return biquad_kernel<8>(exact, interleaved, uniform, sym);
+        case 1: return biquad_kernel<1>(exact, interleaved, uniform, sym, seg);
+        case 2: return biquad_kernel<2>(exact, interleaved, uniform, sym, seg);
+        case 3: return biquad_kernel<3>(exact, interleaved, uniform, sym, seg);
+        case 4: return biquad_kernel<4>(exact, interleaved, uniform, sym, seg);
+        case 5: return biquad_kernel<5>(exact, interleaved, uniform, sym, seg);
+        case 6: return biquad_kernel<6>(exact, interleaved, uniform, sym, seg);
+        case 7: return biquad_kernel<7>(exact, interleaved, uniform, sym, seg);
+        case 8: return biquad_kernel<8>(exact, interleaved, uniform, sym, seg);
     }
     return nullptr;
 }
@@ -300,9 +308,10 @@ struct zg_plan {
     int fir_regs = 0;
     int last_grid = 0;
 
-    Variant variant[6];                     // [0] per-channel parameters, [1] uniform, [2], [3] the same with symmetric biquads;
-                                            // [4], [5]: the lane-per-channel kernel of a K1b plan (time-segmented launches)
+    Variant variant[12];                    // [0] per-channel parameters, [1] uniform, [2], [3] the same with symmetric biquads;
+                                            // [4], [5]: the lane-per-channel kernel of a K1b plan; + 6: built with time segments
     int lanes_now = 1;                      // lanes per channel of the launch being prepared
+    bool seg_now = false;                   // the launch being prepared is cut in time
 
     // Time segments for few, long channels (FAST mode, linear ticks; kernels/zg_stream.cuh StreamArgs::n_segs)
     int linearity = ZG_NONLINEAR;
@@ -386,7 +395,7 @@ Ir split_for_kernel(const Ir& ir, bool interleaved, int io, RingPlan& ring, int&
 }
 
 std::string jit_source(const Ir& ir, bool exact, bool interleaved, bool uniform, unsigned synth_mask, int io,
-                       int n_ring_in = 0, int n_ring_out = 0, int ring_pf = 1) {
+                       int n_ring_in = 0, int n_ring_out = 0, int ring_pf = 1, bool seg = false) {
     std::ostringstream src;
     src << "#define ZG_SYNTH_MASK " << synth_mask << "u\n";
     src << zg_stream_cuh_source << "\n";
@@ -394,7 +403,8 @@ std::string jit_source(const Ir& ir, bool exact, bool interleaved, bool uniform,
     src << "extern \"C\" __global__ void __launch_bounds__(512, 1) zg_graph_kernel("
            "const __grid_constant__ zgk::StreamArgs a) {\n"
            "    zgk::stream_block<ZgTick, "
-        << (interleaved ? "true" : "false") << ", " << (uniform ? "true" : "false") << ", " << io << ">(a);\n}\n";
+        << (interleaved ? "true" : "false") << ", " << (uniform ? "true" : "false") << ", " << io << ", "
+        << (seg ? "true" : "false") /* built with time segments (kSeg) */ << ">(a);\n}\n";
     return src.str();
 }
 
@@ -513,7 +523,7 @@ int jit_compile(zg_plan* p, bool uniform, Variant& v) {
     if (!d.ok) return fail(ZG_ERR_CUDA, d.why);
     std::vector<char> cubin;
     int st = jit_cubin(jit_source(p->kir, p->exact, p->interleaved, uniform, p->synth_mask, p->io, (int)p->ring.taps.size(),
-                                  (int)p->ring.out_lines.size(), p->ring_pf),
+                                  (int)p->ring.out_lines.size(), p->ring_pf, p->seg_now),
                        p->exact, cubin);
     if (st != ZG_OK) return st;
     CUresult cr = d.moduleLoadData(&v.module, cubin.data());
@@ -535,7 +545,7 @@ bool variant_is_sym(const zg_plan* p) {
 }
 int variant_index(const zg_plan* p) {
     const int lane_per_channel_of_k1b = p->lanes > 1 && p->lanes_now == 1 ? 4 : 0;     // never EXACT, hence never sym
-    return (p->uniform_now ? 1 : 0) + (variant_is_sym(p) ? 2 : 0) + lane_per_channel_of_k1b;
+    return (p->uniform_now ? 1 : 0) + (variant_is_sym(p) ? 2 : 0) + lane_per_channel_of_k1b + (p->seg_now ? 6 : 0);
 }
 
 int get_variant(zg_plan* p, bool uniform, Variant*& out) {
@@ -552,7 +562,7 @@ int get_variant(zg_plan* p, bool uniform, Variant*& out) {
     }
     if (p->is_biquad && !p->opts.force_jit) {
         v.prebuilt = p->lanes_now > 1 ? biquad_lanes_kernel_for(p->bq.sections, p->exact, uniform)
-                                      : biquad_kernel_for(p->bq.sections, p->exact, p->interleaved, uniform, variant_is_sym(p));
+                                      : biquad_kernel_for(p->bq.sections, p->exact, p->interleaved, uniform, variant_is_sym(p), p->seg_now);
         if (!v.prebuilt) return fail(ZG_ERR_INTERNAL, "no prebuilt biquad kernel for this section count");
         cudaFuncAttributes fa;
         ZG_CUDA(cudaFuncGetAttributes(&fa, (const void*)v.prebuilt));
@@ -734,6 +744,19 @@ Geometry choose_geometry(const zg_plan* p, int64_t n_warps, int NT, int regs, in
     if (long_runs && per_sm >= 7) {
         wpc = std::min(wpc, 7);
         NB = 4;
+    }
+    // More warps than one wave holds (one CTA per SM: shared memory is sized to fill it): the launch takes
+    // waves x (time of one CTA ~ its warps, they share the SM's issue slots).  131 072 channels = 4096 warps: 16 per
+    // CTA is 256 CTAs = 1.73 waves with a quarter of the SMs idle in the second; 14 per CTA is 293 CTAs = 1.98 waves.
+    if (per_sm > wpc) {
+        int best = wpc;
+        int64_t best_cost = INT64_MAX;
+        for (int w = wpc; w >= std::max(2, wpc / 2); --w) {
+            const int64_t ctas = (n_warps + w - 1) / w;
+            const int64_t cost = (ctas + p->sm_count - 1) / p->sm_count * w;
+            if (cost < best_cost) { best_cost = cost; best = w; }
+        }
+        wpc = best;
     }
     if (int w = tune_env("ZG_TUNE_WPC")) wpc = std::min(std::max(w, 1), 16);
     const int budget = p->max_smem_optin - 1024 /*alignment slack*/ - 16 * 8 * 8 /*barriers*/;
@@ -958,6 +981,7 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     st = choose_segments(p, in, out, T, c_count, sg);
     if (st != ZG_OK) return st;
     p->lanes_now = sg.mode ? 1 : p->lanes;
+    p->seg_now = sg.mode != 0;
     Variant* v = nullptr;
     st = get_variant(p, p->uniform_now, v);
     if (st != ZG_OK) return st;
