@@ -133,9 +133,9 @@ class ClockSampler:
 # ---- the reference arm / cpu baseline: the reference's own loop on the host cores ---------------------
 
 def _ref_lib():
-    """oracle/_ref/libzg_ref.so (the reference's benchmark.cpp compiled where it lies), on ALL host threads:
+    """oracle/_ref/libzg_ref_custom.so (the reference's benchmark.cpp compiled where it lies), on ALL host threads:
     torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would silently time one core."""
-    so = os.path.join(ROOT, "oracle", "_ref", "libzg_ref.so")
+    so = os.path.join(ROOT, "oracle", "_ref", "libzg_ref_custom.so")
     if os.path.exists(so):
         lib = ctypes.CDLL(so)
         try:

@@ -10,7 +10,17 @@
 //     THIS repository's include/flowz/flowz.hpp shim -- i.e. proof that the unmodified reference
 //     source builds and runs on the shim (drop-in check).
 // <benchmark/benchmark.h> resolves to oracle/stubs; <flowz/flowz.hpp> resolves to include/.
+//
+// Built twice (oracle/Makefile) so that the half that pins the oracle and times the CPU arm cannot touch the product:
+//   _ref/libzg_ref_custom.so  -DZG_REF_PART=1: zg_ref_custom, zg_ref_sum_dirac_custom, zg_ref_df1_chain -- the reference's
+//                             own loops only; linked with --no-undefined and WITHOUT libzignal_b200;
+//   _ref/libzg_ref_flow.so    -DZG_REF_PART=2: zg_ref_flow, zg_ref_sum_dirac_flow -- the reference's make_flow() graphs on
+//                             this repository's shim, linked against libzignal_b200 (the drop-in check).
 #include <test/benchmark.cpp>
+
+#ifndef ZG_REF_PART
+#error "compile with -DZG_REF_PART=1 (reference loops only) or -DZG_REF_PART=2 (make_flow on the shim)"
+#endif
 
 #include <cstddef>
 #include <tuple>
@@ -26,6 +36,7 @@ void run_block(F f, const float* x, float* y, long n) {
 
 extern "C" {
 
+#if ZG_REF_PART == 1
 // form: 1 = DF1, 2 = DF2, 3 = DF1 transposed, 4 = DF2 transposed.  Fresh (zero) state, one voice.
 int zg_ref_custom(int form, const float* x, float* y, long n) {
     switch (form) {
@@ -37,6 +48,8 @@ int zg_ref_custom(int form, const float* x, float* y, long n) {
     return -1;
 }
 
+#endif
+#if ZG_REF_PART == 2
 // the same four graphs as flowz expressions, ticked through the shim
 int zg_ref_flow(int form, const float* x, float* y, long n) {
     try {
@@ -51,6 +64,8 @@ int zg_ref_flow(int form, const float* x, float* y, long n) {
     return -1;
 }
 
+#endif
+#if ZG_REF_PART == 1
 // sum_dirac (test/benchmark.cpp:137-147) on the custom loop / on the flowz graph
 float zg_ref_sum_dirac_custom(int form) {
     switch (form) {
@@ -61,6 +76,8 @@ float zg_ref_sum_dirac_custom(int form) {
     }
     return 0.f;
 }
+#endif
+#if ZG_REF_PART == 2
 float zg_ref_sum_dirac_flow(int form) {
     switch (form) {
         case 1: { auto f = biquad::direct_form_1::make_flow(); return sum_dirac(f); }
@@ -71,6 +88,8 @@ float zg_ref_sum_dirac_flow(int form) {
     return 0.f;
 }
 
+#endif
+#if ZG_REF_PART == 1
 // The reference's own CPU loop for the benchmark workload: `sections` hand-written DF1 biquads in
 // series per channel (the way make_custom2, test/benchmark.cpp:49-55, chains two), one sample per
 // call, channels spread over the host cores.  Planar [channels][n].  Coefficients are the
@@ -94,5 +113,6 @@ int zg_ref_df1_chain(int sections, const float* x, float* y, long channels, long
     }
     return 0;
 }
+#endif
 
 }  // extern "C"

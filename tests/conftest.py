@@ -44,17 +44,31 @@ def zg():
     return zignal_b200
 
 
-@pytest.fixture(scope="session")
-def ref_lib():
-    """oracle/_ref: the reference's own benchmark.cpp compiled where it lies (checker only)."""
-    import ctypes
+def _ref_so(name):
     import subprocess
-    so = os.path.join(ROOT, "oracle", "_ref", "libzg_ref.so")
+    so = os.path.join(ROOT, "oracle", "_ref", name)
     if not os.path.exists(so) and os.path.exists("/root/reference/test/benchmark.cpp"):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
     if not os.path.exists(so):
         pytest.skip("oracle/_ref not built and /root/reference absent")
-    lib = ctypes.CDLL(so)
+    return so
+
+
+@pytest.fixture(scope="session")
+def ref_lib():
+    """oracle/_ref/libzg_ref_custom.so: the hand-written loops of the reference's own benchmark.cpp compiled where it
+    lies (checker only; linked without the product)."""
+    import ctypes
+    lib = ctypes.CDLL(_ref_so("libzg_ref_custom.so"))
     lib.zg_ref_sum_dirac_custom.restype = ctypes.c_float
+    return lib
+
+
+@pytest.fixture(scope="session")
+def ref_flow_lib(zg):
+    """oracle/_ref/libzg_ref_flow.so: the reference's make_flow() graphs (the same unmodified translation unit)
+    compiled against this repository's flowz shim and linked with libzignal_b200 -- the drop-in check."""
+    import ctypes
+    lib = ctypes.CDLL(_ref_so("libzg_ref_flow.so"))
     lib.zg_ref_sum_dirac_flow.restype = ctypes.c_float
     return lib

@@ -66,6 +66,28 @@ int main(int argc, char** argv) {
     auto fork = one_pole;                                 // continues from the same state, independently
     CHECK(std::get<0>(fork(0.25f)) == std::get<0>(one_pole(0.25f)));
 
+    // ---- currying (flowz.hpp:1203-1212): with fewer arguments than inputs, operator() returns a closure that holds
+    //      the given arguments and a COPY of the callable (`expr = *this`, state included); the closure is mutable, so
+    //      its copy advances from call to call while the original never moves ----
+    {
+        auto two = compile(~(_2 + _3 + 0.5f * _1[_1]));          // two inputs: y = a + b + 0.5 * y[-1]
+        auto direct = two;                                       // an independent voice, same (zero) state
+        const std::vector<float> zero_state = two.state();
+        auto half = two(1.0f);                                   // waits for the second argument
+        const float d1 = std::get<0>(direct(1.0f, 2.0f)), d2 = std::get<0>(direct(1.0f, 2.0f));
+        CHECK(d1 == 3.0f && d2 == 4.5f);
+        CHECK(std::get<0>(half(2.0f)) == d1);                    // f(x1)(x2) == f(x1, x2)
+        CHECK(std::get<0>(half(2.0f)) == d2);                    // the closure's own copy carries its state on
+        CHECK(two.state() == zero_state);                        // ... and the original has not ticked at all
+        CHECK(std::get<0>(two(1.0f, 2.0f)) == d1);               // so it still starts from zero
+        auto later = two(1.0f);                                  // a closure made now copies the advanced state
+        CHECK(std::get<0>(later(2.0f)) == d2);
+        auto none = two();                                       // no arguments at all: waits for both
+        CHECK(std::get<0>(none(1.0f, 2.0f)) == d2);
+        auto three = compile(_1 + 2.0f * _2 + 4.0f * _3);        // closures curry again: f(a)(b)(c)
+        CHECK(std::get<0>(three(1.0f)(1.0f)(1.0f)) == 7.0f && std::get<0>(three(1.0f, 1.0f)(1.0f)) == 7.0f);
+    }
+
     // ---- expr[_n], a spelling the reference plans (TODO.md:51-52): (_1+_2)[_1] == _1+_2 |= _1[_1] ----
     {
         auto a = compile((_1 + _2)[_1]);

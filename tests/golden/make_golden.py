@@ -1,4 +1,4 @@
-"""Generates tests/golden/biquad_ref.npz from the reference itself (oracle/_ref/libzg_ref.so =
+"""Generates tests/golden/biquad_ref.npz from the reference itself (oracle/_ref/libzg_ref_custom.so =
 /root/reference/test/benchmark.cpp compiled where it lies).  Run in the build container:
     make -C oracle ref && python tests/golden/make_golden.py
 Outputs of the reference's hand-written biquad loops (make_custom, benchmark.cpp:35-126) on the
@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import flowz_oracle as fo  # noqa: E402
 
-lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libzg_ref.so"))
+lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libzg_ref_custom.so"))
 P = ctypes.POINTER(ctypes.c_float)
 dirac = np.zeros(201, np.float32); dirac[0] = 1.0
 noise = fo.noise(1, 4096, seed=3)[0].copy()
