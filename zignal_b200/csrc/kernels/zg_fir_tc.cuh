@@ -1,0 +1,325 @@
+// zignal-b200 :: K3t -- the dense FIR on the 5th-generation tensor cores (tcgen05, TMEM accumulators), FAST mode.
+//
+// What it replaces: the same graph as kernels/zg_fir.cuh -- c0*_1 + c1*_1[_1] + ... + c(N-1)*_1[_(N-1)], N <= 256,
+// which the reference ticks as a 256-term expression over one shifted std::array (flowz/flowz.hpp:130-148, :769-772).
+// With the taps shared by all channels that sum IS a dense channel x tap contraction (BASELINE north_star:
+// "tensor cores used only where a stage is genuinely a dense channel x tap contraction"):
+//
+//     Y[c, t] = sum_j X[c, j] * h[t - j]          Y = X * G^T,   G[t, j] = h[t - j]  (banded Toeplitz)
+//
+// Shape of one MMA (tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 128, K = 8):
+//     D[128 channels, 128 output times]  +=  A[128 channels, 8 input times]  x  B[128 output times, 8 input times]^T
+//   * A is a slice of an input block: 128 channel rows x 32 samples (16 KB) exactly as TMA lands it with
+//     SWIZZLE_128B -- the canonical K-major operand layout, no repacking;
+//   * B is a 128-row window of ONE tall matrix G[r][j] = h[r - 96 - j], r = 0..479, j = 0..31 (60 KB, built once per
+//     CTA): the block of the band that input block jb contributes to output tile o starts at row
+//     128*o - 32*jb + 96, so all twelve band blocks are row windows of the same shared-memory image (each window
+//     start is a multiple of 32 rows = 4 KB, which keeps the 1024-byte swizzle atoms aligned);
+//   * D is one of four 128-column TMEM accumulators: an input block feeds three output tiles (the one it lies in and
+//     the next two), the fourth accumulator is being drained by the epilogue warps.
+//
+// fp32 accuracy out of TF32 operands (3xTF32): x = hi + lo with hi = cvt.rna.tf32(x), lo = x - hi (exact in fp32),
+// the same for the taps; three MMAs hi*hi + lo*hi + hi*lo per K-step, the dropped lo*lo term and the conversion of
+// the lo operands are <= 2^-22 |x||h| each.  Accumulation is fp32 in TMEM, in blocked order -- not the reference's
+// left-to-right association, hence FAST mode only (bar: 1e-5 block-relative against fir_direct, tests/).
+//
+// Roles (320 threads): warps 0-3 epilogue (TMEM -> registers -> global, one thread per channel row), warps 4-7 split
+// every landed block into hi / lo in place (8 LDS.128 + 16 STS.128 per thread per block), warp 8 = TMA producer,
+// warp 9 = MMA issuer (one lane).  CTAs are persistent: each takes a contiguous range of (channel group, output
+// tile) work items; a range that starts in the middle of a row of tiles re-reads its 8 history blocks from the input,
+// a range that starts at tile 0 reads them from the delay-line state ([N-1][channels], oldest first).  The state
+// after the block is written by a separate small kernel (zg_fir_state_kernel), so nothing here writes state.
+#pragma once
+#include "zg_stream.cuh"
+
+namespace zgk {
+
+struct FirTcArgs {
+    TensorMap in_map;               // planar 2-D {T, C}, box {32 samples, 128 channels}, SWIZZLE_128B
+    float* out;                     // [C][ld_out]
+    long long ld_out;
+    const float* state_in;          // [n_taps-1][ch_stride]; slot s = x[t0 - (n_taps-1) + s]
+    const float* taps;              // [n_taps]
+    long long ch_stride;
+    int channels, n_samples, n_taps;
+    int n_groups;                   // ceil(channels / 128)
+    int n_tiles;                    // ceil(n_samples / 128)
+};
+
+constexpr int kTcStages = 3;
+constexpr int kTcBlockBytes = 16384;                     // 128 channel rows x 128 bytes
+constexpr int kTcGRows = 480;
+constexpr int kTcGBytes = kTcGRows * 128;                // 61 440
+constexpr int kTcSmemG = 2 * kTcGBytes;                  // hi, lo
+constexpr int kTcSmemX = 2 * kTcStages * kTcBlockBytes;  // hi[stages], lo[stages]
+constexpr int kTcSmemBars = 256;
+constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kTcSmemG + kTcSmemX + kTcSmemBars;
+constexpr int kTcThreads = 320;
+constexpr unsigned kTcIdesc = (1u << 4) /*D = f32*/ | (2u << 7) /*A = tf32*/ | (2u << 10) /*B = tf32*/ |
+                              ((128u >> 3) << 17) /*N*/ | ((128u >> 4) << 24) /*M*/;       // A, B K-major, dense
+
+// ---- PTX wrappers (tcgen05) ----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_alloc_512(unsigned* smem_dst) {          // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(smem_dst)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc_512(unsigned taddr) {            // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {        // arrives when all MMAs issued so far are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc,
+                                            unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kTcIdesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand, SWIZZLE_128B: rows of 128 bytes, 8-row atoms 1024 bytes apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ unsigned long long tc_desc(unsigned smem_addr) {
+    return (unsigned long long)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) /*LBO, unused with swizzle*/ |
+           ((unsigned long long)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&r)[32]) {   // this warp's 32 lanes x 32 columns
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tf32_rna(float v) {                        // nearest TF32 (10 explicit mantissa bits)
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ int floor_div4(int v) { return v >= 0 ? v >> 2 : -((3 - v) >> 2); }
+
+// The work items of this CTA as runs inside one channel group: f(group, o_begin, o_end)
+template <class F>
+__device__ __forceinline__ void tc_for_each_run(const FirTcArgs& a, F&& f) {
+    const long long total = (long long)a.n_groups * a.n_tiles;
+    const long long per = (total + gridDim.x - 1) / gridDim.x;
+    long long w = (long long)blockIdx.x * per;
+    const long long w_end = w + per < total ? w + per : total;
+    while (w < w_end) {
+        const int g = (int)(w / a.n_tiles), o_s = (int)(w % a.n_tiles);
+        const long long left = w_end - w;
+        const int o_e = o_s + left < a.n_tiles ? (int)(o_s + left) : a.n_tiles;
+        f(g, o_s, o_e);
+        w += o_e - o_s;
+    }
+}
+
+__device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    unsigned char* g_hi = base;
+    unsigned char* g_lo = base + kTcGBytes;
+    unsigned char* x_hi = base + kTcSmemG;
+    unsigned char* x_lo = x_hi + kTcStages * kTcBlockBytes;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + kTcSmemG + kTcSmemX);
+    unsigned long long* full = bars;                     // [stages]  TMA landed (or: stage free for a state fill)
+    unsigned long long* ready = bars + kTcStages;        // [stages]  hi / lo written
+    unsigned long long* empty = bars + 2 * kTcStages;    // [stages]  MMAs that read the stage are done
+    unsigned long long* acc_full = bars + 3 * kTcStages; // [4]       accumulator complete
+    unsigned long long* acc_empty = acc_full + 4;        // [4]       accumulator drained
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(acc_empty + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = a.n_taps - 1;                          // depth of the delay line
+
+    // ---- one-time setup: barriers, TMEM, the Toeplitz image G (hi / lo) ----
+    if (tid == 0) {
+        for (int i = 0; i < kTcStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&ready[i], 128);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        fence_barrier_init();
+        prefetch_tmap(&a.in_map);
+    }
+    if (warp == 0) tc_alloc_512(tmem_slot);
+    for (int e = tid; e < kTcGRows * 32; e += kTcThreads) {
+        const int r = e >> 5, j = e & 31;
+        const int k = r - 96 - j;                        // tap index
+        const float h = (k >= 0 && k < a.n_taps) ? a.taps[k] : 0.f;
+        const float hi = tf32_rna(h);
+        const unsigned off = (unsigned)r * 128u + ((((unsigned)j >> 2) ^ ((unsigned)r & 7u)) << 4) + ((unsigned)j & 3u) * 4u;
+        *reinterpret_cast<float*>(g_hi + off) = hi;
+        *reinterpret_cast<float*>(g_lo + off) = h - hi;
+    }
+    fence_proxy_async();                                 // G: generic-proxy writes -> visible to the tensor core
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const unsigned tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int n = 0;
+            tc_for_each_run(a, [&](int g, int o_s, int o_e) {
+                for (int jb = 4 * o_s - 8; jb <= 4 * o_e - 1; ++jb, ++n) {
+                    const int st = n % kTcStages;
+                    mbar_wait(&empty[st], (unsigned)(((n / kTcStages) & 1) ^ 1));
+                    if (jb >= 0) {
+                        mbar_expect_tx(&full[st], kTcBlockBytes);
+                        tma_load_2d(x_hi + st * kTcBlockBytes, &a.in_map, 32 * jb, 128 * g, &full[st]);
+                    } else {
+                        mbar_arrive(&full[st]);          // before the stream began: the split warps fill it from the state
+                    }
+                }
+            });
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int n = 0, q_base = 0;
+            tc_for_each_run(a, [&](int g, int o_s, int o_e) {
+                (void)g;
+                for (int jb = 4 * o_s - 8; jb <= 4 * o_e - 1; ++jb, ++n) {
+                    const int st = n % kTcStages;
+                    const unsigned ph = (unsigned)((n / kTcStages) & 1);
+                    mbar_wait(&full[st], ph);
+                    mbar_wait(&ready[st], ph);
+                    tc_fence_after_sync();
+                    const int fd = floor_div4(jb);
+                    const int o_lo = fd > o_s ? fd : o_s, o_hi = fd + 2 < o_e - 1 ? fd + 2 : o_e - 1;
+                    const unsigned xa_hi = smem_u32(x_hi + st * kTcBlockBytes), xa_lo = smem_u32(x_lo + st * kTcBlockBytes);
+                    for (int o = o_lo; o <= o_hi; ++o) {
+                        const int q = q_base + (o - o_s);
+                        const int slot = q & 3;
+                        const bool first = jb == 4 * o - 8;
+                        if (first) {
+                            mbar_wait(&acc_empty[slot], (unsigned)(((q >> 2) & 1) ^ 1));
+                            tc_fence_after_sync();
+                        }
+                        const unsigned row = (unsigned)(128 * o - 32 * jb + 96);
+                        const unsigned gb_hi = smem_u32(g_hi) + row * 128u, gb_lo = smem_u32(g_lo) + row * 128u;
+                        const unsigned d = tmem + (unsigned)slot * 128u;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const unsigned long long ah = tc_desc(xa_hi + ks * 32), al = tc_desc(xa_lo + ks * 32);
+                            const unsigned long long bh = tc_desc(gb_hi + ks * 32), bl = tc_desc(gb_lo + ks * 32);
+                            tc_mma_tf32(d, ah, bh, (first && ks == 0) ? 0u : 1u);
+                            tc_mma_tf32(d, al, bh, 1u);
+                            tc_mma_tf32(d, ah, bl, 1u);
+                        }
+                        if (jb == 4 * o + 3) tc_commit(&acc_full[slot]);
+                    }
+                    tc_commit(&empty[st]);
+                }
+                q_base += o_e - o_s;
+            });
+        }
+    } else if (warp >= 4) {
+        // ===== split warps: hi = tf32(x), lo = x - hi, in place / into the lo tile =====
+        const int ts = tid - 128;                        // 0..127
+        int n = 0;
+        tc_for_each_run(a, [&](int g, int o_s, int o_e) {
+            for (int jb = 4 * o_s - 8; jb <= 4 * o_e - 1; ++jb, ++n) {
+                const int st = n % kTcStages;
+                mbar_wait(&full[st], (unsigned)((n / kTcStages) & 1));
+                unsigned char* hi = x_hi + st * kTcBlockBytes;
+                unsigned char* lo = x_lo + st * kTcBlockBytes;
+                if (jb >= 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const unsigned off = (unsigned)(ts + 128 * i) << 4;
+                        const float4 v = *reinterpret_cast<const float4*>(hi + off);
+                        float4 h, l;
+                        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+                        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                        *reinterpret_cast<float4*>(hi + off) = h;
+                        *reinterpret_cast<float4*>(lo + off) = l;
+                    }
+                } else {
+                    // delay-line state: sample time t = 32*jb + j (negative) is slot D + t; older than the line: zero
+                    const int ch = g * 128 + ts;
+                    const unsigned r = (unsigned)ts;
+                    for (int j = 0; j < 32; ++j) {
+                        const int s = D + 32 * jb + j;
+                        const float v = (s >= 0 && ch < a.channels) ? a.state_in[(long long)s * a.ch_stride + ch] : 0.f;
+                        const float h = tf32_rna(v);
+                        const unsigned off = r * 128u + ((((unsigned)j >> 2) ^ (r & 7u)) << 4) + ((unsigned)j & 3u) * 4u;
+                        *reinterpret_cast<float*>(hi + off) = h;
+                        *reinterpret_cast<float*>(lo + off) = v - h;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&ready[st]);
+            }
+        });
+    } else {
+        // ===== epilogue warps 0-3: TMEM lanes 32*warp .. +31 = channel rows; columns = output times =====
+        int q = 0;
+        tc_for_each_run(a, [&](int g, int o_s, int o_e) {
+            const int ch = g * 128 + warp * 32 + lane;
+            for (int o = o_s; o < o_e; ++o, ++q) {
+                const int slot = q & 3;
+                mbar_wait(&acc_full[slot], (unsigned)((q >> 2) & 1));
+                tc_fence_after_sync();
+#pragma unroll 1
+                for (int cc = 0; cc < 4; ++cc) {
+                    unsigned r[32];
+                    tc_ld32(tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(slot * 128 + cc * 32), r);
+                    const int t0 = o * 128 + cc * 32;
+                    if (ch < a.channels && t0 < a.n_samples) {
+                        float* dst = a.out + (long long)ch * a.ld_out + t0;
+                        if (t0 + 32 <= a.n_samples) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                __stcs(reinterpret_cast<float4*>(dst) + i,
+                                       make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (t0 + i < a.n_samples) dst[i] = __uint_as_float(r[i]);
+                        }
+                    }
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[slot]);
+            }
+        });
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (warp == 0) tc_dealloc_512(tmem);
+}
+
+// The delay line after a block of T samples, oldest first: slot s = x[T - D + s], taken from the input where
+// T - D + s >= 0 and from the old line (shifted by T) otherwise.  Separate from the evaluation: the persistent CTAs
+// above cut the block anywhere, and the line is ping-ponged between two buffers like K3's.
+__global__ void zg_fir_state_kernel(const float* __restrict__ in, long long ld_in, const float* __restrict__ state_in,
+                                    float* __restrict__ state_out, long long ch_stride, int channels, int n_samples, int depth) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (ch >= channels || s >= depth) return;
+    const long long t = (long long)n_samples - depth + s;
+    state_out[(long long)s * ch_stride + ch] = t >= 0 ? in[(long long)ch * ld_in + t] : state_in[(long long)(s + n_samples) * ch_stride + ch];
+}
+
+}  // namespace zgk

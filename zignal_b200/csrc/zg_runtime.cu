@@ -24,6 +24,7 @@
 #include "kernels/zg_biquad.cuh"
 #include "kernels/zg_biquad_lanes.cuh"
 #include "kernels/zg_fir.cuh"
+#include "kernels/zg_fir_tc.cuh"
 #include "zg_internal.hpp"
 
 extern const char* const zg_stream_cuh_source;   // kernels/zg_stream.cuh as text (generated at build time)
@@ -208,6 +209,10 @@ int raise_max_smem(const void* fn, int device, int smem) {
     return ZG_OK;
 }
 
+__global__ void __launch_bounds__(zgk::kTcThreads, 1) zg_fir_tc_kernel(const __grid_constant__ zgk::FirTcArgs a) {
+    zgk::fir_tc_block(a);
+}
+
 const void* fir_kernel_for(bool exact, bool interleaved) {
     if (exact) return interleaved ? (const void*)zg_fir_kernel<true, true> : (const void*)zg_fir_kernel<true, false>;
     return interleaved ? (const void*)zg_fir_kernel<false, true> : (const void*)zg_fir_kernel<false, false>;
@@ -301,6 +306,7 @@ struct zg_plan {
     Ir kir;                                 // K2: the kernel-side tick program (long delay lines split off, zg_ir.hpp)
     RingPlan ring;                          //     and where its extra inputs / outputs / window slots live
     int ring_pf = 1;                        //     chunks a far read is requested ahead of use
+    bool fir_tc = false;                    // K3t: the FIR on tensor cores (kernels/zg_fir_tc.cuh): FAST, planar, <= 256 taps
     bool is_fir = false;                    // K3: dense FIR (kernels/zg_fir.cuh)
     FirMatch fir;
     float* d_taps = nullptr;                // [n_taps]
@@ -555,7 +561,7 @@ int get_variant(zg_plan* p, bool uniform, Variant*& out) {
     if (v.ready) return ZG_OK;
     if (p->is_fir) {
         cudaFuncAttributes fa;
-        ZG_CUDA(cudaFuncGetAttributes(&fa, fir_kernel_for(p->exact, p->interleaved)));
+        ZG_CUDA(cudaFuncGetAttributes(&fa, p->fir_tc ? (const void*)zg_fir_tc_kernel : fir_kernel_for(p->exact, p->interleaved)));
         v.regs = fa.numRegs;
         v.ready = true;
         return ZG_OK;
@@ -1138,8 +1144,51 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
 
 // K3 geometry: W warps per CTA (one 32-sample box each per step), ring of H + 2W input boxes, 2 output
 // boxes per warp; time is cut into segments when there are fewer channel groups than ~2 CTAs per SM.
+// K3t: persistent CTAs, one per SM, each a contiguous range of (128-channel group, 128-sample output tile) items
+int launch_fir_tc(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out,
+                  cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance) {
+    const int N = (int)p->fir.taps.size();
+    zgk::FirTcArgs a;
+    std::memset(&a, 0, sizeof a);
+    int st = encode_map(p, &a.in_map, in[0], c_count, T, ld_in, 128);
+    if (st != ZG_OK) return st;
+    a.out = static_cast<float*>(out[0]);
+    a.ld_out = ld_out;
+    a.state_in = p->d_state + c_begin;
+    a.taps = p->d_taps;
+    a.ch_stride = p->ch_stride;
+    a.channels = (int)c_count;
+    a.n_samples = (int)T;
+    a.n_taps = N;
+    a.n_groups = (int)((c_count + 127) / 128);
+    a.n_tiles = (int)((T + 127) / 128);
+    const int64_t total = (int64_t)a.n_groups * a.n_tiles;
+    const int grid = (int)std::min<int64_t>(p->sm_count, total);
+    st = raise_max_smem((const void*)zg_fir_tc_kernel, p->opts.device, zgk::kTcSmemBytes);
+    if (st != ZG_OK) return st;
+    void* args[] = {&a};
+    ZG_CUDA(cudaLaunchKernel((const void*)zg_fir_tc_kernel, dim3(grid), dim3(zgk::kTcThreads), args, zgk::kTcSmemBytes, stream));
+    // the delay line after this block (ping-pong: a later launch reads what this one writes)
+    zgk::zg_fir_state_kernel<<<dim3((unsigned)((c_count + 127) / 128), (unsigned)(N - 1)), 128, 0, stream>>>(
+        static_cast<const float*>(in[0]), ld_in, p->d_state + c_begin, p->d_state_alt + c_begin, p->ch_stride, (int)c_count,
+        (int)T, N - 1);
+    ZG_CUDA(cudaGetLastError());
+    if (advance) {
+        std::swap(p->d_state, p->d_state_alt);
+        p->stream_pos += T;
+    }
+    p->launches += 2;
+    p->last_smem = zgk::kTcSmemBytes;
+    p->last_threads = zgk::kTcThreads;
+    p->last_stages = zgk::kTcStages;
+    p->last_boxes = (int)((total + grid - 1) / grid);
+    p->last_grid = grid;
+    return ZG_OK;
+}
+
 int launch_fir(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out,
                cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance) {
+    if (p->fir_tc && T >= 256) return launch_fir_tc(p, in, out, T, ld_in, ld_out, stream, c_begin, c_count, advance);
     const int N = (int)p->fir.taps.size();
     const int H = (N - 1 + 31) / 32;
     const int n_taps_pad = (N + 15) / 16 * 16;
@@ -1404,8 +1453,12 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     if (p->is_fir) {
         p->kernel_n_state = ir.n_state;
         p->kernel_n_param = 0;
-        p->kernel_name = "zg_fir<" + std::to_string(fir.taps.size()) + (p->exact ? " taps,exact," : " taps,fma,") +
-                         (p->interleaved ? "interleaved>" : "planar>");
+        // FAST mode, planar, 2..256 taps: the Toeplitz contraction on tensor cores (3xTF32); EXACT keeps the CUDA-core
+        // kernel, whose left-to-right sum is bit-identical to the reference (ZG_TUNE_FIR_TC=1 / 2 forces off / on)
+        p->fir_tc = !p->exact && !p->interleaved && fir.taps.size() >= 2 && fir.taps.size() <= 256 && tune_env("ZG_TUNE_FIR_TC") != 1;
+        p->kernel_name = p->fir_tc ? "zg_fir_tc<" + std::to_string(fir.taps.size()) + " taps,3xtf32,planar>"
+                                   : "zg_fir<" + std::to_string(fir.taps.size()) + (p->exact ? " taps,exact," : " taps,fma,") +
+                                         (p->interleaved ? "interleaved>" : "planar>");
     } else if (p->is_biquad && !opts->force_jit) {
         const int S = p->bq.sections;
         p->kernel_n_state = 2 * (S + 1);
