@@ -7,16 +7,19 @@
 //
 //     Y[c, t] = sum_j X[c, j] * h[t - j]          Y = X * G^T,   G[t, j] = h[t - j]  (banded Toeplitz)
 //
-// Shape of one MMA (tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 128, K = 8):
-//     D[128 channels, 128 output times]  +=  A[128 channels, 8 input times]  x  B[128 output times, 8 input times]^T
+// Shape of the MMAs (tcgen05.mma.cta_group::1.kind::tf32, M = 128, K = 8, N = 32 .. 256):
+//     D[128 channels, N output times]  +=  A[128 channels, 8 input times]  x  B[N output times, 8 input times]^T
 //   * A is a slice of an input block: 128 channel rows x 32 samples (16 KB) exactly as TMA lands it with
 //     SWIZZLE_128B -- the canonical K-major operand layout, no repacking;
-//   * B is a 128-row window of ONE tall matrix G[r][j] = h[r - 96 - j], r = 0..479, j = 0..31 (60 KB, built once per
-//     CTA): the block of the band that input block jb contributes to output tile o starts at row
-//     128*o - 32*jb + 96, so all twelve band blocks are row windows of the same shared-memory image (each window
-//     start is a multiple of 32 rows = 4 KB, which keeps the 1024-byte swizzle atoms aligned);
-//   * D is one of four 128-column TMEM accumulators: an input block feeds three output tiles (the one it lies in and
-//     the next two), the fourth accumulator is being drained by the epilogue warps.
+//   * B is a window of ONE matrix G[r][j] = h[r - j], r = 0..287, j = 0..31 (36 KB, built once per CTA): input block
+//     jb (samples 32 jb ..) reaches output times 32 jb .. 32 jb + 287, and the coefficient of input sample j for
+//     output time r (both relative to the block) is h[r - j] whatever the block -- the band is the SAME matrix for
+//     every block, only the accumulator columns it lands on move;
+//   * D: the 512 TMEM columns are a ring of four 128-sample output tiles.  Block jb accumulates into the 256 columns
+//     of output times 32 jb .. 32 jb + 255 (already begun by earlier blocks) and starts the 32 columns after them
+//     (accumulate = 0): two MMAs per K-step and operand product, split once more where the window wraps around the
+//     ring.  A tile is complete after the block that ends it and is drained by the epilogue warps while the next
+//     three fill.
 //
 // fp32 accuracy out of TF32 operands (3xTF32): x = hi + lo with hi = cvt.rna.tf32(x), lo = x - hi (exact in fp32),
 // the same for the taps; three MMAs hi*hi + lo*hi + hi*lo per K-step, the dropped lo*lo term and the conversion of
@@ -36,27 +39,29 @@ namespace zgk {
 
 struct FirTcArgs {
     TensorMap in_map;               // planar 2-D {T, C}, box {32 samples, 128 channels}, SWIZZLE_128B
-    float* out;                     // [C][ld_out]
-    long long ld_out;
+    TensorMap out_map;              // the same over the output block
     const float* state_in;          // [n_taps-1][ch_stride]; slot s = x[t0 - (n_taps-1) + s]
     const float* taps;              // [n_taps]
     long long ch_stride;
     int channels, n_samples, n_taps;
     int n_groups;                   // ceil(channels / 128)
     int n_tiles;                    // ceil(n_samples / 128)
+    long long* prof;                // tuning only (ZG_TUNE_FIR_PROF): [grid][8] cycles the roles of a CTA spent waiting
 };
 
-constexpr int kTcStages = 3;
+constexpr int kTcStages = 4;
 constexpr int kTcBlockBytes = 16384;                     // 128 channel rows x 128 bytes
-constexpr int kTcGRows = 480;
-constexpr int kTcGBytes = kTcGRows * 128;                // 61 440
+constexpr int kTcGRows = 288;                            // output times one input block reaches (256 taps + 32 samples)
+constexpr int kTcGBytes = kTcGRows * 128;                // 36 864
 constexpr int kTcSmemG = 2 * kTcGBytes;                  // hi, lo
 constexpr int kTcSmemX = 2 * kTcStages * kTcBlockBytes;  // hi[stages], lo[stages]
+constexpr int kTcSmemOut = kTcBlockBytes;                // epilogue staging: 128 channels x 32 output times
 constexpr int kTcSmemBars = 256;
-constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kTcSmemG + kTcSmemX + kTcSmemBars;
+constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kTcSmemG + kTcSmemX + kTcSmemOut + kTcSmemBars;
 constexpr int kTcThreads = 320;
-constexpr unsigned kTcIdesc = (1u << 4) /*D = f32*/ | (2u << 7) /*A = tf32*/ | (2u << 10) /*B = tf32*/ |
-                              ((128u >> 3) << 17) /*N*/ | ((128u >> 4) << 24) /*M*/;       // A, B K-major, dense
+// instruction descriptor: D = f32, A = B = tf32, both K-major, dense, M = 128; N (a multiple of 16) is added per MMA
+constexpr unsigned kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
+__device__ __forceinline__ unsigned tc_idesc(unsigned n) { return kTcIdesc | ((n >> 3) << 17); }
 
 // ---- PTX wrappers (tcgen05) ----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
@@ -75,13 +80,13 @@ __device__ __forceinline__ void tc_commit(unsigned long long* bar) {        // a
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc,
-                                            unsigned accumulate) {
+                                            unsigned idesc, unsigned accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kTcIdesc), "r"(accumulate)
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // K-major operand, SWIZZLE_128B: rows of 128 bytes, 8-row atoms 1024 bytes apart (SBO), version 1 (sm_100)
@@ -131,7 +136,8 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
     unsigned char* g_lo = base + kTcGBytes;
     unsigned char* x_hi = base + kTcSmemG;
     unsigned char* x_lo = x_hi + kTcStages * kTcBlockBytes;
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + kTcSmemG + kTcSmemX);
+    unsigned char* y_stage = base + kTcSmemG + kTcSmemX;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + kTcSmemG + kTcSmemX + kTcSmemOut);
     unsigned long long* full = bars;                     // [stages]  TMA landed (or: stage free for a state fill)
     unsigned long long* ready = bars + kTcStages;        // [stages]  hi / lo written
     unsigned long long* empty = bars + 2 * kTcStages;    // [stages]  MMAs that read the stage are done
@@ -155,11 +161,12 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
         }
         fence_barrier_init();
         prefetch_tmap(&a.in_map);
+        prefetch_tmap(&a.out_map);
     }
     if (warp == 0) tc_alloc_512(tmem_slot);
     for (int e = tid; e < kTcGRows * 32; e += kTcThreads) {
         const int r = e >> 5, j = e & 31;
-        const int k = r - 96 - j;                        // tap index
+        const int k = r - j;                             // tap index
         const float h = (k >= 0 && k < a.n_taps) ? a.taps[k] : 0.f;
         const float hi = tf32_rna(h);
         const unsigned off = (unsigned)r * 128u + ((((unsigned)j >> 2) ^ ((unsigned)r & 7u)) << 4) + ((unsigned)j & 3u) * 4u;
@@ -176,10 +183,13 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
         // ===== TMA producer =====
         if (lane == 0) {
             int n = 0;
+            long long w_empty = 0;
             tc_for_each_run(a, [&](int g, int o_s, int o_e) {
                 for (int jb = 4 * o_s - 8; jb <= 4 * o_e - 1; ++jb, ++n) {
                     const int st = n % kTcStages;
+                    const long long t0 = a.prof ? clock64() : 0;
                     mbar_wait(&empty[st], (unsigned)(((n / kTcStages) & 1) ^ 1));
+                    if (a.prof) w_empty += clock64() - t0;
                     if (jb >= 0) {
                         mbar_expect_tx(&full[st], kTcBlockBytes);
                         tma_load_2d(x_hi + st * kTcBlockBytes, &a.in_map, 32 * jb, 128 * g, &full[st]);
@@ -188,47 +198,74 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
                     }
                 }
             });
+            if (a.prof) a.prof[(long long)blockIdx.x * 8 + 5] = w_empty;
         }
     } else if (warp == 9) {
         // ===== MMA issuer =====
         if (lane == 0) {
             int n = 0, q_base = 0;
+            long long w_full = 0, w_ready = 0, w_acc = 0;
+            const long long t_begin = clock64();
             tc_for_each_run(a, [&](int g, int o_s, int o_e) {
                 (void)g;
                 for (int jb = 4 * o_s - 8; jb <= 4 * o_e - 1; ++jb, ++n) {
                     const int st = n % kTcStages;
                     const unsigned ph = (unsigned)((n / kTcStages) & 1);
+                    long long t0 = a.prof ? clock64() : 0;
                     mbar_wait(&full[st], ph);
+                    long long t1 = a.prof ? clock64() : 0;
                     mbar_wait(&ready[st], ph);
+                    if (a.prof) { w_full += t1 - t0; w_ready += clock64() - t1; }
                     tc_fence_after_sync();
-                    const int fd = floor_div4(jb);
-                    const int o_lo = fd > o_s ? fd : o_s, o_hi = fd + 2 < o_e - 1 ? fd + 2 : o_e - 1;
+                    // output times this block reaches, clipped to the tiles of this run; the last 32 are new
+                    const int t_run0 = 128 * o_s, t_run1 = 128 * o_e;
+                    const int t_lo = 32 * jb > t_run0 ? 32 * jb : t_run0;
+                    const int t_new = 32 * jb + 256;
+                    const int t_hi = t_new + 32 < t_run1 ? t_new + 32 : t_run1;
                     const unsigned xa_hi = smem_u32(x_hi + st * kTcBlockBytes), xa_lo = smem_u32(x_lo + st * kTcBlockBytes);
-                    for (int o = o_lo; o <= o_hi; ++o) {
-                        const int q = q_base + (o - o_s);
-                        const int slot = q & 3;
-                        const bool first = jb == 4 * o - 8;
-                        if (first) {
-                            mbar_wait(&acc_empty[slot], (unsigned)(((q >> 2) & 1) ^ 1));
-                            tc_fence_after_sync();
-                        }
-                        const unsigned row = (unsigned)(128 * o - 32 * jb + 96);
-                        const unsigned gb_hi = smem_u32(g_hi) + row * 128u, gb_lo = smem_u32(g_lo) + row * 128u;
-                        const unsigned d = tmem + (unsigned)slot * 128u;
+                    const unsigned gb_hi = smem_u32(g_hi), gb_lo = smem_u32(g_lo);
+                    if ((jb & 3) == 0 && t_new < t_run1) {       // the new columns open tile jb/4 + 2: its slot must be drained
+                        const int q = q_base + (jb / 4 + 2 - o_s);
+                        const long long tw = a.prof ? clock64() : 0;
+                        mbar_wait(&acc_empty[q & 3], (unsigned)(((q >> 2) & 1) ^ 1));
+                        if (a.prof) w_acc += clock64() - tw;
+                        tc_fence_after_sync();
+                    }
+                    // column of output time t in the ring: tile o_s sits in slot q_base & 3
+                    const int col0 = (q_base & 3) * 128 - t_run0;
+                    // D[:, t0 .. t1) (+)= X_blk * G[t0 - 32 jb .. t1 - 32 jb)^T, cut where the ring wraps
+                    auto issue = [&](int t0, int t1, bool fresh) {
+                        while (t0 < t1) {
+                            const int c = (col0 + t0) & 511;
+                            int n = t1 - t0;
+                            if (c + n > 512) n = 512 - c;
+                            const unsigned row = (unsigned)(t0 - 32 * jb);
+                            const unsigned idesc = tc_idesc((unsigned)n);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const unsigned long long ah = tc_desc(xa_hi + ks * 32), al = tc_desc(xa_lo + ks * 32);
-                            const unsigned long long bh = tc_desc(gb_hi + ks * 32), bl = tc_desc(gb_lo + ks * 32);
-                            tc_mma_tf32(d, ah, bh, (first && ks == 0) ? 0u : 1u);
-                            tc_mma_tf32(d, al, bh, 1u);
-                            tc_mma_tf32(d, ah, bl, 1u);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const unsigned long long ah = tc_desc(xa_hi + ks * 32), al = tc_desc(xa_lo + ks * 32);
+                                const unsigned long long bh = tc_desc(gb_hi + row * 128u + ks * 32), bl = tc_desc(gb_lo + row * 128u + ks * 32);
+                                tc_mma_tf32(tmem + (unsigned)c, ah, bh, idesc, (fresh && ks == 0) ? 0u : 1u);
+                                tc_mma_tf32(tmem + (unsigned)c, al, bh, idesc, 1u);
+                                tc_mma_tf32(tmem + (unsigned)c, ah, bl, idesc, 1u);
+                            }
+                            t0 += n;
                         }
-                        if (jb == 4 * o + 3) tc_commit(&acc_full[slot]);
+                    };
+                    issue(t_lo, t_new < t_hi ? t_new : t_hi, false);
+                    if (t_new < t_hi) issue(t_new, t_hi, true);
+                    if ((jb & 3) == 3 && floor_div4(jb) >= o_s) { // this block ends tile floor(jb / 4)
+                        const int q = q_base + (floor_div4(jb) - o_s);
+                        tc_commit(&acc_full[q & 3]);
                     }
                     tc_commit(&empty[st]);
                 }
                 q_base += o_e - o_s;
             });
+            if (a.prof) {
+                long long* pr = a.prof + (long long)blockIdx.x * 8;
+                pr[0] = clock64() - t_begin; pr[1] = w_full; pr[2] = w_ready; pr[3] = w_acc; pr[4] = n;
+            }
         }
     } else if (warp >= 4) {
         // ===== split warps: hi = tf32(x), lo = x - hi, in place / into the lo tile =====
@@ -269,39 +306,45 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
             }
         });
     } else {
-        // ===== epilogue warps 0-3: TMEM lanes 32*warp .. +31 = channel rows; columns = output times =====
+        // ===== epilogue warps 0-3: TMEM lanes 32*warp .. +31 = channel rows; columns = output times.  32 columns at a
+        //       time go through a staging box in the layout of the input blocks (row = channel, SWIZZLE_128B: the eight
+        //       STS.128 of a quarter-warp cover all banks) and leave with one TMA store, which also clips the ragged
+        //       end of the block and of the channels =====
         int q = 0;
+        long long w_accfull = 0, t_store = 0;
+        const unsigned r = (unsigned)(warp * 32 + lane);
         tc_for_each_run(a, [&](int g, int o_s, int o_e) {
-            const int ch = g * 128 + warp * 32 + lane;
             for (int o = o_s; o < o_e; ++o, ++q) {
                 const int slot = q & 3;
+                const long long t0c = a.prof ? clock64() : 0;
                 mbar_wait(&acc_full[slot], (unsigned)((q >> 2) & 1));
+                const long long t1c = a.prof ? clock64() : 0;
                 tc_fence_after_sync();
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
-                    unsigned r[32];
-                    tc_ld32(tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(slot * 128 + cc * 32), r);
-                    const int t0 = o * 128 + cc * 32;
-                    if (ch < a.channels && t0 < a.n_samples) {
-                        float* dst = a.out + (long long)ch * a.ld_out + t0;
-                        if (t0 + 32 <= a.n_samples) {
+                    unsigned v[32];
+                    tc_ld32(tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(slot * 128 + cc * 32), v);
+                    if (tid == 0) tma_wait_read<0>();            // the previous store has read the staging box
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                __stcs(reinterpret_cast<float4*>(dst) + i,
-                                       make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (t0 + i < a.n_samples) dst[i] = __uint_as_float(r[i]);
-                        }
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<uint4*>(y_stage + r * 128u + ((((unsigned)i) ^ (r & 7u)) << 4)) =
+                            make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    fence_proxy_async();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (tid == 0 && o * 128 + cc * 32 < a.n_samples) {
+                        tma_store_2d(&a.out_map, o * 128 + cc * 32, g * 128, y_stage);
+                        tma_commit();
                     }
                 }
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[slot]);
+                if (a.prof) { w_accfull += t1c - t0c; t_store += clock64() - t1c; }
             }
         });
+        if (tid == 0) tma_wait_all<0>();                         // shared memory must outlive the last store
+        if (a.prof && tid == 0) { a.prof[(long long)blockIdx.x * 8 + 6] = w_accfull; a.prof[(long long)blockIdx.x * 8 + 7] = t_store; }
     }
 
     tc_fence_before_sync();

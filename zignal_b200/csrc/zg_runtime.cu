@@ -1152,8 +1152,8 @@ int launch_fir_tc(zg_plan* p, const void* const* in, void* const* out, int64_t T
     std::memset(&a, 0, sizeof a);
     int st = encode_map(p, &a.in_map, in[0], c_count, T, ld_in, 128);
     if (st != ZG_OK) return st;
-    a.out = static_cast<float*>(out[0]);
-    a.ld_out = ld_out;
+    st = encode_map(p, &a.out_map, out[0], c_count, T, ld_out, 128);
+    if (st != ZG_OK) return st;
     a.state_in = p->d_state + c_begin;
     a.taps = p->d_taps;
     a.ch_stride = p->ch_stride;
@@ -1166,8 +1166,21 @@ int launch_fir_tc(zg_plan* p, const void* const* in, void* const* out, int64_t T
     const int grid = (int)std::min<int64_t>(p->sm_count, total);
     st = raise_max_smem((const void*)zg_fir_tc_kernel, p->opts.device, zgk::kTcSmemBytes);
     if (st != ZG_OK) return st;
+    const bool prof = tune_env("ZG_TUNE_FIR_PROF") != 0;          // tuning only: where the roles of a CTA wait
+    if (prof) ZG_CUDA(cudaMalloc(&a.prof, (size_t)grid * 8 * sizeof(long long)));
     void* args[] = {&a};
     ZG_CUDA(cudaLaunchKernel((const void*)zg_fir_tc_kernel, dim3(grid), dim3(zgk::kTcThreads), args, zgk::kTcSmemBytes, stream));
+    if (prof) {
+        std::vector<long long> h((size_t)grid * 8);
+        ZG_CUDA(cudaMemcpy(h.data(), a.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(a.prof);
+        double s[8] = {};
+        for (int b = 0; b < grid; ++b)
+            for (int k = 0; k < 8; ++k) s[k] += (double)h[(size_t)b * 8 + k] / grid;
+        std::fprintf(stderr, "[zg_fir_tc] per CTA: %.0f blocks in %.0f cycles (%.0f / block); MMA thread waits: TMA %.0f, split %.0f, "
+                             "accumulator drain %.0f; producer waits for a free stage %.0f; epilogue waits for an accumulator %.0f, drains %.0f\n",
+                     s[4], s[0], s[0] / std::max(s[4], 1.0), s[1], s[2], s[3], s[5], s[6], s[7]);
+    }
     // the delay line after this block (ping-pong: a later launch reads what this one writes)
     zgk::zg_fir_state_kernel<<<dim3((unsigned)((c_count + 127) / 128), (unsigned)(N - 1)), 128, 0, stream>>>(
         static_cast<const float*>(in[0]), ld_in, p->d_state + c_begin, p->d_state_alt + c_begin, p->ch_stride, (int)c_count,
