@@ -251,9 +251,13 @@ def other_configs(zg, wl, torch, dev, local, world, rank, args, barrier, dist):
                "bf16 out, dirac-excited", wl.poly_voice_expr(), 131072, 4096,
          dict(input_kind=[zg.IN_DIRAC], io_dtype=zg.BF16), None, torch.bfloat16, 2, None),
     ]
+    cases.append(("c4_tc", "configs[3] in FAST mode: the Toeplitz contraction on tcgen05 tensor cores (3xTF32), 256-tap FIR x 32768 "
+                           "channels x 8192 samples, fp32", wl.fir_expr(wl.fir_taps(256)), 32768, 8192, dict(mode=zg.MODE_FAST),
+                  torch.float32, torch.float32, 8, None))
     for name, desc, expr, C, T, kw, in_dt, out_dt, bytes_per_sample, instr_per_sample in cases:
         try:
-            plan = zg.compile(expr).plan(channels=C, device=local, mode=mode, **kw)
+            kw = dict(kw)
+            plan = zg.compile(expr).plan(channels=C, device=local, mode=kw.pop("mode", mode), **kw)
             x = (torch.rand((C, T), device=dev, dtype=torch.float32) * 2 - 1).to(in_dt) if in_dt is not None else None
             y = torch.empty((C, T), device=dev, dtype=out_dt)
             for _ in range(3):
@@ -276,7 +280,22 @@ def other_configs(zg, wl, torch, dev, local, world, rank, args, barrier, dist):
                    "roofline_frac": bytes_per_sample * C * T / (ms * 1e-3) / 1e9 / peak, "kernel": info.kernel.decode(),
                    "jit": info.jit, "regs": info.regs_per_thread, "mode": args.mode}
             if name == "c5":
-                ent["bound"] = "FP32 issue (23 arithmetic instructions per 2-byte sample), not HBM"
+                ent["bound"] = "FP32 issue (21 arithmetic instructions per 2-byte sample after delayed-product reuse), not HBM"
+            if name == "c4_tc":
+                # tensor roofline: algorithmic flops = 2 x 256 taps per sample; executed = 3 operand products x 288/256
+                # band padding.  The TF32 peak is not in MEASURED_PEAKS.json: measured here with a cuBLAS TF32 GEMM.
+                ent["mode"] = "fast"
+                tf32 = _tf32_peak(torch, dev)
+                algo = 2 * 256 * C * T / (ms * 1e-3) / 1e12
+                ent["roofline"] = {"bound": "tensor", "achieved": algo, "unit": "TFLOP/s", "peak": tf32,
+                                   "frac": algo / tf32 if tf32 else None,
+                                   "peak_source": "measured here: torch.matmul fp32 8192^3 with TF32 enabled (cuBLAS), best of 5",
+                                   "executed_tflops": algo * 3 * 288 / 256,
+                                   "executed_frac": algo * 3 * 288 / 256 / tf32 if tf32 else None,
+                                   "note": "3xTF32 (hi*hi + lo*hi + hi*lo) and a 288-row band per 256 taps: 3.375 tensor flops "
+                                           "per algorithmic flop; the kernel is bound by shared-memory operand bandwidth "
+                                           "(profiles/r02_c4_fir_tc_ncu.txt)"}
+                ent["numerics"] = "<= 1e-5 block-relative against the oracle (tests/test_fir_tc.py; measured 2e-7)"
             if instr_per_sample:
                 sm = torch.cuda.get_device_properties(dev).multi_processor_count
                 mhz = ClockSampler(local).max_mhz or 1965
@@ -374,6 +393,28 @@ def edge_step(zg, wl, torch, dist, dev, local, world, rank, args):
     xa.close(); ya.close()
     dist.barrier()
     return res
+
+
+def _tf32_peak(torch, dev, n=8192):
+    """Dense TF32 tensor throughput of this GPU through cuBLAS (TFLOP/s), for the roofline of the tensor-core FIR."""
+    try:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn((n, n), device=dev)
+        b = torch.randn((n, n), device=dev)
+        best = 0.0
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c = a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        del a, b, c
+        return best
+    except Exception:
+        return None
 
 
 def _bind_to_gpu_numa_node(index):
