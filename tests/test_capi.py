@@ -79,7 +79,7 @@ def test_bf16_storage_kernels_compile_for_sm100a(zg):
         cubin = g.kernel(cubin=True, io_dtype=zg.BF16, layout=layout, input_kind=[zg.IN_DIRAC])
         assert cubin[:4] == b"\x7fELF"
     src = g.kernel(io_dtype=zg.BF16).decode()
-    assert "stream_block<ZgTick, false, true, 2>" in src
+    assert "stream_block<ZgTick, false, true, 2, false>" in src
     with pytest.raises(zg.ZgError) as e:
         g.kernel(io_dtype=zg.I32)
     assert e.value.status == zg.ZG_ERR_ARG
@@ -134,15 +134,25 @@ def test_kernel_cache_on_disk(tmp_path):
     assert len(files) == 1 and not [f for f in os.listdir(tmp_path) if ".tmp" in f]
     path = os.path.join(tmp_path, files[0])
     blob = open(path, "rb").read()
-    magic, key_len, check, n = struct.unpack("<4Q", blob[:32])
-    assert n == int(first[0]) == len(blob) - 32 and blob[32:36] == b"\x7fELF"
-    # a well-formed entry is what the next process returns: swap the payload for a marker of the same size
+    magic, key_len, check, n, body_hash = struct.unpack("<5Q", blob[:40])
+    assert n == int(first[0]) == len(blob) - 40 and blob[40:44] == b"\x7fELF"
+
+    def fnv1a(b):
+        h = 0xcbf29ce484222325
+        for c in b:
+            h = ((h ^ c) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+        return h
+    assert body_hash == fnv1a(blob[40:])
+    # a well-formed entry is what the next process returns: swap the payload for a marker of the same size (with its hash)
     marker = b"M" * n
-    open(path, "wb").write(blob[:32] + marker)
+    open(path, "wb").write(struct.pack("<5Q", magic, key_len, check, n, fnv1a(marker)) + marker)
     import hashlib
     assert run() == [str(n), hashlib.sha1(marker).hexdigest()]
-    # a truncated file and one whose key check differs are ignored, recompiled and rewritten
+    # a body of the right length that does not match its hash (bit rot), a truncated file and one whose key check differs
+    # are ignored, recompiled and rewritten
+    open(path, "wb").write(blob[:40] + marker)
+    assert run() == first and open(path, "rb").read() == blob
     open(path, "wb").write(blob[:100])
     assert run() == first and open(path, "rb").read() == blob
-    open(path, "wb").write(struct.pack("<4Q", magic, key_len, check ^ 1, n) + marker)
+    open(path, "wb").write(struct.pack("<5Q", magic, key_len, check ^ 1, n, fnv1a(marker)) + marker)
     assert run() == first and open(path, "rb").read() == blob

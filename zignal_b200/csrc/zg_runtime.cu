@@ -12,6 +12,7 @@
 //       with NVRTC for sm_100a.
 #include <cuda.h>            // driver API *types* only; entry points come from cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges are no-ops unless a profiler has injected its library
 #include <dlfcn.h>
 #include <unistd.h>
 
@@ -132,6 +133,37 @@ Nvrtc& nvrtc() {
     }();
     return n;
 }
+
+// NVTX ranges around the host-side phases of the path (tracing): plan creation, NVRTC
+// specialisation, one zg_process launch, zg_process_host and each of its row chunks.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
+// Calls on a plan run on the plan's device and leave the caller's current device as they found it (a single-process
+// multi-GPU caller -- torch included -- must not find itself on another GPU after a call).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; (void)cudaGetLastError(); }
+        if (prev != device) err = cudaSetDevice(device);
+        else prev = -1;                                   // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ZG_ON_DEVICE(dev)                 \
+    DeviceGuard device_guard_(dev);       \
+    if (device_guard_.err != cudaSuccess) return cuda_fail(device_guard_.err, "cudaSetDevice")
+
+int cuda_fail(cudaError_t e, const char* what);
 
 int cuda_fail(cudaError_t e, const char* what) {
     (void)cudaGetLastError();
@@ -359,6 +391,8 @@ struct zg_plan {
     int last_host_chunks = 0;
 
     ~zg_plan() {
+        int prev_device = -1;
+        if (cudaGetDevice(&prev_device) != cudaSuccess) prev_device = -1;
         if (opts.device >= 0) cudaSetDevice(opts.device);
         for (auto& v : variant)
             if (v.module && driver().moduleUnload) driver().moduleUnload(v.module);
@@ -374,6 +408,7 @@ struct zg_plan {
         if (h2d_stream) cudaStreamDestroy(h2d_stream);
         if (d2h_stream) cudaStreamDestroy(d2h_stream);
         for (cudaEvent_t e : events) cudaEventDestroy(e);
+        if (prev_device >= 0) cudaSetDevice(prev_device);
     }
 };
 
@@ -438,6 +473,11 @@ uint64_t fnv1a(const std::string& s, uint64_t h) {
     for (unsigned char c : s) { h ^= c; h *= 0x100000001b3ull; }
     return h;
 }
+uint64_t fnv1a_bytes(const std::vector<char>& v) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (char c : v) { h ^= (unsigned char)c; h *= 0x100000001b3ull; }
+    return h;
+}
 struct DiskKey {
     std::string path;
     uint64_t len, check;
@@ -456,21 +496,23 @@ bool disk_key(const std::string& key, DiskKey& k) {
 bool disk_load(const DiskKey& k, std::vector<char>& cubin) {
     FILE* f = std::fopen(k.path.c_str(), "rb");
     if (!f) return false;
-    uint64_t head[4] = {0, 0, 0, 0};                          // magic, key length, check hash, cubin bytes
-    bool ok = std::fread(head, sizeof head, 1, f) == 1 && head[0] == 0x31434755425a47ull /* file magic */ &&
+    uint64_t head[5] = {0, 0, 0, 0, 0};                       // magic, key length, check hash, cubin bytes, hash of the cubin
+    bool ok = std::fread(head, sizeof head, 1, f) == 1 && head[0] == 0x32434755425a47ull /* file magic, format 2 */ &&
               head[1] == k.len && head[2] == k.check && head[3] > 0 && head[3] < (64u << 20);
     if (ok) {
         cubin.resize(head[3]);
-        ok = std::fread(cubin.data(), 1, cubin.size(), f) == cubin.size() && std::fgetc(f) == EOF;
+        ok = std::fread(cubin.data(), 1, cubin.size(), f) == cubin.size() && std::fgetc(f) == EOF &&
+             fnv1a_bytes(cubin) == head[4];                   // a damaged body is recompiled and rewritten, never loaded
     }
     std::fclose(f);
+    if (!ok) cubin.clear();
     return ok;
 }
 void disk_store(const DiskKey& k, const std::vector<char>& cubin) {
     const std::string tmp = k.path + ".tmp" + std::to_string((long)getpid());
     FILE* f = std::fopen(tmp.c_str(), "wb");
     if (!f) return;                                           // an unwritable cache directory is not an error
-    const uint64_t head[4] = {0x31434755425a47ull, k.len, k.check, cubin.size()};
+    const uint64_t head[5] = {0x32434755425a47ull, k.len, k.check, cubin.size(), fnv1a_bytes(cubin)};
     const bool ok = std::fwrite(head, sizeof head, 1, f) == 1 && std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
     if (std::fclose(f) != 0 || !ok || std::rename(tmp.c_str(), k.path.c_str()) != 0) std::remove(tmp.c_str());
 }
@@ -499,6 +541,7 @@ int jit_cubin(const std::string& text, bool exact, std::vector<char>& cubin) {
 }
 
 int jit_cubin_uncached(const std::string& text, bool exact, std::vector<char>& cubin) {
+    NvtxRange range("zg: NVRTC compile of a generated kernel");
     Nvrtc& n = nvrtc();
     if (!n.ok) return fail(ZG_ERR_CUDA, n.why);
     void* prog = nullptr;
@@ -1370,6 +1413,7 @@ void zg_plan_opts_default(zg_plan_opts* o) {
 }
 
 int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
+    NvtxRange range("zg_plan_create");
     if (!g || !opts || !out) return fail(ZG_ERR_ARG, "NULL argument");
     *out = nullptr;
     if (opts->channels < 1 || opts->channels > 0x7fffffe0LL) return fail(ZG_ERR_ARG, "channels out of range");
@@ -1410,7 +1454,7 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
                                      " (zignal-b200 has no CPU fallback for block evaluation)");
     }
     if (opts->device < 0 || opts->device >= ndev) return fail(ZG_ERR_ARG, "bad device ordinal");
-    ZG_CUDA(cudaSetDevice(opts->device));
+    ZG_ON_DEVICE(opts->device);
     ZG_CUDA(cudaFree(nullptr));
     cudaDeviceProp prop;
     ZG_CUDA(cudaGetDeviceProperties(&prop, opts->device));
@@ -1564,10 +1608,11 @@ int zg_plan_get_info(const zg_plan* p, zg_plan_info* info) {
 int zg_process(zg_plan* p, const void* const* in, void* const* out, int64_t n_samples, int64_t ld_in,
                int64_t ld_out, void* stream) {
     if (!p) return fail(ZG_ERR_ARG, "plan is NULL");
+    NvtxRange range("zg_process");
     int st = check_io(p, in, out, n_samples, ld_in, ld_out);
     if (st != ZG_OK) return st;
     if (n_samples == 0) return ZG_OK;
-    ZG_CUDA(cudaSetDevice(p->opts.device));
+    ZG_ON_DEVICE(p->opts.device);
     return launch(p, in, out, n_samples, ld_in, ld_out, (cudaStream_t)stream, 0, p->C, true);
 }
 
@@ -1576,7 +1621,8 @@ int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t
     if (!p) return fail(ZG_ERR_ARG, "plan is NULL");
     if (n_samples < 0) return fail(ZG_ERR_ARG, "n_samples < 0");
     if (n_samples == 0) return ZG_OK;
-    ZG_CUDA(cudaSetDevice(p->opts.device));
+    NvtxRange range("zg_process_host");
+    ZG_ON_DEVICE(p->opts.device);
     if (!p->own_stream) ZG_CUDA(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
     if (!p->h2d_stream) ZG_CUDA(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
     if (!p->d2h_stream) ZG_CUDA(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
@@ -1634,6 +1680,7 @@ int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t
         p->events.push_back(e);
     }
     for (int64_t c = 0; c < n_chunks; ++c) {
+        NvtxRange chunk_range("zg_process_host: chunk (H2D, kernel, D2H enqueued)");
         const int64_t r0 = c * chunk_rows, nr = std::min(chunk_rows, rows - r0);
         for (int k = 0; k < p->ir.n_in; ++k) {
             if (!d_in[k]) continue;
@@ -1668,7 +1715,7 @@ int zg_process_host(zg_plan* p, const void* const* in, void* const* out, int64_t
 
 int zg_state_reset(zg_plan* p) {
     if (!p) return fail(ZG_ERR_ARG, "plan is NULL");
-    ZG_CUDA(cudaSetDevice(p->opts.device));
+    ZG_ON_DEVICE(p->opts.device);
     ZG_CUDA(cudaDeviceSynchronize());
     ZG_CUDA(cudaMemset(p->d_state, 0, (size_t)std::max(p->ir.n_state, 1) * p->ch_stride * sizeof(float)));
     p->stream_pos = 0;
@@ -1679,7 +1726,7 @@ int zg_state_get(zg_plan* p, float* host, size_t n_floats) {
     if (!p || !host) return fail(ZG_ERR_ARG, "NULL argument");
     if (n_floats != (size_t)p->ir.n_state * p->C) return fail(ZG_ERR_ARG, "expected n_state * channels floats");
     if (n_floats == 0) return ZG_OK;
-    ZG_CUDA(cudaSetDevice(p->opts.device));
+    ZG_ON_DEVICE(p->opts.device);
     ZG_CUDA(cudaDeviceSynchronize());
     ZG_CUDA(cudaMemcpy2D(host, p->C * 4, p->d_state, p->ch_stride * 4, p->C * 4, p->ir.n_state, cudaMemcpyDeviceToHost));
     rotate_rings(p, host, true);
@@ -1690,7 +1737,7 @@ int zg_state_set(zg_plan* p, const float* host, size_t n_floats) {
     if (!p || !host) return fail(ZG_ERR_ARG, "NULL argument");
     if (n_floats != (size_t)p->ir.n_state * p->C) return fail(ZG_ERR_ARG, "expected n_state * channels floats");
     if (n_floats == 0) return ZG_OK;
-    ZG_CUDA(cudaSetDevice(p->opts.device));
+    ZG_ON_DEVICE(p->opts.device);
     ZG_CUDA(cudaDeviceSynchronize());
     if (p->ring.any()) {
         std::vector<float> tmp(host, host + n_floats);
@@ -1706,7 +1753,7 @@ int zg_param_set(zg_plan* p, int index, const float* host_values, int64_t n) {
     if (!p || !host_values) return fail(ZG_ERR_ARG, "NULL argument");
     if (index < 0 || index >= (int)p->h_params.size()) return fail(ZG_ERR_ARG, "bad parameter index");
     if (n != 1 && n != p->C) return fail(ZG_ERR_ARG, "parameter needs 1 value or one per channel");
-    ZG_CUDA(cudaSetDevice(p->opts.device));
+    ZG_ON_DEVICE(p->opts.device);
     ZG_CUDA(cudaDeviceSynchronize());      // a launch in flight may still be reading d_params
     p->h_params[index].assign(host_values, host_values + n);
     p->param_on_device[index] = 0;
@@ -1718,7 +1765,7 @@ int zg_param_set_device(zg_plan* p, int index, const float* device_values, int64
     if (!p || !device_values) return fail(ZG_ERR_ARG, "NULL argument");
     if (index < 0 || index >= (int)p->h_params.size()) return fail(ZG_ERR_ARG, "bad parameter index");
     if (n != p->C) return fail(ZG_ERR_ARG, "a parameter set from device memory needs one value per channel");
-    ZG_CUDA(cudaSetDevice(p->opts.device));
+    ZG_ON_DEVICE(p->opts.device);
     ZG_CUDA(cudaDeviceSynchronize());      // the producer of device_values and any launch still reading d_params
     if (!p->d_user_params) {
         const size_t bytes = p->h_params.size() * (size_t)p->ch_stride * sizeof(float);
