@@ -24,9 +24,13 @@
 //     whole API), and
 //   * evaluates it block-wise for many channels on a B200 through block_evaluator (new).
 //
-// Known deviations from the reference (documented in DESIGN.md): outputs are float (double if a
-// double is involved) rather than the per-wire C++ result type; canonical forms are compared
-// with operator== on run-time trees, not with std::is_same on types.
+// The tuple operator() returns has the reference's per-wire C++ types: every node carries a constexpr rule
+// (`types`) that propagates the argument types the way the reference's evaluators do -- C++'s usual arithmetic
+// conversions on the leaves, delayed reads are float because the state is (flowz.hpp:136, :1245), fed-back wires
+// take the type of what is fed back (a fixed point, the role of the reference's `absorber`, :523-548) -- and the
+// tick checks it against the types the library computed at run time.
+// Known deviation from the reference (documented in DESIGN.md): canonical forms are compared with operator== on
+// run-time trees, not with std::is_same on types.
 #pragma once
 
 #include <array>
@@ -58,6 +62,44 @@ inline void check(int status) {
 }
 
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+// ---- compile-time result types of one tick ----------------------------------------------------
+// Type codes are zg_dtype (ZG_I32 < ZG_F32 < ZG_F64: promotion is the maximum); kOpen = not typed yet (a fed-back
+// wire before the fixed point has reached it), which any other type absorbs.
+constexpr int kOpen = -1;
+constexpr int promote(int a, int b) { return a == kOpen ? b : b == kOpen ? a : cmax(a, b); }
+template <size_t N> using type_list = std::array<int, N>;
+template <size_t A, size_t B>
+constexpr type_list<A + B> cat(const type_list<A>& a, const type_list<B>& b) {
+    type_list<A + B> r{};
+    for (size_t i = 0; i < A; ++i) r[i] = a[i];
+    for (size_t i = 0; i < B; ++i) r[A + i] = b[i];
+    return r;
+}
+template <size_t K, size_t N>
+constexpr type_list<(K < N ? K : N)> take(const type_list<N>& a) {       // tuple_tools.hpp:92-103
+    type_list<(K < N ? K : N)> r{};
+    for (size_t i = 0; i < r.size(); ++i) r[i] = a[i];
+    return r;
+}
+template <size_t K, size_t N>
+constexpr type_list<(K < N ? N - K : 0)> drop(const type_list<N>& a) {   // tuple_tools.hpp:138-150
+    type_list<(K < N ? N - K : 0)> r{};
+    for (size_t i = 0; i < r.size(); ++i) r[i] = a[K + i];
+    return r;
+}
+template <size_t N>
+constexpr type_list<N> filled(int v) {
+    type_list<N> r{};
+    for (size_t i = 0; i < N; ++i) r[i] = v;
+    return r;
+}
+template <class T> constexpr int type_code() {
+    return std::is_integral<T>::value ? ZG_I32 : std::is_same<T, float>::value ? ZG_F32 : ZG_F64;
+}
+template <int Code> struct code_type { using type = float; };
+template <> struct code_type<ZG_I32> { using type = int; };
+template <> struct code_type<ZG_F64> { using type = double; };
 
 // writer state: parameters ($k) are numbered in order of first appearance
 struct writer {
@@ -98,6 +140,7 @@ struct delayed_expr : expr_tag {
     static constexpr bool has_double = false;
     int n;
     void write(writer& w) const { w.os << "_" << K << "[_" << n << "]"; }
+    template <size_t N> static constexpr type_list<1> types(const type_list<N>&) { return {ZG_F32}; }   // the state is float
 };
 
 template <int K>
@@ -106,6 +149,10 @@ struct placeholder_expr : expr_tag {
     static constexpr int in = K, out = 1;
     static constexpr bool has_double = false;
     void write(writer& w) const { w.os << "_" << K; }
+    template <size_t N> static constexpr type_list<1> types(const type_list<N>& t) {
+        static_assert((size_t)K <= N, "placeholder reads past the wires it is given");
+        return {t[K - 1]};
+    }
     template <int N>
     delayed_expr<K> operator[](placeholder_expr<N>) const { return {{}, N}; }    // _k[_n]
     delayed_expr<K> operator[](int n) const {                                    // _k[-n]
@@ -123,6 +170,10 @@ struct literal_expr : expr_tag {
     static constexpr int in = 0, out = 1;
     static constexpr bool has_double = std::is_same<T, double>::value;
     T value;
+    template <size_t N> static constexpr type_list<1> types(const type_list<N>&) {
+        static_assert(!is_complex<T>::value, "complex terminals are typed by transforms::ResultType, not evaluated (flowz.hpp:1245)");
+        return {type_code<T>()};
+    }
     void write(writer& w) const {
         char buf[64];
         if constexpr (is_complex<T>::value) {          // typed by ResultType, not evaluated (flowz.hpp:1245)
@@ -141,6 +192,7 @@ struct ref_expr : expr_tag {                       // std::ref(x): non-owning, r
     static constexpr bool has_double = false;
     const float* p;
     void write(writer& w) const { w.os << "$" << w.ref_index(p); }
+    template <size_t N> static constexpr type_list<1> types(const type_list<N>&) { return {ZG_F32}; }
 };
 
 // ---- operator nodes ---------------------------------------------------------------------------
@@ -174,6 +226,18 @@ struct unary_expr : expr_tag, delayable<unary_expr<Tag, A>> {
         a.write(w);
         w.os << ")";
     }
+    // ~a: the first out(a) inputs of a are its own outputs.  Their types are the least fixed point of a's own rule,
+    // started from "open" (three rounds reach it: int < float < double); a wire nothing ever types reads as float.
+    template <size_t N> static constexpr type_list<(size_t)out> types(const type_list<N>& t) {
+        if constexpr (std::is_same<Tag, tag::feedback>::value) {
+            type_list<(size_t)A::out> fed = filled<(size_t)A::out>(kOpen);
+            for (int round = 0; round < 4; ++round) fed = A::types(cat(fed, t));
+            for (size_t i = 0; i < fed.size(); ++i) if (fed[i] == kOpen) fed[i] = ZG_F32;
+            return fed;
+        } else {
+            return A::types(t);
+        }
+    }
 };
 
 template <class Tag, class A, class B>
@@ -196,6 +260,23 @@ struct binary_expr : expr_tag, delayable<binary_expr<Tag, A, B>> {
             w.os << "bfb("; a.write(w); w.os << " , "; b.write(w); w.os << ")";
         } else {
             w.os << "("; a.write(w); w.os << symbol<Tag>::s; b.write(w); w.os << ")";
+        }
+    }
+    // the routing rules of the reference's evaluators (sequence :960-1001, parallel :1076-1101, channel :765-768,
+    // binary_feedback :1031-1074), on types instead of values
+    template <size_t N> static constexpr type_list<(size_t)out> types(const type_list<N>& t) {
+        if constexpr (std::is_same<Tag, tag::sequence>::value) {
+            const auto l = A::types(t);
+            const auto r = B::types(cat(l, drop<(size_t)A::in>(t)));
+            return cat(r, drop<(size_t)B::in>(l));
+        } else if constexpr (std::is_same<Tag, tag::parallel>::value) {
+            return cat(A::types(take<(size_t)A::in>(t)), B::types(drop<(size_t)A::in>(t)));
+        } else if constexpr (std::is_same<Tag, tag::channel>::value) {
+            return cat(A::types(t), B::types(t));
+        } else if constexpr (std::is_same<Tag, tag::binary_feedback>::value) {
+            return B::types(cat(filled<(size_t)A::out>(ZG_F32), t));      // the future part reads the fed-back wires delayed
+        } else {
+            return {promote(A::types(t)[0], B::types(t)[0])};            // C++'s usual arithmetic conversions
         }
     }
 };
@@ -424,16 +505,27 @@ public:
 // ---- compile() and the callable it returns -----------------------------------------------------------
 
 namespace detail {
-template <class T, size_t... Is>
-auto make_result_tuple(const double* v, std::index_sequence<Is...>) { return std::make_tuple((T)v[Is]...); }
-
 template <class T> constexpr int dtype_of() {
     return std::is_integral<T>::value ? ZG_I32 : std::is_same<T, float>::value ? ZG_F32 : ZG_F64;
 }
+// The tuple one tick of expression E returns for arguments of types Args... (flowz.hpp:1193-1201: the types fall out
+// of the template-expanded evaluators there; here they are E's constexpr `types` rule, checked at every tick against
+// the types of the tick program the library lowered for this signature).
+template <class E, class... Args>
+struct tick_result {
+    static constexpr auto codes = E::types(type_list<sizeof...(Args)>{dtype_of<Args>()...});
+    template <size_t... Is>
+    static auto make(const double* v, const int* run_time_types, std::index_sequence<Is...>) {
+        if (((run_time_types[Is] != codes[Is]) || ...))
+            throw error("flowz shim: the static result type of this tick differs from the one the library computed");
+        return std::tuple<typename code_type<codes[Is]>::type...>{(typename code_type<codes[Is]>::type)v[Is]...};
+    }
+};
 }  // namespace detail
 
-template <size_t arity, size_t n_out, bool has_double>
+template <class E>
 class stateful_lambda {
+    static constexpr size_t arity = (size_t)E::in, n_out = (size_t)E::out;
     std::shared_ptr<zg_graph> graph_;
     std::unique_ptr<zg_voice, void (*)(zg_voice*)> voice_{nullptr, zg_voice_destroy};
     std::vector<const float*> refs_;
@@ -474,13 +566,13 @@ public:
     auto operator()(const Args&... args) {
         static_assert((std::is_arithmetic<Args>::value && ...), "tick arguments must be arithmetic");
         if constexpr (sizeof...(Args) == arity) {
-            using T = std::conditional_t<has_double || (std::is_same<Args, double>::value || ...), double, float>;
             double in[arity ? arity : 1] = {(double)args...};
             int dt[arity ? arity : 1] = {detail::dtype_of<Args>()...};
             double out[n_out];
+            int out_types[n_out];
             refresh_params();
-            detail::check(zg_voice_tick(voice_.get(), in, dt, out, nullptr));
-            return detail::make_result_tuple<T>(out, std::make_index_sequence<n_out>{});
+            detail::check(zg_voice_tick(voice_.get(), in, dt, out, out_types));
+            return detail::tick_result<E, Args...>::make(out, out_types, std::make_index_sequence<n_out>{});
         } else {
             return [args..., self = *this](const auto&... rest) mutable { return self(args..., rest...); };
         }
@@ -518,7 +610,7 @@ struct compile_fn {
     auto operator()(const E& e) const {
         std::vector<const float*> refs;
         std::string text = detail::to_text(e, &refs);
-        return stateful_lambda<(size_t)E::in, (size_t)E::out, E::has_double>(text, std::move(refs));
+        return stateful_lambda<E>(text, std::move(refs));
     }
 };
 inline constexpr compile_fn compile{};

@@ -88,6 +88,49 @@ int main(int argc, char** argv) {
         CHECK(std::get<0>(three(1.0f)(1.0f)(1.0f)) == 7.0f && std::get<0>(three(1.0f, 1.0f)(1.0f)) == 7.0f);
     }
 
+    // ---- the tuple a tick returns has the reference's per-wire C++ types (flowz.hpp:1193-1201): the reference's own
+    //      integer ticks (test/tests.cpp:88-134) in its spelling, plus the types they imply ----
+    {
+        using std::tuple;
+        using std::is_same;
+        auto wp = compile(_1 |= _2);                             // wire-around (test/tests.cpp:88-95)
+        auto wpr = wp(2, 1337);
+        CHECK(std::make_tuple(1337) == wpr);
+        static_assert(is_same<decltype(wpr), tuple<int>>::value, "int in, int out");
+        auto ws = compile((_1, _1) |= _1);                       // :97-103
+        auto wsr = ws(1337);
+        CHECK(std::make_tuple(1337, 1337) == wsr);
+        static_assert(is_same<decltype(wsr), tuple<int, int>>::value, "");
+        auto identity = compile(_1);                             // :111-114
+        CHECK(std::make_tuple(1337) == identity(1337) && std::make_tuple(42) == identity(42));
+        static_assert(is_same<decltype(identity(42)), tuple<int>>::value && is_same<decltype(identity(4.2)), tuple<double>>::value, "");
+        auto unit_delay = compile(_1[_1]);                       // :117-121: the delayed value comes out of the float state
+        CHECK(std::make_tuple(0) == unit_delay(1337) && std::make_tuple(1337) == unit_delay(42) && std::make_tuple(42) == unit_delay(17));
+        static_assert(is_same<decltype(unit_delay(17)), tuple<float>>::value, "");
+        auto differentiator = compile(_1 - _1[_1]);              // :124-128
+        CHECK(std::make_tuple(1337) == differentiator(1337) && std::make_tuple(42 - 1337) == differentiator(42) &&
+              std::make_tuple(17 - 42) == differentiator(17));
+        static_assert(is_same<decltype(differentiator(17)), tuple<float>>::value, "int - float");
+        auto integrator = compile(~(_1[_1] + _2));               // :131-135
+        CHECK(std::make_tuple(1337) == integrator(1337) && std::make_tuple(1337 + 42) == integrator(42) &&
+              std::make_tuple(1337 + 42 + 17) == integrator(17));
+        static_assert(is_same<decltype(integrator(17)), tuple<float>>::value && is_same<decltype(integrator(1.5)), tuple<double>>::value, "");
+        // mixed wires: every output has its own type (test/tests.cpp:206-211 for the same expressions as ResultType)
+        auto mixed = compile((_1, _1 * 1.0));
+        static_assert(is_same<decltype(mixed(1.0f)), tuple<float, double>>::value, "");
+        static_assert(is_same<decltype(mixed(1)), tuple<int, double>>::value, "");
+        CHECK(mixed(3) == std::make_tuple(3, 3.0));
+        auto swapped = compile((_1 * 1.0, _1) |= (_2, _1));
+        static_assert(is_same<decltype(swapped(1.0f)), tuple<float, double>>::value, "");
+        auto sums = compile(_1 + _2);
+        static_assert(is_same<decltype(sums(1, 2)), tuple<int>>::value && is_same<decltype(sums(1, 2.f)), tuple<float>>::value &&
+                      is_same<decltype(sums(1., 2.f)), tuple<double>>::value, "usual arithmetic conversions");
+        CHECK(sums(7, 2) == std::make_tuple(9) && std::get<0>(compile(_1 / _2)(7, 2)) == 3);    // int / int stays an int division
+        static_assert(is_same<decltype(one_pole(1.0f)), tuple<float>>::value && is_same<decltype(one_pole(1.0)), tuple<double>>::value &&
+                      is_same<decltype(one_pole(1)), tuple<float>>::value, "feedback: the type of what is fed back");
+        static_assert(is_same<decltype(biquad(1.0f)), tuple<float>>::value, "");
+    }
+
     // ---- expr[_n], a spelling the reference plans (TODO.md:51-52): (_1+_2)[_1] == _1+_2 |= _1[_1] ----
     {
         auto a = compile((_1 + _2)[_1]);
