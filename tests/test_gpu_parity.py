@@ -1007,3 +1007,30 @@ def test_in_place_blocks(zg, layout):
     with pytest.raises(zg.ZgError) as e:
         fir.process([buf], [buf])
     assert e.value.status == zg.ZG_ERR_UNSUPPORTED
+
+
+def test_plans_of_one_prebuilt_kernel_with_different_geometry_alternate(zg):
+    """The dynamic shared-memory limit belongs to the kernel function, which all plans of a process share: a small plan
+    launched after a large one must not lower it for the large one's next launch (biquad and FIR kernels)."""
+    torch = _torch()
+    expr = fo.biquad_cascade(4)
+    g = zg.compile(expr)
+    big_x, small_x = fo.noise(16384, 512, seed=1), fo.noise(33, 64, seed=2)
+    big = g.plan(channels=16384, lanes_per_channel=1)
+    small = g.plan(channels=33, lanes_per_channel=1)
+    want_big, want_small = _oracle(expr, [big_x])[0], _oracle(expr, [small_x])[0]
+    for _ in range(3):
+        big.reset(); small.reset()
+        yb = big.process([_to_dev(big_x)])[0]
+        ys = small.process([_to_dev(small_x)])[0]
+        torch.cuda.synchronize()
+        assert big.info().smem_bytes > small.info().smem_bytes
+        assert np.array_equal(yb.cpu().numpy(), want_big) and np.array_equal(ys.cpu().numpy(), want_small)
+    h256, h32 = fo.fir_taps(256), fo.fir_taps(32)
+    f_big, f_small = zg.compile(fo.fir_expr(h256)).plan(channels=64), zg.compile(fo.fir_expr(h32)).plan(channels=64)
+    xf = fo.noise(64, 512, seed=3)
+    for _ in range(3):
+        f_big.reset(); f_small.reset()
+        a = f_big.process([_to_dev(xf)])[0].cpu().numpy()
+        b = f_small.process([_to_dev(xf)])[0].cpu().numpy()
+        assert np.array_equal(a, fo.fir_direct(xf, h256)) and np.array_equal(b, fo.fir_direct(xf, h32))

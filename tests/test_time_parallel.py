@@ -302,3 +302,26 @@ def test_full_size_config1_4096x65536_is_cut_automatically(zg):
     _check_biquad(y[idx].cpu().numpy(), _oracle(expr, [xs])[0], xs)
     # the section-parallel kernel is what EXACT mode (and an explicit lanes_per_channel) still gets
     assert zg.compile(expr).plan(channels=C, mode=zg.MODE_FAST, lanes_per_channel=4).info().lanes_per_channel == 4
+
+
+@pytest.mark.gpu
+def test_segments_with_bf16_storage_two_inputs_and_host_chunks(zg):
+    """The segment logic lives in the streaming skeleton, so it composes with everything the skeleton does: bf16 sample
+    storage, several input wires, and the row chunks of zg_process_host (each chunk is cut on its own)."""
+    import torch
+    expr = "(_1 | _1[_1]) |= ~(_2 + _3 + 0.25f*_1[_2])"
+    C, T = 96, 8192
+    x = [fo.noise(C, T, seed=60), fo.noise(C, T, seed=61)]
+    ref = _oracle(expr, x)[0]
+    g = zg.compile(expr)
+    for tp in (zg.TP_WARMUP, zg.TP_TWO_PASS):
+        plan = g.plan(channels=C, mode=zg.MODE_FAST, time_parallel=tp)
+        y = plan.process_host(x)[0]
+        assert plan.info().time_segments >= 2
+        assert _rel_err(y, ref) <= TOL
+    xb = [torch.from_numpy(fo.bf16_round(a)).cuda().to(torch.bfloat16) for a in x]
+    refb = _oracle(expr, [fo.bf16_round(a) for a in x])[0]
+    plan = g.plan(channels=C, mode=zg.MODE_FAST, time_parallel=zg.TP_WARMUP, io_dtype=zg.BF16)
+    yb = plan.process(xb)[0].float().cpu().numpy()
+    assert plan.info().time_segments >= 2
+    assert _rel_err(yb, refb) <= 2.0 ** -7                      # one bf16 ulp (8 bits of mantissa) block-relative
