@@ -190,7 +190,11 @@ typedef struct zg_plan_opts {
     int input_kind[ZG_MAX_WIRES];
     int force_jit;        /* 1 = never use the prebuilt biquad kernels (tests)                  */
     int time_parallel;    /* zg_time_parallel (ZG_MODE_FAST only; ignored -- serial -- in ZG_MODE_EXACT when AUTO) */
-    int reserved[6];
+    int fir_tensor_cores; /* dense FIR in ZG_MODE_FAST: 0 = auto (planar fp32, 2..256 taps, blocks >= 256 samples run the
+                             banded-Toeplitz contraction on tcgen05 tensor cores, 3xTF32: ~3e-6 block-relative from the
+                             reference's left-to-right sum, dominated by the tensor core's truncating fp32 accumulation),
+                             1 = never (CUDA-core FMA kernel, ~3e-7).  ZG_MODE_EXACT never uses tensor cores.        */
+    int reserved[5];
 } zg_plan_opts;
 
 void zg_plan_opts_default(zg_plan_opts* o);

@@ -47,6 +47,8 @@ struct FirTcArgs {
     int n_groups;                   // ceil(channels / 128)
     int n_tiles;                    // ceil(n_samples / 128)
     long long* prof;                // tuning only (ZG_TUNE_FIR_PROF): [grid][8] cycles the roles of a CTA spent waiting
+    int split_mode;                 // experiment (ZG_TUNE_FIR_SPLIT): 0 = hi rewritten as tf32(x) (default); 1 = hi left as the
+                                    // raw fp32 block, lo = x - trunc_tf32(x); 2 = hi raw, lo = x - rna_tf32(x)
 };
 
 constexpr int kTcStages = 4;
@@ -171,7 +173,7 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
         const float hi = tf32_rna(h);
         const unsigned off = (unsigned)r * 128u + ((((unsigned)j >> 2) ^ ((unsigned)r & 7u)) << 4) + ((unsigned)j & 3u) * 4u;
         *reinterpret_cast<float*>(g_hi + off) = hi;
-        *reinterpret_cast<float*>(g_lo + off) = h - hi;
+        *reinterpret_cast<float*>(g_lo + off) = tf32_rna(h - hi);
     }
     fence_proxy_async();                                 // G: generic-proxy writes -> visible to the tensor core
     tc_fence_before_sync();
@@ -283,9 +285,16 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
                         const unsigned off = (unsigned)(ts + 128 * i) << 4;
                         const float4 v = *reinterpret_cast<const float4*>(hi + off);
                         float4 h, l;
-                        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                        *reinterpret_cast<float4*>(hi + off) = h;
+                        if (a.split_mode == 1) {
+                            h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                            h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                        } else {
+                            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+                        }
+                        // the tensor core truncates an fp32 operand to TF32 (measured: tools/fir_split_check.py), which would
+                        // bias every lo term the same way: round it to nearest here instead
+                        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                        if (a.split_mode == 0) *reinterpret_cast<float4*>(hi + off) = h;
                         *reinterpret_cast<float4*>(lo + off) = l;
                     }
                 } else {
@@ -298,7 +307,7 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
                         const float h = tf32_rna(v);
                         const unsigned off = r * 128u + ((((unsigned)j >> 2) ^ (r & 7u)) << 4) + ((unsigned)j & 3u) * 4u;
                         *reinterpret_cast<float*>(hi + off) = h;
-                        *reinterpret_cast<float*>(lo + off) = v - h;
+                        *reinterpret_cast<float*>(lo + off) = tf32_rna(v - h);
                     }
                 }
                 fence_proxy_async();

@@ -1209,6 +1209,7 @@ int launch_fir_tc(zg_plan* p, const void* const* in, void* const* out, int64_t T
     const int grid = (int)std::min<int64_t>(p->sm_count, total);
     st = raise_max_smem((const void*)zg_fir_tc_kernel, p->opts.device, zgk::kTcSmemBytes);
     if (st != ZG_OK) return st;
+    a.split_mode = tune_env("ZG_TUNE_FIR_SPLIT");
     const bool prof = tune_env("ZG_TUNE_FIR_PROF") != 0;          // tuning only: where the roles of a CTA wait
     if (prof) ZG_CUDA(cudaMalloc(&a.prof, (size_t)grid * 8 * sizeof(long long)));
     void* args[] = {&a};
@@ -1422,6 +1423,7 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     if (opts->mode != ZG_MODE_EXACT && opts->mode != ZG_MODE_FAST) return fail(ZG_ERR_ARG, "bad mode");
     if (opts->layout != ZG_PLANAR && opts->layout != ZG_INTERLEAVED) return fail(ZG_ERR_ARG, "bad layout");
     if (opts->time_parallel < ZG_TP_AUTO || opts->time_parallel > ZG_TP_TWO_PASS) return fail(ZG_ERR_ARG, "bad time_parallel");
+    if (opts->fir_tensor_cores < 0 || opts->fir_tensor_cores > 1) return fail(ZG_ERR_ARG, "bad fir_tensor_cores");
     const Ir& ir = g->ir_f32;
     if (!ir.all_f32())
         return fail(ZG_ERR_UNSUPPORTED,
@@ -1512,7 +1514,8 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
         p->kernel_n_param = 0;
         // FAST mode, planar, 2..256 taps: the Toeplitz contraction on tensor cores (3xTF32); EXACT keeps the CUDA-core
         // kernel, whose left-to-right sum is bit-identical to the reference (ZG_TUNE_FIR_TC=1 / 2 forces off / on)
-        p->fir_tc = !p->exact && !p->interleaved && fir.taps.size() >= 2 && fir.taps.size() <= 256 && tune_env("ZG_TUNE_FIR_TC") != 1;
+        p->fir_tc = !p->exact && !p->interleaved && fir.taps.size() >= 2 && fir.taps.size() <= 256 && opts->fir_tensor_cores != 1 &&
+                    tune_env("ZG_TUNE_FIR_TC") != 1;
         p->kernel_name = p->fir_tc ? "zg_fir_tc<" + std::to_string(fir.taps.size()) + " taps,3xtf32,planar>"
                                    : "zg_fir<" + std::to_string(fir.taps.size()) + (p->exact ? " taps,exact," : " taps,fma,") +
                                          (p->interleaved ? "interleaved>" : "planar>");
