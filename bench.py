@@ -290,7 +290,7 @@ def other_configs(zg, wl, torch, dev, local, world, rank, args, barrier, dist):
                 ent["roofline"] = {"bound": "tensor", "achieved": algo, "unit": "TFLOP/s", "peak": tf32,
                                    "frac": algo / tf32 if tf32 else None,
                                    "peak_source": "measured here: torch.matmul fp32 8192^3 with TF32 enabled (cuBLAS), best of 5",
-                                   "executed_tflops": algo * 3 * 288 / 256,
+                                   "executed_tflops": algo * 3 * 288 / 256, "traffic": _traffic("c4_tc"),
                                    "executed_frac": algo * 3 * 288 / 256 / tf32 if tf32 else None,
                                    "note": "3xTF32 (hi*hi + lo*hi + hi*lo) and a 288-row band per 256 taps: 3.375 tensor flops "
                                            "per algorithmic flop; the kernel is bound by shared-memory operand bandwidth "
@@ -608,7 +608,7 @@ def run_ours(args):
                    "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE,
                    "moved_bytes_per_sample": (8 + 4.0 * K / L) if i_s.time_segments > 1 and K else (12 if i_s.time_segments > 1 else 8),
                    "kernel": i_s.kernel.decode(), "time_segments": i_s.time_segments, "segment_samples": i_s.segment_samples,
-                   "warmup_samples": K, "launches_per_step": launches_s // max(args.steps, 1),
+                   "warmup_samples": K, "launches_per_step": launches_s // max(args.steps, 1), "traffic": _traffic("c2_scan"),
                    "numerics": "FAST: FMA contraction + segments that start from a warmed-up state; held to the FAST bar of "
                                "tests/test_time_parallel.py (<= 3e-5 block-relative on this cascade, no further from float64 "
                                "than the reference)"}
