@@ -26,12 +26,22 @@ int main() {
         zg_graph_kernel_class(g, buf, sizeof buf);
         int lin = 0;
         zg_graph_linearity(g, &lin);
+        if (gi.n_state <= 64 && gi.n_params <= 8) {              // the linear-tick analysis behind time_parallel
+            std::vector<double> A((size_t)gi.n_state * gi.n_state + 1);
+            const float prm[8] = {0.5f, -0.25f, 0.9f, 1.0f, -1.5f, 0.f, 2.f, 0.125f};
+            int K = 0;
+            zg_graph_state_matrix(g, prm, gi.n_params, A.data(), A.size());
+            zg_graph_settling_time(g, prm, gi.n_params, 128, 1024, 1e-9, &K);
+        }
         (void)zg_graph_dump(g);
         zg_voice* v = nullptr;
         if (zg_voice_create(g, &v) == ZG_OK) {
             double in[8] = {1, -2, 3, 0.5, 2, 1, 1, 1}, out[16];
             int idt[8] = {0, 1, 2, 1, 0, 1, 2, 1}, odt[16];
             for (int t = 0; t < 4; ++t) zg_voice_tick(v, in, idt, out, odt);
+            const double edge[8] = {-2147483648.0, -1, 3e10, -3e10, 0.0 / 0.0, 1e300, -1, 0};   // INT_MIN / -1, out-of-range ints, NaN
+            const int all_int[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            zg_voice_tick(v, edge, all_int, out, odt);
             zg_voice* w = nullptr;
             if (zg_voice_clone(v, &w) == ZG_OK) { zg_voice_tick(w, in, idt, out, odt); zg_voice_destroy(w); }
             zg_voice_destroy(v);

@@ -21,7 +21,7 @@ for c in rv.CANONICAL_SPLITS: print(c[0])
 for c in rv.RESULT_TYPES: print(c[0])
 for s in ["", "(", "_", "_0", "_1[", "_1[_0]", "~", "_1 |=", "1e999", "0x", "cplx{", "cplx{1,", "_1<-", "$", "$-1", "bfb(_1", "front(0)",
           "front(99999)", "_99999999999", "_1[_99999999999]", ")" * 10, "(" * 2000, "-" * 3000 + "_1", "~" * 3000 + "_1",
-          "_1" + "[_1]" * 3000, "_1 " + "+ _1 " * 5000, "(" * 1500 + "_1" + ")" * 1500, "_1" + " |= _1" * 1500, "_1" + " + _1[_2]" * 1500]:
+          "_1" + "[_1]" * 3000, "_1[_2000000000]", "_1 * $2000000000", "_1[_4294967297]", "$4294967296", "3000000000*_1", "_1[_1048576]", "_1 / _2", "_1[_1000000] + _1[_999999]", "_1 " + "+ _1 " * 5000, "(" * 1500 + "_1" + ")" * 1500, "_1" + " |= _1" * 1500, "_1" + " + _1[_2]" * 1500]:
     print(s)
 PY
 # sanitizer frames are several times larger than the product's: give the deepest accepted expressions room

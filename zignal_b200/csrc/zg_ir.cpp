@@ -545,7 +545,7 @@ inline void run_tick(const Ir& ir, float* state, const float* params, Cell* v) {
                 break;
             }
             case IrOp::Neg:
-                if (nd.dtype == Dtype::I32) v[i].i = -v[nd.a].i;
+                if (nd.dtype == Dtype::I32) v[i].i = (int32_t)(0u - (uint32_t)v[nd.a].i);   // wraps like the other int ops
                 else if (nd.dtype == Dtype::F32) v[i].f = -v[nd.a].f;
                 else v[i].d = -v[nd.a].d;
                 break;
