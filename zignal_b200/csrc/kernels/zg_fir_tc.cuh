@@ -15,11 +15,11 @@
 //     jb (samples 32 jb ..) reaches output times 32 jb .. 32 jb + 287, and the coefficient of input sample j for
 //     output time r (both relative to the block) is h[r - j] whatever the block -- the band is the SAME matrix for
 //     every block, only the accumulator columns it lands on move;
-//   * D: the 512 TMEM columns are a ring of four 128-sample output tiles.  Block jb accumulates into the 256 columns
-//     of output times 32 jb .. 32 jb + 255 (already begun by earlier blocks) and starts the 32 columns after them
-//     (accumulate = 0): two MMAs per K-step and operand product, split once more where the window wraps around the
-//     ring.  A tile is complete after the block that ends it and is drained by the epilogue warps while the next
-//     three fill.
+//   * D: the 512 TMEM columns are a ring of four 128-sample output tiles, zeroed at the start and again by the
+//     epilogue as it drains a tile, so every MMA accumulates.  Block jb adds into the 288 columns of output times
+//     32 jb .. 32 jb + 287: two MMAs (N = 160 + 128; N <= 256 per instruction) per K-step and operand product, cut once
+//     more where the window wraps around the ring.  A tile is complete after the block that ends it and is drained
+//     by the epilogue warps while the next three fill.
 //
 // fp32 accuracy out of TF32 operands (3xTF32): x = hi + lo with hi = cvt.rna.tf32(x), lo = x - hi (exact in fp32),
 // the same for the taps; three MMAs hi*hi + lo*hi + hi*lo per K-step, the dropped lo*lo term and the conversion of
@@ -108,6 +108,14 @@ __device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&r)[32]) {   /
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_st32_zero(unsigned taddr) {                // zero this warp's 32 lanes x 32 columns
+    const unsigned z = 0;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tf32_rna(float v) {                        // nearest TF32 (10 explicit mantissa bits)
     unsigned r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -180,6 +188,14 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
     __syncthreads();
     tc_fence_after_sync();
     const unsigned tmem = *tmem_slot;
+    // every MMA accumulates: the ring starts zeroed, and the epilogue zeroes a tile again as it drains it
+    if (warp < 4) {
+        for (int c = 0; c < 512; c += 32) tc_st32_zero(tmem + ((unsigned)(warp * 32) << 16) + (unsigned)c);
+        tc_wait_st();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
 
     if (warp == 8) {
         // ===== TMA producer =====
@@ -222,7 +238,7 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
                     // output times this block reaches, clipped to the tiles of this run; the last 32 are new
                     const int t_run0 = 128 * o_s, t_run1 = 128 * o_e;
                     const int t_lo = 32 * jb > t_run0 ? 32 * jb : t_run0;
-                    const int t_new = 32 * jb + 256;
+                    const int t_new = 32 * jb + 256;                    // the last 32 of them are touched for the first time
                     const int t_hi = t_new + 32 < t_run1 ? t_new + 32 : t_run1;
                     const unsigned xa_hi = smem_u32(x_hi + st * kTcBlockBytes), xa_lo = smem_u32(x_lo + st * kTcBlockBytes);
                     const unsigned gb_hi = smem_u32(g_hi), gb_lo = smem_u32(g_lo);
@@ -235,27 +251,36 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
                     }
                     // column of output time t in the ring: tile o_s sits in slot q_base & 3
                     const int col0 = (q_base & 3) * 128 - t_run0;
-                    // D[:, t0 .. t1) (+)= X_blk * G[t0 - 32 jb .. t1 - 32 jb)^T, cut where the ring wraps
-                    auto issue = [&](int t0, int t1, bool fresh) {
-                        while (t0 < t1) {
+                    // D[:, t_lo .. t_hi) += X_blk * G[t_lo - 32 jb .. t_hi - 32 jb)^T: the 288 output times this block reaches
+                    // (fewer at the ends of a run).  An MMA takes N <= 256 columns, so the window is cut once in the middle
+                    // (160 + 128: a lone N = 32 MMA costs ~70 cycles for 16 cycles of work) and where the ring wraps.  All
+                    // MMAs of a piece are issued back to back: changing the accumulator between MMAs stalls the pipe.
+                    struct Seg { int c, n, row; };
+                    Seg seg[4];
+                    int n_seg = 0;
+                    {
+                        int t0 = t_lo;
+                        while (t0 < t_hi) {
                             const int c = (col0 + t0) & 511;
-                            int n = t1 - t0;
+                            int n = t_hi - t0;
+                            if (n > 256) n = 160;
                             if (c + n > 512) n = 512 - c;
-                            const unsigned row = (unsigned)(t0 - 32 * jb);
-                            const unsigned idesc = tc_idesc((unsigned)n);
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const unsigned long long ah = tc_desc(xa_hi + ks * 32), al = tc_desc(xa_lo + ks * 32);
-                                const unsigned long long bh = tc_desc(gb_hi + row * 128u + ks * 32), bl = tc_desc(gb_lo + row * 128u + ks * 32);
-                                tc_mma_tf32(tmem + (unsigned)c, ah, bh, idesc, (fresh && ks == 0) ? 0u : 1u);
-                                tc_mma_tf32(tmem + (unsigned)c, al, bh, idesc, 1u);
-                                tc_mma_tf32(tmem + (unsigned)c, ah, bl, idesc, 1u);
-                            }
+                            seg[n_seg++] = Seg{c, n, t0 - 32 * jb};
                             t0 += n;
                         }
-                    };
-                    issue(t_lo, t_new < t_hi ? t_new : t_hi, false);
-                    if (t_new < t_hi) issue(t_new, t_hi, true);
+                    }
+                    for (int i = 0; i < n_seg; ++i) {
+                        const unsigned idesc = tc_idesc((unsigned)seg[i].n);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const unsigned long long ah = tc_desc(xa_hi + ks * 32), al = tc_desc(xa_lo + ks * 32);
+                            const unsigned long long bh = tc_desc(gb_hi + (unsigned)seg[i].row * 128u + ks * 32);
+                            const unsigned long long bl = tc_desc(gb_lo + (unsigned)seg[i].row * 128u + ks * 32);
+                            tc_mma_tf32(tmem + (unsigned)seg[i].c, ah, bh, idesc, 1u);
+                            tc_mma_tf32(tmem + (unsigned)seg[i].c, al, bh, idesc, 1u);
+                            tc_mma_tf32(tmem + (unsigned)seg[i].c, ah, bl, idesc, 1u);
+                        }
+                    }
                     if ((jb & 3) == 3 && floor_div4(jb) >= o_s) { // this block ends tile floor(jb / 4)
                         const int q = q_base + (floor_div4(jb) - o_s);
                         tc_commit(&acc_full[q & 3]);
@@ -333,6 +358,7 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
                 for (int cc = 0; cc < 4; ++cc) {
                     unsigned v[32];
                     tc_ld32(tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(slot * 128 + cc * 32), v);
+                    tc_st32_zero(tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(slot * 128 + cc * 32));   // ready for the next tile
                     if (tid == 0) tma_wait_read<0>();            // the previous store has read the staging box
                     asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
@@ -346,6 +372,7 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
                         tma_commit();
                     }
                 }
+                tc_wait_st();
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[slot]);
