@@ -26,9 +26,9 @@
 // the lo operands are <= 2^-22 |x||h| each.  Accumulation is fp32 in TMEM, in blocked order -- not the reference's
 // left-to-right association, hence FAST mode only (bar: 1e-5 block-relative against fir_direct, tests/).
 //
-// Roles (320 threads): warps 0-3 epilogue (TMEM -> registers -> global, one thread per channel row), warps 4-7 split
-// every landed block into hi / lo in place (8 LDS.128 + 16 STS.128 per thread per block), warp 8 = TMA producer,
-// warp 9 = MMA issuer (one lane).  CTAs are persistent: each takes a contiguous range of (channel group, output
+// Roles (448 threads): warps 0-3 epilogue (TMEM -> registers -> swizzled staging box -> TMA store; one thread per
+// channel row), warps 4-11 split every landed block into hi / lo in shared memory, warp 12 = TMA producer, warp 13 =
+// MMA issuer (one lane).  CTAs are persistent: each takes a contiguous range of (channel group, output
 // tile) work items; a range that starts in the middle of a row of tiles re-reads its 8 history blocks from the input,
 // a range that starts at tile 0 reads them from the delay-line state ([N-1][channels], oldest first).  The state
 // after the block is written by a separate small kernel (zg_fir_state_kernel), so nothing here writes state.
@@ -60,7 +60,8 @@ constexpr int kTcSmemX = 2 * kTcStages * kTcBlockBytes;  // hi[stages], lo[stage
 constexpr int kTcSmemOut = kTcBlockBytes;                // epilogue staging: 128 channels x 32 output times
 constexpr int kTcSmemBars = 256;
 constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kTcSmemG + kTcSmemX + kTcSmemOut + kTcSmemBars;
-constexpr int kTcThreads = 320;
+constexpr int kTcSplitWarps = 8;                         // warps 4 .. 4 + kTcSplitWarps - 1
+constexpr int kTcThreads = (4 + kTcSplitWarps + 2) * 32;
 // instruction descriptor: D = f32, A = B = tf32, both K-major, dense, M = 128; N (a multiple of 16) is added per MMA
 constexpr unsigned kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
 __device__ __forceinline__ unsigned tc_idesc(unsigned n) { return kTcIdesc | ((n >> 3) << 17); }
@@ -162,7 +163,7 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
     if (tid == 0) {
         for (int i = 0; i < kTcStages; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&ready[i], 128);
+            mbar_init(&ready[i], kTcSplitWarps * 32);
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < 4; ++i) {
@@ -197,7 +198,7 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
     __syncthreads();
     tc_fence_after_sync();
 
-    if (warp == 8) {
+    if (warp == 4 + kTcSplitWarps) {
         // ===== TMA producer =====
         if (lane == 0) {
             int n = 0;
@@ -218,7 +219,7 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
             });
             if (a.prof) a.prof[(long long)blockIdx.x * 8 + 5] = w_empty;
         }
-    } else if (warp == 9) {
+    } else if (warp == 5 + kTcSplitWarps) {
         // ===== MMA issuer =====
         if (lane == 0) {
             int n = 0, q_base = 0;
@@ -256,18 +257,14 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
                     // (160 + 128: a lone N = 32 MMA costs ~70 cycles for 16 cycles of work) and where the ring wraps.  All
                     // MMAs of a piece are issued back to back: changing the accumulator between MMAs stalls the pipe.
                     struct Seg { int c, n, row; };
-                    Seg seg[4];
+                    Seg seg[2];
                     int n_seg = 0;
                     {
-                        int t0 = t_lo;
-                        while (t0 < t_hi) {
-                            const int c = (col0 + t0) & 511;
-                            int n = t_hi - t0;
-                            if (n > 256) n = 160;
-                            if (c + n > 512) n = 512 - c;
-                            seg[n_seg++] = Seg{c, n, t0 - 32 * jb};
-                            t0 += n;
-                        }
+                        const int c_lo = (col0 + t_lo) & 511, len = t_hi - t_lo;
+                        // one cut: at the end of the ring if the window wraps, else in the middle of a full window
+                        const int first = c_lo + len > 512 ? 512 - c_lo : len > 256 ? 160 : len;
+                        seg[n_seg++] = Seg{c_lo, first, t_lo - 32 * jb};
+                        if (first < len) seg[n_seg++] = Seg{(c_lo + first) & 511, len - first, t_lo + first - 32 * jb};
                     }
                     for (int i = 0; i < n_seg; ++i) {
                         const unsigned idesc = tc_idesc((unsigned)seg[i].n);
@@ -296,7 +293,7 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
         }
     } else if (warp >= 4) {
         // ===== split warps: hi = tf32(x), lo = x - hi, in place / into the lo tile =====
-        const int ts = tid - 128;                        // 0..127
+        const int ts = tid - 128;                        // 0 .. 32 * kTcSplitWarps - 1
         int n = 0;
         tc_for_each_run(a, [&](int g, int o_s, int o_e) {
             for (int jb = 4 * o_s - 8; jb <= 4 * o_e - 1; ++jb, ++n) {
@@ -306,8 +303,8 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
                 unsigned char* lo = x_lo + st * kTcBlockBytes;
                 if (jb >= 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const unsigned off = (unsigned)(ts + 128 * i) << 4;
+                    for (int i = 0; i < 1024 / (kTcSplitWarps * 32); ++i) {
+                        const unsigned off = (unsigned)(ts + kTcSplitWarps * 32 * i) << 4;
                         const float4 v = *reinterpret_cast<const float4*>(hi + off);
                         float4 h, l;
                         if (a.split_mode == 1) {
@@ -324,9 +321,9 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
                     }
                 } else {
                     // delay-line state: sample time t = 32*jb + j (negative) is slot D + t; older than the line: zero
-                    const int ch = g * 128 + ts;
-                    const unsigned r = (unsigned)ts;
-                    for (int j = 0; j < 32; ++j) {
+                    const int ch = g * 128 + (ts & 127);
+                    const unsigned r = (unsigned)(ts & 127);
+                    for (int j = ts >> 7; j < 32; j += kTcSplitWarps / 4) {
                         const int s = D + 32 * jb + j;
                         const float v = (s >= 0 && ch < a.channels) ? a.state_in[(long long)s * a.ch_stride + ch] : 0.f;
                         const float h = tf32_rna(v);
