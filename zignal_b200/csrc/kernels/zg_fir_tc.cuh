@@ -391,11 +391,25 @@ __device__ __forceinline__ void fir_tc_block(const FirTcArgs& a) {
 // above cut the block anywhere, and the line is ping-ponged between two buffers like K3's.
 __global__ void zg_fir_state_kernel(const float* __restrict__ in, long long ld_in, const float* __restrict__ state_in,
                                     float* __restrict__ state_out, long long ch_stride, int channels, int n_samples, int depth) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = blockIdx.y;
-    if (ch >= channels || s >= depth) return;
-    const long long t = (long long)n_samples - depth + s;
-    state_out[(long long)s * ch_stride + ch] = t >= 0 ? in[(long long)ch * ld_in + t] : state_in[(long long)(s + n_samples) * ch_stride + ch];
+    // a 32-channel x 32-slot tile through shared memory: the input is read along time (coalesced per channel row), the
+    // line is written along channels (coalesced per slot)
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+    for (int r = ty; r < 32; r += 8) {                               // r: channel of the tile, tx: slot
+        const int ch = c0 + r, s = s0 + tx;
+        float v = 0.f;
+        if (ch < channels && s < depth) {
+            const long long t = (long long)n_samples - depth + s;
+            v = t >= 0 ? in[(long long)ch * ld_in + t] : state_in[(long long)(s + n_samples) * ch_stride + ch];
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {                               // r: slot of the tile, tx: channel
+        const int ch = c0 + tx, s = s0 + r;
+        if (ch < channels && s < depth) state_out[(long long)s * ch_stride + ch] = tile[tx][r];
+    }
 }
 
 }  // namespace zgk

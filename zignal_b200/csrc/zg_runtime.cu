@@ -1226,7 +1226,7 @@ int launch_fir_tc(zg_plan* p, const void* const* in, void* const* out, int64_t T
                      s[4], s[0], s[0] / std::max(s[4], 1.0), s[1], s[2], s[3], s[5], s[6], s[7]);
     }
     // the delay line after this block (ping-pong: a later launch reads what this one writes)
-    zgk::zg_fir_state_kernel<<<dim3((unsigned)((c_count + 127) / 128), (unsigned)(N - 1)), 128, 0, stream>>>(
+    zgk::zg_fir_state_kernel<<<dim3((unsigned)((c_count + 31) / 32), (unsigned)((N - 1 + 31) / 32)), 256, 0, stream>>>(
         static_cast<const float*>(in[0]), ld_in, p->d_state + c_begin, p->d_state_alt + c_begin, p->ch_stride, (int)c_count,
         (int)T, N - 1);
     ZG_CUDA(cudaGetLastError());
