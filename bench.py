@@ -293,7 +293,7 @@ def other_configs(zg, wl, torch, dev, local, world, rank, args, barrier, dist):
                                    "executed_tflops": algo * 3 * 288 / 256, "traffic": _traffic("c4_tc"),
                                    "executed_frac": algo * 3 * 288 / 256 / tf32 if tf32 else None,
                                    "note": "3xTF32 (hi*hi + lo*hi + hi*lo) and a 288-row band per 256 taps: 3.375 tensor flops "
-                                           "per algorithmic flop; the kernel is bound by shared-memory operand bandwidth "
+                                           "per algorithmic flop; executed_frac is against the cuBLAS TF32 GEMM timed here "
                                            "(profiles/r02_c4_fir_tc_ncu.txt)"}
                 ent["numerics"] = "<= 1e-5 block-relative against the oracle (tests/test_fir_tc.py; measured 3e-6: the tensor core truncates its fp32 accumulation)"
             if instr_per_sample:
