@@ -34,6 +34,8 @@ def test_library_has_sm100a_kernels_and_tma():
     sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
     assert "UTMALDG" in sass and "UTMASTG" in sass          # TMA loads and stores
     assert "FFMA" in sass and "LDS.128" in sass
+    # the tensor-core FIR: tcgen05.mma (UTCHMMA), tcgen05.ld / st (LDTM / STTM), tcgen05.commit (UTCBAR)
+    assert "UTCHMMA" in sass and "LDTM" in sass and "STTM" in sass and "UTCBAR" in sass
 
 
 def test_no_gpu_is_a_loud_error(zg):
