@@ -17,6 +17,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -892,23 +894,39 @@ constexpr double kScanTol = 9.3132257461547852e-10;     // 2^-30
 constexpr int kScanMaxWarm = 8192;
 constexpr int64_t kScanMaxChannels = 65536;             // beyond this a launch has enough warps without segments
 
-template <class F>   // f(channel or -1, params of that channel) for the distinct parameter sets of the plan
+// f(channel or -1, params of that channel) for the distinct parameter sets of the plan.  With per-channel parameters the
+// channels are spread over the host's threads (20 us of float64 matrix work per channel: a parameter change on 16 384
+// channels would otherwise stall the next launch for a third of a second); f must only touch per-channel results.
+template <class F>
 int for_each_param_set(zg_plan* p, F&& f) {
     std::vector<std::vector<float>> rows;
     int st = host_params(p, rows);
     if (st != ZG_OK) return st;
     bool per_channel = false;
     for (auto& r : rows) per_channel = per_channel || r.size() != 1;
-    std::vector<float> prm(rows.size());
     if (!per_channel) {
+        std::vector<float> prm(rows.size());
         for (size_t k = 0; k < rows.size(); ++k) prm[k] = rows[k][0];
         f(-1, prm.data());
         return ZG_OK;
     }
-    for (int64_t c = 0; c < p->C; ++c) {
-        for (size_t k = 0; k < rows.size(); ++k) prm[k] = rows[k].size() == 1 ? rows[k][0] : rows[k][c];
-        if (!f((int)c, prm.data())) break;
+    const int64_t C = p->C;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int n_threads = (int)std::min<int64_t>(std::min<unsigned>(hw, 32u), std::max<int64_t>(1, C / 256));
+    auto work = [&](int64_t c0, int64_t c1) {
+        std::vector<float> prm(rows.size());
+        for (int64_t c = c0; c < c1; ++c) {
+            for (size_t k = 0; k < rows.size(); ++k) prm[k] = rows[k].size() == 1 ? rows[k][0] : rows[k][c];
+            f((int)c, prm.data());
+        }
+    };
+    if (n_threads <= 1) {
+        work(0, C);
+        return ZG_OK;
     }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(work, C * t / n_threads, C * (t + 1) / n_threads);
+    for (auto& th : pool) th.join();
     return ZG_OK;
 }
 
@@ -917,17 +935,18 @@ int scan_analyse(zg_plan* p) {
     p->scan_warm = 0;
     if (!p->scan_ok || p->C > kScanMaxChannels) return ZG_OK;
     const int unit = 4 * zgk::box_samples(p->interleaved, p->io);
-    int worst = unit;
-    bool all = true;
-    std::vector<double> A;
+    std::atomic<int> worst{unit};
+    std::atomic<bool> all{true};
     int st = for_each_param_set(p, [&](int, const float* prm) {
+        if (!all.load(std::memory_order_relaxed)) return;            // some channel never forgets: the answer is known
+        std::vector<double> A;
         const int K = tick_matrix(p->ir, prm, A) ? decay_length(A, p->ir.n_state, unit, kScanMaxWarm, kScanTol) : 0;
-        if (K == 0) all = false;
-        worst = std::max(worst, K);
-        return all;
+        if (K == 0) all.store(false, std::memory_order_relaxed);
+        int w = worst.load(std::memory_order_relaxed);
+        while (K > w && !worst.compare_exchange_weak(w, K, std::memory_order_relaxed)) {}
     });
     if (st != ZG_OK) return st;
-    p->scan_warm = all ? worst : 0;
+    p->scan_warm = all.load() ? worst.load() : 0;
     return ZG_OK;
 }
 
@@ -939,20 +958,19 @@ int scan_prepare_AL(zg_plan* p, int L) {
     for (size_t k = 0; k < p->h_params.size(); ++k) per_channel = per_channel || p->h_params[k].size() != 1 || p->param_on_device[k];
     const size_t need = (size_t)n * n * (per_channel ? (size_t)p->ch_stride : 1);
     std::vector<float> host(std::max<size_t>(need, 1), 0.f);
-    std::vector<double> A, AL;
-    bool finite = true;
+    std::atomic<bool> finite{true};
     int st = for_each_param_set(p, [&](int c, const float* prm) {
-        if (!tick_matrix(p->ir, prm, A)) { finite = false; return false; }
+        std::vector<double> A, AL;
+        if (!tick_matrix(p->ir, prm, A)) { finite.store(false); return; }
         mat_pow(A, n, L, AL);
         for (int e = 0; e < n * n; ++e) {
-            if (!std::isfinite(AL[e]) || std::fabs(AL[e]) > 3e38) { finite = false; return false; }
+            if (!std::isfinite(AL[e]) || std::fabs(AL[e]) > 3e38) { finite.store(false); return; }
             if (c < 0) host[e] = (float)AL[e];
             else host[(size_t)e * p->ch_stride + c] = (float)AL[e];
         }
-        return true;
     });
     if (st != ZG_OK) return st;
-    if (!finite) return fail(ZG_ERR_UNSUPPORTED, "the tick's state matrix overflows fp32 over one time segment (unstable graph): "
+    if (!finite.load()) return fail(ZG_ERR_UNSUPPORTED, "the tick's state matrix overflows fp32 over one time segment (unstable graph): "
                                                   "use time_parallel = ZG_TP_OFF");
     if (need > p->AL_floats) {
         if (p->d_AL) cudaFree(p->d_AL);
