@@ -1263,7 +1263,7 @@ int launch_fir_tc(zg_plan* p, const void* const* in, void* const* out, int64_t T
 
 int launch_fir(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out,
                cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance) {
-    if (p->fir_tc && T >= 256) return launch_fir_tc(p, in, out, T, ld_in, ld_out, stream, c_begin, c_count, advance);
+    if (p->fir_tc && T >= 256 && T <= (1ll << 30)) return launch_fir_tc(p, in, out, T, ld_in, ld_out, stream, c_begin, c_count, advance);
     const int N = (int)p->fir.taps.size();
     const int H = (N - 1 + 31) / 32;
     const int n_taps_pad = (N + 15) / 16 * 16;
