@@ -325,3 +325,46 @@ def test_segments_with_bf16_storage_two_inputs_and_host_chunks(zg):
     yb = plan.process(xb)[0].float().cpu().numpy()
     assert plan.info().time_segments >= 2
     assert _rel_err(yb, refb) <= 2.0 ** -7                      # one bf16 ulp (8 bits of mantissa) block-relative
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(3))
+def test_random_linear_graphs_two_pass_equals_serial(zg, seed):
+    """Random LINEAR / AFFINE flowz graphs (series, parallel, fan-out, feedback, delays up to 3, one to three inputs):
+    the two-pass form -- zero-state pass, boundary fix-up with A^L from the tick program, true-state pass -- must
+    reproduce the serial FAST kernel on whatever state layout the lowering produced (several lines, shared lines,
+    several outputs).  Graphs that blow up (poles outside the unit circle amplify rounding without bound) are skipped."""
+    import random
+    from test_fuzz_frontend import _gen
+    rng = random.Random(8800 + seed)
+    C, T = 40, 3000
+    ran = 0
+    for _ in range(400):
+        if ran >= 6:
+            break
+        expr = _gen(rng, rng.randint(3, 5), rng.randint(1, 3), consts=["0.5f", "0.25f", "-0.75f", "0x1p-1f", "-0.5f", "0.125f"], ops="+-*")
+        if "~" not in expr:
+            continue
+        try:
+            g = zg.compile(expr)
+        except zg.ZgError:
+            continue
+        if not g.all_f32 or g.n_in < 1 or g.n_out < 1 or g.n_state < 1 or g.n_state > 32 or g.linearity() == zg.NONLINEAR:
+            continue
+        x = [fo.noise(C, T, seed=500 * seed + 7 * ran + k) for k in range(g.n_in)]
+        try:
+            serial, _, _ = _plan_run(zg, expr, x, zg.TP_OFF)
+            if not all(np.isfinite(s).all() and np.abs(s).max() < 1e4 for s in serial):
+                continue
+            ys, plan, infos = _plan_run(zg, expr, x, zg.TP_TWO_PASS)
+        except zg.ZgError as e:
+            if e.status == zg.ZG_ERR_UNSUPPORTED:
+                continue
+            raise AssertionError(f"{expr}: {e}")
+        assert infos[0].time_segments >= 2, expr
+        for y, s in zip(ys, serial):
+            den = np.maximum(np.abs(s).max(axis=1), 1e-20)
+            err = (np.abs(y.astype(np.float64) - s).max(axis=1) / den).max()
+            assert err <= 2e-5, f"{expr}: {err}"
+        ran += 1
+    assert ran >= 4
