@@ -133,10 +133,14 @@ def arity(expr: str):
 
 
 def delays(expr: str, minimum: bool = False):
-    buf = (C.c_int * 512)()
-    n = C.c_int()
-    _check(lib.zg_expr_delays(expr.encode(), 1 if minimum else 0, buf, 512, C.byref(n)))
-    return list(buf[:n.value])
+    cap = 512
+    while True:                                   # *count is the number of wires, also when it exceeds the capacity
+        buf = (C.c_int * cap)()
+        n = C.c_int()
+        _check(lib.zg_expr_delays(expr.encode(), 1 if minimum else 0, buf, cap, C.byref(n)))
+        if n.value <= cap:
+            return list(buf[:n.value])
+        cap = n.value
 
 
 def canonical(expr: str) -> str:
