@@ -1593,6 +1593,15 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     Variant* v = nullptr;
     st = get_variant(p.get(), p->uniform_now, v);
     if (st != ZG_OK) return st;
+    if (p->scan_ok && opts->time_parallel >= ZG_TP_WARMUP) {
+        // a plan that asks for time segments gets the kernel built with them now, not at its first launch
+        p->seg_now = true;
+        p->lanes_now = 1;
+        st = get_variant(p.get(), p->uniform_now, v);
+        p->seg_now = false;
+        p->lanes_now = p->lanes;
+        if (st != ZG_OK) return st;
+    }
     *out = p.release();
     return ZG_OK;
 }
