@@ -1,0 +1,145 @@
+"""K1s (kernels/zg_biquad_split.cuh): the sections of a biquad cascade spread over the warps of a group that share one
+ring of tiles.  The arithmetic of a section is the lane-per-channel kernel's (BiquadDf1Cascade::tick), so everything here
+is BIT-IDENTICAL: to the oracle in EXACT mode, and to K1 in either mode.  Through the C ABI on cuda:0."""
+import numpy as np
+import pytest
+
+import flowz_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _run(zg, expr, x, mode, section_warps, params=None, blocks=None, in_place=False):
+    torch = _torch()
+    import zignal_b200
+    C, T = x.shape
+    plan = zg.compile(expr).plan(channels=C, mode=mode, lanes_per_channel=1, section_warps=section_warps)
+    for i, p in enumerate(params or []):
+        plan.set_param(i, p)
+    outs, t0 = [], 0
+    for n in (blocks or [T]):
+        xb = zignal_b200.to_block(x[:, t0:t0 + n])
+        y = plan.process([xb], n_samples=n, outputs=[xb] if in_place else None)[0]
+        torch.cuda.synchronize()
+        outs.append(y.cpu().numpy())
+        t0 += n
+    return np.concatenate(outs, axis=1), plan
+
+
+def _is_split(plan):
+    return b"zg_biquad_df1_split" in plan.info().kernel
+
+
+@pytest.mark.parametrize("sections", [2, 3, 4, 6, 8])
+def test_split_exact_is_bit_identical_to_the_oracle(zg, sections):
+    C, T = 200, 1504                    # ragged channel count; 47 boxes: three tiles of 14 and one of 5
+    x = fo.noise(C, T, seed=sections)
+    expr = fo.biquad_cascade(sections)
+    y, plan = _run(zg, expr, x, zg.MODE_EXACT, 2)
+    assert _is_split(plan), plan.info().kernel
+    assert plan.info().launches == 1
+    ref = fo.COracle(expr, C).process([x])[0]
+    assert np.array_equal(y, ref)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_split_equals_lane_per_channel_kernel_many_rows_per_group(zg, mode):
+    """more channel groups than persistent groups: every group walks several rows, the tile stream runs through the row
+    boundaries (state written and read in between), the last round is partly empty"""
+    torch = _torch()
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    C = 32 * (2 * sm * 3 + 37) + 5
+    T = 928                             # 29 boxes: ragged last tile in every row
+    m = zg.MODE_EXACT if mode == "exact" else zg.MODE_FAST
+    x = fo.noise(C, T, seed=3)
+    expr = fo.biquad_cascade(4)
+    y, plan = _run(zg, expr, x, m, 2)
+    assert _is_split(plan)
+    z, plan1 = _run(zg, expr, x, m, 1)
+    assert not _is_split(plan1)
+    assert np.array_equal(y, z)
+    assert np.array_equal(np.asarray(plan.get_state()), np.asarray(plan1.get_state()))
+
+
+def test_split_streams_like_ticks_and_shares_state_rows_with_k1(zg):
+    """consecutive blocks continue the stream; the state a split launch leaves is the state K1 continues from"""
+    torch = _torch()
+    import zignal_b200
+    C, T = 96, 4096
+    x = fo.noise(C, T, seed=11)
+    expr = fo.biquad_cascade(4)
+    ref = fo.COracle(expr, C).process([x])[0]
+    y, plan = _run(zg, expr, x, zg.MODE_EXACT, 2, blocks=[1024, 2048, 1024])
+    assert _is_split(plan)
+    assert np.array_equal(y, ref)
+    # first half on K1s, state moved into a K1 plan, second half there
+    a = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, lanes_per_channel=1, section_warps=2)
+    b = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, lanes_per_channel=1, section_warps=1)
+    y0 = a.process([zignal_b200.to_block(x[:, :2048])], n_samples=2048)[0].cpu().numpy()
+    b.set_state(a.get_state())
+    y1 = b.process([zignal_b200.to_block(x[:, 2048:])], n_samples=2048)[0].cpu().numpy()
+    assert _is_split(a) and not _is_split(b)
+    assert np.array_equal(np.concatenate([y0, y1], axis=1), ref)
+
+
+def test_split_per_channel_coefficients(zg):
+    """$k parameters, one value per channel (b0 == b2 per channel: the product-reusing tick), and a set that is not
+    symmetric (the plain tick)"""
+    C, T = 160, 1024
+    x = fo.noise(C, T, seed=5)
+    expr = fo.biquad_cascade_params(4)
+    for sym in (True, False):
+        rng = np.random.default_rng(17)
+        params = []
+        for k in range(4):
+            f = 200.0 * (k + 1) * (1.0 + np.arange(C) / C)
+            b0, b1, b2, a1, a2 = fo.rbj_lowpass(f, 0.7 + 0.1 * k, 48000.0)
+            if not sym:
+                b2 = (b2 * (1.0 + 0.01 * rng.standard_normal(C))).astype(np.float32)
+            params += [np.asarray(v, np.float32) for v in (b0, b1, b2, a1, a2)]
+        y, plan = _run(zg, expr, x, zg.MODE_EXACT, 2, params=params)
+        assert _is_split(plan)
+        assert (b"+b0=b2" in plan.info().kernel) == sym
+        prm = np.stack([np.broadcast_to(p, (C,)) for p in params], axis=1)
+        ref = fo.COracle(expr, C, params=prm).process([x])[0]
+        assert np.array_equal(y, ref)
+
+
+def test_split_in_place(zg):
+    C, T = 64, 2048
+    x = fo.noise(C, T, seed=7)
+    expr = fo.biquad_cascade(4)
+    y, plan = _run(zg, expr, x, zg.MODE_EXACT, 2, in_place=True)
+    assert _is_split(plan)
+    assert np.array_equal(y, fo.COracle(expr, C).process([x])[0])
+
+
+def test_split_falls_back_when_the_shape_does_not_allow_it(zg):
+    """T not a multiple of 32 samples: the lane-per-channel kernel runs, whatever section_warps says"""
+    C, T = 64, 1000
+    x = fo.noise(C, T, seed=8)
+    expr = fo.biquad_cascade(4)
+    y, plan = _run(zg, expr, x, zg.MODE_EXACT, 2)
+    assert not _is_split(plan)
+    assert np.array_equal(y, fo.COracle(expr, C).process([x])[0])
+
+
+def test_split_is_what_auto_picks_for_many_channels(zg):
+    """the north-star shape class: 65 536 channels -> 2048 channel groups over 2 x SMs persistent groups"""
+    torch = _torch()
+    import zignal_b200
+    C, T = 65536, 512
+    expr = fo.biquad_cascade(4)
+    plan = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT)
+    x = torch.rand((C, T), device="cuda") * 2 - 1
+    y = plan.process([x], n_samples=T)[0]
+    assert _is_split(plan), plan.info().kernel
+    k1 = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, section_warps=1)
+    z = k1.process([x], n_samples=T)[0]
+    assert not _is_split(k1)
+    assert torch.equal(y, z)

@@ -16,6 +16,7 @@ WORK = {"c3": (65536, 16384), "c5": (131072, 4096), "ns": (65536, 8192), "c2": (
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="ns")
+    ap.add_argument("--shape", default="", help="C,T instead of a named workload")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--sections", type=int, default=4)
     ap.add_argument("--pad", type=int, default=0, help="extra floats of row pitch (planar buffers)")
@@ -27,9 +28,9 @@ def main():
     for part in a.points.split(";"):
         k, v = part.split("=")
         axes[k] = v.split(",")
-    for k, d in (("mode", ["exact"]), ("boxes", ["0"]), ("wpc", ["0"]), ("stages", ["0"]), ("layout", ["planar"]), ("coef", ["uniform"]), ("lanes", ["0"]), ("late", ["0"]), ("hint", ["0"]), ("promo", ["0"]), ("cu", ["0"]), ("jit", ["0"]), ("pf", ["0"]), ("pfd", ["0"]), ("tp", ["0"]), ("segs", ["0"]), ("warm", ["0"])):
+    for k, d in (("mode", ["exact"]), ("boxes", ["0"]), ("wpc", ["0"]), ("stages", ["0"]), ("layout", ["planar"]), ("coef", ["uniform"]), ("lanes", ["0"]), ("late", ["0"]), ("hint", ["0"]), ("promo", ["0"]), ("cu", ["0"]), ("jit", ["0"]), ("pf", ["0"]), ("pfd", ["0"]), ("tp", ["0"]), ("segs", ["0"]), ("warm", ["0"]), ("split", ["0"]), ("sg", ["0"]), ("spw", ["0"])):
         axes.setdefault(k, d)
-    C, T = WORK[a.workload]
+    C, T = [int(v) for v in a.shape.split(",")] if a.shape else WORK[a.workload]
     x = torch.empty((C, T + a.pad), device="cuda")[:, :T]
     x.copy_(torch.rand((C, T), device="cuda") * 2 - 1)
     y = torch.empty((C, T + a.pad), device="cuda")[:, :T]
@@ -37,7 +38,7 @@ def main():
     keys = list(axes)
     for combo in itertools.product(*[axes[k] for k in keys]):
         pt = dict(zip(keys, combo))
-        for env, k in (("ZG_TUNE_BOXES", "boxes"), ("ZG_TUNE_WPC", "wpc"), ("ZG_TUNE_STAGES", "stages"), ("ZG_TUNE_LATE_REFILL", "late"), ("ZG_TUNE_L2HINT", "hint"), ("ZG_TUNE_L2PROMO", "promo"), ("ZG_TUNE_CHUNK_UNROLL", "cu"), ("ZG_TUNE_PF", "pf"), ("ZG_TUNE_PFD", "pfd"), ("ZG_TUNE_TP", "tp"), ("ZG_TUNE_SEGS", "segs"), ("ZG_TUNE_WARM", "warm")):
+        for env, k in (("ZG_TUNE_BOXES", "boxes"), ("ZG_TUNE_WPC", "wpc"), ("ZG_TUNE_STAGES", "stages"), ("ZG_TUNE_LATE_REFILL", "late"), ("ZG_TUNE_L2HINT", "hint"), ("ZG_TUNE_L2PROMO", "promo"), ("ZG_TUNE_CHUNK_UNROLL", "cu"), ("ZG_TUNE_PF", "pf"), ("ZG_TUNE_PFD", "pfd"), ("ZG_TUNE_TP", "tp"), ("ZG_TUNE_SEGS", "segs"), ("ZG_TUNE_WARM", "warm"), ("ZG_TUNE_SPLIT", "split"), ("ZG_TUNE_SPLIT_G", "sg"), ("ZG_TUNE_SPLIT_SPW", "spw")):
             if pt[k] != "0": os.environ[env] = pt[k]
             else: os.environ.pop(env, None)
         inter = pt["layout"] == "interleaved"
@@ -80,11 +81,12 @@ def main():
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / a.iters
             info = plan.info()
-            pt.update(pad=a.pad, ms=round(ms, 4), msamples=round(C * T / ms / 1e3), gbs=round(bytes_per_sample * C * T / ms / 1e6),
+            pt.update(kernel=info.kernel.decode(), pad=a.pad, ms=round(ms, 4), msamples=round(C * T / ms / 1e3), gbs=round(bytes_per_sample * C * T / ms / 1e6),
                       threads=info.threads_per_cta, stages_used=info.stages, boxes_used=info.boxes, smem=info.smem_bytes, lanes_used=info.lanes_per_channel, segs_used=info.time_segments, seg_len=info.segment_samples, warm_used=info.warmup_samples,
                       regs=info.regs_per_thread)
         except Exception as e:
             pt["error"] = str(e)[:200]
+        pt = {k: v for k, v in pt.items() if v != "0" or k not in axes}        # axes left at their default are not printed
         print(json.dumps(pt), flush=True)
 
 if __name__ == "__main__":

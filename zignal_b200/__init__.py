@@ -45,7 +45,8 @@ class GraphInfo(C.Structure):
 class PlanOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("channels", C.c_int64), ("mode", C.c_int), ("layout", C.c_int),
                 ("io_dtype", C.c_int), ("lanes_per_channel", C.c_int), ("input_kind", C.c_int * MAX_WIRES),
-                ("force_jit", C.c_int), ("time_parallel", C.c_int), ("fir_tensor_cores", C.c_int), ("reserved", C.c_int * 5)]
+                ("force_jit", C.c_int), ("time_parallel", C.c_int), ("fir_tensor_cores", C.c_int), ("section_warps", C.c_int),
+                ("reserved", C.c_int * 4)]
 
 
 class PlanInfo(C.Structure):
@@ -312,12 +313,13 @@ class Voice:
 
 def _opts(channels: int, device: int = 0, mode: int = MODE_EXACT, layout: int = PLANAR,
           input_kind: Optional[Sequence[int]] = None, lanes_per_channel: int = 0, force_jit: bool = False,
-          io_dtype: int = 1, time_parallel: int = 0, fir_tensor_cores: int = 0) -> PlanOpts:
+          io_dtype: int = 1, time_parallel: int = 0, fir_tensor_cores: int = 0, section_warps: int = 0) -> PlanOpts:
     o = PlanOpts()
     lib.zg_plan_opts_default(C.byref(o))
     o.device, o.channels, o.mode, o.layout, o.io_dtype = device, channels, mode, layout, io_dtype
     o.lanes_per_channel, o.force_jit, o.time_parallel = lanes_per_channel, int(force_jit), time_parallel
     o.fir_tensor_cores = fir_tensor_cores
+    o.section_warps = section_warps
     for i, k in enumerate(input_kind or []):
         o.input_kind[i] = k
     return o

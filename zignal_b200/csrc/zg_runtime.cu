@@ -26,6 +26,7 @@
 
 #include "kernels/zg_biquad.cuh"
 #include "kernels/zg_biquad_lanes.cuh"
+#include "kernels/zg_biquad_split.cuh"
 #include "kernels/zg_fir.cuh"
 #include "kernels/zg_fir_tc.cuh"
 #include "zg_internal.hpp"
@@ -192,6 +193,11 @@ __global__ void __launch_bounds__(512, 1) zg_biquad_lanes_kernel(const __grid_co
     zgk::biquad_lanes_block<S, kExact, kUniform>(a);
 }
 
+template <int S, int SPW, bool kExact, bool kSym, bool kUniform>
+__global__ void __launch_bounds__(1024, 1) zg_biquad_split_kernel(const __grid_constant__ zgk::StreamArgs a) {
+    zgk::biquad_split_block<S, SPW, kExact, kSym, kUniform>(a);
+}
+
 template <bool kExact, bool kInterleaved>
 __global__ void __launch_bounds__(512, 1) zg_fir_kernel(const __grid_constant__ zgk::FirArgs a) {
     zgk::fir_block<kExact, kInterleaved>(a);
@@ -260,6 +266,18 @@ KernelPtr biquad_lanes_kernel_for(int sections, bool exact, bool uniform) {
     ZG_PICK(2, false, false) ZG_PICK(2, false, true) ZG_PICK(2, true, false) ZG_PICK(2, true, true)
     ZG_PICK(4, false, false) ZG_PICK(4, false, true) ZG_PICK(4, true, false) ZG_PICK(4, true, true)
 #undef ZG_PICK
+    return nullptr;
+}
+
+// K1s (kernels/zg_biquad_split.cuh): the sections of a channel group spread over `sections / spw` warps
+KernelPtr biquad_split_kernel_for(int sections, int spw, bool exact, bool sym, bool uniform) {
+#define ZG_PICK3(S, W, E, Y) \
+    if (sections == S && spw == W && exact == E && sym == Y) \
+        return uniform ? (KernelPtr)zg_biquad_split_kernel<S, W, E, Y, true> : (KernelPtr)zg_biquad_split_kernel<S, W, E, Y, false>;
+#define ZG_PICK(S, W) ZG_PICK3(S, W, false, false) ZG_PICK3(S, W, true, false) ZG_PICK3(S, W, true, true)
+    ZG_PICK(2, 1) ZG_PICK(3, 1) ZG_PICK(4, 1) ZG_PICK(4, 2) ZG_PICK(6, 2) ZG_PICK(8, 2)
+#undef ZG_PICK
+#undef ZG_PICK3
     return nullptr;
 }
 
@@ -351,6 +369,8 @@ struct zg_plan {
     Variant variant[12];                    // [0] per-channel parameters, [1] uniform, [2], [3] the same with symmetric biquads;
                                             // [4], [5]: the lane-per-channel kernel of a K1b plan; + 6: built with time segments
     int lanes_now = 1;                      // lanes per channel of the launch being prepared
+    bool split_now = false;                 // the last launch ran K1s (sections spread over the warps of a group)
+    int split_regs = 0, split_spw = 0;
     bool seg_now = false;                   // the launch being prepared is cut in time
 
     // Time segments for few, long channels (FAST mode, linear ticks; kernels/zg_stream.cuh StreamArgs::n_segs)
@@ -1037,6 +1057,94 @@ int choose_segments(zg_plan* p, const void* const* in, void* const* out, int64_t
 int launch_fir(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out,
                cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance);
 
+// K1s (kernels/zg_biquad_split.cuh): many channels, planar fp32, whole boxes.  Persistent CTAs of G groups of
+// `sections / spw` warps; a group owns a ring of S tiles of NB boxes of 32 channel rows.  Returns false when the
+// launch should stay on K1 (shape, or too few channel groups for the persistent walk to balance).
+struct SplitGeometry {
+    int spw, wpg, groups, stages, boxes, grid, smem;
+};
+
+bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g) {
+    // zg_plan_opts.section_warps: 0 = auto, 1 = never, 2 = whenever the shape allows (ZG_TUNE_SPLIT overrides: 1 / 2 / 3)
+    const int mode = tune_env("ZG_TUNE_SPLIT") ? tune_env("ZG_TUNE_SPLIT") - 1 : p->opts.section_warps;
+    if (mode == 1 || !p->is_biquad || p->opts.force_jit || p->interleaved || p->io != 4 || p->lanes != 1) return false;
+    if (T % zgk::kTileT != 0 || T < 4 * zgk::kTileT || T > (1ll << 30)) return false;
+    const int S = p->bq.sections;
+    int spw = S == 2 || S == 3 || S == 4 ? 1 : S == 6 || S == 8 ? 2 : 0;
+    if (int w = tune_env("ZG_TUNE_SPLIT_SPW")) spw = w;
+    if (spw < 1 || S % spw != 0 || !biquad_split_kernel_for(S, spw, p->exact, variant_is_sym(p), p->uniform_now)) return false;
+    g.spw = spw;
+    g.wpg = S / spw;
+    g.groups = 2;
+    if (int t = tune_env("ZG_TUNE_SPLIT_G")) g.groups = std::min(std::max(t, 1), 32 / g.wpg);
+    g.stages = 2;
+    if (int t = tune_env("ZG_TUNE_STAGES")) g.stages = std::min(std::max(t, 2), 8);
+    const int budget = p->max_smem_optin - 1024 /*alignment slack*/;
+    const int64_t row_boxes = T / zgk::kTileT;
+    int nb = 14;
+    if (int t = tune_env("ZG_TUNE_BOXES")) nb = std::min(std::max(t, 1), 32);
+    nb = (int)std::min<int64_t>(nb, row_boxes);
+    auto need = [&](int boxes) {
+        return g.groups * (g.stages * boxes * zgk::kTileBytes + 8 * zgk::split_bar_count(g.stages, boxes, g.wpg));
+    };
+    while (nb > 1 && need(nb) > budget) --nb;
+    if (need(nb) > budget) return false;
+    g.boxes = nb;
+    g.smem = need(nb) + 1024;
+    const int64_t n_cg = (c_count + 31) / 32;
+    g.grid = (int)std::min<int64_t>(p->sm_count, (n_cg + g.groups - 1) / g.groups);
+    if (mode == 2) return true;
+    // auto: the groups walk ceil(n_cg / slots) rows each; worth it from ~4 rows per slot on, when the last round is
+    // nearly full (65 536 channels: 2048 channel groups over 296 slots = 6.92 rounds)
+    const int64_t slots = (int64_t)g.grid * g.groups;
+    const int64_t rounds = (n_cg + slots - 1) / slots;
+    return rounds >= 4 && n_cg * 100 >= rounds * slots * 95;
+}
+
+int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void* const* out, int64_t T, int64_t ld_in,
+                 int64_t ld_out, cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance) {
+    const bool sym = variant_is_sym(p);
+    KernelPtr fn = biquad_split_kernel_for(p->bq.sections, g.spw, p->exact, sym, p->uniform_now);
+    zgk::StreamArgs a;
+    std::memset(&a, 0, sizeof a);
+    if (!encode_map_tile3d(&a.in_map[1], in[0], c_count, T, ld_in, 32, g.boxes) ||
+        !encode_map_tile3d(&a.out_map[1], out[0], c_count, T, ld_out, 32, g.boxes))
+        return fail(ZG_ERR_CUDA, "cuTensorMapEncodeTiled (whole-tile map of the section-split biquad kernel)");
+    a.state = p->d_state + c_begin;
+    a.params = p->d_params ? p->d_params + c_begin : nullptr;
+    a.ch_stride = p->ch_stride;
+    a.stream_pos = p->stream_pos;
+    a.channels = (int)c_count;
+    a.n_samples = (int)T;
+    a.stages = g.stages;
+    a.boxes = g.boxes;
+    for (int j = 0; j < p->kernel_n_state; ++j) a.state_row[j] = p->state_row[j];
+    if (p->uniform_now) std::memcpy(a.uparams, p->uparams, sizeof(float) * std::min(p->kernel_n_param, zgk::kMaxUniform));
+    int st = raise_max_smem((const void*)fn, p->opts.device, g.smem);
+    if (st != ZG_OK) return st;
+    if (!p->split_regs || p->split_spw != g.spw) {
+        cudaFuncAttributes fa;
+        ZG_CUDA(cudaFuncGetAttributes(&fa, (const void*)fn));
+        p->split_regs = fa.numRegs;
+        p->split_spw = g.spw;
+    }
+    void* args[] = {&a};
+    ZG_CUDA(cudaLaunchKernel((const void*)fn, dim3(g.grid), dim3(g.groups * g.wpg * 32), args, g.smem, stream));
+    p->launches += 1;
+    p->split_now = true;
+    p->last_segs = 1;
+    p->last_seg_mode = 0;
+    p->last_seg_len = 0;
+    p->last_seg_warm = 0;
+    if (advance) p->stream_pos += T;
+    p->last_smem = g.smem;
+    p->last_threads = g.groups * g.wpg * 32;
+    p->last_stages = g.stages;
+    p->last_boxes = g.boxes;
+    p->last_grid = g.grid;
+    return ZG_OK;
+}
+
 int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out,
            cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance) {
     Driver& d = driver();
@@ -1047,6 +1155,13 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     Segments sg;
     st = choose_segments(p, in, out, T, c_count, sg);
     if (st != ZG_OK) return st;
+    p->split_now = false;
+    if (sg.mode == 0) {
+        p->lanes_now = p->lanes;
+        p->seg_now = false;
+        SplitGeometry sp{};
+        if (choose_split(p, T, c_count, sp)) return launch_split(p, sp, in, out, T, ld_in, ld_out, stream, c_begin, c_count, advance);
+    }
     p->lanes_now = sg.mode ? 1 : p->lanes;
     p->seg_now = sg.mode != 0;
     Variant* v = nullptr;
@@ -1442,6 +1557,7 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
     if (opts->layout != ZG_PLANAR && opts->layout != ZG_INTERLEAVED) return fail(ZG_ERR_ARG, "bad layout");
     if (opts->time_parallel < ZG_TP_AUTO || opts->time_parallel > ZG_TP_TWO_PASS) return fail(ZG_ERR_ARG, "bad time_parallel");
     if (opts->fir_tensor_cores < 0 || opts->fir_tensor_cores > 1) return fail(ZG_ERR_ARG, "bad fir_tensor_cores");
+    if (opts->section_warps < 0 || opts->section_warps > 2) return fail(ZG_ERR_ARG, "bad section_warps");
     const Ir& ir = g->ir_f32;
     if (!ir.all_f32())
         return fail(ZG_ERR_UNSUPPORTED,
@@ -1614,6 +1730,9 @@ int zg_plan_get_info(const zg_plan* p, zg_plan_info* info) {
     std::string name = p->kernel_name;
     if (p->lanes > 1 && p->lanes_now == 1)                      // a K1b plan whose last launch was cut in time instead
         name = "zg_biquad_df1<" + std::to_string(p->bq.sections) + (p->exact ? ",exact,planar>" : ",fma,planar>");
+    if (p->split_now)
+        name = "zg_biquad_df1_split<" + std::to_string(p->bq.sections) + (p->exact ? ",exact,planar," : ",fma,planar,") +
+               std::to_string(p->bq.sections / std::max(p->split_spw, 1)) + " warps per group>";
     std::snprintf(info->kernel, sizeof info->kernel, "%s%s%s", name.c_str(),
                   variant_is_sym(p) ? "+b0=b2" : "",           // the product-reusing tick (kernels/zg_biquad.cuh)
                   p->last_seg_mode == 1 ? "+segments:warm-up" : p->last_seg_mode == 2 ? "+segments:two-pass" : "");
@@ -1625,7 +1744,7 @@ int zg_plan_get_info(const zg_plan* p, zg_plan_info* info) {
     info->warmup_samples = p->last_seg_warm;
     info->linearity = p->linearity;
     info->host_chunks = p->last_host_chunks;
-    info->regs_per_thread = v.regs;
+    info->regs_per_thread = p->split_now ? p->split_regs : v.regs;
     info->smem_bytes = p->last_smem;
     info->launches = p->launches;
     info->threads_per_cta = p->last_threads;
