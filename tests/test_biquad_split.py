@@ -110,6 +110,37 @@ def test_split_per_channel_coefficients(zg):
         assert np.array_equal(y, ref)
 
 
+@pytest.mark.parametrize("boxes", [1, 3, 5])
+def test_split_rows_cut_between_groups_are_bit_identical(zg, boxes, monkeypatch):
+    """every group gets the same number of tiles, so rows are cut between groups: the head piece of a row leaves its
+    delay lines for the group that runs the tail (EXACT: the same ticks in the same order, still bit-identical).  Small
+    tiles move the cuts around; two blocks per plan: the flags and the CTA tickets run on from launch to launch"""
+    monkeypatch.setenv("ZG_TUNE_BOXES", str(boxes))
+    C, T = 328, 1504                    # 11 channel groups over 3 or 6 groups of warps; 47 boxes per row
+    x = fo.noise(C, T, seed=boxes)
+    expr = fo.biquad_cascade(4)
+    y, plan = _run(zg, expr, x, zg.MODE_EXACT, 2, blocks=[736, 768])
+    assert _is_split(plan), plan.info().kernel
+    assert plan.info().boxes == boxes
+    ref = fo.COracle(expr, C).process([x])[0]
+    assert np.array_equal(y, ref)
+
+
+def test_split_many_launches_of_one_plan(zg):
+    torch = _torch()
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    C = 32 * (7 * sm + 11)
+    T = 640
+    x = fo.noise(C, 4 * T, seed=21)
+    expr = fo.biquad_cascade(4)
+    y, plan = _run(zg, expr, x, zg.MODE_EXACT, 2, blocks=[T, T, T, T])
+    assert _is_split(plan)
+    z, plan1 = _run(zg, expr, x, zg.MODE_EXACT, 1)
+    assert not _is_split(plan1)
+    assert np.array_equal(y, z)
+    assert np.array_equal(np.asarray(plan.get_state()), np.asarray(plan1.get_state()))
+
+
 def test_split_in_place(zg):
     C, T = 64, 2048
     x = fo.noise(C, T, seed=7)
@@ -133,7 +164,7 @@ def test_split_is_what_auto_picks_for_many_channels(zg):
     """the north-star shape class: 65 536 channels -> 2048 channel groups over 2 x SMs persistent groups"""
     torch = _torch()
     import zignal_b200
-    C, T = 65536, 512
+    C, T = 65536, 4096
     expr = fo.biquad_cascade(4)
     plan = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT)
     x = torch.rand((C, T), device="cuda") * 2 - 1

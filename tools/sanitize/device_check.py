@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small invocations of every device kernel family, for compute-sanitizer (memcheck / racecheck / synccheck):
     compute-sanitizer --tool racecheck python tools/sanitize/device_check.py
-K1, K3, generated kernels, bf16 storage, a warm-up time-segmented launch, a comb + echo graph whose delay lines live in
+K1, K1s, K3, generated kernels, bf16 storage, a warm-up time-segmented launch, a comb + echo graph whose delay lines live in
 HBM as rings, an in-place block, the two-pass time-segmented form and the tensor-core FIR; `--k1b` runs ONLY the
 section-parallel biquad kernel (whose intra-warp hand-over through shared memory racecheck reports as warp-level
 warnings -- see profiles/README.md), `--smoke` runs __graft_entry__.smoke() first."""
@@ -48,6 +48,12 @@ assert np.array_equal(zg.compile(fo.fir_expr(taps)).plan(channels=C).process([xd
 yb = zg.compile(expr).plan(channels=C, io_dtype=zg.BF16).process([xd.to(torch.bfloat16)])[0]
 refb = fo.COracle(expr, C).process([fo.bf16_round(x)])[0]
 assert np.array_equal(yb.view(torch.int16).cpu().numpy().view(np.uint16), fo.bf16_bits(refb)), "bf16 storage"
+
+# K1s: sections spread over the warps of a group (box hand-over through mbarriers; rows cut between groups)
+ks = zg.compile(expr).plan(channels=328, lanes_per_channel=1, section_warps=2)
+xs = fo.noise(328, 1504, seed=6)
+assert np.array_equal(ks.process([zg.to_block(xs)])[0].cpu().numpy(), fo.COracle(expr, 328).process([xs])[0]), "K1s"
+assert b"zg_biquad_df1_split" in ks.info().kernel
 
 # long delay lines: rings in HBM
 comb = "~(_2 + 0.5f*_1[_441]) |= (_1 + 0.25f*_1[_1000])"

@@ -18,12 +18,19 @@
 //     shared-memory image as NB single boxes).  Lane 0 of the LAST warp of a group issues both: the store of the tile
 //     it has just finished, and -- one box into the next tile, when that store has read its shared memory -- the load
 //     of the tile S tiles ahead into the same stage.  The first warp waits for the load (mbarrier, tx bytes).
-//   * persistent: grid = SMs; a group walks the channel groups slot, slot + n_slots, ... and the tile stream runs
-//     straight through row boundaries (the loads of the next row's first tiles are in flight while the last tiles of
-//     this row drain), so pipeline fill and drain happen once per launch, not once per row.
+//   * persistent and balanced: grid = SMs, and every group works through a contiguous range of the tile sequence
+//     (row 0 tiles 0.., row 1 tiles 0.., ...), all ranges the same number of tiles.  The tile stream runs straight
+//     through row boundaries (the loads of the next row are in flight while this row drains), so pipeline fill and
+//     drain happen once per launch.  65 536 channels are 2048 rows for 3 x 148 groups = 4.61 rows each: a range begins
+//     and ends in the middle of a row, and the row's delay lines travel from the group that runs its head to the group
+//     that runs its tail through HBM (`carry` + one flag per row and warp).  A group runs the head piece of its LAST
+//     row FIRST and the tail piece of its first row LAST, so the group before it has long published the carry when it
+//     is needed; CTAs number themselves in the order they start (a ticket), so the CTA waited for is always running.
 //   * state: warp `sec` keeps the two-tick history of its input signal and of its SPW output signals (the history of
 //     signal k is both the y-line of section k - 1 and the x-line of section k: two warps hold a copy, the producer
-//     writes it back), read at the first box of a row and written after its last.
+//     writes it back), read at the first box of a piece and written after its last -- after every warp of the group has
+//     read its initial state (one more mbarrier per piece: the producer of a line may be a whole piece ahead of its
+//     consumer).
 //
 // Every section is evaluated by BiquadDf1Cascade<SPW, ...>::tick -- the very code K1 runs -- so EXACT stays
 // bit-identical; only which warp evaluates a section, and when, changes.
@@ -34,13 +41,50 @@
 
 namespace zgk {
 
-// bytes of mbarriers per group: S "tile landed" + (WPG - 1) x ring boxes "box handed over"
+constexpr int kSplitAckRing = 8;           // pieces of work a group may have in flight (>= stages + 2)
+
+struct SplitArgs {
+    TensorMap in_map, out_map;              // 3-D whole-tile maps {32 samples, C channels, T/32 boxes}, box {32, 32, NB}
+    float* state;                           // [n_state][ch_stride]
+    const float* params;                    // [n_params][ch_stride]
+    long long ch_stride;
+    int channels;
+    int n_samples;                          // a multiple of 32
+    int boxes;                              // NB: boxes per tile
+    int stages;                             // S >= 2 tiles in a group's ring
+    unsigned long long* ticket;             // CTAs number themselves in the order they start from this counter ...
+    unsigned long long ticket_base;         // ... which stood here before the launch
+    unsigned* flags;                        // [channel group][warps per group]: the epoch of the launch whose head piece of
+    unsigned epoch;                         //   this row is done
+    float* carry;                           // [warps per group * state floats per warp][ch_stride]: a warp's delay lines
+                                            //   between the two pieces of a row
+    int state_row[kMaxState];
+    float uparams[kMaxUniform];
+};
+
+// mbarriers per group: S "tile landed" + (WPG - 1) x ring boxes "box handed over" + "every warp of the group has read
+// the initial state of this piece"
 __host__ __device__ constexpr int split_bar_count(int stages, int boxes, int wpg) {
-    return stages + (wpg - 1) * stages * boxes;
+    return stages + (wpg - 1) * stages * boxes + kSplitAckRing;
+}
+__host__ __device__ constexpr int split_group_extra_bytes(int stages, int boxes, int wpg) {
+    return 8 * split_bar_count(stages, boxes, wpg);
+}
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void split_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 template <int SECTIONS, int SPW, bool kExact, bool kSym, bool kUniform>
-__device__ __forceinline__ void biquad_split_block(const StreamArgs& a) {
+__device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
     static_assert(SECTIONS % SPW == 0, "sections per warp must divide the cascade");
     constexpr int WPG = SECTIONS / SPW;                        // warps per group
     typedef BiquadDf1Cascade<SPW, kExact, kSym> Tick;
@@ -61,44 +105,73 @@ __device__ __forceinline__ void biquad_split_block(const StreamArgs& a) {
     unsigned char* ring = tiles + (size_t)grp * R * kTileBytes;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + (size_t)G * R * kTileBytes) +
                                (size_t)grp * split_bar_count(S, NB, WPG);
+    volatile int* s_ticket = reinterpret_cast<volatile int*>(tiles + (size_t)G * R * kTileBytes +
+                                                             (size_t)G * split_group_extra_bytes(S, NB, WPG));
     unsigned long long* full = bars;                                       // [S] tile landed
+    unsigned long long* ack_bar = bars + S + (size_t)(WPG - 1) * R;       // [kSplitAckRing]
     // what this warp waits for before a box: the tile (first warp; one barrier per stage, re-checked per box: free
     // once the phase has completed) or the box from the warp before it; and what it signals after a box
     unsigned long long* wait_bar = first ? full : bars + S + (size_t)(sec - 1) * R;
     const int wait_per_box = first ? 0 : 1;
     unsigned long long* hand_out = bars + S + (size_t)(last ? 0 : sec) * R;   // [R] (unused by the last warp)
 
-    if (warp == 0 && lane == 0) {
-        for (int i = 0; i < G * split_bar_count(S, NB, WPG); ++i) mbar_init(&bars[i], 1);
+    if (sec == 0 && lane == 0) {
+        for (int i = 0; i < split_bar_count(S, NB, WPG); ++i) mbar_init(&bars[i], &bars[i] >= ack_bar ? WPG : 1);
         fence_barrier_init();
-        prefetch_tmap(&a.in_map[1]);
-        prefetch_tmap(&a.out_map[1]);
+        prefetch_tmap(&a.in_map);
+        prefetch_tmap(&a.out_map);
     }
+    // CTAs are numbered in the order they START: a CTA only ever waits for the one numbered before it (below), which is
+    // therefore running or finished whatever else occupies the GPU and in whatever order the hardware starts CTAs
+    if (threadIdx.x == 0) *s_ticket = (int)(atomicAdd(a.ticket, 1ull) - a.ticket_base);
     __syncthreads();
 
-    // which channel groups this group walks, and the tile stream through them
+    // ---- the work of this group: a contiguous range of the tile sequence (row 0 tiles 0.., row 1 tiles 0.., ...) ----
+    // Every group gets the same number of tiles (+-1), so a range begins and ends in the middle of a row.  The host
+    // makes ranges at least two rows long: a row is cut at most once.  Order inside the range: FIRST the head piece of
+    // the row the range ends in (tiles [0, k_hi) of row_hi; leaves its delay lines in `carry` and raises the row's flag),
+    // then the whole rows, LAST the tail piece of the row it begins in (tiles [k_lo, ..) of row_lo, continuing from the
+    // carry of the group before -- which wrote it at the very start of the launch).
     const int n_cg = (a.channels + 31) >> 5;
+    const int tpr = (a.n_samples + tile_t - 1) / tile_t;                   // tiles per row
+    const long long total = (long long)n_cg * tpr;
     const int n_slots = (int)gridDim.x * G;
-    const int slot = (int)blockIdx.x * G + grp;
-    const int tiles_per_row = (a.n_samples + tile_t - 1) / tile_t;
-    const int my_rows = slot < n_cg ? (n_cg - slot + n_slots - 1) / n_slots : 0;
-    const int n_tiles = my_rows * tiles_per_row;
+    const int slot = *s_ticket * G + grp;
+    const long long lo = total * slot / n_slots, hi = total * (slot + 1) / n_slots;
+    const int row_lo = (int)(lo / tpr), k_lo = (int)(lo - (long long)row_lo * tpr);
+    const int row_hi = (int)(hi / tpr), k_hi = (int)(hi - (long long)row_hi * tpr);
+    const int has_head = k_hi > 0 && hi > lo ? 1 : 0;
+    const int first_full = k_lo > 0 ? row_lo + 1 : row_lo;
+    const int n_full = row_hi > first_full ? row_hi - first_full : 0;
+    const int has_tail = k_lo > 0 && hi > lo ? 1 : 0;
+    const int n_pieces = has_head + n_full + has_tail;
+    auto piece = [&](int pi, int& row, int& kb, int& ke) {
+        if (has_head) {
+            if (pi == 0) { row = row_hi; kb = 0; ke = k_hi; return; }
+            pi -= 1;
+        }
+        if (pi < n_full) { row = first_full + pi; kb = 0; ke = tpr; return; }
+        row = row_lo; kb = k_lo; ke = tpr;
+    };
 
-    // the load stream (lane 0 of the last warp): tiles in order, tile ld_i = tile ld_k of my row ld_r into stage ld_st
-    int ld_i = 0, ld_r = 0, ld_k = 0, ld_st = 0;
+    // ---- the load stream (lane 0 of the last warp): the tiles of the pieces in that order ----
+    int ld_pi = 0, ld_row = 0, ld_k = 0, ld_ke = 0, ld_st = 0;
+    bool ld_done = n_pieces == 0;
+    if (!ld_done) piece(0, ld_row, ld_k, ld_ke);
     auto issue_load = [&]() {
         mbar_expect_tx(&full[ld_st], (unsigned)(NB * kTileBytes));
-        tma_load_3d(ring + (size_t)ld_st * NB * kTileBytes, &a.in_map[1], 0, (slot + ld_r * n_slots) * 32, ld_k * NB, &full[ld_st]);
-        ++ld_i;
-        if (++ld_k == tiles_per_row) { ld_k = 0; ++ld_r; }
+        tma_load_3d(ring + (size_t)ld_st * NB * kTileBytes, &a.in_map, 0, ld_row * 32, ld_k * NB, &full[ld_st]);
         if (++ld_st == S) ld_st = 0;
+        if (++ld_k == ld_ke) {
+            if (++ld_pi == n_pieces) ld_done = true;
+            else piece(ld_pi, ld_row, ld_k, ld_ke);
+        }
     };
     if (last && lane == 0) {
-        const int pre = n_tiles < S ? n_tiles : S;
-        for (int i = 0; i < pre; ++i) issue_load();
+        for (int i = 0; i < S && !ld_done; ++i) issue_load();
     }
 
-    // parameters of this warp's sections: shared ones once, per-channel ones at every row
+    // parameters of this warp's sections: shared ones once, per-channel ones at every piece
     Arr<NP> prm;
     if (kUniform) {
 #pragma unroll
@@ -135,63 +208,92 @@ __device__ __forceinline__ void biquad_split_block(const StreamArgs& a) {
         }
         if (!last) {
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(obar)) : "memory");
+            if (lane == 0) split_arrive(obar);
         }
     };
 
-    int r = 0, k = 0, st = 0;                          // tile i = tile k of my row r, in stage st
+    int st = 0;                                        // stage of the next tile
     unsigned par = 0;
-    for (int i = 0; i < n_tiles; ++i) {
-        const int t0 = k * tile_t;
-        const int left = (a.n_samples - t0) / kTileT;
-        const int nb = left < NB ? left : NB;          // boxes of this tile that hold samples
-        const int c0 = (slot + r * n_slots) * 32;
+    bool any_tile = false;                             // a tile has been stored by this (last) warp: a stage to refill
+    for (int pi = 0; pi < n_pieces; ++pi) {
+        int row, kb, ke;
+        piece(pi, row, kb, ke);
+        const int c0 = row * 32;
         const int ch = c0 + lane;
         const bool ch_ok = ch < a.channels;
-        unsigned char* stage = ring + (size_t)st * NB * kTileBytes;
-        unsigned long long* wb = wait_bar + (first ? st : st * NB);
-        unsigned long long* ob = hand_out + st * NB;
+        const bool from_carry = kb > 0, to_carry = ke < tpr;
+        unsigned* my_flag = a.flags + (size_t)row * WPG + sec;
+        unsigned long long* ack = &ack_bar[pi & (kSplitAckRing - 1)];
 
-        if (k == 0) {                                  // a new row: its delay lines (and coefficients)
+        // its delay lines (and coefficients): from the state rows, or -- the tail piece of a row -- from what the same
+        // warp of the group before left in `carry` (ld.cg: these lines were written by another SM during this launch)
+        if (from_carry) {
+            while (ld_acquire_gpu(my_flag) != a.epoch) {}
+#pragma unroll
+            for (int j = 0; j < NS; ++j) s[j] = ch_ok ? __ldcg(&a.carry[(long long)(sec * NS + j) * a.ch_stride + ch]) : 0.f;
+        } else {
 #pragma unroll
             for (int j = 0; j < NS; ++j)
                 s[j] = ch_ok ? a.state[(long long)a.state_row[2 * SPW * sec + j] * a.ch_stride + ch] : 0.f;
-            if (!kUniform) {
+        }
+        // the state rows of a signal are read by the warp that consumes it and written by the warp that produces it,
+        // which may be a whole piece ahead: nobody writes before everybody has read
+        __syncwarp();
+        if (lane == 0) split_arrive(ack);
+        if (!kUniform) {
 #pragma unroll
-                for (int j = 0; j < NP; ++j) prm[j] = ch_ok ? a.params[(long long)(sec * NP + j) * a.ch_stride + ch] : 0.f;
+            for (int j = 0; j < NP; ++j) prm[j] = ch_ok ? a.params[(long long)(sec * NP + j) * a.ch_stride + ch] : 0.f;
+        }
+        if constexpr (NE > 0) Tick::init(s, prm, ex);
+
+        for (int k = kb; k < ke; ++k) {
+            const int t0 = k * tile_t;
+            const int left = (a.n_samples - t0) / kTileT;
+            const int nb = left < NB ? left : NB;      // boxes of this tile that hold samples
+            unsigned char* stage = ring + (size_t)st * NB * kTileBytes;
+            unsigned long long* wb = wait_bar + (first ? st : st * NB);
+            unsigned long long* ob = hand_out + st * NB;
+
+            do_box(stage, wb, par, ob, true);
+            if (last && lane == 0 && any_tile && !ld_done) {
+                tma_wait_read<0>();                    // the store of the previous tile has read its stage:
+                issue_load();                          // the tile S - 1 tiles ahead goes there
             }
-            if constexpr (NE > 0) Tick::init(s, prm, ex);
-        }
-
-        do_box(stage, wb, par, ob, true);
-        if (last && lane == 0 && i >= 1 && ld_i < n_tiles) {
-            tma_wait_read<0>();                        // the store of tile i-1 has read its stage:
-            issue_load();                              // tile i-1+S goes there
-        }
 #pragma unroll 1
-        for (int b = 1; b < nb; ++b) do_box(stage + (size_t)b * kTileBytes, wb + b * wait_per_box, par, ob + b, true);
+            for (int b = 1; b < nb; ++b) do_box(stage + (size_t)b * kTileBytes, wb + b * wait_per_box, par, ob + b, true);
 #pragma unroll 1
-        for (int b = nb; b < NB; ++b) do_box(stage, wb + b * wait_per_box, par, ob + b, false);    // past the end of the row
+            for (int b = nb; b < NB; ++b) do_box(stage, wb + b * wait_per_box, par, ob + b, false);    // past the end of the row
 
-        if (last) {
-            fence_proxy_async();                       // generic-proxy writes -> visible to TMA
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_3d(&a.out_map[1], 0, c0, k * NB, stage);
-                tma_commit();
+            if (last) {
+                fence_proxy_async();                   // generic-proxy writes -> visible to TMA
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(&a.out_map, 0, c0, k * NB, stage);
+                    tma_commit();
+                }
+                any_tile = true;
             }
+            if (++st == S) { st = 0; par ^= 1u; }
         }
 
-        if (++k == tiles_per_row) {                    // the row is finished: its delay lines back to HBM
+        // ---- the piece is finished: its delay lines to the group that continues the row, or -- at the end of the row --
+        //      back to the state rows (every line by the warp that produces it) ----
+        mbar_wait(ack, (unsigned)((pi / kSplitAckRing) & 1));
+        if (to_carry) {
             if (ch_ok) {
 #pragma unroll
-                for (int j = 0; j < NS; ++j)
-                    if (j >= 2 || first) a.state[(long long)a.state_row[2 * SPW * sec + j] * a.ch_stride + ch] = s[j];
+                for (int j = 0; j < NS; ++j) a.carry[(long long)(sec * NS + j) * a.ch_stride + ch] = s[j];
             }
-            k = 0;
-            ++r;
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                st_release_gpu(my_flag, a.epoch);
+            }
+        } else if (ch_ok) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j)
+                if (j >= 2 || first) a.state[(long long)a.state_row[2 * SPW * sec + j] * a.ch_stride + ch] = s[j];
         }
-        if (++st == S) { st = 0; par ^= 1u; }
     }
     if (last && lane == 0) tma_wait_all<0>();           // shared memory must outlive the last stores
 }

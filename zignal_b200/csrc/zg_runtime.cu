@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(512, 1) zg_biquad_lanes_kernel(const __grid_co
 }
 
 template <int S, int SPW, bool kExact, bool kSym, bool kUniform>
-__global__ void __launch_bounds__(1024, 1) zg_biquad_split_kernel(const __grid_constant__ zgk::StreamArgs a) {
+__global__ void __launch_bounds__(1024, 1) zg_biquad_split_kernel(const __grid_constant__ zgk::SplitArgs a) {
     zgk::biquad_split_block<S, SPW, kExact, kSym, kUniform>(a);
 }
 
@@ -270,10 +270,11 @@ KernelPtr biquad_lanes_kernel_for(int sections, bool exact, bool uniform) {
 }
 
 // K1s (kernels/zg_biquad_split.cuh): the sections of a channel group spread over `sections / spw` warps
-KernelPtr biquad_split_kernel_for(int sections, int spw, bool exact, bool sym, bool uniform) {
+using SplitKernelPtr = void (*)(zgk::SplitArgs);
+SplitKernelPtr biquad_split_kernel_for(int sections, int spw, bool exact, bool sym, bool uniform) {
 #define ZG_PICK3(S, W, E, Y) \
     if (sections == S && spw == W && exact == E && sym == Y) \
-        return uniform ? (KernelPtr)zg_biquad_split_kernel<S, W, E, Y, true> : (KernelPtr)zg_biquad_split_kernel<S, W, E, Y, false>;
+        return uniform ? (SplitKernelPtr)zg_biquad_split_kernel<S, W, E, Y, true> : (SplitKernelPtr)zg_biquad_split_kernel<S, W, E, Y, false>;
 #define ZG_PICK(S, W) ZG_PICK3(S, W, false, false) ZG_PICK3(S, W, true, false) ZG_PICK3(S, W, true, true)
     ZG_PICK(2, 1) ZG_PICK(3, 1) ZG_PICK(4, 1) ZG_PICK(4, 2) ZG_PICK(6, 2) ZG_PICK(8, 2)
 #undef ZG_PICK
@@ -371,6 +372,12 @@ struct zg_plan {
     int lanes_now = 1;                      // lanes per channel of the launch being prepared
     bool split_now = false;                 // the last launch ran K1s (sections spread over the warps of a group)
     int split_regs = 0, split_spw = 0;
+    unsigned long long* d_split_ticket = nullptr;  // the CTAs of a K1s launch number themselves from this counter; it is
+    unsigned long long split_tickets = 0;          // never reset: the host knows where every launch leaves it
+    unsigned* d_split_flags = nullptr;             // [channel groups][warps per group]: epoch of the row's head piece
+    float* d_split_carry = nullptr;                // [warps per group * state per warp][ch_stride]: delay lines of a cut row
+    int split_wpg_alloc = 0;
+    unsigned split_epoch = 0;
     bool seg_now = false;                   // the launch being prepared is cut in time
 
     // Time segments for few, long channels (FAST mode, linear ticks; kernels/zg_stream.cuh StreamArgs::n_segs)
@@ -426,6 +433,9 @@ struct zg_plan {
         if (d_stage) cudaFree(d_stage);
         if (d_seg_state) cudaFree(d_seg_state);
         if (d_AL) cudaFree(d_AL);
+        if (d_split_ticket) cudaFree(d_split_ticket);
+        if (d_split_flags) cudaFree(d_split_flags);
+        if (d_split_carry) cudaFree(d_split_carry);
         if (own_stream) cudaStreamDestroy(own_stream);
         if (h2d_stream) cudaStreamDestroy(h2d_stream);
         if (d2h_stream) cudaStreamDestroy(d2h_stream);
@@ -1057,9 +1067,12 @@ int choose_segments(zg_plan* p, const void* const* in, void* const* out, int64_t
 int launch_fir(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64_t ld_in, int64_t ld_out,
                cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance);
 
-// K1s (kernels/zg_biquad_split.cuh): many channels, planar fp32, whole boxes.  Persistent CTAs of G groups of
-// `sections / spw` warps; a group owns a ring of S tiles of NB boxes of 32 channel rows.  Returns false when the
-// launch should stay on K1 (shape, or too few channel groups for the persistent walk to balance).
+// K1s (kernels/zg_biquad_split.cuh): biquad cascades with many channels, planar fp32, whole boxes.  Persistent CTAs of G
+// groups of `sections / spw` warps; a group owns a ring of S tiles of NB boxes of 32 channel rows and works through a
+// contiguous range of the tile sequence (row after row), every group the same number of tiles: 65 536 channels x 8192
+// samples are 2048 rows over 3 x 148 groups = 4.61 rows each, so a range begins and ends in the middle of a row and the
+// delay lines of that row travel from one group to the next through HBM.  Ranges are at least two rows long (fewer
+// groups otherwise): a row is cut at most once.  Returns false when the launch should stay on K1.
 struct SplitGeometry {
     int spw, wpg, groups, stages, boxes, grid, smem;
 };
@@ -1075,49 +1088,80 @@ bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g
     if (spw < 1 || S % spw != 0 || !biquad_split_kernel_for(S, spw, p->exact, variant_is_sym(p), p->uniform_now)) return false;
     g.spw = spw;
     g.wpg = S / spw;
-    g.groups = 2;
+    const int64_t n_cg = (c_count + 31) / 32;
+    // three groups put three independent recurrences on every scheduler (EXACT: 3 dependent instructions of 8 per
+    // sample and section)
+    g.groups = std::max(1, std::min(3, 32 / g.wpg));
     if (int t = tune_env("ZG_TUNE_SPLIT_G")) g.groups = std::min(std::max(t, 1), 32 / g.wpg);
+    g.groups = (int)std::max<int64_t>(1, std::min<int64_t>(g.groups, n_cg / 2));
+    g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->sm_count, n_cg / (2 * g.groups)));
     g.stages = 2;
-    if (int t = tune_env("ZG_TUNE_STAGES")) g.stages = std::min(std::max(t, 2), 8);
+    if (int t = tune_env("ZG_TUNE_STAGES")) g.stages = std::min(std::max(t, 2), zgk::kSplitAckRing - 2);
     const int budget = p->max_smem_optin - 1024 /*alignment slack*/;
     const int64_t row_boxes = T / zgk::kTileT;
     int nb = 14;
     if (int t = tune_env("ZG_TUNE_BOXES")) nb = std::min(std::max(t, 1), 32);
     nb = (int)std::min<int64_t>(nb, row_boxes);
     auto need = [&](int boxes) {
-        return g.groups * (g.stages * boxes * zgk::kTileBytes + 8 * zgk::split_bar_count(g.stages, boxes, g.wpg));
+        return g.groups * (g.stages * boxes * zgk::kTileBytes + zgk::split_group_extra_bytes(g.stages, boxes, g.wpg)) + 16;
     };
     while (nb > 1 && need(nb) > budget) --nb;
     if (need(nb) > budget) return false;
+    // tiles that divide the row leave no ragged tile at its end (8192 samples: 8 boxes rather than 9)
+    if (!tune_env("ZG_TUNE_BOXES"))
+        for (int d = nb; d >= std::max(2, nb - 2); --d)
+            if (row_boxes % d == 0) { nb = d; break; }
     g.boxes = nb;
     g.smem = need(nb) + 1024;
-    const int64_t n_cg = (c_count + 31) / 32;
-    g.grid = (int)std::min<int64_t>(p->sm_count, (n_cg + g.groups - 1) / g.groups);
     if (mode == 2) return true;
-    // auto: the groups walk ceil(n_cg / slots) rows each; worth it from ~4 rows per slot on, when the last round is
-    // nearly full (65 536 channels: 2048 channel groups over 296 slots = 6.92 rounds)
-    const int64_t slots = (int64_t)g.grid * g.groups;
-    const int64_t rounds = (n_cg + slots - 1) / slots;
-    return rounds >= 4 && n_cg * 100 >= rounds * slots * 95;
+    // auto: a GPU's worth of groups with at least two rows each, rows of at least eight tiles
+    return g.grid == p->sm_count && (row_boxes + nb - 1) / nb >= 8;
 }
 
 int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void* const* out, int64_t T, int64_t ld_in,
                  int64_t ld_out, cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance) {
     const bool sym = variant_is_sym(p);
-    KernelPtr fn = biquad_split_kernel_for(p->bq.sections, g.spw, p->exact, sym, p->uniform_now);
-    zgk::StreamArgs a;
+    SplitKernelPtr fn = biquad_split_kernel_for(p->bq.sections, g.spw, p->exact, sym, p->uniform_now);
+    zgk::SplitArgs a;
     std::memset(&a, 0, sizeof a);
-    if (!encode_map_tile3d(&a.in_map[1], in[0], c_count, T, ld_in, 32, g.boxes) ||
-        !encode_map_tile3d(&a.out_map[1], out[0], c_count, T, ld_out, 32, g.boxes))
+    if (!encode_map_tile3d(&a.in_map, in[0], c_count, T, ld_in, 32, g.boxes) ||
+        !encode_map_tile3d(&a.out_map, out[0], c_count, T, ld_out, 32, g.boxes))
         return fail(ZG_ERR_CUDA, "cuTensorMapEncodeTiled (whole-tile map of the section-split biquad kernel)");
+    const size_t n_cg_plan = (size_t)(p->ch_stride + 31) / 32;
+    if (!p->d_split_ticket || p->split_wpg_alloc < g.wpg) {
+        if (p->d_split_ticket) cudaFree(p->d_split_ticket);
+        if (p->d_split_flags) cudaFree(p->d_split_flags);
+        if (p->d_split_carry) cudaFree(p->d_split_carry);
+        p->d_split_ticket = nullptr;
+        p->d_split_flags = nullptr;
+        p->d_split_carry = nullptr;
+        ZG_CUDA(cudaMalloc(&p->d_split_ticket, sizeof(unsigned long long)));
+        ZG_CUDA(cudaMemset(p->d_split_ticket, 0, sizeof(unsigned long long)));
+        ZG_CUDA(cudaMalloc(&p->d_split_flags, n_cg_plan * g.wpg * sizeof(unsigned)));
+        ZG_CUDA(cudaMemset(p->d_split_flags, 0, n_cg_plan * g.wpg * sizeof(unsigned)));
+        ZG_CUDA(cudaMalloc(&p->d_split_carry, (size_t)p->kernel_n_state * 2 * p->ch_stride * sizeof(float)));
+        p->split_wpg_alloc = g.wpg;
+        p->split_tickets = 0;
+        p->split_epoch = 0;
+    }
+    // a row's flag holds the epoch of the launch whose head piece of that row is done; epochs never repeat (the flags
+    // start over when the counter wraps)
+    if (++p->split_epoch == 0) {
+        ZG_CUDA(cudaMemsetAsync(p->d_split_flags, 0, n_cg_plan * g.wpg * sizeof(unsigned), stream));
+        p->split_epoch = 1;
+    }
     a.state = p->d_state + c_begin;
     a.params = p->d_params ? p->d_params + c_begin : nullptr;
     a.ch_stride = p->ch_stride;
-    a.stream_pos = p->stream_pos;
     a.channels = (int)c_count;
     a.n_samples = (int)T;
     a.stages = g.stages;
     a.boxes = g.boxes;
+    a.ticket = p->d_split_ticket;
+    a.ticket_base = p->split_tickets;
+    a.flags = p->d_split_flags + (c_begin / 32) * g.wpg;
+    a.carry = p->d_split_carry + c_begin;
+    a.epoch = p->split_epoch;
     for (int j = 0; j < p->kernel_n_state; ++j) a.state_row[j] = p->state_row[j];
     if (p->uniform_now) std::memcpy(a.uparams, p->uparams, sizeof(float) * std::min(p->kernel_n_param, zgk::kMaxUniform));
     int st = raise_max_smem((const void*)fn, p->opts.device, g.smem);
@@ -1130,6 +1174,7 @@ int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void
     }
     void* args[] = {&a};
     ZG_CUDA(cudaLaunchKernel((const void*)fn, dim3(g.grid), dim3(g.groups * g.wpg * 32), args, g.smem, stream));
+    p->split_tickets += (unsigned long long)g.grid;      // every CTA draws one
     p->launches += 1;
     p->split_now = true;
     p->last_segs = 1;
