@@ -462,7 +462,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_rate(workload, coef=None, mode_name=None):
+    def device_rate(workload, coef=None, mode_name=None, **plan_kw):
         """K launches of one zg_process() each between CUDA events; returns the plan, buffers and timing."""
         C, T = WORKLOADS[workload]
         coef = coef or args.coef
@@ -479,7 +479,7 @@ def run_ours(args):
                 params += [per[:, j].copy() for j in range(5)]
         mode = zg.MODE_EXACT if mode_name == "exact" else zg.MODE_FAST
         plan = graph.plan(channels=C, device=local, mode=mode,
-                          layout=zg.INTERLEAVED if args.layout == "interleaved" else zg.PLANAR)
+                          layout=zg.INTERLEAVED if args.layout == "interleaved" else zg.PLANAR, **plan_kw)
         for i, p in enumerate(params):
             plan.set_param(i, p)
         shape = (T, C) if args.layout == "interleaved" else (C, T)
@@ -640,6 +640,19 @@ def run_ours(args):
             del plan_p, xp, yp
         except Exception as e:
             also["ns_per_channel"] = {"error": str(e)[:300]}
+        torch.cuda.empty_cache()
+        try:
+            # the same shape on the lane-per-channel kernel (K1; zg_plan_opts.section_warps = 1), what round 1 timed
+            Cn, Tn = WORKLOADS["ns"]
+            plan_k, xk, yk, _, ms_k, _, _ = device_rate("ns", mode_name=args.mode, section_warps=1)
+            i_k = plan_k.info()
+            also["ns_k1"] = {"workload": workload_string("ns", args.layout) + ", one lane per channel (section_warps = 1)",
+                             "value": world * Cn * Tn / (ms_k * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_k,
+                             "roofline_frac": BYTES_PER_SAMPLE * Cn * Tn / (ms_k * 1e-3) / 1e9 / peak_hbm,
+                             "kernel": i_k.kernel.decode(), "mode": args.mode}
+            del plan_k, xk, yk
+        except Exception as e:
+            also["ns_k1"] = {"error": str(e)[:300]}
         torch.cuda.empty_cache()
         also.update(other_configs(zg, wl, torch, dev, local, world, rank, args, barrier, dist))
 

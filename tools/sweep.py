@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="ns")
     ap.add_argument("--shape", default="", help="C,T instead of a named workload")
+    ap.add_argument("--brief", action="store_true", help="print the axes, the kernel, ms and GB/s only")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--sections", type=int, default=4)
     ap.add_argument("--pad", type=int, default=0, help="extra floats of row pitch (planar buffers)")
@@ -87,6 +88,8 @@ def main():
         except Exception as e:
             pt["error"] = str(e)[:200]
         pt = {k: v for k, v in pt.items() if v != "0" or k not in axes}        # axes left at their default are not printed
+        if a.brief:
+            pt = {k: v for k, v in pt.items() if k in axes or k in ("kernel", "ms", "gbs", "threads", "stages_used", "boxes_used", "error")}
         print(json.dumps(pt), flush=True)
 
 if __name__ == "__main__":

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(512, 1) zg_biquad_lanes_kernel(const __grid_co
 }
 
 template <int S, int SPW, bool kExact, bool kSym, bool kUniform>
-__global__ void __launch_bounds__(1024, 1) zg_biquad_split_kernel(const __grid_constant__ zgk::SplitArgs a) {
+__global__ void __launch_bounds__(512, 1) zg_biquad_split_kernel(const __grid_constant__ zgk::SplitArgs a) {
     zgk::biquad_split_block<S, SPW, kExact, kSym, kUniform>(a);
 }
 
@@ -276,7 +276,7 @@ SplitKernelPtr biquad_split_kernel_for(int sections, int spw, bool exact, bool s
     if (sections == S && spw == W && exact == E && sym == Y) \
         return uniform ? (SplitKernelPtr)zg_biquad_split_kernel<S, W, E, Y, true> : (SplitKernelPtr)zg_biquad_split_kernel<S, W, E, Y, false>;
 #define ZG_PICK(S, W) ZG_PICK3(S, W, false, false) ZG_PICK3(S, W, true, false) ZG_PICK3(S, W, true, true)
-    ZG_PICK(2, 1) ZG_PICK(3, 1) ZG_PICK(4, 1) ZG_PICK(4, 2) ZG_PICK(6, 2) ZG_PICK(8, 2)
+    ZG_PICK(2, 1) ZG_PICK(3, 1) ZG_PICK(4, 1) ZG_PICK(5, 1) ZG_PICK(6, 1) ZG_PICK(7, 1) ZG_PICK(8, 1) ZG_PICK(4, 2) ZG_PICK(6, 2) ZG_PICK(8, 2)
 #undef ZG_PICK
 #undef ZG_PICK3
     return nullptr;
@@ -1083,16 +1083,21 @@ bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g
     if (mode == 1 || !p->is_biquad || p->opts.force_jit || p->interleaved || p->io != 4 || p->lanes != 1) return false;
     if (T % zgk::kTileT != 0 || T < 4 * zgk::kTileT || T > (1ll << 30)) return false;
     const int S = p->bq.sections;
-    int spw = S == 2 || S == 3 || S == 4 ? 1 : S == 6 || S == 8 ? 2 : 0;
+    // sections per warp and groups per CTA, measured on 65 536 x 8192 (EXACT, GB/s of 8 B/sample; K1 in brackets):
+    //   3 sections: 1 x 3 groups 6306 (5345)   4: 1 x 3 6087 (5555)   5: 1 x 3 5078 (4780)   6: 2 x 4 4893 (4096)
+    //   7: 1 x 2 3486 (3281)   8: 2 x 4 3844 (2748);   2 sections: 5791 (5977) -- two warps per group have nothing to
+    //   overlap, K1 stays.  Three groups of single-section warps put three independent recurrences on every scheduler
+    //   (EXACT: 3 dependent instructions of the 8 per sample and section).  FAST with 3 sections: no gain, K1 stays.
+    int spw = S == 6 || S == 8 ? 2 : 1;
+    int groups = S == 6 || S == 8 ? 4 : S == 7 ? 2 : 3;
     if (int w = tune_env("ZG_TUNE_SPLIT_SPW")) spw = w;
     if (spw < 1 || S % spw != 0 || !biquad_split_kernel_for(S, spw, p->exact, variant_is_sym(p), p->uniform_now)) return false;
+    if (mode == 0 && (S < 3 || (S == 3 && !p->exact))) return false;
     g.spw = spw;
     g.wpg = S / spw;
     const int64_t n_cg = (c_count + 31) / 32;
-    // three groups put three independent recurrences on every scheduler (EXACT: 3 dependent instructions of 8 per
-    // sample and section)
-    g.groups = std::max(1, std::min(3, 32 / g.wpg));
-    if (int t = tune_env("ZG_TUNE_SPLIT_G")) g.groups = std::min(std::max(t, 1), 32 / g.wpg);
+    g.groups = std::max(1, std::min(groups, 16 / g.wpg));
+    if (int t = tune_env("ZG_TUNE_SPLIT_G")) g.groups = std::min(std::max(t, 1), 16 / g.wpg);
     g.groups = (int)std::max<int64_t>(1, std::min<int64_t>(g.groups, n_cg / 2));
     g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->sm_count, n_cg / (2 * g.groups)));
     g.stages = 2;
