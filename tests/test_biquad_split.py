@@ -141,6 +141,18 @@ def test_split_many_launches_of_one_plan(zg):
     assert np.array_equal(np.asarray(plan.get_state()), np.asarray(plan1.get_state()))
 
 
+def test_split_form_for_the_race_checker_is_the_same_arithmetic(zg, monkeypatch):
+    """ZG_TUNE_SPLIT_ARRIVE=1: every lane arrives on the hand-over barriers itself (what compute-sanitizer racecheck runs,
+    tools/sanitize/device_check.py) -- same results"""
+    monkeypatch.setenv("ZG_TUNE_SPLIT_ARRIVE", "1")
+    C, T = 328, 1504
+    x = fo.noise(C, T, seed=31)
+    expr = fo.biquad_cascade(4)
+    y, plan = _run(zg, expr, x, zg.MODE_EXACT, 2)
+    assert _is_split(plan)
+    assert np.array_equal(y, fo.COracle(expr, C).process([x])[0])
+
+
 def test_split_in_place(zg):
     C, T = 64, 2048
     x = fo.noise(C, T, seed=7)

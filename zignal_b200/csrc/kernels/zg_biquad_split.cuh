@@ -12,8 +12,8 @@
 // per SM are decoupled: two groups of four warps issue like eight, but only 64 rows share the shared memory, so a
 // tile is 12-14 boxes = 1.5-1.75 KB of every row in one TMA request.
 //
-//   * hand-over: one mbarrier per (section boundary, ring box); lane 0 of the producing warp arrives after a
-//     __syncwarp, all lanes of the consuming warp wait.  Steady state: the wait succeeds at once.
+//   * hand-over: one mbarrier per (section boundary, ring box); all lanes of the producing warp arrive, all lanes of
+//     the consuming warp wait.  Steady state: the wait succeeds at once.
 //   * TMA: one 3-D operation per tile and direction (box {32 samples, 32 channels, NB boxes}, SWIZZLE_128B, the same
 //     shared-memory image as NB single boxes).  Lane 0 of the LAST warp of a group issues both: the store of the tile
 //     it has just finished, and -- one box into the next tile, when that store has read its shared memory -- the load
@@ -63,9 +63,9 @@ struct SplitArgs {
 };
 
 // mbarriers per group: S "tile landed" + (WPG - 1) x ring boxes "box handed over" + "every warp of the group has read
-// the initial state of this piece"
+// the initial state of this piece" + S "the last warp is done with the tile that was in this stage"
 __host__ __device__ constexpr int split_bar_count(int stages, int boxes, int wpg) {
-    return stages + (wpg - 1) * stages * boxes + kSplitAckRing;
+    return stages + (wpg - 1) * stages * boxes + kSplitAckRing + stages;
 }
 __host__ __device__ constexpr int split_group_extra_bytes(int stages, int boxes, int wpg) {
     return 8 * split_bar_count(stages, boxes, wpg);
@@ -83,7 +83,10 @@ __device__ __forceinline__ void split_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int SECTIONS, int SPW, bool kExact, bool kSym, bool kUniform>
+// kAllArrive: every lane arrives on the hand-over barriers itself instead of lane 0 after a __syncwarp -- the form
+// compute-sanitizer racecheck can follow (it tracks a thread's own arrivals only); 4.6 % slower in EXACT mode (32
+// arrivals per box serialise), so it is built for the 4-section kernel only and chosen by ZG_TUNE_SPLIT_ARRIVE=1.
+template <int SECTIONS, int SPW, bool kExact, bool kSym, bool kUniform, bool kAllArrive = false>
 __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
     static_assert(SECTIONS % SPW == 0, "sections per warp must divide the cascade");
     constexpr int WPG = SECTIONS / SPW;                        // warps per group
@@ -109,6 +112,8 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
                                                              (size_t)G * split_group_extra_bytes(S, NB, WPG));
     unsigned long long* full = bars;                                       // [S] tile landed
     unsigned long long* ack_bar = bars + S + (size_t)(WPG - 1) * R;       // [kSplitAckRing]
+    unsigned long long* empty = ack_bar + kSplitAckRing;                   // [S]
+    constexpr unsigned lanes_arriving = kAllArrive ? 32u : 1u;
     // what this warp waits for before a box: the tile (first warp; one barrier per stage, re-checked per box: free
     // once the phase has completed) or the box from the warp before it; and what it signals after a box
     unsigned long long* wait_bar = first ? full : bars + S + (size_t)(sec - 1) * R;
@@ -116,7 +121,12 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
     unsigned long long* hand_out = bars + S + (size_t)(last ? 0 : sec) * R;   // [R] (unused by the last warp)
 
     if (sec == 0 && lane == 0) {
-        for (int i = 0; i < split_bar_count(S, NB, WPG); ++i) mbar_init(&bars[i], &bars[i] >= ack_bar ? WPG : 1);
+        // a tile lands once (one expect_tx arrival); a box / an initial state / a finished tile is handed over by lane 0 of a
+        // warp after a __syncwarp, or by every lane for itself
+        for (int i = 0; i < split_bar_count(S, NB, WPG); ++i) {
+            unsigned long long* b = &bars[i];
+            mbar_init(b, i < S ? 1u : b >= ack_bar && b < empty ? lanes_arriving * WPG : lanes_arriving);
+        }
         fence_barrier_init();
         prefetch_tmap(&a.in_map);
         prefetch_tmap(&a.out_map);
@@ -185,6 +195,15 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) offs[j] = (unsigned)lane * 128u + ((((unsigned)j) ^ (unsigned)(lane & 7)) << 4);
 
+    // a warp signals: lane 0 for all lanes (their stores are ordered before its arrival by the __syncwarp), or -- for the
+    // race checker, which follows a thread's own arrivals only -- every lane for itself
+    auto warp_arrive = [&](unsigned long long* bar) {
+        if constexpr (kAllArrive) split_arrive(bar);
+        else {
+            __syncwarp();
+            if (lane == 0) split_arrive(bar);
+        }
+    };
     // one box: wait until it is ours, 32 ticks of this warp's sections in place, hand it on
     auto do_box = [&](unsigned char* box, unsigned long long* wbar, unsigned par, unsigned long long* obar, bool compute) {
         mbar_wait(wbar, par);
@@ -206,13 +225,10 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
                 *reinterpret_cast<uint4*>(box + offs[j]) = Io<4>::pack(yv);
             }
         }
-        if (!last) {
-            __syncwarp();
-            if (lane == 0) split_arrive(obar);
-        }
+        if (!last) warp_arrive(obar);
     };
 
-    int st = 0;                                        // stage of the next tile
+    int st = 0, tile_no = 0;                           // stage / number of the next tile
     unsigned par = 0;
     bool any_tile = false;                             // a tile has been stored by this (last) warp: a stage to refill
     for (int pi = 0; pi < n_pieces; ++pi) {
@@ -238,8 +254,7 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
         }
         // the state rows of a signal are read by the warp that consumes it and written by the warp that produces it,
         // which may be a whole piece ahead: nobody writes before everybody has read
-        __syncwarp();
-        if (lane == 0) split_arrive(ack);
+        warp_arrive(ack);
         if (!kUniform) {
 #pragma unroll
             for (int j = 0; j < NP; ++j) prm[j] = ch_ok ? a.params[(long long)(sec * NP + j) * a.ch_stride + ch] : 0.f;
@@ -254,6 +269,10 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
             unsigned long long* wb = wait_bar + (first ? st : st * NB);
             unsigned long long* ob = hand_out + st * NB;
 
+            // (the load into this stage was issued after the store of the tile before it had read the stage, so this wait
+            //  never blocks: it states, for the memory model and the race checker, that the last warp's stores to the
+            //  stage happened before the first warp's loads from it S tiles later)
+            if (first && tile_no >= S) mbar_wait(&empty[st], par ^ 1u);
             do_box(stage, wb, par, ob, true);
             if (last && lane == 0 && any_tile && !ld_done) {
                 tma_wait_read<0>();                    // the store of the previous tile has read its stage:
@@ -272,7 +291,9 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
                     tma_commit();
                 }
                 any_tile = true;
+                warp_arrive(&empty[st]);
             }
+            ++tile_no;
             if (++st == S) { st = 0; par ^= 1u; }
         }
 

@@ -193,9 +193,9 @@ __global__ void __launch_bounds__(512, 1) zg_biquad_lanes_kernel(const __grid_co
     zgk::biquad_lanes_block<S, kExact, kUniform>(a);
 }
 
-template <int S, int SPW, bool kExact, bool kSym, bool kUniform>
+template <int S, int SPW, bool kExact, bool kSym, bool kUniform, bool kAllArrive = false>
 __global__ void __launch_bounds__(512, 1) zg_biquad_split_kernel(const __grid_constant__ zgk::SplitArgs a) {
-    zgk::biquad_split_block<S, SPW, kExact, kSym, kUniform>(a);
+    zgk::biquad_split_block<S, SPW, kExact, kSym, kUniform, kAllArrive>(a);
 }
 
 template <bool kExact, bool kInterleaved>
@@ -269,9 +269,19 @@ KernelPtr biquad_lanes_kernel_for(int sections, bool exact, bool uniform) {
     return nullptr;
 }
 
+int tune_env(const char* name);          // ZG_TUNE_* overrides, below
+
 // K1s (kernels/zg_biquad_split.cuh): the sections of a channel group spread over `sections / spw` warps
 using SplitKernelPtr = void (*)(zgk::SplitArgs);
 SplitKernelPtr biquad_split_kernel_for(int sections, int spw, bool exact, bool sym, bool uniform) {
+    // the form the race checker can follow (kernels/zg_biquad_split.cuh kAllArrive): the 4-section kernel only
+    if (tune_env("ZG_TUNE_SPLIT_ARRIVE") == 1 && sections == 4 && spw == 1) {
+#define ZG_PICK3(E, Y) \
+    if (exact == E && sym == Y) \
+        return uniform ? (SplitKernelPtr)zg_biquad_split_kernel<4, 1, E, Y, true, true> : (SplitKernelPtr)zg_biquad_split_kernel<4, 1, E, Y, false, true>;
+        ZG_PICK3(false, false) ZG_PICK3(true, false) ZG_PICK3(true, true)
+#undef ZG_PICK3
+    }
 #define ZG_PICK3(S, W, E, Y) \
     if (sections == S && spw == W && exact == E && sym == Y) \
         return uniform ? (SplitKernelPtr)zg_biquad_split_kernel<S, W, E, Y, true> : (SplitKernelPtr)zg_biquad_split_kernel<S, W, E, Y, false>;
