@@ -153,6 +153,37 @@ def test_split_form_for_the_race_checker_is_the_same_arithmetic(zg, monkeypatch)
     assert np.array_equal(y, fo.COracle(expr, C).process([x])[0])
 
 
+def test_split_replayed_from_a_cuda_graph(zg):
+    """nothing about a K1s launch lives on the host (the CTA tickets and the epoch of the row flags are kept by the kernel
+    itself), so captured launches can be replayed: every replay continues the stream"""
+    torch = _torch()
+    C, T, NBLK = 1000, 256, 4
+    expr = fo.biquad_cascade(4)
+    plan = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, lanes_per_channel=1, section_warps=2)
+    x = fo.noise(C, 3 * NBLK * T, seed=77)
+    xin = torch.empty((C, NBLK * T), device="cuda")
+    yout = torch.empty_like(xin)
+    plan.process([xin[:, :T]], [yout[:, :T]])                 # warm: buffers allocated, kernel attributes set
+    assert _is_split(plan)
+    plan.reset()
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for b in range(NBLK):
+                plan.process([xin[:, b * T:(b + 1) * T]], [yout[:, b * T:(b + 1) * T]])
+    plan.reset()
+    outs = []
+    for rep in range(3):
+        xin.copy_(torch.from_numpy(x[:, rep * NBLK * T:(rep + 1) * NBLK * T]))
+        graph.replay()
+        torch.cuda.synchronize()
+        outs.append(yout.cpu().numpy().copy())
+    idx = [0, 31, 32, 517, 999]
+    ref = fo.COracle(expr, len(idx)).process([x[idx]])[0]
+    assert np.array_equal(np.concatenate(outs, axis=1)[idx], ref)
+
+
 def test_split_in_place(zg):
     C, T = 64, 2048
     x = fo.noise(C, T, seed=7)

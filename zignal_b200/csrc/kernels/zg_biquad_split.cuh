@@ -52,10 +52,12 @@ struct SplitArgs {
     int n_samples;                          // a multiple of 32
     int boxes;                              // NB: boxes per tile
     int stages;                             // S >= 2 tiles in a group's ring
-    unsigned long long* ticket;             // CTAs number themselves in the order they start from this counter ...
-    unsigned long long ticket_base;         // ... which stood here before the launch
-    unsigned* flags;                        // [channel group][warps per group]: the epoch of the launch whose head piece of
-    unsigned epoch;                         //   this row is done
+    unsigned long long* ctl;                // [0] tickets drawn: CTAs number themselves in the order they start;
+                                            // [1] CTAs finished; [2] launches finished = the epoch before this launch.
+                                            // The last CTA to finish zeroes [0], [1] and bumps [2]: nothing about a launch
+                                            // lives on the host, so a captured launch can be replayed from a CUDA graph
+    unsigned long long* flags;              // [channel group][warps per group]: the epoch of the launch whose head piece of
+                                            //   this row is done
     float* carry;                           // [warps per group * state floats per warp][ch_stride]: a warp's delay lines
                                             //   between the two pieces of a row
     int state_row[kMaxState];
@@ -71,13 +73,13 @@ __host__ __device__ constexpr int split_group_extra_bytes(int stages, int boxes,
     return 8 * split_bar_count(stages, boxes, wpg);
 }
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void split_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -108,8 +110,8 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
     unsigned char* ring = tiles + (size_t)grp * R * kTileBytes;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + (size_t)G * R * kTileBytes) +
                                (size_t)grp * split_bar_count(S, NB, WPG);
-    volatile int* s_ticket = reinterpret_cast<volatile int*>(tiles + (size_t)G * R * kTileBytes +
-                                                             (size_t)G * split_group_extra_bytes(S, NB, WPG));
+    volatile unsigned long long* s_ctl = reinterpret_cast<volatile unsigned long long*>(
+        tiles + (size_t)G * R * kTileBytes + (size_t)G * split_group_extra_bytes(S, NB, WPG));      // [0] ticket, [1] epoch
     unsigned long long* full = bars;                                       // [S] tile landed
     unsigned long long* ack_bar = bars + S + (size_t)(WPG - 1) * R;       // [kSplitAckRing]
     unsigned long long* empty = ack_bar + kSplitAckRing;                   // [S]
@@ -133,8 +135,12 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
     }
     // CTAs are numbered in the order they START: a CTA only ever waits for the one numbered before it (below), which is
     // therefore running or finished whatever else occupies the GPU and in whatever order the hardware starts CTAs
-    if (threadIdx.x == 0) *s_ticket = (int)(atomicAdd(a.ticket, 1ull) - a.ticket_base);
+    if (threadIdx.x == 0) {
+        s_ctl[0] = atomicAdd(&a.ctl[0], 1ull);
+        s_ctl[1] = ld_acquire_gpu(&a.ctl[2]) + 1ull;    // stays put until every CTA of this launch has finished
+    }
     __syncthreads();
+    const unsigned long long epoch = s_ctl[1];
 
     // ---- the work of this group: a contiguous range of the tile sequence (row 0 tiles 0.., row 1 tiles 0.., ...) ----
     // Every group gets the same number of tiles (+-1), so a range begins and ends in the middle of a row.  The host
@@ -146,7 +152,7 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
     const int tpr = (a.n_samples + tile_t - 1) / tile_t;                   // tiles per row
     const long long total = (long long)n_cg * tpr;
     const int n_slots = (int)gridDim.x * G;
-    const int slot = *s_ticket * G + grp;
+    const int slot = (int)s_ctl[0] * G + grp;
     const long long lo = total * slot / n_slots, hi = total * (slot + 1) / n_slots;
     const int row_lo = (int)(lo / tpr), k_lo = (int)(lo - (long long)row_lo * tpr);
     const int row_hi = (int)(hi / tpr), k_hi = (int)(hi - (long long)row_hi * tpr);
@@ -238,13 +244,13 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
         const int ch = c0 + lane;
         const bool ch_ok = ch < a.channels;
         const bool from_carry = kb > 0, to_carry = ke < tpr;
-        unsigned* my_flag = a.flags + (size_t)row * WPG + sec;
+        unsigned long long* my_flag = a.flags + (size_t)row * WPG + sec;
         unsigned long long* ack = &ack_bar[pi & (kSplitAckRing - 1)];
 
         // its delay lines (and coefficients): from the state rows, or -- the tail piece of a row -- from what the same
         // warp of the group before left in `carry` (ld.cg: these lines were written by another SM during this launch)
         if (from_carry) {
-            while (ld_acquire_gpu(my_flag) != a.epoch) {}
+            while (ld_acquire_gpu(my_flag) != epoch) {}
 #pragma unroll
             for (int j = 0; j < NS; ++j) s[j] = ch_ok ? __ldcg(&a.carry[(long long)(sec * NS + j) * a.ch_stride + ch]) : 0.f;
         } else {
@@ -308,7 +314,7 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
             __syncwarp();
             if (lane == 0) {
                 __threadfence();
-                st_release_gpu(my_flag, a.epoch);
+                st_release_gpu(my_flag, epoch);
             }
         } else if (ch_ok) {
 #pragma unroll
@@ -317,6 +323,18 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
         }
     }
     if (last && lane == 0) tma_wait_all<0>();           // shared memory must outlive the last stores
+
+    // the last CTA to finish leaves the counters ready for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&a.ctl[1], 1ull) + 1ull == gridDim.x) {
+            a.ctl[0] = 0ull;
+            a.ctl[1] = 0ull;
+            __threadfence();
+            st_release_gpu(&a.ctl[2], epoch);
+        }
+    }
 }
 
 }  // namespace zgk

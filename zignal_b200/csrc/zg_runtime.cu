@@ -382,12 +382,10 @@ struct zg_plan {
     int lanes_now = 1;                      // lanes per channel of the launch being prepared
     bool split_now = false;                 // the last launch ran K1s (sections spread over the warps of a group)
     int split_regs = 0, split_spw = 0;
-    unsigned long long* d_split_ticket = nullptr;  // the CTAs of a K1s launch number themselves from this counter; it is
-    unsigned long long split_tickets = 0;          // never reset: the host knows where every launch leaves it
-    unsigned* d_split_flags = nullptr;             // [channel groups][warps per group]: epoch of the row's head piece
+    unsigned long long* d_split_ctl = nullptr;     // K1s: tickets drawn / CTAs finished / launches finished (kept by the kernel)
+    unsigned long long* d_split_flags = nullptr;   // [channel groups][warps per group]: epoch of the row's head piece
     float* d_split_carry = nullptr;                // [warps per group * state per warp][ch_stride]: delay lines of a cut row
     int split_wpg_alloc = 0;
-    unsigned split_epoch = 0;
     bool seg_now = false;                   // the launch being prepared is cut in time
 
     // Time segments for few, long channels (FAST mode, linear ticks; kernels/zg_stream.cuh StreamArgs::n_segs)
@@ -443,7 +441,7 @@ struct zg_plan {
         if (d_stage) cudaFree(d_stage);
         if (d_seg_state) cudaFree(d_seg_state);
         if (d_AL) cudaFree(d_AL);
-        if (d_split_ticket) cudaFree(d_split_ticket);
+        if (d_split_ctl) cudaFree(d_split_ctl);
         if (d_split_flags) cudaFree(d_split_flags);
         if (d_split_carry) cudaFree(d_split_carry);
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -1143,27 +1141,19 @@ int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void
         !encode_map_tile3d(&a.out_map, out[0], c_count, T, ld_out, 32, g.boxes))
         return fail(ZG_ERR_CUDA, "cuTensorMapEncodeTiled (whole-tile map of the section-split biquad kernel)");
     const size_t n_cg_plan = (size_t)(p->ch_stride + 31) / 32;
-    if (!p->d_split_ticket || p->split_wpg_alloc < g.wpg) {
-        if (p->d_split_ticket) cudaFree(p->d_split_ticket);
+    if (!p->d_split_ctl || p->split_wpg_alloc < g.wpg) {
+        if (p->d_split_ctl) cudaFree(p->d_split_ctl);
         if (p->d_split_flags) cudaFree(p->d_split_flags);
         if (p->d_split_carry) cudaFree(p->d_split_carry);
-        p->d_split_ticket = nullptr;
+        p->d_split_ctl = nullptr;
         p->d_split_flags = nullptr;
         p->d_split_carry = nullptr;
-        ZG_CUDA(cudaMalloc(&p->d_split_ticket, sizeof(unsigned long long)));
-        ZG_CUDA(cudaMemset(p->d_split_ticket, 0, sizeof(unsigned long long)));
-        ZG_CUDA(cudaMalloc(&p->d_split_flags, n_cg_plan * g.wpg * sizeof(unsigned)));
-        ZG_CUDA(cudaMemset(p->d_split_flags, 0, n_cg_plan * g.wpg * sizeof(unsigned)));
+        ZG_CUDA(cudaMalloc(&p->d_split_ctl, 4 * sizeof(unsigned long long)));
+        ZG_CUDA(cudaMemset(p->d_split_ctl, 0, 4 * sizeof(unsigned long long)));
+        ZG_CUDA(cudaMalloc(&p->d_split_flags, n_cg_plan * g.wpg * sizeof(unsigned long long)));
+        ZG_CUDA(cudaMemset(p->d_split_flags, 0, n_cg_plan * g.wpg * sizeof(unsigned long long)));
         ZG_CUDA(cudaMalloc(&p->d_split_carry, (size_t)p->kernel_n_state * 2 * p->ch_stride * sizeof(float)));
         p->split_wpg_alloc = g.wpg;
-        p->split_tickets = 0;
-        p->split_epoch = 0;
-    }
-    // a row's flag holds the epoch of the launch whose head piece of that row is done; epochs never repeat (the flags
-    // start over when the counter wraps)
-    if (++p->split_epoch == 0) {
-        ZG_CUDA(cudaMemsetAsync(p->d_split_flags, 0, n_cg_plan * g.wpg * sizeof(unsigned), stream));
-        p->split_epoch = 1;
     }
     a.state = p->d_state + c_begin;
     a.params = p->d_params ? p->d_params + c_begin : nullptr;
@@ -1172,11 +1162,9 @@ int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void
     a.n_samples = (int)T;
     a.stages = g.stages;
     a.boxes = g.boxes;
-    a.ticket = p->d_split_ticket;
-    a.ticket_base = p->split_tickets;
+    a.ctl = p->d_split_ctl;
     a.flags = p->d_split_flags + (c_begin / 32) * g.wpg;
     a.carry = p->d_split_carry + c_begin;
-    a.epoch = p->split_epoch;
     for (int j = 0; j < p->kernel_n_state; ++j) a.state_row[j] = p->state_row[j];
     if (p->uniform_now) std::memcpy(a.uparams, p->uparams, sizeof(float) * std::min(p->kernel_n_param, zgk::kMaxUniform));
     int st = raise_max_smem((const void*)fn, p->opts.device, g.smem);
@@ -1189,7 +1177,6 @@ int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void
     }
     void* args[] = {&a};
     ZG_CUDA(cudaLaunchKernel((const void*)fn, dim3(g.grid), dim3(g.groups * g.wpg * 32), args, g.smem, stream));
-    p->split_tickets += (unsigned long long)g.grid;      // every CTA draws one
     p->launches += 1;
     p->split_now = true;
     p->last_segs = 1;
