@@ -20,7 +20,8 @@ Channels are independent, so N GPUs = N x the channels (weak scaling), no data-p
             the GPU legs come from zignal_b200/workloads.py
   also      the other biquad shape (c2 when the headline is ns and vice versa), device-resident, same rules;
             c2_scan = configs[1] in FAST mode, cut in time (zg_plan_opts.time_parallel, DESIGN.md 3 K5);
-            ns_per_channel = the north-star shape with the per-channel coefficients SURVEY.md 8(d) prescribes
+            ns_per_channel = the north-star shape with the per-channel coefficients SURVEY.md 8(d) prescribes;
+            ns_k1 = the north-star shape on the lane-per-channel kernel (zg_plan_opts.section_warps = 1)
   edge      (N > 1) a 65 536 x 8192 block resident on rank 0 -> N shard plans -> back on rank 0, three ways:
             NCCL scatter + compute + gather, kernels working on the root's block over NVLink peer memory, compute only
 Default mode is EXACT: bit-identical to the reference's x86 build, checked on sampled channels.
@@ -559,6 +560,36 @@ def run_ours(args):
         e2e["limiter"] = ("host link: a step moves 2 x %.2f GB per rank; the kernel is %.1f %% of the step" %
                           (C * T * 4 / 1e9, 100 * ms_per_step / (dt / e2e_steps * 1e3)))
         del hx, hy
+        # the one lever on a link-bound step: bf16 sample storage halves the bytes (state, coefficients and arithmetic stay
+        # fp32; outputs rounded to nearest even -- bit-identical to the oracle fed the bf16-rounded block,
+        # tests/test_gpu_parity.py).  Reported beside the fp32 number, never instead of it.
+        try:
+            plan_h = zg.compile(wl.biquad_cascade(SECTIONS)).plan(
+                channels=C, device=local, mode=zg.MODE_EXACT if args.mode == "exact" else zg.MODE_FAST,
+                layout=zg.INTERLEAVED if args.layout == "interleaved" else zg.PLANAR, io_dtype=zg.BF16)
+            hxb = torch.empty(shape, dtype=torch.bfloat16).pin_memory()
+            hyb = torch.empty(shape, dtype=torch.bfloat16).pin_memory()
+            hxb.copy_(x)
+            plan_h.process_host([hxb], [hyb])
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                plan_h.process_host([hxb], [hyb])
+                _ = float(hyb[0, 0])
+            torch.cuda.synchronize()
+            dtb = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([dtb], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dtb = float(t.item())
+            e2e["bf16_io"] = {"value": world * C * T * e2e_steps / dtb / 1e6, "unit": "Msamples/s",
+                              "h2d_bytes_per_step": int(C * T * 2), "d2h_bytes_per_step": int(C * T * 2),
+                              "ms_per_step": dtb / e2e_steps * 1e3, "kernel": plan_h.info().kernel.decode(),
+                              "gbs_per_rank_both_directions": 2 * C * T * 2 * e2e_steps / dtb / 1e9,
+                              "note": "zg_plan_opts.io_dtype = ZG_BF16: samples cross the link and live in HBM as bf16"}
+            del plan_h, hxb, hyb
+        except Exception as e:
+            e2e["bf16_io"] = {"error": str(e)[:300]}
 
     # ---- CPU leg, part 1 (rank 0, N = 1 only; the one place this arm may execute oracle/): a spot check of the
     #      timed kernel's output against the oracle -- the checker, not the thing measured ----

@@ -6,7 +6,9 @@
 //
 // Kernel selection at plan time:
 //   K1  tick program is a cascade of direct-form-1 biquads (zg_match.cpp)  -> prebuilt kernel
-//       zg_biquad_df1<SECTIONS, exact, interleaved, uniform> compiled by nvcc into this library;
+//       zg_biquad_df1<SECTIONS, exact, interleaved, uniform> compiled by nvcc into this library; per launch, by shape:
+//       K1s (many channels: sections spread over the warps of a persistent CTA, kernels/zg_biquad_split.cuh),
+//       K1b (few channels: sections across the lanes of a warp) or K1 cut in time (FAST, linear ticks);
 //   K2  anything else -> the same hand-written streaming skeleton (kernels/zg_stream.cuh) with the
 //       straight-line tick body generated from the graph (zg_codegen.cpp), compiled once per plan
 //       with NVRTC for sm_100a.
