@@ -87,10 +87,11 @@ def test_split_streams_like_ticks_and_shares_state_rows_with_k1(zg):
     assert np.array_equal(np.concatenate([y0, y1], axis=1), ref)
 
 
-def test_split_per_channel_coefficients(zg):
+@pytest.mark.parametrize("C", [160, 800])
+def test_split_per_channel_coefficients(zg, C):
     """$k parameters, one value per channel (b0 == b2 per channel: the product-reusing tick), and a set that is not
-    symmetric (the plain tick)"""
-    C, T = 160, 1024
+    symmetric (the plain tick); 160 channels = one group per SM, 800 = three per CTA"""
+    T = 1024
     x = fo.noise(C, T, seed=5)
     expr = fo.biquad_cascade_params(4)
     for sym in (True, False):
@@ -104,7 +105,8 @@ def test_split_per_channel_coefficients(zg):
             params += [np.asarray(v, np.float32) for v in (b0, b1, b2, a1, a2)]
         y, plan = _run(zg, expr, x, zg.MODE_EXACT, 2, params=params)
         assert _is_split(plan)
-        assert (b"+b0=b2" in plan.info().kernel) == sym
+        # (160 channels run one group per SM: that form evaluates plain sections, it has no use for the product reuse)
+        assert b"boxes per hand-over" in plan.info().kernel or (b"+b0=b2" in plan.info().kernel) == sym
         prm = np.stack([np.broadcast_to(p, (C,)) for p in params], axis=1)
         ref = fo.COracle(expr, C, params=prm).process([x])[0]
         assert np.array_equal(y, ref)
@@ -116,7 +118,8 @@ def test_split_rows_cut_between_groups_are_bit_identical(zg, boxes, monkeypatch)
     delay lines for the group that runs the tail (EXACT: the same ticks in the same order, still bit-identical).  Small
     tiles move the cuts around; two blocks per plan: the flags and the CTA tickets run on from launch to launch"""
     monkeypatch.setenv("ZG_TUNE_BOXES", str(boxes))
-    C, T = 328, 1504                    # 11 channel groups over 3 or 6 groups of warps; 47 boxes per row
+    monkeypatch.setenv("ZG_TUNE_SPLIT_G", "3")      # (so few channels would run one group per SM, whole rows each)
+    C, T = 328, 1504                    # 11 channel groups over 9 groups of warps; 47 boxes per row
     x = fo.noise(C, T, seed=boxes)
     expr = fo.biquad_cascade(4)
     y, plan = _run(zg, expr, x, zg.MODE_EXACT, 2, blocks=[736, 768])
@@ -182,6 +185,48 @@ def test_split_replayed_from_a_cuda_graph(zg):
     idx = [0, 31, 32, 517, 999]
     ref = fo.COracle(expr, len(idx)).process([x[idx]])[0]
     assert np.array_equal(np.concatenate(outs, axis=1)[idx], ref)
+
+
+def test_split_few_channels_one_group_per_sm(zg):
+    """few channels, EXACT, long blocks (BASELINE configs[1] in small): the auto rule runs a warp per section with one
+    group per SM, whole rows per group, four boxes per hand-over -- bit-identical to the oracle, streams like ticks
+    (second block ragged: 131 boxes), shares its state rows with the lanes kernel K1b"""
+    torch = _torch()
+    import zignal_b200
+    C = 100
+    T1, T2 = 8192, 4192
+    x = fo.noise(C, T1 + T2, seed=41)
+    expr = fo.biquad_cascade(4)
+    ref = fo.COracle(expr, C).process([x])[0]
+    plan = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT)
+    assert plan.info().lanes_per_channel == 4                 # sized for K1b ...
+    y1 = plan.process([zignal_b200.to_block(x[:, :T1])], n_samples=T1)[0].cpu().numpy()
+    i = plan.info()
+    assert b"zg_biquad_df1_split<4,exact,planar,4 warps per group,4 boxes per hand-over>" in i.kernel and i.lanes_per_channel == 1
+    y2 = plan.process([zignal_b200.to_block(x[:, T1:])], n_samples=T2)[0].cpu().numpy()
+    assert np.array_equal(np.concatenate([y1, y2], axis=1), ref)
+    # a short block of the same plan runs on K1b; the state rows are the same
+    k1b = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, lanes_per_channel=4)
+    k1b.process([zignal_b200.to_block(x[:, :T1])], n_samples=T1)
+    plan2 = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT)
+    plan2.set_state(k1b.get_state())
+    z2 = plan2.process([zignal_b200.to_block(x[:, T1:])], n_samples=T2)[0].cpu().numpy()
+    assert np.array_equal(z2, ref[:, T1:])
+    # per-channel coefficients
+    pexpr = fo.biquad_cascade_params(4)
+    params = []
+    for k in range(4):
+        f = 300.0 * (k + 1) * (1.0 + np.arange(C) / C)
+        params += [np.asarray(v, np.float32) for v in fo.rbj_lowpass(f, 0.8, 48000.0)]
+    pp = zg.compile(pexpr).plan(channels=C, mode=zg.MODE_EXACT)
+    for j, v in enumerate(params):
+        pp.set_param(j, v)
+    yp = pp.process([zignal_b200.to_block(x[:, :T1])], n_samples=T1)[0].cpu().numpy()
+    assert b"boxes per hand-over" in pp.info().kernel
+    prm = np.stack(params, axis=1)
+    assert np.array_equal(yp, fo.COracle(pexpr, C, params=prm).process([x[:, :T1]])[0])
+    # FAST keeps K1b / the time segments; an explicit lanes_per_channel is respected
+    assert b"split" not in k1b.info().kernel
 
 
 def test_split_in_place(zg):

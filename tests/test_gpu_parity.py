@@ -663,7 +663,12 @@ def test_full_size_config2_4096x65536(zg):
     x = torch.rand((C, T), generator=gen, device="cuda") * 2 - 1
     plan = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT)
     y = plan.process([x])[0]
-    assert plan.info().lanes_per_channel == 4            # too few channels for a lane each: K1b
+    # too few channels for a lane each, EXACT, long block: a warp per section, one group per SM (K1s, few-channel form)
+    assert plan.info().lanes_per_channel == 1 and b"zg_biquad_df1_split<4,exact,planar,4 warps per group,4 boxes per hand-over>" in plan.info().kernel
+    # ... bit-identical to the section-parallel lanes kernel (K1b) it replaced on this shape
+    k1b = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, lanes_per_channel=4)
+    z = k1b.process([x], n_samples=T)[0]
+    assert k1b.info().lanes_per_channel == 4 and torch.equal(y, z)
     idx = [0, 5, 4095]
     assert np.array_equal(y[idx].cpu().numpy(), _oracle(expr, [x[idx].cpu().numpy()])[0])
     y1 = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, lanes_per_channel=1).process([x])[0]

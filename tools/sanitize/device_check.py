@@ -59,6 +59,11 @@ ks = zg.compile(expr).plan(channels=328, lanes_per_channel=1, section_warps=2)
 xs = fo.noise(328, 1504, seed=6)
 assert np.array_equal(ks.process([zg.to_block(xs)])[0].cpu().numpy(), fo.COracle(expr, 328).process([xs])[0]), "K1s"
 assert b"zg_biquad_df1_split" in ks.info().kernel
+# ... and its few-channel form (one group per SM, four boxes per hand-over), what an auto plan of 64 channels runs on a long block
+kf = zg.compile(expr).plan(channels=C)
+xf8 = fo.noise(C, 8192, seed=9)
+assert np.array_equal(kf.process([zg.to_block(xf8)])[0].cpu().numpy(), fo.COracle(expr, C).process([xf8])[0]), "K1s, few channels"
+assert b"boxes per hand-over" in kf.info().kernel
 os.environ.pop("ZG_TUNE_SPLIT_ARRIVE", None)
 
 # long delay lines: rings in HBM

@@ -29,7 +29,7 @@ def main():
     for part in a.points.split(";"):
         k, v = part.split("=")
         axes[k] = v.split(",")
-    for k, d in (("mode", ["exact"]), ("boxes", ["0"]), ("wpc", ["0"]), ("stages", ["0"]), ("layout", ["planar"]), ("coef", ["uniform"]), ("lanes", ["0"]), ("late", ["0"]), ("hint", ["0"]), ("promo", ["0"]), ("cu", ["0"]), ("jit", ["0"]), ("pf", ["0"]), ("pfd", ["0"]), ("tp", ["0"]), ("segs", ["0"]), ("warm", ["0"]), ("split", ["0"]), ("sg", ["0"]), ("spw", ["0"])):
+    for k, d in (("mode", ["exact"]), ("boxes", ["0"]), ("wpc", ["0"]), ("stages", ["0"]), ("layout", ["planar"]), ("coef", ["uniform"]), ("lanes", ["0"]), ("late", ["0"]), ("hint", ["0"]), ("promo", ["0"]), ("cu", ["0"]), ("jit", ["0"]), ("pf", ["0"]), ("pfd", ["0"]), ("tp", ["0"]), ("segs", ["0"]), ("warm", ["0"]), ("split", ["0"]), ("sg", ["0"]), ("spw", ["0"]), ("hb", ["0"])):
         axes.setdefault(k, d)
     C, T = [int(v) for v in a.shape.split(",")] if a.shape else WORK[a.workload]
     x = torch.empty((C, T + a.pad), device="cuda")[:, :T]
@@ -39,7 +39,7 @@ def main():
     keys = list(axes)
     for combo in itertools.product(*[axes[k] for k in keys]):
         pt = dict(zip(keys, combo))
-        for env, k in (("ZG_TUNE_BOXES", "boxes"), ("ZG_TUNE_WPC", "wpc"), ("ZG_TUNE_STAGES", "stages"), ("ZG_TUNE_LATE_REFILL", "late"), ("ZG_TUNE_L2HINT", "hint"), ("ZG_TUNE_L2PROMO", "promo"), ("ZG_TUNE_CHUNK_UNROLL", "cu"), ("ZG_TUNE_PF", "pf"), ("ZG_TUNE_PFD", "pfd"), ("ZG_TUNE_TP", "tp"), ("ZG_TUNE_SEGS", "segs"), ("ZG_TUNE_WARM", "warm"), ("ZG_TUNE_SPLIT", "split"), ("ZG_TUNE_SPLIT_G", "sg"), ("ZG_TUNE_SPLIT_SPW", "spw")):
+        for env, k in (("ZG_TUNE_BOXES", "boxes"), ("ZG_TUNE_WPC", "wpc"), ("ZG_TUNE_STAGES", "stages"), ("ZG_TUNE_LATE_REFILL", "late"), ("ZG_TUNE_L2HINT", "hint"), ("ZG_TUNE_L2PROMO", "promo"), ("ZG_TUNE_CHUNK_UNROLL", "cu"), ("ZG_TUNE_PF", "pf"), ("ZG_TUNE_PFD", "pfd"), ("ZG_TUNE_TP", "tp"), ("ZG_TUNE_SEGS", "segs"), ("ZG_TUNE_WARM", "warm"), ("ZG_TUNE_SPLIT", "split"), ("ZG_TUNE_SPLIT_G", "sg"), ("ZG_TUNE_SPLIT_SPW", "spw"), ("ZG_TUNE_SPLIT_HB", "hb")):
             if pt[k] != "0": os.environ[env] = pt[k]
             else: os.environ.pop(env, None)
         inter = pt["layout"] == "interleaved"

@@ -88,8 +88,13 @@ __device__ __forceinline__ void split_arrive(unsigned long long* bar) {
 // kAllArrive: every lane arrives on the hand-over barriers itself instead of lane 0 after a __syncwarp -- the form
 // compute-sanitizer racecheck can follow (it tracks a thread's own arrivals only); 4.6 % slower in EXACT mode (32
 // arrivals per box serialise), so it is built for the 4-section kernel only and chosen by ZG_TUNE_SPLIT_ARRIVE=1.
-template <int SECTIONS, int SPW, bool kExact, bool kSym, bool kUniform, bool kAllArrive = false>
+// kHB: boxes per hand-over.  1 for many channels (three groups per SM hide a hand-over behind each other's arithmetic).
+// With few channels -- one group per SM, every warp alone on its scheduler -- the fixed cost of a hand-over (barrier
+// round trip, first load of the box, drain of the stores) sits on the critical path of every box: kHB = 4 pays it once
+// per four boxes (the warps of a group then run four boxes apart).
+template <int SECTIONS, int SPW, bool kExact, bool kSym, bool kUniform, bool kAllArrive = false, int kHB = 1>
 __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
+    static_assert(kHB == 1 || (SPW == 1 && !kSym), "runs of boxes are evaluated one plain section per warp");
     static_assert(SECTIONS % SPW == 0, "sections per warp must divide the cascade");
     constexpr int WPG = SECTIONS / SPW;                        // warps per group
     typedef BiquadDf1Cascade<SPW, kExact, kSym> Tick;
@@ -210,10 +215,9 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
             if (lane == 0) split_arrive(bar);
         }
     };
-    // one box: wait until it is ours, 32 ticks of this warp's sections in place, hand it on
-    auto do_box = [&](unsigned char* box, unsigned long long* wbar, unsigned par, unsigned long long* obar, bool compute) {
-        mbar_wait(wbar, par);
-        if (compute) {
+    // 32 ticks of this warp's sections on one box, in place
+    auto compute_box = [&](unsigned char* box) {
+        {
             uint4 xn = *reinterpret_cast<const uint4*>(box + offs[0]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -231,6 +235,11 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
                 *reinterpret_cast<uint4*>(box + offs[j]) = Io<4>::pack(yv);
             }
         }
+    };
+    // one box: wait until it is ours, evaluate it, hand it on
+    auto do_box = [&](unsigned char* box, unsigned long long* wbar, unsigned par, unsigned long long* obar, bool compute) {
+        mbar_wait(wbar, par);
+        if (compute) compute_box(box);
         if (!last) warp_arrive(obar);
     };
 
@@ -279,6 +288,48 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
             //  never blocks: it states, for the memory model and the race checker, that the last warp's stores to the
             //  stage happened before the first warp's loads from it S tiles later)
             if (first && tile_no >= S) mbar_wait(&empty[st], par ^ 1u);
+            if constexpr (kHB > 1) {
+                // boxes in runs of kHB (NB is a multiple of kHB, and at least two runs): one wait and one arrival per run
+#pragma unroll 1
+                for (int b0 = 0; b0 < NB; b0 += kHB) {
+                    mbar_wait(wb + b0 * wait_per_box, par);
+                    if (b0 == kHB && last && lane == 0 && any_tile && !ld_done) {
+                        tma_wait_read<0>();
+                        issue_load();
+                    }
+                    // the ticks of the run through Df1Lane::step4 (zg_biquad_lanes.cuh): the recurrence
+                    // y = (v + a1*y1) + a2*y2 -- three dependent instructions per sample, all a lone warp has to wait
+                    // for -- with the feed-forward half of the NEXT four samples computed in its shadow.  Same
+                    // operations in the same association as the tick: bit-identical.
+                    const int cnt = nb - b0 < kHB ? nb - b0 : kHB;
+                    if (cnt > 0) {
+                        Df1Lane<kExact> f;
+                        f.b0 = prm[0]; f.b1 = prm[1]; f.b2 = prm[2]; f.a1 = prm[3]; f.a2 = prm[4];
+                        f.x2 = s[0]; f.x1 = s[1]; f.y2 = s[2]; f.y1 = s[3];
+                        unsigned char* bx = stage + (size_t)b0 * kTileBytes;
+                        float4 c = *reinterpret_cast<const float4*>(bx + offs[0]);
+                        float v[4], o[4];
+                        f.prime(c, v);
+#pragma unroll
+                        for (int h = 0; h < kHB; ++h) {
+                            if (h < cnt) {
+                                unsigned char* box = bx + (size_t)h * kTileBytes;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float4 n = c;
+                                    if (j < 7) n = *reinterpret_cast<const float4*>(box + offs[j + 1]);
+                                    else if (h + 1 < cnt) n = *reinterpret_cast<const float4*>(box + kTileBytes + offs[0]);
+                                    f.step4(c, n, v, o);
+                                    *reinterpret_cast<float4*>(box + offs[j]) = make_float4(o[0], o[1], o[2], o[3]);
+                                    c = n;
+                                }
+                            }
+                        }
+                        s[0] = f.x2; s[1] = f.x1; s[2] = f.y2; s[3] = f.y1;
+                    }
+                    if (!last) warp_arrive(ob + b0);
+                }
+            } else {
             do_box(stage, wb, par, ob, true);
             if (last && lane == 0 && any_tile && !ld_done) {
                 tma_wait_read<0>();                    // the store of the previous tile has read its stage:
@@ -288,6 +339,7 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
             for (int b = 1; b < nb; ++b) do_box(stage + (size_t)b * kTileBytes, wb + b * wait_per_box, par, ob + b, true);
 #pragma unroll 1
             for (int b = nb; b < NB; ++b) do_box(stage, wb + b * wait_per_box, par, ob + b, false);    // past the end of the row
+            }
 
             if (last) {
                 fence_proxy_async();                   // generic-proxy writes -> visible to TMA

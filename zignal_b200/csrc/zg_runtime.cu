@@ -195,9 +195,9 @@ __global__ void __launch_bounds__(512, 1) zg_biquad_lanes_kernel(const __grid_co
     zgk::biquad_lanes_block<S, kExact, kUniform>(a);
 }
 
-template <int S, int SPW, bool kExact, bool kSym, bool kUniform, bool kAllArrive = false>
+template <int S, int SPW, bool kExact, bool kSym, bool kUniform, bool kAllArrive = false, int kHB = 1>
 __global__ void __launch_bounds__(512, 1) zg_biquad_split_kernel(const __grid_constant__ zgk::SplitArgs a) {
-    zgk::biquad_split_block<S, SPW, kExact, kSym, kUniform, kAllArrive>(a);
+    zgk::biquad_split_block<S, SPW, kExact, kSym, kUniform, kAllArrive, kHB>(a);
 }
 
 template <bool kExact, bool kInterleaved>
@@ -275,7 +275,23 @@ int tune_env(const char* name);          // ZG_TUNE_* overrides, below
 
 // K1s (kernels/zg_biquad_split.cuh): the sections of a channel group spread over `sections / spw` warps
 using SplitKernelPtr = void (*)(zgk::SplitArgs);
-SplitKernelPtr biquad_split_kernel_for(int sections, int spw, bool exact, bool sym, bool uniform) {
+SplitKernelPtr biquad_split_kernel_for(int sections, int spw, bool exact, bool sym, bool uniform, int hand_boxes = 1) {
+    // few channels, one group per SM: several boxes per hand-over (kernels/zg_biquad_split.cuh kHB); 4 sections only, no
+    // product reuse (a lone warp waits for its recurrence, not for issue slots)
+    if (hand_boxes > 1) {
+        if (sections != 4 || spw != 1) return nullptr;
+#define ZG_PICK3(H, E) \
+    if (hand_boxes == H && exact == E) \
+        return uniform ? (SplitKernelPtr)zg_biquad_split_kernel<4, 1, E, false, true, false, H> : (SplitKernelPtr)zg_biquad_split_kernel<4, 1, E, false, false, false, H>;
+        if (tune_env("ZG_TUNE_SPLIT_ARRIVE") == 1 && hand_boxes == 4)      // the form the race checker can follow
+            return exact ? (uniform ? (SplitKernelPtr)zg_biquad_split_kernel<4, 1, true, false, true, true, 4>
+                                    : (SplitKernelPtr)zg_biquad_split_kernel<4, 1, true, false, false, true, 4>)
+                         : (uniform ? (SplitKernelPtr)zg_biquad_split_kernel<4, 1, false, false, true, true, 4>
+                                    : (SplitKernelPtr)zg_biquad_split_kernel<4, 1, false, false, false, true, 4>);
+        ZG_PICK3(2, false) ZG_PICK3(2, true) ZG_PICK3(4, false) ZG_PICK3(4, true)
+#undef ZG_PICK3
+        return nullptr;
+    }
     // the form the race checker can follow (kernels/zg_biquad_split.cuh kAllArrive): the 4-section kernel only
     if (tune_env("ZG_TUNE_SPLIT_ARRIVE") == 1 && sections == 4 && spw == 1) {
 #define ZG_PICK3(E, Y) \
@@ -383,7 +399,8 @@ struct zg_plan {
                                             // [4], [5]: the lane-per-channel kernel of a K1b plan; + 6: built with time segments
     int lanes_now = 1;                      // lanes per channel of the launch being prepared
     bool split_now = false;                 // the last launch ran K1s (sections spread over the warps of a group)
-    int split_regs = 0, split_spw = 0;
+    int split_regs = 0, split_spw = 0, split_hand_boxes = 1;
+    const void* split_fn = nullptr;
     unsigned long long* d_split_ctl = nullptr;     // K1s: tickets drawn / CTAs finished / launches finished (kept by the kernel)
     unsigned long long* d_split_flags = nullptr;   // [channel groups][warps per group]: epoch of the row's head piece
     float* d_split_carry = nullptr;                // [warps per group * state per warp][ch_stride]: delay lines of a cut row
@@ -1084,15 +1101,19 @@ int launch_fir(zg_plan* p, const void* const* in, void* const* out, int64_t T, i
 // delay lines of that row travel from one group to the next through HBM.  Ranges are at least two rows long (fewer
 // groups otherwise): a row is cut at most once.  Returns false when the launch should stay on K1.
 struct SplitGeometry {
-    int spw, wpg, groups, stages, boxes, grid, smem;
+    int spw, wpg, groups, stages, boxes, grid, smem, hand_boxes;
 };
 
 bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g) {
     // zg_plan_opts.section_warps: 0 = auto, 1 = never, 2 = whenever the shape allows (ZG_TUNE_SPLIT overrides: 1 / 2 / 3)
     const int mode = tune_env("ZG_TUNE_SPLIT") ? tune_env("ZG_TUNE_SPLIT") - 1 : p->opts.section_warps;
-    if (mode == 1 || !p->is_biquad || p->opts.force_jit || p->interleaved || p->io != 4 || p->lanes != 1) return false;
+    if (mode == 1 || !p->is_biquad || p->opts.force_jit || p->interleaved || p->io != 4) return false;
     if (T % zgk::kTileT != 0 || T < 4 * zgk::kTileT || T > (1ll << 30)) return false;
+    // a plan sized for K1b (few channels): only when the auto rule, not the caller, chose the lanes
+    if (p->lanes > 1 && (p->opts.lanes_per_channel != 0 || tune_env("ZG_TUNE_LANES"))) return false;
     const int S = p->bq.sections;
+    const int64_t n_cg = (c_count + 31) / 32;
+    const int64_t row_boxes = T / zgk::kTileT;
     // sections per warp and groups per CTA, measured on 65 536 x 8192 (EXACT, GB/s of 8 B/sample; K1 in brackets):
     //   3 sections: 1 x 3 groups 6306 (5345)   4: 1 x 3 6087 (5555)   5: 1 x 3 5078 (4780)   6: 2 x 4 4893 (4096)
     //   7: 1 x 2 3486 (3281)   8: 2 x 4 3844 (2748);   2 sections: 5791 (5977) -- two warps per group have nothing to
@@ -1105,16 +1126,43 @@ bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g
     if (mode == 0 && (S < 3 || (S == 3 && !p->exact))) return false;
     g.spw = spw;
     g.wpg = S / spw;
-    const int64_t n_cg = (c_count + 31) / 32;
-    g.groups = std::max(1, std::min(groups, 16 / g.wpg));
-    if (int t = tune_env("ZG_TUNE_SPLIT_G")) g.groups = std::min(std::max(t, 1), 16 / g.wpg);
-    g.groups = (int)std::max<int64_t>(1, std::min<int64_t>(g.groups, n_cg / 2));
-    g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(p->sm_count, n_cg / (2 * g.groups)));
-    g.stages = 2;
+    g.hand_boxes = 1;
+    groups = std::max(1, std::min(groups, 16 / g.wpg));
+    // every group's range is at least one row long, so that a row is cut at most once
+    auto grid_for = [&](int G) { return (int)std::max<int64_t>(1, std::min<int64_t>(p->sm_count, n_cg / G)); };
+    bool fits_k1s = true;                              // auto: is this the kernel for the shape?
+    if (S == 4 && spw == 1) {
+        // Fewer channel groups than 3 x SMs: fewer groups per CTA keep every SM busy.  A group advances one sample of its 32
+        // channels in c(G) cycles when G groups share an SM -- measured (EXACT / FAST): c(1) = 19.9 / 17.7 (BASELINE
+        // configs[1], four boxes per hand-over: every warp is alone on its scheduler and only its recurrence bounds it;
+        // K1b: 21.3), c(2) = 29.5 / 25.6 (8192 x 32 768: 0.49 ms against K1b's 0.58), c(3) = 37.5 / 36 (HBM-bound from
+        // there on: 16 384 x 16 384 runs at 0.91 of the copy peak, K1: 0.55) -- and a launch takes rows per group x c(G).
+        const double cyc[2][3] = {{17.7, 25.6, 36.0}, {19.9, 29.5, 37.5}};
+        double best = 0;
+        int best_g = 0;
+        for (int G = 1; G <= 3; ++G) {
+            if (G > n_cg) break;
+            const double cost = (double)n_cg / ((double)G * grid_for(G)) * cyc[p->exact ? 1 : 0][G - 1];
+            if (!best_g || cost < best) { best = cost; best_g = G; }
+        }
+        groups = best_g;
+        // below ~2.5 warps of channels per SM a FAST plan has K1b and the time segments, which this kernel does not beat
+        if (!p->exact && p->lanes > 1) fits_k1s = false;
+    } else if (p->lanes > 1) {
+        fits_k1s = false;
+    }
+    if (int t = tune_env("ZG_TUNE_SPLIT_G")) groups = std::min(std::max(t, 1), 16 / g.wpg);
+    g.groups = (int)std::max<int64_t>(1, std::min<int64_t>(groups, n_cg));
+    g.grid = grid_for(g.groups);
+    if (g.groups == 1 && S == 4 && spw == 1) {
+        const int hb = tune_env("ZG_TUNE_SPLIT_HB") ? tune_env("ZG_TUNE_SPLIT_HB") : 4;
+        if (hb > 1 && biquad_split_kernel_for(S, 1, p->exact, false, p->uniform_now, hb)) g.hand_boxes = hb;
+    }
+    // the ring: one group per SM runs its four warps four boxes apart (3 x 16 boxes); else two stages, as long as they fit
+    g.stages = g.hand_boxes > 1 ? 3 : 2;
     if (int t = tune_env("ZG_TUNE_STAGES")) g.stages = std::min(std::max(t, 2), zgk::kSplitAckRing - 2);
     const int budget = p->max_smem_optin - 1024 /*alignment slack*/;
-    const int64_t row_boxes = T / zgk::kTileT;
-    int nb = 14;
+    int nb = g.hand_boxes > 1 ? 16 : 14;
     if (int t = tune_env("ZG_TUNE_BOXES")) nb = std::min(std::max(t, 1), 32);
     nb = (int)std::min<int64_t>(nb, row_boxes);
     auto need = [&](int boxes) {
@@ -1122,21 +1170,28 @@ bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g
     };
     while (nb > 1 && need(nb) > budget) --nb;
     if (need(nb) > budget) return false;
-    // tiles that divide the row leave no ragged tile at its end (8192 samples: 8 boxes rather than 9)
-    if (!tune_env("ZG_TUNE_BOXES"))
+    if (g.hand_boxes > 1) {
+        nb = nb / g.hand_boxes * g.hand_boxes;
+        if (nb < 2 * g.hand_boxes) return false;
+    } else if (!tune_env("ZG_TUNE_BOXES")) {
+        // tiles that divide the row leave no ragged tile at its end (8192 samples: 8 boxes rather than 9)
         for (int d = nb; d >= std::max(2, nb - 2); --d)
             if (row_boxes % d == 0) { nb = d; break; }
+    }
     g.boxes = nb;
     g.smem = need(nb) + 1024;
     if (mode == 2) return true;
-    // auto: a GPU's worth of groups with at least two rows each, rows of at least eight tiles
-    return g.grid == p->sm_count && (row_boxes + nb - 1) / nb >= 8;
+    // auto: rows of at least eight tiles (the ring fills once per launch), and -- other than for 4 sections, where the
+    // group count follows the channel count -- a GPU's worth of groups
+    if ((row_boxes + nb - 1) / nb < 8) return false;
+    if (S == 4 && spw == 1) return fits_k1s;
+    return fits_k1s && g.grid == p->sm_count;
 }
 
 int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void* const* out, int64_t T, int64_t ld_in,
                  int64_t ld_out, cudaStream_t stream, int64_t c_begin, int64_t c_count, bool advance) {
-    const bool sym = variant_is_sym(p);
-    SplitKernelPtr fn = biquad_split_kernel_for(p->bq.sections, g.spw, p->exact, sym, p->uniform_now);
+    const bool sym = g.hand_boxes == 1 && variant_is_sym(p);
+    SplitKernelPtr fn = biquad_split_kernel_for(p->bq.sections, g.spw, p->exact, sym, p->uniform_now, g.hand_boxes);
     zgk::SplitArgs a;
     std::memset(&a, 0, sizeof a);
     if (!encode_map_tile3d(&a.in_map, in[0], c_count, T, ld_in, 32, g.boxes) ||
@@ -1171,16 +1226,18 @@ int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void
     if (p->uniform_now) std::memcpy(a.uparams, p->uparams, sizeof(float) * std::min(p->kernel_n_param, zgk::kMaxUniform));
     int st = raise_max_smem((const void*)fn, p->opts.device, g.smem);
     if (st != ZG_OK) return st;
-    if (!p->split_regs || p->split_spw != g.spw) {
+    if (p->split_fn != (const void*)fn) {
         cudaFuncAttributes fa;
         ZG_CUDA(cudaFuncGetAttributes(&fa, (const void*)fn));
         p->split_regs = fa.numRegs;
-        p->split_spw = g.spw;
+        p->split_fn = (const void*)fn;
     }
+    p->split_spw = g.spw;
     void* args[] = {&a};
     ZG_CUDA(cudaLaunchKernel((const void*)fn, dim3(g.grid), dim3(g.groups * g.wpg * 32), args, g.smem, stream));
     p->launches += 1;
     p->split_now = true;
+    p->split_hand_boxes = g.hand_boxes;
     p->last_segs = 1;
     p->last_seg_mode = 0;
     p->last_seg_len = 0;
@@ -1209,7 +1266,10 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
         p->lanes_now = p->lanes;
         p->seg_now = false;
         SplitGeometry sp{};
-        if (choose_split(p, T, c_count, sp)) return launch_split(p, sp, in, out, T, ld_in, ld_out, stream, c_begin, c_count, advance);
+        if (choose_split(p, T, c_count, sp)) {
+            p->lanes_now = 1;
+            return launch_split(p, sp, in, out, T, ld_in, ld_out, stream, c_begin, c_count, advance);
+        }
     }
     p->lanes_now = sg.mode ? 1 : p->lanes;
     p->seg_now = sg.mode != 0;
@@ -1781,9 +1841,10 @@ int zg_plan_get_info(const zg_plan* p, zg_plan_info* info) {
         name = "zg_biquad_df1<" + std::to_string(p->bq.sections) + (p->exact ? ",exact,planar>" : ",fma,planar>");
     if (p->split_now)
         name = "zg_biquad_df1_split<" + std::to_string(p->bq.sections) + (p->exact ? ",exact,planar," : ",fma,planar,") +
-               std::to_string(p->bq.sections / std::max(p->split_spw, 1)) + " warps per group>";
+               std::to_string(p->bq.sections / std::max(p->split_spw, 1)) + " warps per group" +
+               (p->split_hand_boxes > 1 ? "," + std::to_string(p->split_hand_boxes) + " boxes per hand-over>" : ">");
     std::snprintf(info->kernel, sizeof info->kernel, "%s%s%s", name.c_str(),
-                  variant_is_sym(p) ? "+b0=b2" : "",           // the product-reusing tick (kernels/zg_biquad.cuh)
+                  variant_is_sym(p) && !(p->split_now && p->split_hand_boxes > 1) ? "+b0=b2" : "",           // the product-reusing tick (kernels/zg_biquad.cuh)
                   p->last_seg_mode == 1 ? "+segments:warm-up" : p->last_seg_mode == 2 ? "+segments:two-pass" : "");
     const Variant& v = p->variant[variant_index(p)];
     info->jit = (v.prebuilt || p->is_fir) ? 0 : 1;
