@@ -60,6 +60,15 @@ struct SplitArgs {
                                             //   this row is done
     float* carry;                           // [warps per group * state floats per warp][ch_stride]: a warp's delay lines
                                             //   between the two pieces of a row
+    // Time segments (FAST mode, warm-up form; zg_runtime.cu choose_segments): with n_segs > 1 a "row" of the
+    // tile sequence is (32 channels, segment g): boxes [g * seg_boxes, g * seg_boxes + seg_boxes + warm_boxes) of the block.
+    // Segment 0 continues from the state rows; segment g > 0 starts from ZERO state and discards the outputs of its first
+    // warm_boxes boxes (the host has checked that the graph forgets its state within that many ticks), so it answers for
+    // the boxes from g * seg_boxes + warm_boxes on; the last segment takes the ragged end and leaves the block's final
+    // state in state_out (another buffer than `state`: a first segment may still have to read that).
+    int n_segs, seg_boxes, warm_boxes;      // seg_boxes and warm_boxes are multiples of `boxes`
+    float* state_out;
+    long long carry_stride;                 // floats per row of `carry`: ch_stride x n_segs
     int state_row[kMaxState];
     float uparams[kMaxUniform];
 };
@@ -154,8 +163,11 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
     // then the whole rows, LAST the tail piece of the row it begins in (tiles [k_lo, ..) of row_lo, continuing from the
     // carry of the group before -- which wrote it at the very start of the launch).
     const int n_cg = (a.channels + 31) >> 5;
-    const int tpr = (a.n_samples + tile_t - 1) / tile_t;                   // tiles per row
-    const long long total = (long long)n_cg * tpr;
+    const int n_segs = a.n_segs > 1 ? a.n_segs : 1;
+    const int block_boxes = a.n_samples / kTileT;
+    // tiles per row; a row is a channel group, or (channel group, segment): row = cg * n_segs + g
+    const int tpr = n_segs > 1 ? (a.seg_boxes + a.warm_boxes) / NB : (a.n_samples + tile_t - 1) / tile_t;
+    const long long total = (long long)n_cg * n_segs * tpr;
     const int n_slots = (int)gridDim.x * G;
     const int slot = (int)s_ctl[0] * G + grp;
     const long long lo = total * slot / n_slots, hi = total * (slot + 1) / n_slots;
@@ -181,7 +193,8 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
     if (!ld_done) piece(0, ld_row, ld_k, ld_ke);
     auto issue_load = [&]() {
         mbar_expect_tx(&full[ld_st], (unsigned)(NB * kTileBytes));
-        tma_load_3d(ring + (size_t)ld_st * NB * kTileBytes, &a.in_map, 0, ld_row * 32, ld_k * NB, &full[ld_st]);
+        const int ld_cg = ld_row / n_segs, ld_g = ld_row - ld_cg * n_segs;
+        tma_load_3d(ring + (size_t)ld_st * NB * kTileBytes, &a.in_map, 0, ld_cg * 32, ld_g * a.seg_boxes + ld_k * NB, &full[ld_st]);
         if (++ld_st == S) ld_st = 0;
         if (++ld_k == ld_ke) {
             if (++ld_pi == n_pieces) ld_done = true;
@@ -249,23 +262,29 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
     for (int pi = 0; pi < n_pieces; ++pi) {
         int row, kb, ke;
         piece(pi, row, kb, ke);
-        const int c0 = row * 32;
+        const int cg = row / n_segs, seg = row - cg * n_segs;
+        const int c0 = cg * 32;
         const int ch = c0 + lane;
         const bool ch_ok = ch < a.channels;
         const bool from_carry = kb > 0, to_carry = ke < tpr;
+        const int box_first = seg * a.seg_boxes;                            // of the row, in boxes of the block
+        const int box_end = n_segs > 1 && box_first + a.seg_boxes + a.warm_boxes < block_boxes
+                                ? box_first + a.seg_boxes + a.warm_boxes : block_boxes;
+        const int k_keep = seg > 0 ? a.warm_boxes / NB : 0;                 // tiles before this one produce state only
         unsigned long long* my_flag = a.flags + (size_t)row * WPG + sec;
         unsigned long long* ack = &ack_bar[pi & (kSplitAckRing - 1)];
+        const long long carry_col = (long long)row * 32 + lane;             // (n_segs == 1: the channel)
 
-        // its delay lines (and coefficients): from the state rows, or -- the tail piece of a row -- from what the same
-        // warp of the group before left in `carry` (ld.cg: these lines were written by another SM during this launch)
+        // its delay lines (and coefficients): from the state rows (a later segment: zero), or -- the tail piece of a row --
+        // from what the same warp of the group before left in `carry` (ld.cg: written by another SM during this launch)
         if (from_carry) {
             while (ld_acquire_gpu(my_flag) != epoch) {}
 #pragma unroll
-            for (int j = 0; j < NS; ++j) s[j] = ch_ok ? __ldcg(&a.carry[(long long)(sec * NS + j) * a.ch_stride + ch]) : 0.f;
+            for (int j = 0; j < NS; ++j) s[j] = ch_ok ? __ldcg(&a.carry[(long long)(sec * NS + j) * a.carry_stride + carry_col]) : 0.f;
         } else {
 #pragma unroll
             for (int j = 0; j < NS; ++j)
-                s[j] = ch_ok ? a.state[(long long)a.state_row[2 * SPW * sec + j] * a.ch_stride + ch] : 0.f;
+                s[j] = ch_ok && seg == 0 ? a.state[(long long)a.state_row[2 * SPW * sec + j] * a.ch_stride + ch] : 0.f;
         }
         // the state rows of a signal are read by the warp that consumes it and written by the warp that produces it,
         // which may be a whole piece ahead: nobody writes before everybody has read
@@ -277,9 +296,9 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
         if constexpr (NE > 0) Tick::init(s, prm, ex);
 
         for (int k = kb; k < ke; ++k) {
-            const int t0 = k * tile_t;
-            const int left = (a.n_samples - t0) / kTileT;
-            const int nb = left < NB ? left : NB;      // boxes of this tile that hold samples
+            const int box0 = box_first + k * NB;       // first box of the tile, in boxes of the block
+            const int left = box_end - box0;
+            const int nb = left < NB ? (left > 0 ? left : 0) : NB;      // boxes of this tile that hold samples
             unsigned char* stage = ring + (size_t)st * NB * kTileBytes;
             unsigned long long* wb = wait_bar + (first ? st : st * NB);
             unsigned long long* ob = hand_out + st * NB;
@@ -330,7 +349,7 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
                     if (!last) warp_arrive(ob + b0);
                 }
             } else {
-            do_box(stage, wb, par, ob, true);
+            do_box(stage, wb, par, ob, nb > 0);         // (a segment's last tiles may lie past the end of the block)
             if (last && lane == 0 && any_tile && !ld_done) {
                 tma_wait_read<0>();                    // the store of the previous tile has read its stage:
                 issue_load();                          // the tile S - 1 tiles ahead goes there
@@ -338,14 +357,14 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
 #pragma unroll 1
             for (int b = 1; b < nb; ++b) do_box(stage + (size_t)b * kTileBytes, wb + b * wait_per_box, par, ob + b, true);
 #pragma unroll 1
-            for (int b = nb; b < NB; ++b) do_box(stage, wb + b * wait_per_box, par, ob + b, false);    // past the end of the row
+            for (int b = nb > 1 ? nb : 1; b < NB; ++b) do_box(stage, wb + b * wait_per_box, par, ob + b, false);    // past the end of the row
             }
 
             if (last) {
                 fence_proxy_async();                   // generic-proxy writes -> visible to TMA
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_3d(&a.out_map, 0, c0, k * NB, stage);
+                    if (k >= k_keep) tma_store_3d(&a.out_map, 0, c0, box0, stage);      // (warm-up tiles: state, not samples)
                     tma_commit();
                 }
                 any_tile = true;
@@ -361,17 +380,17 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
         if (to_carry) {
             if (ch_ok) {
 #pragma unroll
-                for (int j = 0; j < NS; ++j) a.carry[(long long)(sec * NS + j) * a.ch_stride + ch] = s[j];
+                for (int j = 0; j < NS; ++j) a.carry[(long long)(sec * NS + j) * a.carry_stride + carry_col] = s[j];
             }
             __syncwarp();
             if (lane == 0) {
                 __threadfence();
                 st_release_gpu(my_flag, epoch);
             }
-        } else if (ch_ok) {
+        } else if (ch_ok && seg == n_segs - 1) {       // the end of the block for these channels
 #pragma unroll
             for (int j = 0; j < NS; ++j)
-                if (j >= 2 || first) a.state[(long long)a.state_row[2 * SPW * sec + j] * a.ch_stride + ch] = s[j];
+                if (j >= 2 || first) a.state_out[(long long)a.state_row[2 * SPW * sec + j] * a.ch_stride + ch] = s[j];
         }
     }
     if (last && lane == 0) tma_wait_all<0>();           // shared memory must outlive the last stores

@@ -404,7 +404,7 @@ struct zg_plan {
     unsigned long long* d_split_ctl = nullptr;     // K1s: tickets drawn / CTAs finished / launches finished (kept by the kernel)
     unsigned long long* d_split_flags = nullptr;   // [channel groups][warps per group]: epoch of the row's head piece
     float* d_split_carry = nullptr;                // [warps per group * state per warp][ch_stride]: delay lines of a cut row
-    int split_wpg_alloc = 0;
+    int split_wpg_alloc = 0, split_segs_alloc = 0;
     bool seg_now = false;                   // the launch being prepared is cut in time
 
     // Time segments for few, long channels (FAST mode, linear ticks; kernels/zg_stream.cuh StreamArgs::n_segs)
@@ -935,6 +935,8 @@ struct Segments {
     int mode = 0;       // 0 none, 1 warm-up, 2 two-pass
     int n = 1, len = 0, warm = 0;
 };
+int segments_count(const Segments* sg) { return sg->n; }
+int segments_warm(const Segments* sg) { return sg->warm; }
 
 // per-channel parameter values on the host: row k has 1 (scalar) or C values
 int host_params(zg_plan* p, std::vector<std::vector<float>>& rows) {
@@ -1102,9 +1104,15 @@ int launch_fir(zg_plan* p, const void* const* in, void* const* out, int64_t T, i
 // groups otherwise): a row is cut at most once.  Returns false when the launch should stay on K1.
 struct SplitGeometry {
     int spw, wpg, groups, stages, boxes, grid, smem, hand_boxes;
+    int n_segs, seg_boxes, warm_boxes;      // time segments (FAST, warm-up form): rows are (channel group, segment)
 };
 
-bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g) {
+struct Segments;
+bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g, const Segments* sg = nullptr);
+int segments_count(const Segments* sg);
+int segments_warm(const Segments* sg);
+
+bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g, const Segments* sg) {
     // zg_plan_opts.section_warps: 0 = auto, 1 = never, 2 = whenever the shape allows (ZG_TUNE_SPLIT overrides: 1 / 2 / 3)
     const int mode = tune_env("ZG_TUNE_SPLIT") ? tune_env("ZG_TUNE_SPLIT") - 1 : p->opts.section_warps;
     if (mode == 1 || !p->is_biquad || p->opts.force_jit || p->interleaved || p->io != 4) return false;
@@ -1112,8 +1120,13 @@ bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g
     // a plan sized for K1b (few channels): only when the auto rule, not the caller, chose the lanes
     if (p->lanes > 1 && (p->opts.lanes_per_channel != 0 || tune_env("ZG_TUNE_LANES"))) return false;
     const int S = p->bq.sections;
-    const int64_t n_cg = (c_count + 31) / 32;
-    const int64_t row_boxes = T / zgk::kTileT;
+    // with time segments a row of the tile sequence is (channel group, segment)
+    const int want_segs = sg ? segments_count(sg) : 1;
+    int64_t n_cg = (c_count + 31) / 32 * want_segs;
+    int64_t row_boxes = T / zgk::kTileT;
+    if (sg) row_boxes = std::max<int64_t>(8, (row_boxes - segments_warm(sg) / zgk::kTileT) / want_segs + segments_warm(sg) / zgk::kTileT);
+    g.n_segs = 1;
+    g.seg_boxes = g.warm_boxes = 0;
     // sections per warp and groups per CTA, measured on 65 536 x 8192 (EXACT, GB/s of 8 B/sample; K1 in brackets):
     //   3 sections: 1 x 3 groups 6306 (5345)   4: 1 x 3 6087 (5555)   5: 1 x 3 5078 (4780)   6: 2 x 4 4893 (4096)
     //   7: 1 x 2 3486 (3281)   8: 2 x 4 3844 (2748);   2 sections: 5791 (5977) -- two warps per group have nothing to
@@ -1146,9 +1159,10 @@ bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g
             if (!best_g || cost < best) { best = cost; best_g = G; }
         }
         groups = best_g;
-        // below ~2.5 warps of channels per SM a FAST plan has K1b and the time segments, which this kernel does not beat
-        if (!p->exact && p->lanes > 1) fits_k1s = false;
-    } else if (p->lanes > 1) {
+        // below ~2.5 warps of channels per SM a FAST plan has K1b, which this kernel does not beat (uncut; cut in time
+        // it is this kernel again, with (channel group, segment) rows)
+        if (!p->exact && p->lanes > 1 && !sg) fits_k1s = false;
+    } else if (p->lanes > 1 || sg) {
         fits_k1s = false;
     }
     if (int t = tune_env("ZG_TUNE_SPLIT_G")) groups = std::min(std::max(t, 1), 16 / g.wpg);
@@ -1173,6 +1187,8 @@ bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g
     if (g.hand_boxes > 1) {
         nb = nb / g.hand_boxes * g.hand_boxes;
         if (nb < 2 * g.hand_boxes) return false;
+    } else if (sg) {
+        if (nb >= 8 && !tune_env("ZG_TUNE_BOXES")) nb = 8;      // segment length and warm-up are rounded to whole tiles below
     } else if (!tune_env("ZG_TUNE_BOXES")) {
         // tiles that divide the row leave no ragged tile at its end (8192 samples: 8 boxes rather than 9)
         for (int d = nb; d >= std::max(2, nb - 2); --d)
@@ -1180,6 +1196,23 @@ bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g
     }
     g.boxes = nb;
     g.smem = need(nb) + 1024;
+    if (sg) {
+        // segment length and warm-up in whole tiles; the last segment takes the ragged end of the block
+        const int64_t block_boxes = T / zgk::kTileT;
+        const int64_t Kb = (segments_warm(sg) / zgk::kTileT + nb - 1) / nb * nb;
+        if (block_boxes <= Kb + nb) return false;
+        const int64_t Lb = std::max<int64_t>(2 * Kb, ((block_boxes - Kb + want_segs - 1) / want_segs + nb - 1) / nb * nb);
+        const int64_t n = (block_boxes - Kb + Lb - 1) / Lb;
+        if (n < 2 || !fits_k1s || S != 4 || p->ir.n_state != p->kernel_n_state) return false;
+        g.n_segs = (int)n;
+        g.seg_boxes = (int)Lb;
+        g.warm_boxes = (int)Kb;
+        n_cg = (c_count + 31) / 32 * n;
+        row_boxes = Lb + Kb;
+        g.groups = (int)std::max<int64_t>(1, std::min<int64_t>(g.groups, n_cg));
+        g.grid = grid_for(g.groups);
+        return true;
+    }
     if (mode == 2) return true;
     // auto: rows of at least eight tiles (the ring fills once per launch), and -- other than for 4 sections, where the
     // group count follows the channel count -- a GPU's worth of groups
@@ -1198,7 +1231,7 @@ int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void
         !encode_map_tile3d(&a.out_map, out[0], c_count, T, ld_out, 32, g.boxes))
         return fail(ZG_ERR_CUDA, "cuTensorMapEncodeTiled (whole-tile map of the section-split biquad kernel)");
     const size_t n_cg_plan = (size_t)(p->ch_stride + 31) / 32;
-    if (!p->d_split_ctl || p->split_wpg_alloc < g.wpg) {
+    if (!p->d_split_ctl || p->split_wpg_alloc < g.wpg || p->split_segs_alloc < g.n_segs) {
         if (p->d_split_ctl) cudaFree(p->d_split_ctl);
         if (p->d_split_flags) cudaFree(p->d_split_flags);
         if (p->d_split_carry) cudaFree(p->d_split_carry);
@@ -1207,10 +1240,12 @@ int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void
         p->d_split_carry = nullptr;
         ZG_CUDA(cudaMalloc(&p->d_split_ctl, 4 * sizeof(unsigned long long)));
         ZG_CUDA(cudaMemset(p->d_split_ctl, 0, 4 * sizeof(unsigned long long)));
-        ZG_CUDA(cudaMalloc(&p->d_split_flags, n_cg_plan * g.wpg * sizeof(unsigned long long)));
-        ZG_CUDA(cudaMemset(p->d_split_flags, 0, n_cg_plan * g.wpg * sizeof(unsigned long long)));
-        ZG_CUDA(cudaMalloc(&p->d_split_carry, (size_t)p->kernel_n_state * 2 * p->ch_stride * sizeof(float)));
-        p->split_wpg_alloc = g.wpg;
+        const int wpg_alloc = std::max(p->split_wpg_alloc, g.wpg), segs_alloc = std::max(p->split_segs_alloc, g.n_segs);
+        ZG_CUDA(cudaMalloc(&p->d_split_flags, n_cg_plan * wpg_alloc * segs_alloc * sizeof(unsigned long long)));
+        ZG_CUDA(cudaMemset(p->d_split_flags, 0, n_cg_plan * wpg_alloc * segs_alloc * sizeof(unsigned long long)));
+        ZG_CUDA(cudaMalloc(&p->d_split_carry, (size_t)p->kernel_n_state * 2 * p->ch_stride * segs_alloc * sizeof(float)));
+        p->split_wpg_alloc = wpg_alloc;
+        p->split_segs_alloc = segs_alloc;
     }
     a.state = p->d_state + c_begin;
     a.params = p->d_params ? p->d_params + c_begin : nullptr;
@@ -1220,8 +1255,19 @@ int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void
     a.stages = g.stages;
     a.boxes = g.boxes;
     a.ctl = p->d_split_ctl;
-    a.flags = p->d_split_flags + (c_begin / 32) * g.wpg;
-    a.carry = p->d_split_carry + c_begin;
+    a.flags = p->d_split_flags + (c_begin / 32) * g.wpg * g.n_segs;
+    a.carry = p->d_split_carry + c_begin * g.n_segs;
+    a.carry_stride = p->ch_stride * g.n_segs;
+    a.state_out = a.state;
+    if (g.n_segs > 1) {
+        // the last segments leave the block's final state in another buffer (a first segment may still have to read the old
+        // one), copied back behind the kernel
+        if (!p->d_state_alt) ZG_CUDA(cudaMalloc(&p->d_state_alt, (size_t)std::max(p->ir.n_state, 1) * p->ch_stride * sizeof(float)));
+        a.state_out = p->d_state_alt + c_begin;
+        a.n_segs = g.n_segs;
+        a.seg_boxes = g.seg_boxes;
+        a.warm_boxes = g.warm_boxes;
+    }
     for (int j = 0; j < p->kernel_n_state; ++j) a.state_row[j] = p->state_row[j];
     if (p->uniform_now) std::memcpy(a.uparams, p->uparams, sizeof(float) * std::min(p->kernel_n_param, zgk::kMaxUniform));
     int st = raise_max_smem((const void*)fn, p->opts.device, g.smem);
@@ -1235,13 +1281,17 @@ int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void
     p->split_spw = g.spw;
     void* args[] = {&a};
     ZG_CUDA(cudaLaunchKernel((const void*)fn, dim3(g.grid), dim3(g.groups * g.wpg * 32), args, g.smem, stream));
+    if (g.n_segs > 1)
+        ZG_CUDA(cudaMemcpy2DAsync(p->d_state + c_begin, p->ch_stride * sizeof(float), p->d_state_alt + c_begin,
+                                  p->ch_stride * sizeof(float), (size_t)c_count * sizeof(float), (size_t)p->kernel_n_state,
+                                  cudaMemcpyDeviceToDevice, stream));
     p->launches += 1;
     p->split_now = true;
     p->split_hand_boxes = g.hand_boxes;
-    p->last_segs = 1;
-    p->last_seg_mode = 0;
-    p->last_seg_len = 0;
-    p->last_seg_warm = 0;
+    p->last_segs = g.n_segs;
+    p->last_seg_mode = g.n_segs > 1 ? 1 : 0;
+    p->last_seg_len = g.seg_boxes * zgk::kTileT;
+    p->last_seg_warm = g.warm_boxes * zgk::kTileT;
     if (advance) p->stream_pos += T;
     p->last_smem = g.smem;
     p->last_threads = g.groups * g.wpg * 32;
@@ -1262,11 +1312,11 @@ int launch(zg_plan* p, const void* const* in, void* const* out, int64_t T, int64
     st = choose_segments(p, in, out, T, c_count, sg);
     if (st != ZG_OK) return st;
     p->split_now = false;
-    if (sg.mode == 0) {
-        p->lanes_now = p->lanes;
-        p->seg_now = false;
+    if (sg.mode <= 1) {
+        p->lanes_now = sg.mode ? 1 : p->lanes;
+        p->seg_now = false;                 // (K1s is one kernel with and without segments)
         SplitGeometry sp{};
-        if (choose_split(p, T, c_count, sp)) {
+        if (choose_split(p, T, c_count, sp, sg.mode == 1 ? &sg : nullptr)) {
             p->lanes_now = 1;
             return launch_split(p, sp, in, out, T, ld_in, ld_out, stream, c_begin, c_count, advance);
         }
