@@ -19,7 +19,7 @@ Channels are independent, so N GPUs = N x the channels (weak scaling), no data-p
             against the oracle rides along as cpu_baseline.parity_spot_check); graphs and coefficients of
             the GPU legs come from zignal_b200/workloads.py
   also      the other biquad shape (c2 when the headline is ns and vice versa), device-resident, same rules;
-            c2_scan = configs[1] in FAST mode, cut in time (zg_plan_opts.time_parallel, DESIGN.md 3 K5);
+            c2_scan = configs[1] in FAST mode, cut in time (zg_plan_opts.time_parallel, DESIGN.md 3 K5 / K1s);
             ns_per_channel = the north-star shape with the per-channel coefficients SURVEY.md 8(d) prescribes;
             ns_k1 = the north-star shape on the lane-per-channel kernel (zg_plan_opts.section_warps = 1)
   edge      (N > 1) a 65 536 x 8192 block resident on rank 0 -> N shard plans -> back on rank 0, three ways:
@@ -623,7 +623,7 @@ def run_ours(args):
         if other == "c2" and args.mode == "exact":
             also[other]["bound"] = ("recurrence latency, not HBM: 4096 channels x 4 sections = one warp per scheduler, "
                                     "y = (v + a1*y1) + a2*y2 is three dependent 5-cycle instructions per sample, so "
-                                    "0.50 ms / 0.67 of the HBM roofline is the ceiling of EXACT arithmetic (DESIGN.md K1b)")
+                                    "0.50 ms / 0.67 of the HBM roofline is the ceiling of EXACT arithmetic (DESIGN.md K1s, one group per SM; K1b)")
         del plan_o, xo, yo
         torch.cuda.empty_cache()
         peak_hbm = _peak_hbm()[0]

@@ -194,11 +194,13 @@ typedef struct zg_plan_opts {
                              banded-Toeplitz contraction on tcgen05 tensor cores, 3xTF32: ~3e-6 block-relative from the
                              reference's left-to-right sum, dominated by the tensor core's truncating fp32 accumulation),
                              1 = never (CUDA-core FMA kernel, ~3e-7).  ZG_MODE_EXACT never uses tensor cores.        */
-    int section_warps;    /* biquad cascades with one lane per channel, planar fp32, blocks of whole 32-sample boxes: the
-                             sections of a group of 32 channels spread over the warps of a CTA that share one ring of
-                             tiles (same arithmetic, bit-identical in EXACT mode), so that every channel row is moved in
-                             runs of 1.5-1.75 KB instead of 512 bytes.  0 = auto (many channels: at least four rows
-                             per persistent group, evenly divided), 1 = never, 2 = whenever the shape allows      */
+    int section_warps;    /* biquad cascades, planar fp32, blocks of whole 32-sample boxes: the sections of a group of 32
+                             channels spread over the warps of a persistent CTA that share one ring of tiles (same
+                             arithmetic, bit-identical in EXACT mode), every channel row moved in runs of 1 KB and more,
+                             rows handed from one CTA to the next in the middle of a block.  0 = auto (4 sections: every
+                             channel count; 3, 5-8 sections: from ~28 000 channels on; blocks of at least 8 tiles),
+                             1 = never, 2 = whenever the shape allows.  Calls on one plan must be stream-ordered (as for
+                             any plan: its state rows live in device memory).                                     */
     int reserved[4];
 } zg_plan_opts;
 

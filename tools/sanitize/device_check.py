@@ -18,6 +18,13 @@ import __graft_entry__ as entry
 import flowz_oracle as fo
 import zignal_b200 as zg
 
+# The race checker follows a thread's OWN mbarrier arrivals only, so for it every lane of a K1s warp arrives itself
+# (ZG_TUNE_SPLIT_ARRIVE=1, kernels/zg_biquad_split.cuh kAllArrive); the production form -- lane 0 arrives for the warp
+# after a __syncwarp -- is what memcheck / synccheck see (ZG_SANITIZER=memcheck|synccheck), and what `--k1s-elected`
+# forces under racecheck too (it then reports the hand-over of every box as a hazard).
+if "--k1s-elected" not in sys.argv and os.environ.get("ZG_SANITIZER", "racecheck") == "racecheck":
+    os.environ["ZG_TUNE_SPLIT_ARRIVE"] = "1"
+
 C, T = 64, 2048
 x = fo.noise(C, T, seed=3)
 xd = zg.to_block(x)
@@ -49,22 +56,18 @@ yb = zg.compile(expr).plan(channels=C, io_dtype=zg.BF16).process([xd.to(torch.bf
 refb = fo.COracle(expr, C).process([fo.bf16_round(x)])[0]
 assert np.array_equal(yb.view(torch.int16).cpu().numpy().view(np.uint16), fo.bf16_bits(refb)), "bf16 storage"
 
-# K1s: sections spread over the warps of a group (box hand-over through mbarriers; rows cut between groups).  The race
-# checker follows a thread's OWN mbarrier arrivals only, so for it every lane arrives itself (ZG_TUNE_SPLIT_ARRIVE=1);
-# the production form -- lane 0 arrives for the warp after a __syncwarp -- is what memcheck / synccheck see
-# (`--k1s-elected` forces it under racecheck too: it then reports the hand-over of every box as a hazard).
-if "--k1s-elected" not in sys.argv and os.environ.get("ZG_SANITIZER", "racecheck") == "racecheck":
-    os.environ["ZG_TUNE_SPLIT_ARRIVE"] = "1"
+# K1s: sections spread over the warps of a group (box hand-over through mbarriers; rows cut between groups)
+os.environ["ZG_TUNE_SPLIT_G"] = "3"          # three groups per CTA, as on many channels (328 channels alone would run one group per SM)
 ks = zg.compile(expr).plan(channels=328, lanes_per_channel=1, section_warps=2)
 xs = fo.noise(328, 1504, seed=6)
 assert np.array_equal(ks.process([zg.to_block(xs)])[0].cpu().numpy(), fo.COracle(expr, 328).process([xs])[0]), "K1s"
-assert b"zg_biquad_df1_split" in ks.info().kernel
+assert b"zg_biquad_df1_split<4,exact,planar,4 warps per group>" in ks.info().kernel
+os.environ.pop("ZG_TUNE_SPLIT_G")
 # ... and its few-channel form (one group per SM, four boxes per hand-over), what an auto plan of 64 channels runs on a long block
 kf = zg.compile(expr).plan(channels=C)
 xf8 = fo.noise(C, 8192, seed=9)
 assert np.array_equal(kf.process([zg.to_block(xf8)])[0].cpu().numpy(), fo.COracle(expr, C).process([xf8])[0]), "K1s, few channels"
 assert b"boxes per hand-over" in kf.info().kernel
-os.environ.pop("ZG_TUNE_SPLIT_ARRIVE", None)
 
 # long delay lines: rings in HBM
 comb = "~(_2 + 0.5f*_1[_441]) |= (_1 + 0.25f*_1[_1000])"
