@@ -1,19 +1,22 @@
 // zignal-b200 :: biquad cascade with the SECTIONS of a channel group spread over the warps of a CTA (K1s).
 //
 // Same graph, same arithmetic, same state rows as zg_biquad.cuh (reference spelling test/benchmark.cpp:25-33,
-// `fwd |= bwd` chained SECTIONS times); for MANY channels, where the lane-per-channel kernel (K1) is limited by the
-// length of the contiguous run each channel row contributes to an HBM request: K1 needs ~7 resident warps per SM to
+// `fwd |= bwd` chained SECTIONS times).  Built for MANY channels, where the lane-per-channel kernel (K1) is limited by
+// the length of the contiguous run each channel row contributes to an HBM request: K1 needs ~7 resident warps per SM to
 // issue its arithmetic, every warp owns 32 channel rows, and 227 KB of shared memory over 7 x 32 rows x 2 stages is
-// 512 bytes per row at a time (the skeleton streams 5.87 TB/s at 512 B, 6.23 TB/s at 1 KB).
+// 512 bytes per row at a time (the skeleton streams 5.87 TB/s at 512 B, 6.23 TB/s at 1 KB) -- and
+// since then the kernel of every channel count of the 4-section cascade (fewer groups per CTA for fewer channels, down
+// to one group per SM with several boxes per hand-over, kHB below), also cut in time (FAST mode, SplitArgs::n_segs).
 //
 // Here a GROUP of WPG = SECTIONS / SPW warps shares one ring of tiles of 32 channel rows: warp `sec` of the group
 // evaluates sections [sec * SPW, (sec + 1) * SPW) of those 32 channels (lane = channel, as in K1) IN PLACE, one
 // 32-sample box behind warp sec - 1 -- the hand-over between sections is the tile itself.  Warps per SM and rows
-// per SM are decoupled: two groups of four warps issue like eight, but only 64 rows share the shared memory, so a
-// tile is 12-14 boxes = 1.5-1.75 KB of every row in one TMA request.
+// per SM are decoupled: three groups of four warps issue like twelve, but only 96 rows share the shared memory, so a
+// tile is 8 boxes = 1 KB of every row in one TMA request.
 //
-//   * hand-over: one mbarrier per (section boundary, ring box); all lanes of the producing warp arrive, all lanes of
-//     the consuming warp wait.  Steady state: the wait succeeds at once.
+//   * hand-over: one mbarrier per (section boundary, ring box); lane 0 of the producing warp arrives after a
+//     __syncwarp (kAllArrive: every lane for itself), all lanes of the consuming warp wait.  Steady state: the wait
+//     succeeds at once.
 //   * TMA: one 3-D operation per tile and direction (box {32 samples, 32 channels, NB boxes}, SWIZZLE_128B, the same
 //     shared-memory image as NB single boxes).  Lane 0 of the LAST warp of a group issues both: the store of the tile
 //     it has just finished, and -- one box into the next tile, when that store has read its shared memory -- the load
@@ -158,7 +161,7 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
 
     // ---- the work of this group: a contiguous range of the tile sequence (row 0 tiles 0.., row 1 tiles 0.., ...) ----
     // Every group gets the same number of tiles (+-1), so a range begins and ends in the middle of a row.  The host
-    // makes ranges at least two rows long: a row is cut at most once.  Order inside the range: FIRST the head piece of
+    // makes ranges at least one row long: a row is cut at most once.  Order inside the range: FIRST the head piece of
     // the row the range ends in (tiles [0, k_hi) of row_hi; leaves its delay lines in `carry` and raises the row's flag),
     // then the whole rows, LAST the tail piece of the row it begins in (tiles [k_lo, ..) of row_lo, continuing from the
     // carry of the group before -- which wrote it at the very start of the launch).
