@@ -198,7 +198,7 @@ typedef struct zg_plan_opts {
                              channels spread over the warps of a persistent CTA that share one ring of tiles (same
                              arithmetic, bit-identical in EXACT mode), every channel row moved in runs of 1 KB and more,
                              rows handed from one CTA to the next in the middle of a block.  0 = auto (4 sections: every
-                             channel count; 3, 5-8 sections: from ~28 000 channels on; blocks of at least 8 tiles),
+                             channel count; 3, 5-8 sections: from ~9500 channels on; blocks of at least 8 tiles),
                              1 = never, 2 = whenever the shape allows.  Calls on one plan must be stream-ordered (as for
                              any plan: its state rows live in device memory).                                     */
     int reserved[4];

@@ -248,6 +248,22 @@ def test_split_falls_back_when_the_shape_does_not_allow_it(zg):
     assert np.array_equal(y, fo.COracle(expr, C).process([x])[0])
 
 
+@pytest.mark.parametrize("sections", [3, 8])
+def test_split_auto_other_section_counts_between_few_and_many_channels(zg, sections):
+    """9600 channels = 300 channel groups: two groups per CTA on every SM; bit-identical to the lane-per-channel kernel"""
+    torch = _torch()
+    C, T = 9600, 4096
+    expr = fo.biquad_cascade(sections)
+    x = torch.rand((C, T), device="cuda") * 2 - 1
+    plan = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT)
+    y = plan.process([x], n_samples=T)[0]
+    assert _is_split(plan), plan.info().kernel
+    k1 = zg.compile(expr).plan(channels=C, mode=zg.MODE_EXACT, section_warps=1)
+    assert torch.equal(y, k1.process([x], n_samples=T)[0]) and not _is_split(k1)
+    idx = [0, 31, 4800, 9599]
+    assert np.array_equal(y[idx].cpu().numpy(), fo.COracle(expr, len(idx)).process([x[idx].cpu().numpy()])[0])
+
+
 def test_split_is_what_auto_picks_for_many_channels(zg):
     """the north-star shape class: 65 536 channels -> 2048 channel groups over 2 x SMs persistent groups"""
     torch = _torch()

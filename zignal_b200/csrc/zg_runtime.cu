@@ -1164,6 +1164,13 @@ bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g
         if (!p->exact && p->lanes > 1 && !sg) fits_k1s = false;
     } else if (p->lanes > 1 || sg) {
         fits_k1s = false;
+    } else {
+        // other section counts: as many groups per CTA (up to the measured optimum) as still give every SM its groups,
+        // at least two -- one group per SM needs the several-boxes-per-hand-over form, which exists for 4 sections only.
+        // Measured on 16 384 x 16 384 (EXACT, ms, K1 in brackets): 3 sections 0.356 (0.514), 5: 0.441 (0.802),
+        // 6: 0.593 (0.890), 8: 0.606 (1.792); 9600 x 16 384: 3 sections 0.264 (0.509), 8: 0.420 (1.758)
+        while (groups > 2 && n_cg < (int64_t)groups * p->sm_count) --groups;
+        if (n_cg < (int64_t)groups * p->sm_count) fits_k1s = false;
     }
     if (int t = tune_env("ZG_TUNE_SPLIT_G")) groups = std::min(std::max(t, 1), 16 / g.wpg);
     g.groups = (int)std::max<int64_t>(1, std::min<int64_t>(groups, n_cg));
@@ -1217,8 +1224,7 @@ bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g
     // auto: rows of at least eight tiles (the ring fills once per launch), and -- other than for 4 sections, where the
     // group count follows the channel count -- a GPU's worth of groups
     if ((row_boxes + nb - 1) / nb < 8) return false;
-    if (S == 4 && spw == 1) return fits_k1s;
-    return fits_k1s && g.grid == p->sm_count;
+    return fits_k1s;
 }
 
 int launch_split(zg_plan* p, const SplitGeometry& g, const void* const* in, void* const* out, int64_t T, int64_t ld_in,
