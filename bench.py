@@ -485,7 +485,7 @@ def run_ours(args):
             plan.set_param(i, p)
         shape = (T, C) if args.layout == "interleaved" else (C, T)
         gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-        x = torch.rand(shape, generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+        x = torch.empty(shape, device=dev, dtype=torch.float32).uniform_(-1.0, 1.0, generator=gen)     # U(-1, 1), in place
         y = torch.empty_like(x)
         for _ in range(max(args.warmup, 3)):
             plan.process([x], [y])
