@@ -271,6 +271,22 @@ int zg_param_set_device(zg_plan* p, int index, const float* device_values, int64
  * the caller's process group -- zignal_b200/shard.py does it over torch.distributed.                             */
 int zg_shard_range(int64_t channels, int world_size, int rank, int64_t* begin, int64_t* end);
 
+/* ---- how a launch of the section-split biquad kernel (zg_plan_opts.section_warps) would be laid out ----------------
+ * Host-only (needs no device): the geometry the launch planner picks for a planar fp32 cascade of `sections` direct-
+ * form-1 biquads over `channels` x `samples` on a GPU of `sm_count` SMs with `max_smem` bytes of shared memory per
+ * CTA; `segments` > 1 asks for the block cut in time (FAST, warm-up of `warmup_samples`).  Returns 1 and fills *out
+ * when that kernel would run, 0 when the block stays on the other biquad kernels.  What the persistent CTAs rely on
+ * -- at least as many rows of 32 channels (x segments) as groups of warps, so that a row is handed from one group to
+ * the next at most once; a ring that fits; runs of boxes that divide the tile -- is checked over thousands of shapes
+ * without a GPU (tests/test_split_plan.py).                                                                        */
+typedef struct zg_split_plan {
+    int groups_per_cta, warps_per_group, sections_per_warp, grid, threads_per_cta;
+    int stages, boxes_per_tile, boxes_per_handover, smem_bytes;
+    int segments, segment_boxes, warmup_boxes;
+} zg_split_plan;
+int zg_split_plan_query(int sections, int exact, int64_t channels, int64_t samples, int sm_count, int max_smem,
+                        int segments, int warmup_samples, zg_split_plan* out);
+
 #ifdef __cplusplus
 }
 #endif

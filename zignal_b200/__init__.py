@@ -57,6 +57,22 @@ class PlanInfo(C.Structure):
                 ("segment_samples", C.c_int), ("warmup_samples", C.c_int), ("linearity", C.c_int)]
 
 
+class SplitPlan(C.Structure):              # zg_split_plan
+    _fields_ = [(n, C.c_int) for n in ("groups_per_cta", "warps_per_group", "sections_per_warp", "grid", "threads_per_cta",
+                                      "stages", "boxes_per_tile", "boxes_per_handover", "smem_bytes",
+                                      "segments", "segment_boxes", "warmup_boxes")]
+
+
+def split_plan(sections: int, channels: int, samples: int, exact: bool = True, sm_count: int = 148,
+               max_smem: int = 232448, segments: int = 1, warmup_samples: int = 0):
+    """The geometry a launch of the section-split biquad kernel would get (host only), or None when the block stays on
+    the other biquad kernels."""
+    o = SplitPlan()
+    if not lib.zg_split_plan_query(sections, int(exact), channels, samples, sm_count, max_smem, segments, warmup_samples, C.byref(o)):
+        return None
+    return o
+
+
 def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is not built; run `python zignal_b200/build.py` "
@@ -99,6 +115,7 @@ def _load() -> C.CDLL:
         "zg_param_set": (ci, [vp, ci, P(C.c_float), i64]),
         "zg_param_set_device": (ci, [vp, ci, vp, i64]),
         "zg_shard_range": (ci, [i64, ci, ci, P(i64), P(i64)]),
+        "zg_split_plan_query": (ci, [ci, ci, i64, i64, ci, ci, ci, ci, P(SplitPlan)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here = header and library disagree
@@ -113,7 +130,7 @@ EXPORTED = ["zg_last_error", "zg_version", "zg_expr_arity", "zg_expr_delays", "z
             "zg_voice_create", "zg_voice_clone", "zg_voice_destroy", "zg_voice_tick", "zg_voice_set_param",
             "zg_voice_state", "zg_plan_opts_default", "zg_graph_kernel_compile", "zg_plan_create",
             "zg_plan_destroy", "zg_plan_get_info", "zg_process", "zg_process_host", "zg_state_reset",
-            "zg_state_get", "zg_state_set", "zg_param_set", "zg_param_set_device", "zg_shard_range"]
+            "zg_state_get", "zg_state_set", "zg_param_set", "zg_param_set_device", "zg_shard_range", "zg_split_plan_query"]
 
 
 def _check(status: int) -> None:

@@ -1889,6 +1889,47 @@ int zg_plan_create(const zg_graph* g, const zg_plan_opts* opts, zg_plan** out) {
 
 void zg_plan_destroy(zg_plan* p) { delete p; }
 
+int zg_split_plan_query(int sections, int exact, int64_t channels, int64_t samples, int sm_count, int max_smem,
+                        int segments, int warmup_samples, zg_split_plan* out) {
+    if (!out || sections < 1 || sections > 8 || channels < 1 || samples < 1 || sm_count < 1 || max_smem < 1) return 0;
+    // the planner reads a plan: one with just the fields it looks at (no device is touched)
+    std::unique_ptr<zg_plan> p(new zg_plan());
+    p->opts.device = -1;
+    p->is_biquad = true;
+    p->exact = exact != 0;
+    p->bq.sections = sections;
+    p->C = channels;
+    p->ch_stride = (channels + 31) / 32 * 32;
+    p->sm_count = sm_count;
+    p->max_smem_optin = max_smem;
+    p->uniform_now = true;
+    p->kernel_n_state = p->ir.n_state = 2 * (sections + 1);
+    // the lanes the auto rule of zg_plan_create gives a cascade of 2 or 4 sections on few channels
+    p->lanes = (sections == 2 || sections == 4) && (channels + 31) / 32 < (int64_t)sm_count * 5 / 2 ? sections : 1;
+    p->lanes_now = 1;
+    Segments sg;
+    if (segments > 1) {
+        sg.mode = 1;
+        sg.n = segments;
+        sg.warm = warmup_samples;
+    }
+    SplitGeometry g{};
+    if (!choose_split(p.get(), samples, channels, g, segments > 1 ? &sg : nullptr)) return 0;
+    out->groups_per_cta = g.groups;
+    out->warps_per_group = g.wpg;
+    out->sections_per_warp = g.spw;
+    out->grid = g.grid;
+    out->threads_per_cta = g.groups * g.wpg * 32;
+    out->stages = g.stages;
+    out->boxes_per_tile = g.boxes;
+    out->boxes_per_handover = g.hand_boxes;
+    out->smem_bytes = g.smem;
+    out->segments = g.n_segs;
+    out->segment_boxes = g.seg_boxes;
+    out->warmup_boxes = g.warm_boxes;
+    return 1;
+}
+
 int zg_plan_get_info(const zg_plan* p, zg_plan_info* info) {
     if (!p || !info) return fail(ZG_ERR_ARG, "NULL argument");
     std::memset(info, 0, sizeof *info);
