@@ -1121,7 +1121,11 @@ bool choose_split(const zg_plan* p, int64_t T, int64_t c_count, SplitGeometry& g
     if (p->lanes > 1 && (p->opts.lanes_per_channel != 0 || tune_env("ZG_TUNE_LANES"))) return false;
     const int S = p->bq.sections;
     // with time segments a row of the tile sequence is (channel group, segment)
-    const int want_segs = sg ? segments_count(sg) : 1;
+    // (as few segments as give three groups per CTA a row each: every segment pays its warm-up; BASELINE configs[1]:
+    //  4 segments 0.366 ms, 8 segments 0.375)
+    const int want_segs = sg ? (int)std::min<int64_t>(segments_count(sg),
+                                                      std::max<int64_t>(2, (3 * (int64_t)p->sm_count + (c_count + 31) / 32 - 1) / ((c_count + 31) / 32)))
+                             : 1;
     int64_t n_cg = (c_count + 31) / 32 * want_segs;
     int64_t row_boxes = T / zgk::kTileT;
     if (sg) row_boxes = std::max<int64_t>(8, (row_boxes - segments_warm(sg) / zgk::kTileT) / want_segs + segments_warm(sg) / zgk::kTileT);
