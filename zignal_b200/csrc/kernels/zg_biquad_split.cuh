@@ -281,7 +281,11 @@ __device__ __forceinline__ void biquad_split_block(const SplitArgs& a) {
         // its delay lines (and coefficients): from the state rows (a later segment: zero), or -- the tail piece of a row --
         // from what the same warp of the group before left in `carry` (ld.cg: written by another SM during this launch)
         if (from_carry) {
-            while (ld_acquire_gpu(my_flag) != epoch) {}
+            // (the group before this one published the carry at the very start of the launch, so this wait is over before
+            //  it begins; should it ever not end -- a planner bug: nobody runs that head piece -- the launch fails with an
+            //  error after ~10 s of polling instead of hanging the GPU)
+            for (unsigned polls = 0; ld_acquire_gpu(my_flag) != epoch;)
+                if (++polls > (1u << 24)) __trap();
 #pragma unroll
             for (int j = 0; j < NS; ++j) s[j] = ch_ok ? __ldcg(&a.carry[(long long)(sec * NS + j) * a.carry_stride + carry_col]) : 0.f;
         } else {
